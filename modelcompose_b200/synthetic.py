@@ -1,0 +1,169 @@
+"""Deterministic synthetic checkpoints and inputs.
+
+There is no network: every benchmark/test input is seeded random data of the shapes the
+reference's training scripts produce (``train_multimodal.py:516-521`` saves every
+``requires_grad`` parameter as ``adapter_model.bin``).  Used by tests, ``bench.py`` and
+``__graft_entry__.smoke()``; contains no merge/forward arithmetic.
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from typing import Dict, List, Tuple
+
+import torch
+
+# (name, in_features_attr, out_features_attr) of the 7 LocalLoraLinear per decoder layer
+# (multimodal_llama.py:184-187, :357-359)
+LINEAR_NAMES = ["self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj",
+                "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj"]
+
+# which config key announces each modality's encoder (merge_unimodal_modelcompose.py:15-21)
+MODAL_ENCODER_KEY = {"vision": "mm_vision_tower", "audio": "mm_audio_encoder", "video": "mm_video_encoder",
+                     "point": "mm_point_encoder"}
+# projector config keys read by multimodal_projector/builder.py:203-244
+MODAL_HIDDEN_KEY = {"vision": "mm_hidden_size", "audio": "mm_audio_hidden_size", "video": "mm_video_hidden_size",
+                    "point": "mm_point_hidden_size"}
+MODAL_PROJ_KEY = {"vision": "mm_projector_type", "audio": "mm_audio_projector_type",
+                  "video": "mm_video_projector_type", "point": "mm_point_projector_type"}
+
+TINY = dict(hidden_size=256, intermediate_size=688, num_attention_heads=4, num_key_value_heads=4,
+            num_hidden_layers=2, vocab_size=1000, rms_norm_eps=1e-5, max_position_embeddings=2048,
+            hidden_act="silu")
+VICUNA_7B = dict(hidden_size=4096, intermediate_size=11008, num_attention_heads=32, num_key_value_heads=32,
+                 num_hidden_layers=32, vocab_size=32000, rms_norm_eps=1e-5, max_position_embeddings=4096,
+                 hidden_act="silu")
+# encoder feature dims / token counts (CLIP-L 576x1024, BEATs 256x768 synthetic, LanguageBind 8x257x1024, PointBERT 513x384)
+MODAL_FEATURE_DIM = {"vision": 1024, "audio": 768, "video": 1024, "point": 384}
+MODAL_TOKENS = {"vision": 576, "audio": 256, "video": 2056, "point": 513}
+
+
+def linear_shape(llama: dict, name: str) -> Tuple[int, int]:
+    """(out_features, in_features) of a decoder linear."""
+    H, I = llama["hidden_size"], llama["intermediate_size"]
+    if name.endswith(("gate_proj", "up_proj")):
+        return I, H
+    if name.endswith("down_proj"):
+        return H, I
+    return H, H
+
+
+def _uniform(gen, shape, bound, dtype):
+    return ((torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * bound).to(dtype)
+
+
+def _normal(gen, shape, std, dtype):
+    return (torch.randn(shape, generator=gen, dtype=torch.float32) * std).to(dtype)
+
+
+def make_unimodal_checkpoint(modal: str, seed: int, llama: dict = TINY, r: int = 8, lora_alpha: int = 16,
+                             feat_dim: int = 64, n_prefix: int = 5, n_suffix: int = 5,
+                             dtype=torch.bfloat16, projector_type: str = "mlp2x_gelu",
+                             layers: int | None = None) -> Tuple[Dict[str, torch.Tensor], dict]:
+    """One DAMC unimodal checkpoint (``lora_strategy modal+language``): adapters ``default`` and
+    ``{modal}`` on all 7 linears of every layer, the modality projector, prefix/suffix tokens.
+    Key order follows ``named_parameters()`` of the reference model.  LoRA A ~ U(±1/sqrt(in)) (peft
+    init), LoRA B ~ N(0, 0.02) (peft's zeros would make parity vacuous), projector = nn.Linear default init."""
+    g = torch.Generator().manual_seed(seed)
+    H = llama["hidden_size"]
+    L = llama["num_hidden_layers"] if layers is None else layers
+    sd: Dict[str, torch.Tensor] = {}
+    if n_prefix:
+        for a in ("default", modal):
+            sd[f"prefix_tokens.{a}"] = _normal(g, (1, n_prefix, H), 0.02, dtype)
+    if n_suffix:
+        for a in ("default", modal):
+            sd[f"suffix_tokens.{a}"] = _normal(g, (1, n_suffix, H), 0.02, dtype)
+    if projector_type == "linear":
+        dims = [(H, feat_dim)]
+        idx = [None]
+    else:
+        depth = int(projector_type[3:projector_type.index("x")])
+        dims = [(H, feat_dim)] + [(H, H)] * (depth - 1)
+        idx = [2 * i for i in range(depth)]
+    for (o, i), k in zip(dims, idx):
+        stem = f"model.modal_projectors.{modal}" + ("" if k is None else f".{k}")
+        sd[f"{stem}.weight"] = _uniform(g, (o, i), 1.0 / math.sqrt(i), dtype)
+        sd[f"{stem}.bias"] = _uniform(g, (o,), 1.0 / math.sqrt(i), dtype)
+    for l in range(L):
+        for name in LINEAR_NAMES:
+            out_f, in_f = linear_shape(llama, name)
+            for a in ("default", modal):
+                sd[f"model.layers.{l}.{name}.lora_A.{a}.weight"] = _uniform(g, (r, in_f), 1.0 / math.sqrt(in_f), dtype)
+            for a in ("default", modal):
+                sd[f"model.layers.{l}.{name}.lora_B.{a}.weight"] = _normal(g, (out_f, r), 0.02, dtype)
+    cfg = dict(llama)
+    cfg.update({"model_type": "multimodal", "architectures": ["MultimodalLlamaForCausalLM"],
+                "lora_strategy": "modal+language", "lora_r": r, "lora_alpha": lora_alpha, "lora_dropout": 0.05,
+                "local_prefix_tokens": n_prefix, "local_suffix_tokens": n_suffix,
+                MODAL_ENCODER_KEY[modal]: f"synthetic-{modal}-encoder",
+                MODAL_HIDDEN_KEY[modal]: feat_dim, MODAL_PROJ_KEY[modal]: projector_type})
+    if modal == "vision":
+        cfg["mm_vision_encoder"] = cfg["mm_vision_tower"]
+    return sd, cfg
+
+
+def save_checkpoint_dir(path: str, sd: Dict[str, torch.Tensor], cfg: dict) -> None:
+    os.makedirs(path, exist_ok=True)
+    torch.save(sd, os.path.join(path, "adapter_model.bin"))
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(cfg, f, indent=4)
+
+
+def make_base_llm(seed: int, llama: dict = TINY, dtype=torch.bfloat16, std: float = 0.02) -> Dict[str, torch.Tensor]:
+    """Random-init base LLM state dict with vicuna key names (what ``model_base`` provides)."""
+    g = torch.Generator().manual_seed(seed)
+    H, V = llama["hidden_size"], llama["vocab_size"]
+    sd = {"model.embed_tokens.weight": _normal(g, (V, H), std, dtype)}
+    for l in range(llama["num_hidden_layers"]):
+        for name in LINEAR_NAMES:
+            sd[f"model.layers.{l}.{name}.weight"] = _normal(g, linear_shape(llama, name), std, dtype)
+        sd[f"model.layers.{l}.input_layernorm.weight"] = (1.0 + _normal(g, (H,), 0.02, torch.float32)).to(dtype)
+        sd[f"model.layers.{l}.post_attention_layernorm.weight"] = (1.0 + _normal(g, (H,), 0.02, torch.float32)).to(dtype)
+    sd["model.norm.weight"] = (1.0 + _normal(g, (H,), 0.02, torch.float32)).to(dtype)
+    sd["lm_head.weight"] = _normal(g, (V, H), std, dtype)
+    return sd
+
+
+def dense_7b_tensor_shapes(llama: dict = VICUNA_7B) -> List[Tuple[str, Tuple[int, ...]]]:
+    """The 291 dense tensors of a vicuna-7B-shaped checkpoint (6,738,415,616 elements) — config C2."""
+    H, V = llama["hidden_size"], llama["vocab_size"]
+    shapes = [("model.embed_tokens.weight", (V, H))]
+    for l in range(llama["num_hidden_layers"]):
+        for name in LINEAR_NAMES:
+            shapes.append((f"model.layers.{l}.{name}.weight", linear_shape(llama, name)))
+        shapes.append((f"model.layers.{l}.input_layernorm.weight", (H,)))
+        shapes.append((f"model.layers.{l}.post_attention_layernorm.weight", (H,)))
+    shapes.append(("model.norm.weight", (H,)))
+    shapes.append(("lm_head.weight", (V, H)))
+    return shapes
+
+
+def shard_tensors_greedy(sizes: List[int], world: int) -> List[List[int]]:
+    """Greedy largest-first size balancing of tensor indices over ``world`` ranks; no collective."""
+    order = sorted(range(len(sizes)), key=lambda i: (-sizes[i], i))
+    loads = [0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (loads[k], k))
+        out[r].append(i)
+        loads[r] += sizes[i]
+    return [sorted(x) for x in out]
+
+
+def make_prompt_ids(batch: int, modal_order: List[str], n_text: int, vocab: int, seed: int,
+                    modal_token_indexes: Dict[str, int], n_head: int = 36) -> torch.Tensor:
+    """Equal-length prompts: ``n_head`` system/USER tokens, then one sentinel per modality each followed by
+    2 separator tokens, then ``n_text`` question tokens (ragged inference batches crash the reference,
+    multimodal_arch.py:414-429, so every request shares the layout).  Token ids uniform in [3, vocab)."""
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for _ in range(batch):
+        parts = [torch.randint(3, vocab, (n_head,), generator=g)]
+        for m in modal_order:
+            parts.append(torch.tensor([modal_token_indexes[m]]))
+            parts.append(torch.randint(3, vocab, (2,), generator=g))
+        parts.append(torch.randint(3, vocab, (n_text,), generator=g))
+        rows.append(torch.cat(parts))
+    return torch.stack(rows).to(torch.int64)
