@@ -1,0 +1,106 @@
+/*
+ * modelcompose_b200 — C ABI of the B200-native ModelCompose composition hot path.
+ *
+ * The reference (THUNLP-MT/ModelCompose) is pure Python: it has no FFI / plugin interface.
+ * The seams this library sits behind are the Python call signatures listed in SURVEY.md §8(b);
+ * every entry point below names the reference code it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes stubs a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all pointers are caller-owned.
+ *   - "device pointer" arguments must be valid on the CURRENT CUDA device; kernels are
+ *     enqueued on the given stream (cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and the call returns without synchronising unless documented otherwise.
+ *   - return value: MC_OK (0) or a negative mc_status; mc_last_error() gives a
+ *     thread-local human-readable message for the last failure on the calling thread.
+ *   - no hidden global state except a per-device attribute cache (SM count); thread-safe
+ *     across streams.  Plan objects own a few KB/MB of device memory for pointer tables.
+ *   - there is NO CPU fallback: with no usable sm_100 device every compute entry point
+ *     returns MC_ERR_CUDA.
+ */
+#ifndef MODELCOMPOSE_B200_H
+#define MODELCOMPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MC_API __attribute__((visibility("default")))
+#else
+#define MC_API
+#endif
+
+typedef void* mc_stream_t; /* cudaStream_t */
+
+typedef enum mc_status {
+  MC_OK = 0,
+  MC_ERR_INVALID = -1,     /* bad argument (NULL pointer, size, dtype, count out of range) */
+  MC_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed (see mc_last_error) */
+  MC_ERR_UNSUPPORTED = -3, /* valid request this build does not cover */
+  MC_ERR_NOMEM = -4
+} mc_status;
+
+typedef enum mc_dtype { MC_F32 = 0, MC_F16 = 1, MC_BF16 = 2 } mc_dtype;
+
+MC_API int mc_abi_version(void);
+MC_API const char* mc_last_error(void);
+/* Fills name (<= cap bytes), SM count and compute capability (major*10+minor) of the current device. */
+MC_API int mc_device_info(char* name, size_t cap, int* sm_count, int* cc);
+
+/* ------------------------------------------------------------------------------------------------
+ * N-source parameter merge
+ *
+ * Replaces the elementwise arithmetic of the reference merge:
+ *   - scripts/model_composition/merge_unimodal_modelcompose.py:105-112  (`sum` / `mean` strategies:
+ *     Python sum() of N same-shape tensors, every add rounded in the storage dtype, then `/ N`)
+ *   - the materialised form of the online-merge-reset blend executed per forward in
+ *     modelcompose/model/language_model/multimodal_llama.py:130-149 with the coefficients of :93-106,
+ *     i.e. W_eff = (1 - Σ w_m)·W_base + Σ w_m·ckpt_m   (reference's own full-weight
+ *     formula: scripts/convert_to_multimodal.py:111-113, scripts/model_composition/delta_weights_compare.py:61)
+ *
+ * MC_MERGE_WEIGHTED : dst = rn_dst( ((w0*s0) + w1*s1) + ... )   fp32 products, fp32 left-to-right adds,
+ *                     separate multiply and add (never contracted to FMA), ONE rounding to dst dtype.
+ *                     Bit-identical to torch `(w0*t0.float() + w1*t1.float() + ...).to(dst)` on CPU.
+ * MC_MERGE_REF_SUM  : dst = (((0 + s0) + s1) + ...) with every add rounded to the storage dtype
+ *                     (src dtype == dst dtype required; weights ignored) — the reference `sum` strategy.
+ * MC_MERGE_REF_MEAN : REF_SUM followed by an IEEE division by n_src, rounded to the storage dtype.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum mc_merge_mode { MC_MERGE_WEIGHTED = 0, MC_MERGE_REF_SUM = 1, MC_MERGE_REF_MEAN = 2 } mc_merge_mode;
+
+#define MC_MERGE_MAX_SRC 8
+
+typedef struct mc_merge_plan mc_merge_plan_t;
+
+/* Builds the device-side pointer / chunk tables for merging `n_tensors` parameter tensors from `n_src`
+ * checkpoints.  src[s * n_tensors + t] is the device pointer of tensor t in source s, dst[t] its output,
+ * numel[t] its element count (may be 0).  Tensors that are contiguous in every source and in dst are fused
+ * into one segment.  `tuning` selects a kernel variant (0 = default).  Synchronous. */
+MC_API int mc_merge_plan_create(mc_merge_plan_t** plan, int n_tensors, int n_src, const void* const* src,
+                         void* const* dst, const int64_t* numel, int src_dtype, int dst_dtype, int tuning);
+/* Enqueues ONE kernel launch that merges every tensor of the plan.  weights: n_src host floats. */
+MC_API int mc_merge_plan_run(const mc_merge_plan_t* plan, const float* weights, int mode, mc_stream_t stream);
+/* Algorithmic bytes one run moves: (n_src * sizeof(src) + sizeof(dst)) * total elements. */
+MC_API int64_t mc_merge_plan_bytes(const mc_merge_plan_t* plan);
+MC_API int mc_merge_plan_destroy(mc_merge_plan_t* plan);
+
+/* One-shot form (create + run + stream-synchronise + destroy) for device-resident tensors. */
+MC_API int mc_merge_tensors(int n_tensors, int n_src, const void* const* src, void* const* dst, const int64_t* numel,
+                     const float* weights, int mode, int src_dtype, int dst_dtype, mc_stream_t stream);
+
+/* Host-buffer form used by the merge CLI: tensors live in HOST memory (pinned or pageable); the call
+ * streams them through device staging buffers (H2D, merge kernel, D2H overlapped on three streams),
+ * and returns after the last output byte has landed in h_dst.  staging_bytes = size of ONE staging
+ * slab per stream buffer (0 = 64 MiB).  Allocates and frees its own staging memory. */
+MC_API int mc_merge_host(int n_tensors, int n_src, const void* const* h_src, void* const* h_dst, const int64_t* numel,
+                  const float* weights, int mode, int src_dtype, int dst_dtype, size_t staging_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODELCOMPOSE_B200_H */

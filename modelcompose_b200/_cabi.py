@@ -1,0 +1,98 @@
+"""ctypes binding of ``include/modelcompose_b200.h`` — the only way Python reaches the CUDA kernels.
+
+The signatures carry plain pointers and sizes (no torch types): tensors are passed as
+``tensor.data_ptr()`` and the stream as ``torch.cuda.current_stream().cuda_stream``.
+There is no CPU fallback: a missing library or a failing call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_LIB: Optional[C.CDLL] = None
+
+MC_OK = 0
+MC_F32, MC_F16, MC_BF16 = 0, 1, 2
+MC_MERGE_WEIGHTED, MC_MERGE_REF_SUM, MC_MERGE_REF_MEAN = 0, 1, 2
+MC_MERGE_MAX_SRC = 8
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmodelcompose_b200.so")
+
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); must list every MC_API symbol of include/modelcompose_b200.h
+SIGNATURES = {
+    "mc_abi_version": (_i, []),
+    "mc_last_error": (C.c_char_p, []),
+    "mc_device_info": (_i, [C.c_char_p, _sz, C.POINTER(_i), C.POINTER(_i)]),
+    "mc_merge_plan_create": (_i, [C.POINTER(_vp), _i, _i, _pp, _pp, C.POINTER(_i64), _i, _i, _i]),
+    "mc_merge_plan_run": (_i, [_vp, C.POINTER(C.c_float), _i, _vp]),
+    "mc_merge_plan_bytes": (_i64, [_vp]),
+    "mc_merge_plan_destroy": (_i, [_vp]),
+    "mc_merge_tensors": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), C.POINTER(C.c_float), _i, _i, _i, _vp]),
+    "mc_merge_host": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), C.POINTER(C.c_float), _i, _i, _i, _sz]),
+}
+
+
+class McError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library (built in-tree by ``modelcompose_b200.build``).  Fails loudly."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise McError(
+                f"{LIB_PATH} is missing: build it with `python -m modelcompose_b200.build` "
+                "(modelcompose_b200 has no CPU or PyTorch fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        if handle.mc_abi_version() != 1:
+            raise McError("libmodelcompose_b200.so ABI version mismatch; rebuild")
+        _LIB = handle
+    return _LIB
+
+
+def check(rc: int, what: str) -> None:
+    if rc != MC_OK:
+        msg = lib().mc_last_error()
+        raise McError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    table = {torch.float32: MC_F32, torch.float16: MC_F16, torch.bfloat16: MC_BF16}
+    if torch_dtype not in table:
+        raise McError(f"unsupported dtype {torch_dtype} (float32 / float16 / bfloat16 only)")
+    return table[torch_dtype]
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def i64_array(vals):
+    arr = (C.c_int64 * len(vals))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+    return arr
+
+
+def f32_array(vals):
+    arr = (C.c_float * len(vals))()
+    for i, v in enumerate(vals):
+        arr[i] = float(v)
+    return arr
+
+
+def current_stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,245 @@
+"""Checkpoint merge: host logic of the reference CLI + the CUDA N-source merge behind it.
+
+Host side mirrors ``scripts/model_composition/merge_unimodal_modelcompose.py`` of the reference
+(same function names, arguments, on-disk outputs and error behaviour).
+All tensor arithmetic goes through the C ABI (``mc_merge_*`` in include/modelcompose_b200.h) —
+there is no torch/CPU arithmetic path in this module.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+from collections import defaultdict
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+
+# reference merge_unimodal_modelcompose.py:15-21 — first matching key wins
+MODAL_DICT = {
+    "mm_vision_encoder": "vision",
+    "mm_vision_tower": "vision",
+    "mm_vision2_encoder": "vision2",
+    "mm_vision2_tower": "vision2",
+    "mm_video_encoder": "video",
+    "mm_audio_encoder": "audio",
+    "mm_point_encoder": "point",
+}
+
+MODES = {"weighted": _cabi.MC_MERGE_WEIGHTED, "sum": _cabi.MC_MERGE_REF_SUM, "mean": _cabi.MC_MERGE_REF_MEAN}
+
+
+def get_modal_from_config(config: dict) -> str:
+    """reference :22-26."""
+    for key, modal in MODAL_DICT.items():
+        value = config.get(key) if key in config.keys() else None
+        if isinstance(value, str) and len(value) > 0:
+            return modal
+    assert False, "No modality is recognized, please check the config."
+
+
+# ------------------------------------------------------------------------------------------------ device API
+class MergePlan:
+    """Pointer/chunk tables for merging N same-shaped tensor lists resident on ONE device.
+
+    ``sources[s][t]`` and ``outputs[t]`` are contiguous CUDA tensors; ``run(weights, mode)`` enqueues one
+    kernel launch on the current stream.  The plan keeps references to the tensors it points at."""
+
+    def __init__(self, sources: Sequence[Sequence[torch.Tensor]], outputs: Sequence[torch.Tensor], tuning: int = 0):
+        n_src, n_t = len(sources), len(outputs)
+        if not 1 <= n_src <= _cabi.MC_MERGE_MAX_SRC:
+            raise ValueError(f"need 1..{_cabi.MC_MERGE_MAX_SRC} sources, got {n_src}")
+        src_dtype = sources[0][0].dtype if n_t else torch.bfloat16
+        dst_dtype = outputs[0].dtype if n_t else torch.bfloat16
+        for s in sources:
+            if len(s) != n_t:
+                raise ValueError("every source must hold the same number of tensors")
+        for t in range(n_t):
+            o = outputs[t]
+            _check_device_tensor(o, dst_dtype, o.numel(), f"outputs[{t}]")
+            for k in range(n_src):
+                _check_device_tensor(sources[k][t], src_dtype, o.numel(), f"sources[{k}][{t}]")
+        self._keep = (list(map(list, sources)), list(outputs))
+        self.n_src, self.n_tensors = n_src, n_t
+        self._h = C.c_void_p()
+        src_ptrs = _cabi.ptr_array([sources[k][t].data_ptr() for k in range(n_src) for t in range(n_t)])
+        dst_ptrs = _cabi.ptr_array([o.data_ptr() for o in outputs])
+        numel = _cabi.i64_array([o.numel() for o in outputs])
+        _cabi.check(_cabi.lib().mc_merge_plan_create(C.byref(self._h), n_t, n_src, src_ptrs, dst_ptrs, numel,
+                                                     _cabi.dtype_code(src_dtype), _cabi.dtype_code(dst_dtype), tuning),
+                    "mc_merge_plan_create")
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        return int(_cabi.lib().mc_merge_plan_bytes(self._h))
+
+    def run(self, weights: Optional[Sequence[float]] = None, mode: str = "weighted") -> None:
+        if mode == "weighted":
+            if weights is None or len(weights) != self.n_src:
+                raise ValueError("weighted merge needs one weight per source")
+            w = _cabi.f32_array(weights)
+        else:
+            w = _cabi.f32_array([1.0] * self.n_src)
+        _cabi.check(_cabi.lib().mc_merge_plan_run(self._h, w, MODES[mode], _cabi.current_stream_ptr()),
+                    "mc_merge_plan_run")
+
+    def close(self) -> None:
+        if self._h:
+            _cabi.lib().mc_merge_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _check_device_tensor(t: torch.Tensor, dtype, numel: int, what: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{what} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype or t.numel() != numel or not t.is_contiguous():
+        raise ValueError(f"{what}: expected contiguous {dtype} with {numel} elements, got {t.dtype} {tuple(t.shape)}")
+
+
+def merge_state_dicts_device(state_dicts: Sequence[Dict[str, torch.Tensor]], weights: Sequence[float],
+                             out_dtype=None, mode: str = "weighted") -> Dict[str, torch.Tensor]:
+    """Merge N device-resident state dicts with identical keys/shapes: ``out[k] = Σ_m w_m · sd_m[k]``
+    (one kernel launch for all tensors).  This is the materialised online-merge-reset blend
+     when ``state_dicts = [base, ckpt_1, …]`` and
+    ``weights = [1-Σw, w_1, …]``."""
+    keys = list(state_dicts[0].keys())
+    srcs = [[sd[k].contiguous() for k in keys] for sd in state_dicts]
+    outs = [torch.empty_like(t, dtype=out_dtype or t.dtype) for t in srcs[0]]
+    plan = MergePlan(srcs, outs)
+    plan.run(weights, mode)
+    torch.cuda.current_stream().synchronize()
+    plan.close()
+    return dict(zip(keys, outs))
+
+
+def merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], weights: Optional[Sequence[float]] = None,
+                       mode: str = "weighted", out_dtype=None, staging_bytes: int = 0) -> List[torch.Tensor]:
+    """Merge HOST tensors through the GPU (``mc_merge_host``: H2D, kernel, D2H pipelined).
+    ``tensor_lists[s][t]``: CPU tensors; returns new CPU tensors.  Used by the CLI's ``sum``/``mean``."""
+    n_src, n_t = len(tensor_lists), len(tensor_lists[0])
+    if not torch.cuda.is_available():
+        raise _cabi.McError("merging tensors needs a CUDA device (modelcompose_b200 has no CPU fallback)")
+    srcs = [[t.contiguous() for t in lst] for lst in tensor_lists]
+    src_dtype = srcs[0][0].dtype if n_t else torch.bfloat16
+    for lst in srcs:
+        for a, b in zip(lst, srcs[0]):
+            if a.dtype != src_dtype or a.shape != b.shape or a.is_cuda:
+                raise ValueError("sources must be CPU tensors of identical dtype and shape per key")
+    out_dtype = out_dtype or src_dtype
+    outs = [torch.empty(t.shape, dtype=out_dtype) for t in srcs[0]]
+    w = _cabi.f32_array(weights if weights is not None else [1.0] * n_src)
+    _cabi.check(_cabi.lib().mc_merge_host(
+        n_t, n_src, _cabi.ptr_array([srcs[k][t].data_ptr() for k in range(n_src) for t in range(n_t)]),
+        _cabi.ptr_array([o.data_ptr() for o in outs]), _cabi.i64_array([o.numel() for o in outs]), w, MODES[mode],
+        _cabi.dtype_code(src_dtype), _cabi.dtype_code(out_dtype), staging_bytes), "mc_merge_host")
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------ CLI host logic
+def _load_checkpoint_dir(filepath: str):
+    """reference :31-36 — adapter_model.bin (fallback mm_projector.bin) + config.json."""
+    adapter_path = os.path.join(filepath, "adapter_model.bin")
+    if not os.path.exists(adapter_path):
+        adapter_path = os.path.join(filepath, "mm_projector.bin")
+    weights = torch.load(adapter_path, map_location=torch.device("cpu"))
+    with open(os.path.join(filepath, "config.json")) as f:
+        config = json.load(f)
+    return weights, config
+
+
+def _elementwise_strategy(weights_to_merge: Dict[str, List[torch.Tensor]], strategy: str) -> Dict[str, torch.Tensor]:
+    """reference :105-112 (`sum`, `mean`) on the GPU.  Keys are grouped by source count so each group is one
+    multi-tensor launch; results are bit-identical to the reference's per-add storage-dtype rounding."""
+    merged: Dict[str, torch.Tensor] = {}
+    by_count: Dict[tuple, List[str]] = defaultdict(list)
+    for key, tensors in weights_to_merge.items():
+        by_count[(len(tensors), tensors[0].dtype)].append(key)
+    for (n_src, _), keys in by_count.items():
+        lists = [[weights_to_merge[k][s] for k in keys] for s in range(n_src)]
+        outs = merge_host_tensors(lists, mode=strategy)
+        merged.update(zip(keys, outs))
+    return {k: merged[k] for k in weights_to_merge}  # first-seen key order, as the reference dict has
+
+
+def merge_checkpoints(filepaths, output_path, strategy="sum", K=20):
+    """Drop-in for reference ``merge_checkpoints`` (:28-145): same inputs, same three output files.
+
+    Strategies: ``online-merge-[reset-]…`` (key rename + coefficient string into config.json; no arithmetic,
+    exactly as the reference), ``sum`` / ``mean`` (N-source elementwise merge on the GPU).  The ``ties-*`` and
+    ``convert-*`` families are outside this round's scope and raise NotImplementedError."""
+    configs, weights_to_merge = [], defaultdict(list)
+    for filepath in filepaths:
+        adapter_weights, modal_config = _load_checkpoint_dir(filepath)
+        configs.append(modal_config)
+        for key in adapter_weights:
+            weights_to_merge[key].append(adapter_weights[key])
+
+    if strategy.startswith("convert-") or strategy.startswith("ties-"):
+        raise NotImplementedError(f"strategy family of [{strategy}] is not part of the B200 hot path (SURVEY.md §8(f))")
+    print(strategy, strategy.startswith("ties-"))
+
+    if strategy.startswith("online-merge-"):
+        merged_weights = {}
+        modal_names = [get_modal_from_config(config) for config in configs]
+        for key, tensors in weights_to_merge.items():
+            if len(tensors) == 1:
+                merged_weights[key] = tensors[0]
+                continue
+            assert "default" in key
+            for modal_name, weight in zip(modal_names, tensors):
+                merged_weights[key.replace("default", f"default-{modal_name}")] = weight
+    elif strategy in ("sum", "mean"):
+        merged_weights = _elementwise_strategy(weights_to_merge, strategy)
+    else:
+        print(f"Merge strategy [{strategy}] not implemented, DO NOTHING.")
+        # the reference falls through to torch.save(merged_weights) with the name unbound (:113-115,:139)
+        raise UnboundLocalError("cannot access local variable 'merged_weights' where it is not associated with a value")
+
+    merged_configs = {}
+    for config in configs:
+        for key, value in config.items():
+            merged_configs[key] = (merged_configs[key] or value) if key in merged_configs else value
+        if strategy.startswith("online-merge-"):  # consumed on the first config only (:124-129)
+            strategy = strategy.replace("online-merge-", "")
+            if strategy.startswith("reset-"):
+                merged_configs["reset_scaling_weights"] = strategy.replace("reset-", "")
+            else:
+                merged_configs["merge_default_weights"] = strategy
+    for config in configs:
+        modal_name = get_modal_from_config(config)
+        merged_configs[f"{modal_name}_lora_alpha"] = config["lora_alpha"]
+        merged_configs[f"{modal_name}_lora_r"] = config["lora_r"]
+
+    os.makedirs(output_path, exist_ok=True)
+    torch.save(merged_weights, os.path.join(output_path, "adapter_model.bin"))
+    with open(os.path.join(output_path, "config.json"), "w") as f:
+        json.dump(merged_configs, f, indent=4)
+    with open(os.path.join(output_path, "merge_info.txt"), "w") as fout:
+        inputs = "\n".join(filepaths)
+        fout.write(f"Inputs:\n{inputs}\n\nOutput({strategy}):{output_path}")
+    print(f"Merged checkpoints saved to {output_path}")
+    return merged_weights, merged_configs
+
+
+def main(argv=None):
+    """reference :151-159 — identical flags."""
+    parser = argparse.ArgumentParser(description="Merge multiple torch checkpoints")
+    parser.add_argument("filepaths", nargs="+", help="List of checkpoint file paths to merge")
+    parser.add_argument("-o", "--output", default="merged_checkpoint.pth", help="Output file path")
+    parser.add_argument("--strategy", default="sum", help="Merge strategy")
+    parser.add_argument("-K", default=20, type=int, help="K for ties-merging")
+    args = parser.parse_args(argv)
+    merge_checkpoints(args.filepaths, args.output, args.strategy, args.K)
+
+
+if __name__ == "__main__":
+    main()
