@@ -80,7 +80,8 @@ typedef struct mc_merge_plan mc_merge_plan_t;
 /* Builds the device-side pointer / chunk tables for merging `n_tensors` parameter tensors from `n_src`
  * checkpoints.  src[s * n_tensors + t] is the device pointer of tensor t in source s, dst[t] its output,
  * numel[t] its element count (may be 0).  Tensors that are contiguous in every source and in dst are fused
- * into one segment.  `tuning` selects a kernel variant (0 = default).  Synchronous. */
+ * into one segment.  `tuning` selects a kernel variant (0 = library default; explicit codes: bit 24 set, bits 0-7 variant,
+ * bits 8-15 CTAs/SM cap, bit 16 one CTA per chunk instead of a persistent grid).  Synchronous. */
 MC_API int mc_merge_plan_create(mc_merge_plan_t** plan, int n_tensors, int n_src, const void* const* src,
                          void* const* dst, const int64_t* numel, int src_dtype, int dst_dtype, int tuning);
 /* Enqueues ONE kernel launch that merges every tensor of the plan.  weights: n_src host floats. */

@@ -48,6 +48,10 @@ extern "C" int mc_merge_plan_create(mc_merge_plan_t** out, int n_tensors, int n_
   MC_REQUIRE(n_src >= 1 && n_src <= MC_MERGE_MAX_SRC, "n_src %d outside [1, %d]", n_src, MC_MERGE_MAX_SRC);
   MC_REQUIRE(dtype_valid(src_dtype) && dtype_valid(dst_dtype), "bad dtype");
   MC_REQUIRE(n_tensors == 0 || (src && dst && numel), "NULL table");
+  // tuning == 0 → library default, chosen by the sweep in profiles/r01_merge_sweep.txt: 128-bit accesses,
+  // 2 vectors per source in flight per thread, 512-thread CTAs, one CTA per chunk (7.04 TB/s on B200).
+  // Explicit codes set bit 24: bits 0-7 variant, 8-15 CTAs/SM cap, 16 grid = #chunks instead of persistent.
+  if (tuning == 0) tuning = (1 << 24) | (1 << 16) | 2;
   const int variant = tuning & 0xff;
   const int ctas_per_sm_override = (tuning >> 8) & 0xff;
   const bool non_persistent = (tuning >> 16) & 1;

@@ -76,7 +76,10 @@ def test_reference_sum_mean_bit_exact(dtype, n_src, mode):
         assert bits_equal(outs[t], want), (n, dtype, mode)
 
 
-@pytest.mark.parametrize("tuning", [0, 1, 2, 3, 4, 5, 0 | (1 << 16), 1 | (2 << 8)])
+X = 1 << 24  # explicit tuning code
+
+
+@pytest.mark.parametrize("tuning", [0, X | 0, X | 1, X | 2, X | 3, X | 4, X | 5, X | (1 << 16), X | 1 | (2 << 8)])
 def test_every_tuning_variant(tuning):
     sizes = [(1 << 21) + 77, 12345, 4096 * 11008 // 64]
     srcs = make_sources(3, sizes, torch.bfloat16, seed=99, special=False)

@@ -51,7 +51,7 @@ def main():
     for ctas in [int(x) for x in args.ctas.split(",")]:
         for base in [int(x) for x in args.tunings.split(",")]:
             for nonpers in (0, 1):
-                tuning = base | (ctas << 8) | (nonpers << 16)
+                tuning = (1 << 24) | base | (ctas << 8) | (nonpers << 16)
                 plan = M.MergePlan(srcs, outs, tuning=tuning)
                 best, med = timeit(lambda: plan.run(w), args.iters)
                 gb = plan.algorithmic_bytes / 1e9
