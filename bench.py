@@ -200,12 +200,17 @@ def run_merge(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    shapes, sizes, mine = merge_shard(world, rank)
+    if args.emulate_world > 1:  # profiling aid: rank 0's shard of a K-way job in one process (never a bench value)
+        shapes, sizes, mine = merge_shard(args.emulate_world, 0)
+    else:
+        shapes, sizes, mine = merge_shard(world, rank)
     srcs = make_device_sources(shapes, mine, device)
     outs = [torch.empty(shapes[i][1], dtype=torch.bfloat16, device=device) for i in mine]
     plan = M.MergePlan(srcs, outs, tuning=args.tuning)
     my_bytes = plan.algorithmic_bytes
     total_bytes = sum(sizes) * 2 * (len(WEIGHTS) + 1)
+    if args.emulate_world > 1:
+        total_bytes = my_bytes
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,6 +249,11 @@ def run_merge(args):
             raise SystemExit(f"PARITY FAILURE on tensor {shapes[mine[j]][0]}")
 
     # ---- e2e: same merge through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timing)
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"profiling_only": True, "ms_per_step": round(ms_per_step, 4), "GBps": round(value, 1),
+                              "launch_ms": round(launch_ms, 4), "emulate_world": args.emulate_world}), flush=True)
+        return
     e2e = run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barrier, dist)
 
     if rank == 0:
@@ -335,6 +345,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="merge", choices=["merge"])
     ap.add_argument("--tuning", type=int, default=0)
+    ap.add_argument("--emulate-world", type=int, default=1,
+                    help="profiling aid: run rank 0's shard of a K-way job on one GPU (ncu captures)")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer e2e and CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
