@@ -101,6 +101,66 @@ MC_API int mc_merge_tensors(int n_tensors, int n_src, const void* const* src, vo
 MC_API int mc_merge_host(int n_tensors, int n_src, const void* const* h_src, void* const* h_dst, const int64_t* numel,
                   const float* weights, int mode, int src_dtype, int dst_dtype, size_t staging_bytes);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Modality-token splice
+ *
+ * Replaces modelcompose/model/multimodal_arch.py:287-459 (prepare_inputs_labels_for_multimodal), its helper
+ * modal_token_match (:270-285, sentinel ids from modelcompose/constants.py:23-30) and the prefix/suffix
+ * torch.cat of encode_modal_inputs (:244-253).  Every sentinel id in input_ids is replaced by the next
+ * feature block of its modality (cursor global across the batch, :302,:365) framed by that modality's
+ * prefix/suffix rows; text ids are looked up in the embedding table.  Rows are copied bit-exactly.
+ * Outputs have B x max_len rows; samples shorter than max_len are right-padded as the reference does for
+ * ragged batches (:390-430: zero rows, IGNORE_INDEX labels, False masks).
+ * ---------------------------------------------------------------------------------------------- */
+#define MC_SPLICE_MAX_MODAL 6
+#define MC_SPLICE_ERR_BAD_TOKEN 1 /* negative id that is no configured sentinel, or id >= vocab */
+#define MC_SPLICE_ERR_CURSOR 2    /* more sentinels of a modality than feature blocks supplied */
+
+typedef struct mc_splice_modal {
+  int64_t sentinel;      /* token id marking this modality (negative), e.g. -200 vision */
+  int32_t n_blocks;      /* feature blocks available: features is [n_blocks, n_rows, hidden] */
+  int32_t n_rows;
+  int32_t n_prefix;      /* rows of `prefix` spliced before every block (0 = none) */
+  int32_t n_suffix;
+  const void* features;  /* device; ignored by mc_splice_plan_create */
+  const void* prefix;    /* device [n_prefix, hidden] or NULL */
+  const void* suffix;    /* device [n_suffix, hidden] or NULL */
+  void* mask_out;        /* device [B, max_len] of mask_elem_size bytes: 1 where the row belongs to this modality; NULL = skip */
+} mc_splice_modal_t;
+
+typedef struct mc_splice_io {
+  int32_t dtype;                 /* mc_dtype of embed_table / features / out_embeds */
+  int32_t hidden;                /* row length in elements; hidden * sizeof(dtype) must be a multiple of 16 */
+  const void* embed_table;       /* device [vocab, hidden] */
+  const void* attention_mask_in; /* device [B, S] of mask_elem_size bytes, or NULL */
+  int32_t mask_elem_size;        /* 1 (torch.bool) or 8 (torch.int64): dtype of every mask in and out */
+  const int64_t* labels_in;      /* device [B, S] or NULL */
+  void* out_embeds;              /* device [B, max_len, hidden] */
+  uint8_t* out_modal_id;         /* device [B, max_len]: 0 = text ("default") or padding, 1 + m = modality m */
+  void* out_attention_mask;      /* device [B, max_len] (left-extended by the added length, :445-448), or NULL */
+  int64_t* out_labels;           /* device [B, max_len] (IGNORE_INDEX = -100 over spliced rows), or NULL */
+  uint8_t* out_default_mask;     /* device bool [B, max_len]: rows of no modality (:452-453), or NULL */
+} mc_splice_io_t;
+
+typedef struct mc_splice_plan mc_splice_plan_t;
+
+/* Scans input_ids (device, int64 [B, S]) on the GPU: output offsets, batch-global block cursors, padded length.
+ * Synchronises `stream` once (the output shape depends on the data).  Fails with MC_ERR_INVALID where the
+ * reference raises (unknown negative id, id >= vocab, sentinel without a feature block left). */
+MC_API int mc_splice_plan_create(mc_splice_plan_t** plan, const int64_t* d_input_ids, int B, int S, int vocab,
+                          const mc_splice_modal_t* modals, int n_modal, mc_stream_t stream);
+/* max_len / min_len over the batch (ragged iff they differ), per-sample lengths (B ints, may be NULL) and
+ * feature blocks consumed per modality (MC_SPLICE_MAX_MODAL ints, may be NULL). */
+MC_API int mc_splice_plan_info(const mc_splice_plan_t* plan, int* max_len, int* min_len, int32_t* out_len,
+                        int32_t* blocks_used);
+/* Algorithmic bytes of one mc_splice_run: B * max_len rows, each read once and written once. */
+MC_API int64_t mc_splice_plan_bytes(const mc_splice_plan_t* plan, int row_bytes);
+/* Enqueues ONE gather launch on `stream`.  `modals` must repeat the plan's geometry and carry the device pointers. */
+MC_API int mc_splice_run(const mc_splice_plan_t* plan, const mc_splice_io_t* io, const mc_splice_modal_t* modals,
+                  mc_stream_t stream);
+MC_API int mc_splice_plan_destroy(mc_splice_plan_t* plan);
+
 #ifdef __cplusplus
 }
 #endif
