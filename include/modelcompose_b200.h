@@ -161,6 +161,71 @@ MC_API int mc_splice_run(const mc_splice_plan_t* plan, const mc_splice_io_t* io,
                   mc_stream_t stream);
 MC_API int mc_splice_plan_destroy(mc_splice_plan_t* plan);
 
+/* ------------------------------------------------------------------------------------------------
+ * Grouped / modality-routed linear (tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM)
+ *
+ * Replaces the GEMMs of the composed-model prefill:
+ *   - modelcompose/model/language_model/multimodal_llama.py:120-160 (LocalLoraLinear.forward) as routed by
+ *     :262-268,:335-336 (attention q/k/v/o) and :380-390 (MLP gate/up/down): the reference evaluates every
+ *     adapter on every token and mask-sums; here a token only runs the adapter its modality mask selects
+ *   - modelcompose/model/multimodal_projector/builder.py:202-219 (mlp2x_gelu / linear projectors), one
+ *     problem per modality in a single launch
+ * Each problem computes  C[M,N] = epilogue( A0[M,K0]·B0[N,K0]^T + A1[M,K1]·B1[N,K1]^T ), all operands
+ * row-major 16-bit (bf16 or fp16, K contiguous), C in the same dtype.
+ *
+ * Routing (optional).  Rows carry a group id (row_group[m]: 0 = text/"default", 1 + i = modality i; the
+ * splice writes it) and mtile_mask[t] is the OR of (1 << group) over the rows of 128-row tile t
+ * (mc_route_tile_masks).  group_cols[0..n_groups] (HOST array) assigns a contiguous column range to every group:
+ *   - epilogue MC_LINEAR_EPI_ROWMASK (the LoRA down-projection T = x·A_all^T): the ranges partition N;
+ *     C[m,n] = acc * col_scale[n] if n lies in the range of row m's group, else 0; N tiles whose groups are
+ *     all absent from the M tile are skipped (their C is left untouched and is never read by the next step);
+ *   - K1 > 0 with n_groups > 0 (the up-projection y = x·W^T + T·B_all^T): the ranges partition K1 (boundaries
+ *     multiples of 64); 64-wide K1 blocks of groups absent from the M tile are skipped.
+ * ---------------------------------------------------------------------------------------------- */
+#define MC_LINEAR_MAX_PROBLEMS 4
+
+typedef enum mc_linear_epilogue {
+  MC_LINEAR_EPI_NONE = 0,
+  MC_LINEAR_EPI_BIAS = 1,      /* + bias[n] */
+  MC_LINEAR_EPI_BIAS_GELU = 2, /* gelu_erf(acc + bias[n])  (projector builder.py:214-217) */
+  MC_LINEAR_EPI_ROWMASK = 3,   /* see above */
+  MC_LINEAR_EPI_RESIDUAL = 4   /* + residual[m,n] (decoder residual adds, multimodal_llama.py:448,461) */
+} mc_linear_epilogue;
+
+typedef struct mc_linear_desc {
+  int32_t M, N, K0, K1;       /* K1 = 0: no second product */
+  const void* A0; int64_t lda0; /* device [M, K0], leading dimension in elements (multiple of 8) */
+  const void* B0; int64_t ldb0; /* device [N, K0] (nn.Linear weight layout) */
+  const void* A1; int64_t lda1; /* device [M, K1] or NULL */
+  const void* B1; int64_t ldb1; /* device [N, K1] or NULL */
+  void* C; int64_t ldc;         /* device [M, N] */
+  const void* bias;             /* device [N], same dtype as C, or NULL */
+  const void* residual; int64_t ldr; /* device [M, N] or NULL */
+  const float* col_scale;       /* device fp32 [N] (ROWMASK) or NULL */
+  const uint8_t* row_group;     /* device [M] (ROWMASK) or NULL */
+  const uint32_t* mtile_mask;   /* device [ceil(M/128)] or NULL (= every group present) */
+  const int32_t* group_cols;    /* HOST [n_groups + 1] or NULL */
+  int32_t n_groups;
+  int32_t epilogue;             /* mc_linear_epilogue */
+} mc_linear_desc_t;
+
+typedef struct mc_linear_plan mc_linear_plan_t;
+
+/* Encodes the TMA descriptors and tile schedule of 1..MC_LINEAR_MAX_PROBLEMS problems that run as ONE launch.
+ * dtype: MC_BF16 or MC_F16.  tuning: 0 = default tile, 1 = 128x128, 2 = 128x256.  The plan stays valid while the
+ * pointers in `desc` do (activations are normally static per-shape buffers, so plans are built once and reused). */
+MC_API int mc_linear_plan_create(mc_linear_plan_t** plan, const mc_linear_desc_t* desc, int n_problems, int dtype, int tuning);
+MC_API int mc_linear_plan_run(const mc_linear_plan_t* plan, mc_stream_t stream);
+/* Nominal FLOPs of one run: sum of 2*M*N*(K0+K1) (skipped K1 blocks / N tiles are NOT subtracted). */
+MC_API double mc_linear_plan_flops(const mc_linear_plan_t* plan);
+MC_API int mc_linear_plan_destroy(mc_linear_plan_t* plan);
+/* mtile_mask[t] = OR over rows of 128-row tile t of (1 << row_group[row]). */
+MC_API int mc_route_tile_masks(const uint8_t* d_row_group, int M, uint32_t* d_mtile_mask, mc_stream_t stream);
+/* out = silu(gate) * up, elementwise over [rows, cols] (multimodal_llama.py:381-388; act rounded to the storage
+ * dtype before the product, as the reference's separate ops do). */
+MC_API int mc_silu_mul(const void* gate, const void* up, void* out, int64_t rows, int cols, int64_t ld_gate, int64_t ld_up,
+                int64_t ld_out, int dtype, mc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

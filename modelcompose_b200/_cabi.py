@@ -39,6 +39,12 @@ SIGNATURES = {
     "mc_splice_plan_bytes": (_i64, [_vp, _i]),
     "mc_splice_run": (_i, [_vp, _vp, _vp, _vp]),
     "mc_splice_plan_destroy": (_i, [_vp]),
+    "mc_linear_plan_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i]),
+    "mc_linear_plan_run": (_i, [_vp, _vp]),
+    "mc_linear_plan_flops": (C.c_double, [_vp]),
+    "mc_linear_plan_destroy": (_i, [_vp]),
+    "mc_route_tile_masks": (_i, [_vp, _i, _vp, _vp]),
+    "mc_silu_mul": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _i64, _i, _vp]),
 }
 
 

@@ -1,0 +1,672 @@
+// Grouped / modality-routed linear on tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
+//
+// Replaces (reference paths):
+//   modelcompose/model/language_model/multimodal_llama.py:120-160  LocalLoraLinear.forward (base + per-adapter LoRA)
+//   :262-268,:335-336 (attention projections) and :380-390 (MLP): evaluate every adapter on every token, then
+//                     mask-and-sum; here each token only runs its own adapter (bit-identical routing)
+//   modelcompose/model/multimodal_projector/builder.py:202-219     mlp2x_gelu / linear projectors (grouped by modality)
+//
+// One kernel computes, for every problem p of a launch (problems = modalities for the projector, 1 otherwise):
+//     C[M,N] = epilogue( A0[M,K0] · B0[N,K0]^T  +  A1[M,K1] · B1[N,K1]^T )
+// The second product is the K-extension that carries the LoRA update: A1 = T (the rank-space activations,
+// one column block per adapter group, zero outside a token's own group) and B1 = [s·B_g | ...].  64-wide K1
+// blocks whose group has no token in the 128-row tile are skipped (per-tile group bitmask), so a tile that is
+// all-image only pays rank 128, a text tile pays the concatenated default rank (N_modal·128).
+// The same kernel produces T (epilogue ROWMASK: columns of group g keep only rows of group g, scaled by the
+// adapter scaling; whole N tiles whose groups are absent from the M tile are skipped).
+//
+// Tile: 128 x BN (BN = 256 or 128) x 64, cta_group::1, bf16/fp16 operands (K-major, 128B swizzle), fp32
+// accumulation in TMEM (2 accumulator stages x BN columns, so the epilogue of tile i overlaps the MMAs of
+// tile i+1).  Persistent grid (one CTA per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer,
+// warp 2 TMEM allocator, warps 4-7 epilogue.  Roofline: tensor pipe (bf16 dense).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "mc_common.cuh"
+
+namespace mc {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kMaxProb = MC_LINEAR_MAX_PROBLEMS;
+constexpr int kThreads = 256;
+constexpr int kGroupM = 8;  // tile rasterisation: 8 M-tiles share a sweep over N (keeps the B working set in L2)
+
+struct alignas(64) LinProblem {
+  CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  void* C;
+  const void* bias;
+  const float* col_scale;
+  const unsigned char* row_group;
+  const unsigned char* col_group;
+  const unsigned int* mtile_mask;
+  const unsigned int* ntile_mask;
+  const unsigned int* kb1_mask;
+  const void* residual;
+  long long ldc, ldr;
+  int M, N, nkb0, nkb1, tiles_m, tiles_n, tile_end, epilogue;
+};
+
+struct alignas(64) LinParams {
+  LinProblem prob[kMaxProb];
+  int n_prob, total_tiles, is_f16;
+  unsigned int idesc;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] · B[smem]^T, 128 x N x 16, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of 64 x 16-bit = 128 B, 128B swizzle (what TMA SWIZZLE_128B writes):
+// start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 8 rows x 128 B = 1024 B, version 1, layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---- tile scheduling (identical in all three roles) -----------------------------------------------------
+struct Tile {
+  int p, mt, nt;
+  unsigned int gmask;  // groups present in the M tile (all ones when unrouted)
+  bool skip;
+};
+
+__device__ __forceinline__ Tile decode_tile(const LinParams& P, int tile) {
+  Tile t;
+  int p = 0, begin = 0;
+  while (p < P.n_prob - 1 && tile >= P.prob[p].tile_end) {
+    begin = P.prob[p].tile_end;
+    ++p;
+  }
+  const LinProblem& pr = P.prob[p];
+  const int local = tile - begin;
+  const int per_group = kGroupM * pr.tiles_n;
+  const int g = local / per_group, within = local % per_group;
+  const int gsize = min(kGroupM, pr.tiles_m - g * kGroupM);
+  t.p = p;
+  t.mt = g * kGroupM + within % gsize;
+  t.nt = within / gsize;
+  t.gmask = pr.mtile_mask ? pr.mtile_mask[t.mt] : 0xffffffffu;
+  t.skip = pr.ntile_mask != nullptr && (pr.ntile_mask[t.nt] & t.gmask) == 0u;
+  return t;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, bool is_f16, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (is_f16) {
+      const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      f[2 * i] = __low2float(h);
+      f[2 * i + 1] = __high2float(h);
+    } else {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      f[2 * i] = __low2float(h);
+      f[2 * i + 1] = __high2float(h);
+    }
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], bool is_f16) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (is_f16) {
+      const __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = kBM * kBK * 2;
+  static constexpr int B_BYTES = BN * kBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for the manual 1024-byte alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_constant__ LinParams P) {
+  using L = SmemLayout<BN, STAGES>;
+  constexpr int TMEM_COLS = 2 * BN;  // power of two: 256 or 512
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.n_prob; ++p) {
+      tma_prefetch_desc(&P.prob[p].tmA0);
+      tma_prefetch_desc(&P.prob[p].tmB0);
+      if (P.prob[p].nkb1) {
+        tma_prefetch_desc(&P.prob[p].tmA1);
+        tma_prefetch_desc(&P.prob[p].tmB1);
+      }
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const Tile t = decode_tile(P, tile);
+        if (t.skip) continue;
+        const LinProblem& pr = P.prob[t.p];
+        const int m0 = t.mt * kBM, n0 = t.nt * BN;
+        for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
+          const bool ext = kb >= pr.nkb0;
+          const int k = ext ? kb - pr.nkb0 : kb;
+          if (ext && pr.kb1_mask && (pr.kb1_mask[k] & t.gmask) == 0u) continue;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          tma_load_2d(ext ? &pr.tmA1 : &pr.tmA0, &full_bar[stage], sa, k * kBK, m0);
+          tma_load_2d(ext ? &pr.tmB1 : &pr.tmB0, &full_bar[stage], sa + L::A_BYTES, k * kBK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const Tile t = decode_tile(P, tile);
+        if (t.skip) continue;
+        const LinProblem& pr = P.prob[t.p];
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
+          const bool ext = kb >= pr.nkb0;
+          if (ext && pr.kb1_mask && (pr.kb1_mask[kb - pr.nkb0] & t.gmask) == 0u) continue;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t a_desc = umma_smem_desc(sa), b_desc = umma_smem_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes (16 elements) along K inside the 128-byte swizzle row: start-address field += 2
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    const bool is_f16 = P.is_f16 != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const Tile t = decode_tile(P, tile);
+      if (t.skip) continue;
+      const LinProblem& pr = P.prob[t.p];
+      const int row = t.mt * kBM + q * 32 + lane;
+      const int n0 = t.nt * BN;
+      const bool row_ok = row < pr.M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const int rg = (pr.epilogue == MC_LINEAR_EPI_ROWMASK && row_ok) ? (int)pr.row_group[row] : -1;
+      char* crow = reinterpret_cast<char*>(pr.C) + (long long)row * pr.ldc * 2;
+      const char* rrow = pr.residual ? reinterpret_cast<const char*>(pr.residual) + (long long)row * pr.ldr * 2 : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= pr.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = n0 + c + 8 * j;
+            if (col < pr.N) {  // N % 8 == 0: the whole 8-column vector is in range
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+              if (pr.epilogue == MC_LINEAR_EPI_BIAS || pr.epilogue == MC_LINEAR_EPI_BIAS_GELU) {
+                float b[8];
+                unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(pr.bias) + (long long)col * 2), is_f16, b);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += b[e];
+                if (pr.epilogue == MC_LINEAR_EPI_BIAS_GELU) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+                }
+              } else if (pr.epilogue == MC_LINEAR_EPI_ROWMASK) {
+                const uint2 cg = *reinterpret_cast<const uint2*>(pr.col_group + col);
+                const float4 s0 = *reinterpret_cast<const float4*>(pr.col_scale + col);
+                const float4 s1 = *reinterpret_cast<const float4*>(pr.col_scale + col + 4);
+                const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const int g = (int)(((e < 4 ? cg.x : cg.y) >> (8 * (e & 3))) & 0xffu);
+                  f[e] = (g == rg) ? f[e] * s[e] : 0.0f;
+                }
+              } else if (pr.epilogue == MC_LINEAR_EPI_RESIDUAL) {
+                float r[8];
+                unpack8(*reinterpret_cast<const uint4*>(rrow + (long long)col * 2), is_f16, r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += r[e];
+              }
+              *reinterpret_cast<uint4*>(crow + (long long)col * 2) = pack8(f, is_f16);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---- routing helpers ------------------------------------------------------------------------------------
+// mask[t] = OR over the rows of 128-row tile t of (1 << group[row])
+__global__ void route_tile_mask_kernel(const unsigned char* __restrict__ group, int M, unsigned int* __restrict__ mask, int n_tiles) {
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  unsigned int m = 0;
+  for (int r = tile * kBM + lane; r < min(M, (tile + 1) * kBM); r += 32) m |= 1u << (group[r] & 31);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
+  if (lane == 0) mask[tile] = m;
+}
+
+// out[i] = silu(gate[i]) * up[i]   (multimodal_llama.py:381-388: act_fn(gate_proj(x)) * up_proj(x)); rounding points
+// as the reference: silu result rounded to the storage dtype, then the product rounded.
+template <typename T>
+__global__ void __launch_bounds__(256) silu_mul_kernel(const T* __restrict__ gate, const T* __restrict__ up, T* __restrict__ out,
+                                                       long long rows, int cols, long long ldg, long long ldu, long long ldo) {
+  const long long vec_per_row = cols / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row, c = (i % vec_per_row) * 8;
+    const uint4 g = *reinterpret_cast<const uint4*>(gate + r * ldg + c);
+    const uint4 u = *reinterpret_cast<const uint4*>(up + r * ldu + c);
+    const T* ge = reinterpret_cast<const T*>(&g);
+    const T* ue = reinterpret_cast<const T*>(&u);
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x = to_f32<T>(ge[e]);
+      const T s = from_f32<T>(x / (1.0f + expf(-x)));
+      oe[e] = from_f32<T>(to_f32<T>(s) * to_f32<T>(ue[e]));
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = o;
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+  static std::mutex mu;
+  static encode_tiled_fn fn = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major [rows, cols] 16-bit tensor, box = box_rows x 64 columns, 128B swizzle, zero fill out of bounds
+static int encode_operand(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, int dtype) {
+  encode_tiled_fn fn = get_encode_fn();
+  if (!fn) return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dtype == MC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d) for [%lld x %lld] ld %lld", (int)r, rows, cols, ld);
+  return MC_OK;
+}
+
+}  // namespace mc
+
+using namespace mc;
+
+struct mc_linear_plan {
+  LinParams params;
+  int bn, grid, dtype;
+  size_t smem_bytes;
+  double flops;
+  std::vector<void*> owned;  // device arrays built by the plan (group tables)
+};
+
+template <int BN, int STAGES>
+static cudaError_t launch_linear(const mc_linear_plan* p, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(linear_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  linear_kernel<BN, STAGES><<<p->grid, kThreads, L::DYN_BYTES, stream>>>(p->params);
+  return cudaGetLastError();
+}
+
+static void linear_plan_free(mc_linear_plan* p) {
+  if (!p) return;
+  for (void* d : p->owned) cudaFree(d);
+  delete p;
+}
+
+template <typename T>
+static cudaError_t upload(mc_linear_plan* p, const std::vector<T>& host, const T** dev_out) {
+  T* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, std::max<size_t>(host.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  p->owned.push_back(d);
+  if (!host.empty()) e = cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+  *dev_out = d;
+  return e;
+}
+
+extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_desc_t* desc, int n_problems, int dtype, int tuning) {
+  MC_REQUIRE(out != nullptr, "plan out-pointer is NULL");
+  *out = nullptr;
+  MC_REQUIRE(desc != nullptr && n_problems >= 1 && n_problems <= kMaxProb, "n_problems %d outside [1, %d]", n_problems, kMaxProb);
+  MC_REQUIRE(dtype == MC_BF16 || dtype == MC_F16, "linear: dtype must be bf16 or fp16");
+  // tuning: 0 = default (BN 256 when every problem has N >= 256, else 128); 1 = force BN 128; 2 = force BN 256
+  int bn = 256;
+  for (int i = 0; i < n_problems; ++i)
+    if (desc[i].N < 256) bn = 128;
+  if (tuning == 1) bn = 128;
+  if (tuning == 2) bn = 256;
+  mc_linear_plan* p = new (std::nothrow) mc_linear_plan();
+  if (!p) return fail(MC_ERR_NOMEM, "host allocation failed");
+  memset(&p->params, 0, sizeof(p->params));
+  p->bn = bn;
+  p->dtype = dtype;
+  p->flops = 0;
+  int tile_end = 0;
+  int rc = MC_OK;
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < n_problems && rc == MC_OK && e == cudaSuccess; ++i) {
+    const mc_linear_desc_t& d = desc[i];
+    LinProblem& pr = p->params.prob[i];
+#define PLAN_REQUIRE(cond, ...)                    \
+  if (!(cond)) {                                   \
+    rc = fail(MC_ERR_INVALID, __VA_ARGS__);        \
+    break;                                         \
+  }
+    PLAN_REQUIRE(d.M >= 1 && d.N >= 8 && d.K0 >= 8, "problem %d: need M >= 1, N >= 8, K0 >= 8", i);
+    PLAN_REQUIRE(d.N % 8 == 0 && d.K0 % 8 == 0 && d.K1 % 8 == 0, "problem %d: N, K0, K1 must be multiples of 8", i);
+    PLAN_REQUIRE(d.A0 && d.B0 && d.C, "problem %d: A0 / B0 / C is NULL", i);
+    PLAN_REQUIRE(d.lda0 >= d.K0 && d.ldb0 >= d.K0 && d.ldc >= d.N && d.lda0 % 8 == 0 && d.ldb0 % 8 == 0 && d.ldc % 8 == 0,
+                 "problem %d: leading dimensions must cover the row and be multiples of 8 elements", i);
+    PLAN_REQUIRE((((uintptr_t)d.A0 | (uintptr_t)d.B0 | (uintptr_t)d.C | (uintptr_t)d.A1 | (uintptr_t)d.B1 | (uintptr_t)d.bias |
+                   (uintptr_t)d.residual) & 15) == 0, "problem %d: operand pointers must be 16-byte aligned", i);
+    PLAN_REQUIRE(d.K1 == 0 || (d.A1 && d.B1 && d.lda1 >= d.K1 && d.ldb1 >= d.K1 && d.lda1 % 8 == 0 && d.ldb1 % 8 == 0),
+                 "problem %d: K1 > 0 needs A1 / B1 with valid leading dimensions", i);
+    PLAN_REQUIRE(d.epilogue >= MC_LINEAR_EPI_NONE && d.epilogue <= MC_LINEAR_EPI_RESIDUAL, "problem %d: bad epilogue %d", i, d.epilogue);
+    PLAN_REQUIRE((d.epilogue != MC_LINEAR_EPI_BIAS && d.epilogue != MC_LINEAR_EPI_BIAS_GELU) || d.bias, "problem %d: bias is NULL", i);
+    PLAN_REQUIRE(d.epilogue != MC_LINEAR_EPI_RESIDUAL || (d.residual && d.ldr >= d.N && d.ldr % 8 == 0), "problem %d: residual missing", i);
+    const bool routed_n = d.epilogue == MC_LINEAR_EPI_ROWMASK;
+    const bool routed_k = d.K1 > 0 && d.n_groups > 0;
+    PLAN_REQUIRE(!routed_n || (d.n_groups >= 1 && d.n_groups <= 32 && d.group_cols && d.row_group && d.col_scale),
+                 "problem %d: ROWMASK epilogue needs n_groups in [1,32], group_cols, row_group and col_scale", i);
+    PLAN_REQUIRE(!routed_k || (d.n_groups <= 32 && d.group_cols && d.mtile_mask), "problem %d: routed K1 needs group_cols and mtile_mask", i);
+    pr.M = d.M;
+    pr.N = d.N;
+    pr.nkb0 = (d.K0 + kBK - 1) / kBK;
+    pr.nkb1 = (d.K1 + kBK - 1) / kBK;
+    pr.tiles_m = (d.M + kBM - 1) / kBM;
+    pr.tiles_n = (d.N + bn - 1) / bn;
+    tile_end += pr.tiles_m * pr.tiles_n;
+    pr.tile_end = tile_end;
+    pr.epilogue = d.epilogue;
+    pr.C = d.C;
+    pr.ldc = d.ldc;
+    pr.bias = d.bias;
+    pr.residual = d.residual;
+    pr.ldr = d.ldr;
+    pr.col_scale = d.col_scale;
+    pr.row_group = d.row_group;
+    pr.mtile_mask = d.mtile_mask;
+    if (routed_n || routed_k) {
+      const int extent = routed_n ? d.N : d.K1;
+      PLAN_REQUIRE(d.group_cols[0] == 0 && d.group_cols[d.n_groups] == extent, "problem %d: group_cols must span [0, %d]", i, extent);
+      std::vector<unsigned char> cg(extent);
+      for (int g = 0; g < d.n_groups; ++g) {
+        PLAN_REQUIRE(d.group_cols[g] <= d.group_cols[g + 1], "problem %d: group_cols not ascending", i);
+        for (int c = d.group_cols[g]; c < d.group_cols[g + 1]; ++c) cg[c] = (unsigned char)g;
+      }
+      if (rc != MC_OK) break;
+      const int blk = routed_n ? bn : kBK;
+      std::vector<unsigned int> bm((extent + blk - 1) / blk, 0u);
+      for (int c = 0; c < extent; ++c) bm[c / blk] |= 1u << cg[c];
+      if (routed_n) {
+        e = upload(p, cg, &pr.col_group);
+        if (e == cudaSuccess) e = upload(p, bm, &pr.ntile_mask);
+      } else {
+        for (size_t b = 0; b < bm.size(); ++b)
+          PLAN_REQUIRE((bm[b] & (bm[b] - 1)) == 0, "problem %d: K1 group boundaries must be multiples of %d", i, kBK);
+        if (rc != MC_OK) break;
+        e = upload(p, bm, &pr.kb1_mask);
+      }
+      if (e != cudaSuccess) break;
+    }
+    rc = encode_operand(&pr.tmA0, d.A0, d.M, d.K0, d.lda0, kBM, dtype);
+    if (rc == MC_OK) rc = encode_operand(&pr.tmB0, d.B0, d.N, d.K0, d.ldb0, bn, dtype);
+    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmA1, d.A1, d.M, d.K1, d.lda1, kBM, dtype);
+    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmB1, d.B1, d.N, d.K1, d.ldb1, bn, dtype);
+    p->flops += 2.0 * d.M * (double)d.N * (double)(d.K0 + d.K1);
+#undef PLAN_REQUIRE
+  }
+  if (rc == MC_OK && e != cudaSuccess) rc = fail(MC_ERR_CUDA, "linear plan setup failed: %s", cudaGetErrorString(e));
+  if (rc != MC_OK) {
+    linear_plan_free(p);
+    return rc;
+  }
+  p->params.n_prob = n_problems;
+  p->params.total_tiles = tile_end;
+  p->params.is_f16 = dtype == MC_F16;
+  // instruction descriptor: D = F32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12: 0 = F16, 1 = BF16), both K-major,
+  // N >> 3 at bit 17, M >> 4 at bit 24
+  const unsigned int fmt = dtype == MC_F16 ? 0u : 1u;
+  p->params.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(kBM >> 4) << 24);
+  const int sms = sm_count();
+  if (sms <= 0) {
+    linear_plan_free(p);
+    return fail(MC_ERR_CUDA, "no CUDA device");
+  }
+  p->grid = std::min(sms, tile_end);
+  *out = p;
+  return MC_OK;
+}
+
+extern "C" int mc_linear_plan_run(const mc_linear_plan_t* p, mc_stream_t stream) {
+  MC_REQUIRE(p != nullptr, "plan is NULL");
+  cudaError_t e = p->bn == 256 ? launch_linear<256, 4>(p, (cudaStream_t)stream) : launch_linear<128, 6>(p, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(MC_ERR_CUDA, "linear launch failed: %s", cudaGetErrorString(e));
+  return MC_OK;
+}
+
+extern "C" double mc_linear_plan_flops(const mc_linear_plan_t* p) { return p ? p->flops : 0.0; }
+
+extern "C" int mc_linear_plan_destroy(mc_linear_plan_t* p) {
+  linear_plan_free(p);
+  return MC_OK;
+}
+
+extern "C" int mc_route_tile_masks(const uint8_t* d_row_group, int M, uint32_t* d_mtile_mask, mc_stream_t stream) {
+  MC_REQUIRE(d_row_group && d_mtile_mask && M >= 1, "route masks: NULL pointer or M < 1");
+  const int n_tiles = (M + kBM - 1) / kBM;
+  route_tile_mask_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_row_group, M, d_mtile_mask, n_tiles);
+  MC_CUDA_OK(cudaGetLastError());
+  return MC_OK;
+}
+
+extern "C" int mc_silu_mul(const void* gate, const void* up, void* out, int64_t rows, int cols, int64_t ld_gate, int64_t ld_up,
+                           int64_t ld_out, int dtype, mc_stream_t stream) {
+  MC_REQUIRE(gate && up && out, "silu_mul: NULL pointer");
+  MC_REQUIRE(dtype == MC_BF16 || dtype == MC_F16, "silu_mul: dtype must be bf16 or fp16");
+  MC_REQUIRE(rows >= 0 && cols >= 8 && cols % 8 == 0 && ld_gate % 8 == 0 && ld_up % 8 == 0 && ld_out % 8 == 0,
+             "silu_mul: cols and leading dimensions must be multiples of 8");
+  MC_REQUIRE((((uintptr_t)gate | (uintptr_t)up | (uintptr_t)out) & 15) == 0, "silu_mul: pointers must be 16-byte aligned");
+  if (rows == 0) return MC_OK;
+  const long long total = rows * (cols / 8);
+  const int sms = sm_count();
+  MC_REQUIRE(sms > 0, "no CUDA device");
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
+  if (dtype == MC_BF16)
+    silu_mul_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up,
+                                                                          (__nv_bfloat16*)out, rows, cols, ld_gate, ld_up, ld_out);
+  else
+    silu_mul_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)gate, (const __half*)up, (__half*)out, rows, cols,
+                                                                    ld_gate, ld_up, ld_out);
+  MC_CUDA_OK(cudaGetLastError());
+  return MC_OK;
+}
