@@ -226,6 +226,20 @@ MC_API int mc_route_tile_masks(const uint8_t* d_row_group, int M, uint32_t* d_mt
 MC_API int mc_silu_mul(const void* gate, const void* up, void* out, int64_t rows, int cols, int64_t ld_gate, int64_t ld_up,
                 int64_t ld_out, int dtype, mc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise glue of the decoder layer (transformers==4.31.0 semantics, which the reference star-imports at
+ * modelcompose/model/language_model/multimodal_llama.py:66):
+ *   mc_rmsnorm : LlamaRMSNorm (used at :405-406,:441,:455,:603) — fp32 variance, x*rsqrt(var+eps) rounded to the
+ *                storage dtype, then weight * that, rounded again.
+ *   mc_rope    : apply_rotary_pos_emb (:281-282) in place on q and k viewed as [tokens, n_heads, head_dim];
+ *                cos/sin tables [>= seq_len, head_dim] in the storage dtype; position of token t is t % seq_len
+ *                (prefill: position_ids = arange(seq_len), :526-533).
+ * ---------------------------------------------------------------------------------------------- */
+MC_API int mc_rmsnorm(const void* x, const void* weight, void* out, int64_t rows, int hidden, int64_t ldx, int64_t ldo,
+               float eps, int dtype, mc_stream_t stream);
+MC_API int mc_rope(void* q, void* k, const void* cos_table, const void* sin_table, int64_t tokens, int seq_len, int n_heads,
+            int head_dim, int64_t ldq, int64_t ldk, int dtype, mc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,440 @@
+"""Composed-model prefill: host mirror of the reference model classes over the CUDA library.
+
+Mirrors (all paths relative to the reference root):
+  modelcompose/model/language_model/multimodal_llama.py   MultimodalConfig (:33-61), LocalLoraLinear coefficient
+      handling (:70-118), routed attention / MLP (:262-268, :335-336, :380-390), decoder layer / model / CausalLM
+      forward (:408-468, :488-619, :676-745)
+  modelcompose/model/multimodal_encoder/builder.py:119-130   infer_modals
+  modelcompose/model/multimodal_arch.py:197-268              encode_modal_inputs (projector + prefix/suffix)
+  modelcompose/model/multimodal_projector/builder.py:202-219 projector types
+
+Every matrix product, the splice, RMSNorm, RoPE and SiLU·mul run in ``libmodelcompose_b200.so`` (no torch fallback; a
+missing library raises).  Causal attention is the one stock-library call (flash-attn).  The modality
+encoders are frozen third-party feature extractors outside the hot path: ``modal_inputs`` here
+carries their OUTPUT features (``[b, n, d]``, video ``[b, t, n, d]``), i.e. what ``encoder(inputs)`` returns at
+multimodal_arch.py:231-243.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from . import linear as LN
+from . import splice as SP
+
+ADAPTER_ORDER = ("audio", "vision", "video", "point")
+
+
+class MultimodalConfig:
+    """Attribute bag with the reference defaults (multimodal_llama.py:33-61) over LLaMA's config fields."""
+    model_type = "multimodal"
+    lora_strategy = None
+    lora_name = "default"
+    lora_r = 128
+    lora_alpha = 256
+    lora_dropout = 0.05
+    local_prefix_tokens = 0
+    local_suffix_tokens = 0
+    merge_default_weights = None
+    reset_scaling_weights = None
+    mm_vision_encoder = None
+    mm_vision_tower = None
+    mm_audio_encoder = None
+    mm_video_encoder = None
+    mm_point_encoder = None
+    hidden_size = 4096
+    intermediate_size = 11008
+    num_attention_heads = 32
+    num_key_value_heads = None
+    num_hidden_layers = 32
+    vocab_size = 32000
+    rms_norm_eps = 1e-6
+    max_position_embeddings = 2048
+    rope_theta = 10000.0
+    hidden_act = "silu"
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+        if self.num_key_value_heads is None:
+            self.num_key_value_heads = self.num_attention_heads
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "MultimodalConfig":
+        return cls(**d)
+
+    def to_dict(self) -> dict:
+        return {k: v for k, v in vars(self).items()}
+
+
+def infer_modals(config) -> List[str]:
+    """multimodal_encoder/builder.py:119-130 — adapter / modality order (fixes the summation order of A9)."""
+    modals = ["default"]
+    if getattr(config, "mm_audio_encoder", None) is not None:
+        modals.append("audio")
+    if getattr(config, "mm_vision_encoder", None) is not None or getattr(config, "mm_vision_tower", None) is not None:
+        modals.append("vision")
+    if getattr(config, "mm_video_encoder", None):
+        modals.append("video")
+    if getattr(config, "mm_point_encoder", None):
+        modals.append("point")
+    return modals
+
+
+def extract_params(input_string: str) -> Dict[str, float]:
+    """multimodal_llama.py:109-118."""
+    params = {}
+    for pair in input_string.split(","):
+        key, value = pair.split("=")
+        params[key.strip()] = float(value)
+    return params
+
+
+def adapter_scaling(modal_names: Sequence[str], r: int, lora_alpha: float, reset_scaling_weights: Optional[str]):
+    """multimodal_llama.py:84-106 — (adapter names, scaling dict, default_adapter_names or None); float64 like Python."""
+    names = list(modal_names)
+    scaling = {n: lora_alpha / r for n in names}
+    default_adapter_names = None
+    if reset_scaling_weights is not None:
+        reset = extract_params(reset_scaling_weights)
+        if any("default-" in k for k in reset):
+            default_adapter_names = [f"default-{n}" for n in names[1:]]
+            for n in default_adapter_names:
+                names.append(n)
+                scaling[n] = lora_alpha / r
+        for k in reset:
+            if k in scaling:
+                scaling[k] = scaling[k] * reset[k]
+    return names, scaling, default_adapter_names
+
+
+@dataclass
+class CausalLMOutputWithPast:
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    past_key_values: Optional[list] = None
+    hidden_states: Optional[tuple] = None
+    attentions: Optional[tuple] = None
+    modal_id: Optional[torch.Tensor] = None  # extra: uint8 [B, S'] routing ids (0 = default)
+
+
+LINEARS = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+
+
+def _linear_key(layer: int, name: str) -> str:
+    block = "self_attn" if name in ("q_proj", "k_proj", "v_proj", "o_proj") else "mlp"
+    return f"model.layers.{layer}.{block}.{name}"
+
+
+@dataclass
+class _Layer:
+    W: Dict[str, torch.Tensor] = field(default_factory=dict)
+    ad: Dict[str, LN.PackedAdapters] = field(default_factory=dict)
+    ln1: torch.Tensor = None
+    ln2: torch.Tensor = None
+
+
+class _Workspace:
+    """Static activation buffers and launch plans for one (batch, padded length) shape."""
+
+    def __init__(self, model: "MultimodalLlamaForCausalLM", B: int, S: int):
+        cfg, dev, dt = model.config, model.device, model.dtype
+        T, H, I, V = B * S, cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+        R = model.rank_total
+        self.B, self.S, self.T = B, S, T
+
+        def buf(*shape, dtype=dt):
+            return torch.empty(shape, dtype=dtype, device=dev)
+        self.x = buf(T, H)
+        self.xn = buf(T, H)
+        self.q, self.k, self.v, self.attn = buf(T, H), buf(T, H), buf(T, H), buf(T, H)
+        self.t = [buf(T, R) for _ in range(3)]
+        self.gate, self.up = buf(T, I), buf(T, I)
+        self.logits = buf(T, V)
+        self.row_group = torch.zeros(T, dtype=torch.uint8, device=dev)
+        self.mtile = torch.zeros((T + LN.TILE_M - 1) // LN.TILE_M, dtype=torch.int32, device=dev)
+        self.plans: List[Dict[str, LN.LinearPlan]] = []
+        for layer in model.layers:
+            self.plans.append(self._layer_plans(layer))
+        self.lm_head = LN.LinearPlan([LN.Problem(self.xn, model.lm_head, self.logits)])
+
+    def _down(self, src, layer: _Layer, names, tbufs):
+        return LN.LinearPlan([LN.Problem(src, layer.ad[n].A_all, t, col_scale=layer.ad[n].col_scale, row_group=self.row_group,
+                                         mtile_mask=self.mtile, group_cols=layer.ad[n].group_cols, epilogue=LN.EPI_ROWMASK)
+                              for n, t in zip(names, tbufs)])
+
+    def _up(self, src, layer: _Layer, names, tbufs, outs, residual=None):
+        return LN.LinearPlan([LN.Problem(src, layer.W[n], o, A1=t, B1=layer.ad[n].B_all, mtile_mask=self.mtile,
+                                         group_cols=layer.ad[n].group_cols, residual=residual,
+                                         epilogue=LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE)
+                              for n, t, o in zip(names, tbufs, outs)])
+
+    def _layer_plans(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
+        qkv, gu = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
+        return {
+            "down_qkv": self._down(self.xn, layer, qkv, self.t),
+            "up_qkv": self._up(self.xn, layer, qkv, self.t, (self.q, self.k, self.v)),
+            "down_o": self._down(self.attn, layer, ("o_proj",), self.t[:1]),
+            "up_o": self._up(self.attn, layer, ("o_proj",), self.t[:1], (self.x,), residual=self.x),
+            "down_gu": self._down(self.xn, layer, gu, self.t[:2]),
+            "up_gu": self._up(self.xn, layer, gu, self.t[:2], (self.gate, self.up)),
+            "down_d": self._down(self.gate, layer, ("down_proj",), self.t[:1]),
+            "up_d": self._up(self.gate, layer, ("down_proj",), self.t[:1], (self.x,), residual=self.x),
+        }
+
+
+class MultimodalLlamaForCausalLM:
+    """Inference-only drop-in for the reference class of the same name (multimodal_llama.py:622-767)."""
+
+    def __init__(self, config: MultimodalConfig, base_state_dict: Dict[str, torch.Tensor],
+                 adapter_state_dict: Optional[Dict[str, torch.Tensor]] = None, device="cuda", dtype=torch.float16):
+        _cabi.lib()  # fail loudly if the CUDA library is missing
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("inference dtype must be float16 (reference builder.py:185) or bfloat16")
+        self.config, self.device, self.dtype = config, torch.device(device), dtype
+        self.modal_names = infer_modals(config)
+        sd = adapter_state_dict or {}
+        r, alpha = config.lora_r, config.lora_alpha
+        self.adapter_names, self.scaling, self.default_adapter_names = adapter_scaling(
+            self.modal_names, r, alpha, config.reset_scaling_weights)
+
+        def dev(t):
+            return t.to(device=self.device, dtype=dtype).contiguous()
+        H = config.hidden_size
+        self.embed_tokens = dev(base_state_dict["model.embed_tokens.weight"])
+        self.norm = dev(base_state_dict["model.norm.weight"])
+        self.lm_head = dev(base_state_dict["lm_head.weight"])
+        self.layers: List[_Layer] = []
+        for li in range(config.num_hidden_layers):
+            layer = _Layer()
+            layer.ln1 = dev(base_state_dict[f"model.layers.{li}.input_layernorm.weight"])
+            layer.ln2 = dev(base_state_dict[f"model.layers.{li}.post_attention_layernorm.weight"])
+            for name in LINEARS:
+                key = _linear_key(li, name)
+                W = dev(base_state_dict[key + ".weight"])
+                layer.W[name] = W
+                # adapters present in the checkpoint; absent ones keep the loader's reset init (B = 0, builder.py:150-153)
+                # and contribute exactly nothing, so they are simply left out of the packed layout
+                A = {a: dev(sd[f"{key}.lora_A.{a}.weight"]) for a in self.adapter_names if f"{key}.lora_A.{a}.weight" in sd}
+                Bm = {a: dev(sd[f"{key}.lora_B.{a}.weight"]) for a in A}
+                layer.ad[name] = LN.pack_adapters(A, Bm, self.scaling, self.modal_names, self.default_adapter_names,
+                                                  W.shape[1], W.shape[0], dtype, self.device)
+            self.layers.append(layer)
+        self.rank_total = self.layers[0].ad["q_proj"].A_all.shape[0] if self.layers else LN.K_BLOCK
+        for layer in self.layers:
+            for name in LINEARS:
+                if layer.ad[name].A_all.shape[0] != self.rank_total:
+                    raise ValueError("every linear must carry the same adapter ranks")
+
+        # projectors (multimodal_projector/builder.py:202-219): 'linear' or 'mlp{N}x_gelu'
+        self.projectors: Dict[str, List[Tuple[torch.Tensor, torch.Tensor]]] = {}
+        for modal in self.modal_names[1:]:
+            stem = f"model.modal_projectors.{modal}"
+            if f"{stem}.weight" in sd:
+                self.projectors[modal] = [(dev(sd[f"{stem}.weight"]), dev(sd[f"{stem}.bias"]))]
+            else:
+                layers, i = [], 0
+                while f"{stem}.{i}.weight" in sd:
+                    layers.append((dev(sd[f"{stem}.{i}.weight"]), dev(sd[f"{stem}.{i}.bias"])))
+                    i += 2
+                if layers:
+                    self.projectors[modal] = layers
+        # prefix / suffix tokens (multimodal_llama.py:634-649): zeros unless the checkpoint carries them
+        self.prefix_tokens = self._local_tokens(sd, "prefix", config.local_prefix_tokens)
+        self.suffix_tokens = self._local_tokens(sd, "suffix", config.local_suffix_tokens)
+        self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+        self._ws: Dict[Tuple[int, int], _Workspace] = {}
+        self._proj_cache: Dict[tuple, tuple] = {}
+
+    # ------------------------------------------------------------------------------------------ construction helpers
+    def _local_tokens(self, sd, kind: str, n_default: int):
+        if not n_default:
+            return None
+        out = {}
+        for modal in self.modal_names:
+            n = getattr(self.config, f"local_{modal}_{kind}_tokens", None)
+            n = n_default if n is None else n
+            key = f"{kind}_tokens.{modal}"
+            if key in sd:
+                out[modal] = sd[key].to(device=self.device, dtype=self.dtype).contiguous()
+            else:
+                out[modal] = torch.zeros((1, n, self.config.hidden_size), dtype=self.dtype, device=self.device)
+        return out
+
+    def _rope_tables(self, seq_len: int):
+        """transformers 4.31 LlamaRotaryEmbedding: fp32 cache built on the host, cast to the model dtype on use."""
+        n = max(seq_len, self.config.max_position_embeddings)
+        if self._rope is None or self._rope[0].shape[0] < n:
+            D = self.config.hidden_size // self.config.num_attention_heads
+            base = float(getattr(self.config, "rope_theta", 10000.0) or 10000.0)
+            inv_freq = 1.0 / (base ** (torch.arange(0, D, 2).float() / D))
+            t = torch.arange(n, dtype=inv_freq.dtype)
+            freqs = torch.einsum("i,j->ij", t, inv_freq)
+            emb = torch.cat((freqs, freqs), dim=-1)
+            self._rope = (emb.cos().to(self.dtype).to(self.device).contiguous(),
+                          emb.sin().to(self.dtype).to(self.device).contiguous())
+        return self._rope
+
+    def get_model(self):
+        return self
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------------------------------ encode_modal_inputs
+    def project_modal_features(self, modal_inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """multimodal_arch.py:197-243 after the (frozen, out-of-scope) encoders: one grouped launch per projector depth."""
+        feats, order = {}, [m for m in self.modal_names[1:] if m in modal_inputs]
+        for m in order:
+            f = modal_inputs[m]
+            if f.dim() == 4:  # video [b, t, n, d] -> [b, t*n, d] (:236-240)
+                f = f.reshape(f.shape[0], f.shape[1] * f.shape[2], f.shape[3])
+            if f.dim() != 3:
+                raise ValueError(f"modal_inputs[{m}] must be encoder features [b, n, d] (video [b, t, n, d])")
+            if m not in self.projectors:
+                raise KeyError(f"no projector weights for modality {m}")
+            feats[m] = f.to(device=self.device, dtype=self.dtype).contiguous()
+        if not order:
+            return {}
+        key = tuple((m, tuple(feats[m].shape), feats[m].data_ptr()) for m in order)
+        if key not in self._proj_cache:
+            self._proj_cache.clear()
+            depth = max(len(self.projectors[m]) for m in order)
+            cur = {m: feats[m].view(-1, feats[m].shape[-1]) for m in order}
+            plans, keep = [], []
+            for d in range(depth):
+                probs, nxt = [], dict(cur)
+                for m in order:
+                    if d >= len(self.projectors[m]):
+                        continue
+                    W, b = self.projectors[m][d]
+                    out = torch.empty((cur[m].shape[0], W.shape[0]), dtype=self.dtype, device=self.device)
+                    last = d == len(self.projectors[m]) - 1
+                    probs.append(LN.Problem(cur[m], W, out, bias=b, epilogue=LN.EPI_BIAS if last else LN.EPI_BIAS_GELU))
+                    nxt[m] = out
+                    keep.append(out)
+                for i in range(0, len(probs), LN.MAX_PROBLEMS):
+                    plans.append(LN.LinearPlan(probs[i:i + LN.MAX_PROBLEMS]))
+                cur = nxt
+            outs = {m: cur[m].view(feats[m].shape[0], feats[m].shape[1], -1) for m in order}
+            self._proj_cache[key] = (plans, outs, [feats[m] for m in order])
+        plans, outs, _ = self._proj_cache[key]
+        for p in plans:
+            p.run()
+        return outs
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _rmsnorm(self, x, w, out):
+        _cabi.check(_cabi.lib().mc_rmsnorm(x.data_ptr(), w.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0),
+                                           out.stride(0), float(self.config.rms_norm_eps), _cabi.dtype_code(self.dtype),
+                                           _cabi.current_stream_ptr()), "mc_rmsnorm")
+
+    def _attention(self, ws: _Workspace, attention_mask: Optional[torch.Tensor]):
+        cfg = self.config
+        nH = cfg.num_attention_heads
+        D = cfg.hidden_size // nH
+        B, S = ws.B, ws.S
+        cos, sin = self._rope_tables(S)
+        _cabi.check(_cabi.lib().mc_rope(ws.q.data_ptr(), ws.k.data_ptr(), cos.data_ptr(), sin.data_ptr(), ws.T, S, nH, D,
+                                        ws.q.stride(0), ws.k.stride(0), _cabi.dtype_code(self.dtype),
+                                        _cabi.current_stream_ptr()), "mc_rope")
+        q, k, v = (t.view(B, S, nH, D) for t in (ws.q, ws.k, ws.v))
+        full = attention_mask is None or bool(attention_mask.all())
+        if full:
+            try:
+                from flash_attn import flash_attn_func
+                o = flash_attn_func(q, k, v, causal=True, softmax_scale=1.0 / math.sqrt(D))
+            except (ImportError, RuntimeError):
+                o = torch.nn.functional.scaled_dot_product_attention(
+                    q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True).transpose(1, 2)
+        else:
+            # padded batch: additive mask as transformers 4.31 _prepare_decoder_attention_mask builds it (:543-545)
+            neg = torch.finfo(self.dtype).min
+            causal = torch.full((S, S), neg, dtype=self.dtype, device=self.device).triu(1)[None, None]
+            pad = (~attention_mask.bool())[:, None, None, :].to(self.dtype) * neg
+            o = torch.nn.functional.scaled_dot_product_attention(
+                q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=(causal + pad).clamp_min(neg)).transpose(1, 2)
+        ws.attn.view(B, S, nH, D).copy_(o)
+
+    def prefill(self, inputs_embeds: torch.Tensor, modal_id: Optional[torch.Tensor], attention_mask=None,
+                use_cache: bool = False, output_hidden_states: bool = False):
+        """MultimodalLlamaModel.forward + lm_head (:488-619, :720) on spliced embeddings; returns (logits, kv, hidden)."""
+        B, S, H = inputs_embeds.shape
+        key = (B, S)
+        if key not in self._ws:
+            self._ws.clear()  # one resident shape: the buffers are GBs at 7B width
+            self._ws[key] = _Workspace(self, B, S)
+        ws = self._ws[key]
+        ws.x.view(B, S, H).copy_(inputs_embeds)
+        if modal_id is None:
+            ws.row_group.zero_()
+        else:
+            ws.row_group.view(B, S).copy_(modal_id)
+        LN.route_tile_masks(ws.row_group, ws.mtile)
+        kv, hidden = [], []
+        for layer, plans in zip(self.layers, ws.plans):
+            if output_hidden_states:
+                hidden.append(ws.x.view(B, S, H).clone())
+            self._rmsnorm(ws.x, layer.ln1, ws.xn)
+            plans["down_qkv"].run()
+            plans["up_qkv"].run()
+            self._attention(ws, attention_mask)
+            if use_cache:
+                nH = self.config.num_attention_heads
+                kv.append((ws.k.view(B, S, nH, H // nH).transpose(1, 2).clone(), ws.v.view(B, S, nH, H // nH).transpose(1, 2).clone()))
+            plans["down_o"].run()
+            plans["up_o"].run()
+            self._rmsnorm(ws.x, layer.ln2, ws.xn)
+            plans["down_gu"].run()
+            plans["up_gu"].run()
+            LN.silu_mul(ws.gate, ws.up, ws.gate)
+            plans["down_d"].run()
+            plans["up_d"].run()
+        self._rmsnorm(ws.x, self.norm, ws.xn)
+        if output_hidden_states:
+            hidden.append(ws.xn.view(B, S, H).clone())
+        ws.lm_head.run()
+        return ws.logits.view(B, S, -1), (kv if use_cache else None), (tuple(hidden) if output_hidden_states else None)
+
+    def forward(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, modal_inputs=None, return_dict=None):
+        """Reference signature (multimodal_llama.py:676-688).  Prefill only: the decode step (default adapter, KV cache)
+        is SURVEY §8(f) item 2 and raises NotImplementedError."""
+        if output_attentions:
+            raise NotImplementedError("attention probabilities are never materialised on this path")
+        if past_key_values is not None or (input_ids is not None and input_ids.shape[1] == 1 and modal_inputs is not None):
+            raise NotImplementedError("decode step with past_key_values is not part of the prefill hot path (SURVEY §8(f))")
+        modal_id = None
+        if input_ids is not None:
+            feats = self.project_modal_features(modal_inputs) if modal_inputs else {}
+            pre = {m: self.prefix_tokens[m] for m in feats} if self.prefix_tokens is not None else None
+            suf = {m: self.suffix_tokens[m] for m in feats} if self.suffix_tokens is not None else None
+            r = SP.splice(input_ids.to(self.device), None if attention_mask is None else attention_mask.to(self.device),
+                          None if labels is None else labels.to(self.device), self.embed_tokens, feats, pre, suf,
+                          list(modal_inputs.keys()) if modal_inputs else None)
+            inputs_embeds, attention_mask, labels = r.inputs_embeds, r.attention_mask, r.labels
+            if r.modal_names:
+                # splice ids follow the order of `feats`; routing ids follow self.modal_names (0 = default)
+                lut = torch.zeros(SP.MAX_MODAL + 1, dtype=torch.uint8, device=self.device)
+                for i, m in enumerate(r.modal_names):
+                    lut[1 + i] = self.modal_names.index(m)
+                modal_id = lut[r.modal_id.long()]
+            if self.config.lora_strategy not in ("modal", "modal+language"):  # :703-704
+                modal_id = None
+        logits, kv, hidden = self.prefill(inputs_embeds, modal_id, attention_mask, bool(use_cache), bool(output_hidden_states))
+        loss = None
+        if labels is not None:  # :723-733
+            shift_logits = logits[..., :-1, :].contiguous().view(-1, self.config.vocab_size)
+            shift_labels = labels[..., 1:].contiguous().view(-1)
+            loss = torch.nn.functional.cross_entropy(shift_logits.float(), shift_labels)
+        out = CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=kv, hidden_states=hidden, modal_id=modal_id)
+        if return_dict is False:
+            t = (logits, kv) if kv is not None else (logits,)
+            return (loss,) + t if loss is not None else t
+        return out
+
+    __call__ = forward

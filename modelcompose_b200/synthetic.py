@@ -167,3 +167,85 @@ def make_prompt_ids(batch: int, modal_order: List[str], n_text: int, vocab: int,
         parts.append(torch.randint(3, vocab, (n_text,), generator=g))
         rows.append(torch.cat(parts))
     return torch.stack(rows).to(torch.int64)
+
+
+def make_composed_on_device(modals: List[str], device, dtype=torch.bfloat16, llama: dict = VICUNA_7B, r: int = 128,
+                            lora_alpha: int = 256, coeff: float = 0.333, n_prefix: int = 5, n_suffix: int = 5,
+                            seed: int = 1, layers: int | None = None, feature_dims: Dict[str, int] | None = None):
+    """A composed (online-merge-reset) model generated directly in device memory: returns
+    ``(config dict, base_state_dict, merged_adapter_state_dict)`` with the key schema the reference merge CLI writes
+    (``lora_{A,B}.default-{modal}`` + ``lora_{A,B}.{modal}`` per linear, projectors, prefix/suffix tokens;
+    merge_unimodal_modelcompose.py:94-103).  Same distributions as ``make_base_llm`` / ``make_unimodal_checkpoint``;
+    used by bench.py and the full-size GPU tests where CPU generation of 7B tensors would dominate the run."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    cfg = dict(llama)
+    if layers is not None:
+        cfg["num_hidden_layers"] = layers
+    H, V, L = cfg["hidden_size"], cfg["vocab_size"], cfg["num_hidden_layers"]
+    fd = dict(MODAL_FEATURE_DIM)
+    fd.update(feature_dims or {})
+
+    def normal(shape, std):
+        return torch.empty(shape, dtype=torch.float32, device=device).normal_(0.0, std, generator=g).to(dtype)
+
+    def uniform(shape, bound):
+        return torch.empty(shape, dtype=torch.float32, device=device).uniform_(-bound, bound, generator=g).to(dtype)
+
+    base = {"model.embed_tokens.weight": normal((V, H), 0.02)}
+    ad: Dict[str, torch.Tensor] = {}
+    for m in modals:
+        d = fd[m]
+        ad[f"model.modal_projectors.{m}.0.weight"] = uniform((H, d), 1.0 / math.sqrt(d))
+        ad[f"model.modal_projectors.{m}.0.bias"] = uniform((H,), 1.0 / math.sqrt(d))
+        ad[f"model.modal_projectors.{m}.2.weight"] = uniform((H, H), 1.0 / math.sqrt(H))
+        ad[f"model.modal_projectors.{m}.2.bias"] = uniform((H,), 1.0 / math.sqrt(H))
+        if n_prefix:
+            ad[f"prefix_tokens.{m}"] = normal((1, n_prefix, H), 0.02)
+        if n_suffix:
+            ad[f"suffix_tokens.{m}"] = normal((1, n_suffix, H), 0.02)
+    for l in range(L):
+        for name in LINEAR_NAMES:
+            out_f, in_f = linear_shape(cfg, name)
+            base[f"model.layers.{l}.{name}.weight"] = normal((out_f, in_f), 0.02)
+            for m in modals:
+                for a in (f"default-{m}", m):
+                    ad[f"model.layers.{l}.{name}.lora_A.{a}.weight"] = uniform((r, in_f), 1.0 / math.sqrt(in_f))
+                    ad[f"model.layers.{l}.{name}.lora_B.{a}.weight"] = normal((out_f, r), 0.02)
+        base[f"model.layers.{l}.input_layernorm.weight"] = (1.0 + normal((H,), 0.02).float()).to(dtype)
+        base[f"model.layers.{l}.post_attention_layernorm.weight"] = (1.0 + normal((H,), 0.02).float()).to(dtype)
+    base["model.norm.weight"] = (1.0 + normal((H,), 0.02).float()).to(dtype)
+    base["lm_head.weight"] = normal((V, H), 0.02)
+    cfg.update({"model_type": "multimodal", "architectures": ["MultimodalLlamaForCausalLM"],
+                "lora_strategy": "modal+language", "lora_r": r, "lora_alpha": lora_alpha, "lora_dropout": 0.05,
+                "local_prefix_tokens": n_prefix, "local_suffix_tokens": n_suffix,
+                "reset_scaling_weights": ",".join(f"default-{m}={coeff}" for m in modals)})
+    for m in modals:
+        cfg[MODAL_ENCODER_KEY[m]] = f"synthetic-{m}-encoder"
+        cfg[MODAL_HIDDEN_KEY[m]] = fd[m]
+        cfg[MODAL_PROJ_KEY[m]] = "mlp2x_gelu"
+        if m == "vision":
+            cfg["mm_vision_encoder"] = cfg["mm_vision_tower"]
+    return cfg, base, ad
+
+
+def prefill_flops(cfg: dict, modals_present: Dict[str, int], n_text: int, n_modal_adapters: int, r: int,
+                  feature_dims: Dict[str, int] | None = None, n_prefix: int = 5, n_suffix: int = 5) -> Dict[str, float]:
+    """ALGORITHMIC FLOPs of ONE sequence: every token runs the 7 base linears per layer; a modality
+    token (features + prefix/suffix rows) adds one rank-r adapter, a text token the N concatenated default sub-adapters;
+    projector 2·(d·H + H·H) per feature row; lm_head on every position; causal attention 2·2·S²·H/2 per layer."""
+    H, I, V, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"], cfg["num_hidden_layers"]
+    fd = dict(MODAL_FEATURE_DIM)
+    fd.update(feature_dims or {})
+    per_tok_base = 2.0 * L * (4 * H * H + 3 * H * I)
+    per_tok_lora = 2.0 * L * r * (4 * 2 * H + 3 * (H + I))
+    n_modal_rows = sum(n + n_prefix + n_suffix for n in modals_present.values())
+    S = n_text + n_modal_rows
+    out = {"seq_len": S,
+           "base": per_tok_base * S,
+           "lora": per_tok_lora * (n_modal_rows + n_modal_adapters * n_text),
+           "projector": sum(2.0 * n * (fd[m] * H + H * H) for m, n in modals_present.items()),
+           "lm_head": 2.0 * V * H * S,
+           "attention": L * 2.0 * S * S * H}
+    out["linears"] = out["base"] + out["lora"] + out["projector"] + out["lm_head"]
+    out["total"] = out["linears"] + out["attention"]
+    return out

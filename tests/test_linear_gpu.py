@@ -1,0 +1,217 @@
+"""GPU parity of the tcgen05 routed/grouped linear kernels and the row-wise glue (through the C ABI).
+
+Floating point: the kernels accumulate in fp32 and round ONCE to bf16/fp16, the reference's eager path rounds after
+every op.  Tolerance (stated per north_star): against an fp32 evaluation of the same formula on the same 16-bit
+inputs, |got - ref| <= 2^-7*|ref| + 2^-8*max|ref| (bf16; = 1 ulp of the element plus half an ulp of the row scale),
+fp16: 2^-10*|ref| + 2^-11*max|ref|.  Against the reference's own 16-bit outputs (golden fixtures) the bound is
+2^-6 (bf16) / 2^-9 (fp16) of the output scale, the same bar tests/test_oracle_golden.py uses for the oracle."""
+import pytest
+import torch
+
+from modelcompose_b200 import _cabi
+from modelcompose_b200 import linear as LN
+from oracle import model_oracle as XO
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {torch.bfloat16: 2 ** -7, torch.float16: 2 ** -10}
+
+
+def check(got, ref, dtype, what=""):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    scale = ref.abs().max().item() + 1e-12
+    err = (got - ref).abs()
+    bound = RTOL[dtype] * ref.abs() + RTOL[dtype] / 2 * scale
+    bad = err > bound
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} outside tolerance, max err {err.max().item():.4g} at scale {scale:.4g}"
+
+
+def rnd(shape, dtype, seed, std=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * std).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,tuning", [(1, 8, 8, 0), (128, 256, 64, 0), (129, 264, 72, 0), (48, 192, 256, 0), (300, 136, 688, 1),
+                                          (1000, 1000, 1000, 2), (513, 4096, 384, 0), (960, 688, 256, 0), (77, 32000, 256, 0)])
+def test_plain_linear(dtype, M, N, K, tuning):
+    A, B = rnd((M, K), dtype, 1), rnd((N, K), dtype, 2, std=0.05)
+    C = torch.full((M, N), 9.0, dtype=dtype, device="cuda")
+    LN.LinearPlan([LN.Problem(A.cuda(), B.cuda(), C)], tuning=tuning).run()
+    torch.cuda.synchronize()
+    check(C, A.float() @ B.float().t(), dtype, f"{M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_strided_views_and_epilogues(dtype):
+    M, N, K = 200, 320, 136
+    Abig, B = rnd((M, K + 24), dtype, 3).cuda(), rnd((N, K), dtype, 4, std=0.1).cuda()
+    A = Abig[:, 8:8 + K]  # leading dimension > K, 16-byte aligned start
+    bias = rnd((N,), dtype, 5).cuda()
+    res = rnd((M, N), dtype, 6).cuda()
+    ref = A.float() @ B.float().t()
+    C = torch.empty((M, N + 8), dtype=dtype, device="cuda")[:, :N]
+    LN.LinearPlan([LN.Problem(A, B, C, bias=bias, epilogue=LN.EPI_BIAS)]).run()
+    check(C, ref + bias.float(), dtype, "bias")
+    LN.LinearPlan([LN.Problem(A, B, C, bias=bias, epilogue=LN.EPI_BIAS_GELU)]).run()
+    check(C, torch.nn.functional.gelu(ref + bias.float()), dtype, "bias+gelu")
+    LN.LinearPlan([LN.Problem(A, B, C, residual=res, epilogue=LN.EPI_RESIDUAL)]).run()
+    check(C, ref + res.float(), dtype, "residual")
+    x = res.clone()  # in place: C aliases the residual (how the decoder layer uses it)
+    LN.LinearPlan([LN.Problem(A, B, x, residual=x, epilogue=LN.EPI_RESIDUAL)]).run()
+    check(x, ref + res.float(), dtype, "residual in place")
+
+
+def test_k_extension_unrouted():
+    dtype = torch.bfloat16
+    M, N, K0, K1 = 260, 512, 192, 128
+    A0, B0 = rnd((M, K0), dtype, 1).cuda(), rnd((N, K0), dtype, 2, 0.1).cuda()
+    A1, B1 = rnd((M, K1), dtype, 3).cuda(), rnd((N, K1), dtype, 4, 0.1).cuda()
+    C = torch.empty((M, N), dtype=dtype, device="cuda")
+    LN.LinearPlan([LN.Problem(A0, B0, C, A1=A1, B1=B1)]).run()
+    check(C, A0.float() @ B0.float().t() + A1.float() @ B1.float().t(), dtype, "k-extension")
+
+
+def make_modal_id(T, seed, n_groups, runs=True):
+    g = torch.Generator().manual_seed(seed)
+    if not runs:
+        return torch.randint(0, n_groups, (T,), generator=g).to(torch.uint8)
+    out, i = torch.zeros(T, dtype=torch.uint8), 0
+    while i < T:
+        n = int(torch.randint(1, 300, (1,), generator=g))
+        out[i:i + n] = int(torch.randint(0, n_groups, (1,), generator=g))
+        i += n
+    return out
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("T,in_f,out_f,r,runs", [(1000, 256, 512, 8, True), (700, 688, 256, 8, False), (1500, 512, 1024, 128, True)])
+def test_routed_lora_linear_vs_oracle(dtype, T, in_f, out_f, r, runs):
+    """LocalLoraLinear.forward + masked-sum routing (oracle, fp32 on the same 16-bit values) vs the two routed launches."""
+    modal_names = ["default", "audio", "vision", "video"]
+    dnames = [f"default-{m}" for m in modal_names[1:]]
+    names = modal_names[1:] + dnames
+    W = rnd((out_f, in_f), dtype, 1, 0.05)
+    A = {n: rnd((r, in_f), dtype, 10 + i, 0.1) for i, n in enumerate(names)}
+    Bm = {n: rnd((out_f, r), dtype, 30 + i, 0.1) for i, n in enumerate(names)}
+    scaling = {n: 2.0 for n in names}
+    for n in dnames:
+        scaling[n] = 2.0 * 0.333
+    scaling["default"] = 2.0
+    x = rnd((T, in_f), dtype, 7)
+    mid = make_modal_id(T, 5, len(modal_names), runs)
+    # oracle in fp32
+    f32 = lambda d: {k: v.float() for k, v in d.items()}
+    outs = XO.lora_linear_forward(x.float()[None], W.float(), f32(A), f32(Bm), scaling, modal_names, dnames)
+    masks = {m: (mid == i)[None] for i, m in enumerate(modal_names)}
+    ref = XO.routed_sum(outs, masks, x.float()[None])[0]
+    # CUDA path
+    pk = LN.pack_adapters({k: v.cuda() for k, v in A.items()}, {k: v.cuda() for k, v in Bm.items()}, scaling, modal_names,
+                          dnames, in_f, out_f, dtype, torch.device("cuda"))
+    assert pk.group_cols[1] == LN.pad64(3 * r) and pk.A_all.shape[0] == pk.group_cols[-1]
+    xd, rg = x.cuda(), mid.cuda()
+    mt = LN.route_tile_masks(rg)
+    Tb = torch.full((T, pk.A_all.shape[0]), float("nan"), dtype=dtype, device="cuda")  # skipped tiles must never be read
+    y = torch.empty((T, out_f), dtype=dtype, device="cuda")
+    LN.LinearPlan([LN.Problem(xd, pk.A_all, Tb, col_scale=pk.col_scale, row_group=rg, mtile_mask=mt, group_cols=pk.group_cols,
+                              epilogue=LN.EPI_ROWMASK)]).run()
+    LN.LinearPlan([LN.Problem(xd, W.cuda(), y, A1=Tb, B1=pk.B_all, mtile_mask=mt, group_cols=pk.group_cols)]).run()
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any()
+    # T is rounded to 16 bits between the two launches (the reference rounds there too): allow one extra ulp of scale
+    got, ref = y.float().cpu(), ref
+    scale = ref.abs().max().item()
+    err = (got - ref).abs()
+    assert (err <= RTOL[dtype] * ref.abs() + RTOL[dtype] * scale).all(), err.max().item() / scale
+
+
+def test_route_tile_masks():
+    mid = make_modal_id(1000, 3, 5)
+    got = LN.route_tile_masks(mid.cuda()).cpu()
+    for t in range(got.numel()):
+        want = 0
+        for g in mid[t * 128:(t + 1) * 128].unique().tolist():
+            want |= 1 << g
+        assert got[t].item() == want
+
+
+@pytest.mark.parametrize("key", ["torch.bfloat16", "torch.float16"])
+def test_projector_grouped_vs_reference_fixture(golden, key):
+    """Both modalities' mlp2x_gelu projectors as ONE grouped launch per layer vs the reference's own outputs."""
+    dtype = {"torch.bfloat16": torch.bfloat16, "torch.float16": torch.float16}[key]
+    m = golden("merge_c1.pt")["runs"]["online-merge-reset-default-vision=0.5,default-audio=0.5"]["state_dict"]
+    g = golden("projector.pt")
+    probs1, probs2, outs = [], [], {}
+    for modal in ("vision", "audio"):
+        pre = f"model.modal_projectors.{modal}."
+        x = g[modal]["x"].to(dtype).cuda()
+        x2 = x.view(-1, x.shape[-1])
+        W0, b0, W2, b2 = (m[pre + k].to(dtype).cuda() for k in ("0.weight", "0.bias", "2.weight", "2.bias"))
+        h = torch.empty((x2.shape[0], W0.shape[0]), dtype=dtype, device="cuda")
+        o = torch.empty((x2.shape[0], W2.shape[0]), dtype=dtype, device="cuda")
+        probs1.append(LN.Problem(x2, W0, h, bias=b0, epilogue=LN.EPI_BIAS_GELU))
+        probs2.append(LN.Problem(h, W2, o, bias=b2, epilogue=LN.EPI_BIAS))
+        outs[modal] = (o, x.shape)
+    LN.LinearPlan(probs1).run()
+    LN.LinearPlan(probs2).run()
+    torch.cuda.synchronize()
+    tol = {"torch.bfloat16": 2 ** -6, "torch.float16": 2 ** -9}[key]
+    for modal, (o, shp) in outs.items():
+        ref = g[modal][key].float()
+        got = o.view(shp[0], shp[1], -1).float().cpu()
+        scale = ref.abs().max().item()
+        assert (got - ref).abs().max().item() <= tol * scale, modal
+        # and against the oracle evaluated in fp32
+        pre = f"model.modal_projectors.{modal}."
+        want = XO.projector_forward(g[modal]["x"].to(dtype).float(), [m[pre + "0.weight"].to(dtype).float(), m[pre + "2.weight"].to(dtype).float()],
+                                    [m[pre + "0.bias"].to(dtype).float(), m[pre + "2.bias"].to(dtype).float()])
+        assert (got - want).abs().max().item() <= tol * scale
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_rowwise_glue_bit_exact_vs_oracle(dtype):
+    """RMSNorm / RoPE / SiLU·mul restate the eager reference ops with the same rounding points."""
+    T, H, nH = 77, 256, 4
+    D = H // nH
+    x = rnd((T, H), dtype, 1)
+    w = (1 + rnd((H,), torch.float32, 2, 0.02)).to(dtype)
+    lib = _cabi.lib()
+    code, st = _cabi.dtype_code(dtype), _cabi.current_stream_ptr()
+    xd, wd = x.cuda(), w.cuda()
+    out = torch.empty_like(xd)
+    _cabi.check(lib.mc_rmsnorm(xd.data_ptr(), wd.data_ptr(), out.data_ptr(), T, H, H, H, 1e-5, code, st), "rmsnorm")
+    ref = XO.rms_norm(x, w, 1e-5)
+    # fp32 sum order differs (warp tree vs torch): allow one ulp on a handful of elements, none elsewhere
+    diff = (out.cpu().float() - ref.float()).abs()
+    assert (diff <= RTOL[dtype] * 2 * ref.float().abs() + 1e-6).all()
+    assert (diff > 0).float().mean().item() < 0.02
+    # rope: S = 11 positions, 7 sequences
+    S, Bn = 11, 7
+    q, k = rnd((Bn * S, H), dtype, 3), rnd((Bn * S, H), dtype, 4)
+    cos, sin = XO.rope_cos_sin(D, 64, dtype)
+    qd, kd, cos_d, sin_d = q.cuda(), k.cuda(), cos.cuda(), sin.cuda()
+    _cabi.check(lib.mc_rope(qd.data_ptr(), kd.data_ptr(), cos_d.data_ptr(), sin_d.data_ptr(), Bn * S, S, nH, D, H, H,
+                            code, st), "rope")
+    pos = torch.arange(S)[None].expand(Bn, S)
+    qr, kr = XO.apply_rope(q.view(Bn, S, nH, D).transpose(1, 2), k.view(Bn, S, nH, D).transpose(1, 2), cos, sin, pos)
+    assert torch.equal(qd.cpu().view(Bn, S, nH, D).transpose(1, 2), qr)
+    assert torch.equal(kd.cpu().view(Bn, S, nH, D).transpose(1, 2), kr)
+    # silu * mul
+    g_, u_ = rnd((T, 688), dtype, 5, 2.0), rnd((T, 688), dtype, 6)
+    got = LN.silu_mul(g_.cuda(), u_.cuda()).cpu()
+    want = torch.nn.functional.silu(g_) * u_
+    d = (got.float() - want.float()).abs()
+    assert (d <= RTOL[dtype] * 2 * want.float().abs() + 1e-7).all() and (d > 0).float().mean().item() < 0.01
+
+
+def test_argument_errors():
+    a = torch.zeros((8, 8), dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        LN.LinearPlan([LN.Problem(a.cpu(), a, a)])
+    with pytest.raises(_cabi.McError, match="multiples of 8"):
+        LN.LinearPlan([LN.Problem(torch.zeros((8, 16), dtype=torch.bfloat16, device="cuda")[:, :12],
+                                  torch.zeros((8, 12), dtype=torch.bfloat16, device="cuda"), a)])
+    with pytest.raises(_cabi.McError, match="ROWMASK"):
+        LN.LinearPlan([LN.Problem(a, a, a.clone(), epilogue=LN.EPI_ROWMASK)])
+    with pytest.raises(_cabi.McError, match="dtype"):
+        LN.LinearPlan([LN.Problem(a.float(), a.float(), a.float())])
