@@ -184,12 +184,16 @@ def run_reference_arm(args):
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload in ("all", "prefill"):
+        pre = cpu_prefill_layer_rate(args.prefill_config)
+        line["prefill"] = {"impl": "reference", "metric": "composed-prefill tokens/s", "value": pre["value"], "unit": "tokens/s",
+                           "config": {"workload": PREFILL_CONFIGS[args.prefill_config][0]}, "cpu_baseline": pre,
+                           "e2e": {"value": pre["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_merge(args):
+def setup_dist(args):
     import torch.distributed as dist
-    from modelcompose_b200 import merge as M
     rank, local_rank, world = dist_env()
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
@@ -200,6 +204,17 @@ def run_merge(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    return dist, rank, world, device, barrier
+
+
+def run_merge(args, dist, rank, world, device, barrier):
+    from modelcompose_b200 import merge as M
+    local_rank = device.index
     if args.emulate_world > 1:  # profiling aid: rank 0's shard of a K-way job in one process (never a bench value)
         shapes, sizes, mine = merge_shard(args.emulate_world, 0)
     else:
@@ -211,12 +226,6 @@ def run_merge(args):
     total_bytes = sum(sizes) * 2 * (len(WEIGHTS) + 1)
     if args.emulate_world > 1:
         total_bytes = my_bytes
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         plan.run(WEIGHTS)
@@ -253,7 +262,7 @@ def run_merge(args):
         if rank == 0:
             print(json.dumps({"profiling_only": True, "ms_per_step": round(ms_per_step, 4), "GBps": round(value, 1),
                               "launch_ms": round(launch_ms, 4), "emulate_world": args.emulate_world}), flush=True)
-        return
+        return None
     e2e = run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barrier, dist)
 
     if rank == 0:
@@ -279,9 +288,11 @@ def run_merge(args):
             "gpu_launches": args.steps * world,
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    else:
+        line = None
+    del plan, srcs, outs
+    torch.cuda.empty_cache()
+    return line
 
 
 def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barrier, dist):
@@ -337,13 +348,221 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             "timer": "host wall clock around the synchronous call, max over ranks"}
 
 
+# ------------------------------------------------------------------------------------------------ prefill workload
+PREFILL_CONFIGS = {
+    # name: (BASELINE config, requests per GPU, merged adapters (infer_modals order), modalities in every request, text tokens)
+    "c3": ("composed image+audio prefill, vicuna-7B shape, batch 32, 576 image + 256 audio + 128 text tokens (C3)",
+           32, ["audio", "vision", "video"], ["vision", "audio"], 128),
+    "c4": ("composed video+image+audio prefill (MUSIC-AVQA shape), 8 requests per GPU (C4)",
+           8, ["audio", "vision", "video"], ["video", "vision", "audio"], 128),
+    "c5": ("4-modality MCUB-4 composition prefill, 16 requests per GPU (C5)",
+           16, ["audio", "vision", "video", "point"], ["vision", "audio", "video", "point"], 128),
+}
+
+
+def bf16_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def build_prefill(cfg_name: str, device, rank: int, layers=None):
+    """Random-init composed model + one batch of requests (ids on host and device, encoder features on host and device)."""
+    from modelcompose_b200 import model as MD
+    from modelcompose_b200 import splice as SP
+    from modelcompose_b200 import synthetic as syn
+    desc, batch, merged, present, n_text_total = PREFILL_CONFIGS[cfg_name]
+    coeff = 0.25 if len(merged) == 4 else 0.333
+    cfg, base, adapters = syn.make_composed_on_device(merged, device, torch.bfloat16, coeff=coeff, seed=1, layers=layers)
+    model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, adapters, device=device, dtype=torch.bfloat16)
+    del base, adapters
+    n_head = 36
+    n_text = n_text_total - n_head - 2 * len(present)
+    # request 0 is identical on every rank (cross-rank verification probe), the others are rank-specific
+    ids0 = syn.make_prompt_ids(1, present, n_text, cfg["vocab_size"], 3, SP.MODAL_TOKEN_INDEXES, n_head)
+    ids = torch.cat([ids0, syn.make_prompt_ids(batch - 1, present, n_text, cfg["vocab_size"], 30 + rank, SP.MODAL_TOKEN_INDEXES, n_head)])
+    feats = {}
+    for m in present:
+        g = torch.Generator().manual_seed(2000 + len(m))
+        probe = torch.randn(1, syn.MODAL_TOKENS[m], syn.MODAL_FEATURE_DIM[m], generator=g)
+        g2 = torch.Generator().manual_seed(2100 + len(m) + 10 * rank)
+        # cheap deterministic fill for the rank-specific requests (randn over 100+ MB on the host would dominate set-up)
+        rest = torch.randn(1, syn.MODAL_TOKENS[m], syn.MODAL_FEATURE_DIM[m], generator=g2).repeat(batch - 1, 1, 1)
+        rest = rest * torch.linspace(0.5, 1.5, batch - 1).view(-1, 1, 1)
+        feats[m] = torch.cat([probe, rest]).to(torch.bfloat16).pin_memory()
+    ids_h = ids.pin_memory()
+    mask_h = torch.ones_like(ids).pin_memory()
+    flops = syn.prefill_flops(cfg, {m: syn.MODAL_TOKENS[m] for m in present}, n_text_total, len(merged), cfg["lora_r"])
+    return model, desc, batch, ids_h, mask_h, feats, flops
+
+
+def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
+    """Composed prefill, batch-sharded (every rank holds a full replica and its own requests; no collective on the timed
+    path).  Returns the result dict (rank 0) with tokens/s, roofline of the routed-linear kernel, e2e and verification."""
+    from modelcompose_b200 import _cabi
+    from modelcompose_b200 import linear as LN
+    model, desc, batch, ids_h, mask_h, feats_h, flops = build_prefill(cfg_name, device, rank, layers=args.prefill_layers)
+    ids_d, mask_d = ids_h.to(device), mask_h.to(device)
+    feats_d = {m: v.to(device) for m, v in feats_h.items()}
+    S_out = int(flops["seq_len"])
+    steps, warmup = max(1, args.prefill_steps), max(3, min(args.warmup, 3))
+
+    def step_resident():
+        return model.forward(ids_d, mask_d, modal_inputs=feats_d)
+
+    for _ in range(warmup):
+        out = step_resident()
+    assert out.logits.shape[1] == S_out, (out.logits.shape, S_out)
+    barrier()
+    n0 = _cabi.LAUNCHES
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(device.index) as clocks:
+        t0.record()
+        for _ in range(steps):
+            out = step_resident()
+        t1.record()
+        barrier()
+    launches = _cabi.LAUNCHES - n0
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    tokens = batch * S_out * world
+    value = tokens / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel: the routed/grouped linear launches, timed with CUDA events on the launching stream
+    LN.start_profile()
+    for _ in range(2):
+        step_resident()
+    lin_ms, lin_n = LN.stop_profile()
+    lin_ms /= 2
+    lin_flops = flops["linears"] * batch
+    achieved = lin_flops / (lin_ms * 1e-3) / 1e12
+
+    # ---- e2e through the public forward API: pinned host ids/features -> device, last-position logits -> host, per step
+    last = torch.empty((batch, model.config.vocab_size), dtype=torch.bfloat16).pin_memory()
+    h2d = ids_h.numel() * 8 + mask_h.numel() * 8 + sum(v.numel() * 2 for v in feats_h.values())
+    d2h = last.numel() * 2
+
+    def step_e2e():
+        i = ids_h.to(device, non_blocking=True)
+        m = mask_h.to(device, non_blocking=True)
+        f = {k: v.to(device, non_blocking=True) for k, v in feats_h.items()}
+        o = model.forward(i, m, modal_inputs=f)
+        last.copy_(o.logits[:, -1, :], non_blocking=True)
+        torch.cuda.synchronize()
+    step_e2e()
+    barrier()
+    e_steps = max(1, min(steps, 3))
+    w0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_e2e()
+    dt = time.perf_counter() - w0
+    te = torch.tensor([dt], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = tokens / (float(te.item()) / e_steps)
+
+    # ---- verification: request 0 is the same on every rank; NCCL all-gather of its last-position logits (untimed)
+    probe = out.logits[0, -1, :].float().contiguous()
+    finite = bool(torch.isfinite(out.logits[:, -1, :]).all())
+    verified = None
+    if world > 1:
+        gathered = [torch.empty_like(probe) for _ in range(world)]
+        dist.all_gather(gathered, probe)
+        verified = all(torch.equal(g, gathered[0]) for g in gathered)
+    peak_sus, peak_burst, peak_src = bf16_peaks()
+    res = {
+        "metric": "composed-prefill tokens/s", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
+        "data": "synthetic", "vs_baseline": None,
+        "config": {"workload": desc, "requests_per_gpu": batch, "seq_len_after_splice": S_out, "prefix_suffix": "5+5",
+                   "layers": model.config.num_hidden_layers, "sharding": f"by request batch x{world}, full replica per GPU",
+                   "l2": "weights 13.5 GB + activations per step, far larger than L2",
+                   "algorithmic_tflop_per_step_per_gpu": round(flops["total"] * batch / 1e12, 2)},
+        "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s",
+                     "frac": round(achieved / peak_sus, 4), "traffic": None, "peak_source": peak_src,
+                     "kernel": "mc::linear_kernel<256,4> (routed LoRA linears, projector, lm_head)",
+                     "launches_per_step": lin_n // 2, "kernel_ms_per_step": round(lin_ms, 3),
+                     "kernel_share_of_step": round(lin_ms / ms_per_step, 4),
+                     "algorithmic_tflop_per_step": round(lin_flops / 1e12, 2), "frac_of_burst_peak": round(achieved / peak_burst, 4),
+                     "whole_step_tflops": round(flops["total"] * batch / (ms_per_step * 1e-3) / 1e12, 1)},
+        "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e_steps, "api": "MultimodalLlamaForCausalLM.forward(input_ids, attention_mask, modal_inputs=...) from pinned host "
+                "buffers; last-position logits copied back", "timer": "host wall clock incl. synchronize, max over ranks"},
+        "gpu_launches": int(launches) * world,
+        "verification": {"finite_logits": finite, "probe_request_identical_across_ranks": verified,
+                         "collective": "ncclAllGather of request 0 last-position logits, outside the timed region" if world > 1 else None},
+        "clocks": clocks.summary(),
+    }
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def cpu_prefill_layer_rate(cfg_name: str, max_seconds: float = 25.0):
+    """Reference schedule on host cores (oracle port of LocalLoraAttention / LocalLoraMLP: every adapter on every token,
+    then mask-and-sum) for ONE full-width decoder layer, batch 1, bf16; extrapolated x layers to tokens/s."""
+    from modelcompose_b200 import synthetic as syn
+    from oracle import merge_oracle as MO
+    from oracle import model_oracle as XO
+    desc, batch, merged, present, n_text = PREFILL_CONFIGS[cfg_name]
+    llama = syn.VICUNA_7B
+    H, I, r = llama["hidden_size"], llama["intermediate_size"], 128
+    S = n_text + sum(syn.MODAL_TOKENS[m] + 10 for m in present)
+    g = torch.Generator().manual_seed(0)
+    names = ["default"] + merged
+    _, scaling, dnames = MO.effective_scaling(names, r, 256, ",".join(f"default-{m}=0.333" for m in merged))
+    layer = {"input_layernorm": torch.ones(H, dtype=torch.bfloat16), "post_attention_layernorm": torch.ones(H, dtype=torch.bfloat16)}
+    for ln in syn.LINEAR_NAMES:
+        o, i = syn.linear_shape(llama, ln)
+        W = (torch.randn(o, i, generator=g) * 0.02).to(torch.bfloat16)
+        A = {a: (torch.randn(r, i, generator=g) * 0.01).to(torch.bfloat16) for a in merged + dnames}
+        Bm = {a: (torch.randn(o, r, generator=g) * 0.02).to(torch.bfloat16) for a in merged + dnames}
+        layer[ln.split(".")[1]] = XO.LinearParams(W, A, Bm, scaling, dnames)
+    x = (torch.randn(1, S, H, generator=g) * 0.5).to(torch.bfloat16)
+    seg = torch.zeros(S, dtype=torch.long)
+    o = 40
+    for m in present:
+        n = syn.MODAL_TOKENS[m] + 10
+        seg[o:o + n] = names.index(m)
+        o += n + 3
+    masks = {m: (seg == names.index(m))[None] for m in merged}
+    masks["default"] = (seg == 0)[None]
+    ordered = {m: masks[m] for m in names}
+    pos = torch.arange(S)[None]
+    add = XO.causal_additive_mask(1, S, torch.bfloat16)
+    t0 = time.perf_counter()
+    reps = 0
+    with torch.no_grad():
+        while True:
+            XO.decoder_layer_forward(x, layer, ordered, names, llama["num_attention_heads"], pos, add, 1e-5)
+            reps += 1
+            if time.perf_counter() - t0 > max_seconds or reps >= 3:
+                break
+    per_layer = (time.perf_counter() - t0) / reps
+    tok_s = S / (per_layer * llama["num_hidden_layers"])
+    return {"value": round(tok_s, 2), "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"one full-width decoder layer (reference dense-then-mask schedule), batch 1, S'={S}, bf16, {reps} rep(s), "
+                      f"{per_layer:.2f} s/layer; extrapolated x{llama['num_hidden_layers']} layers (projector, splice, lm_head excluded)",
+            "host_cpus": os.cpu_count()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="merge", choices=["merge"])
+    ap.add_argument("--workload", default="all", choices=["all", "merge", "prefill"],
+                    help="all (default): the merge line (BASELINE config 2) carrying the prefill result under \"prefill\"; "
+                         "merge / prefill: that workload alone as the primary line")
+    ap.add_argument("--prefill-config", default="c3", choices=sorted(PREFILL_CONFIGS))
+    ap.add_argument("--prefill-steps", type=int, default=5)
+    ap.add_argument("--prefill-layers", type=int, default=None, help="development aid: fewer decoder layers (never a bench value)")
     ap.add_argument("--tuning", type=int, default=0)
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="profiling aid: run rank 0's shard of a K-way job on one GPU (ncu captures)")
@@ -353,7 +572,23 @@ def main():
         run_reference_arm(args)
         return
     args.warmup = max(args.warmup, 3)
-    run_merge(args)
+    dist, rank, world, device, barrier = setup_dist(args)
+    line = None
+    if args.workload in ("all", "merge"):
+        line = run_merge(args, dist, rank, world, device, barrier)
+    if args.workload in ("all", "prefill") and not args.no_e2e:
+        pre = run_prefill(args, device, rank, world, dist, barrier, args.prefill_config)
+        if rank == 0:
+            pre["cpu_baseline"] = cpu_prefill_layer_rate(args.prefill_config)
+            if args.workload == "prefill":
+                line = pre
+            elif line is not None:
+                line["prefill"] = pre
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

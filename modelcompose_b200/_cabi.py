@@ -54,6 +54,14 @@ class McError(RuntimeError):
     pass
 
 
+LAUNCHES = 0  # kernels of this library launched through the Python wrappers (bench.py's `gpu_launches`)
+
+
+def count_launch(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def lib() -> C.CDLL:
     """Load the CUDA library (built in-tree by ``modelcompose_b200.build``).  Fails loudly."""
     global _LIB

@@ -22,6 +22,23 @@ TILE_M = 128
 K_BLOCK = 64
 
 
+_PROFILE = None  # list of (start, end) CUDA events around every linear launch while profiling is on
+
+
+def start_profile() -> None:
+    """Record a CUDA-event pair (on the launching stream) around every linear launch until ``stop_profile``."""
+    global _PROFILE
+    _PROFILE = []
+
+
+def stop_profile():
+    """Returns (total milliseconds inside linear launches, number of launches); synchronises."""
+    global _PROFILE
+    ev, _PROFILE = _PROFILE or [], None
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev), len(ev)
+
+
 class LinearDesc(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K0", C.c_int32), ("K1", C.c_int32),
                 ("A0", C.c_void_p), ("lda0", C.c_int64), ("B0", C.c_void_p), ("ldb0", C.c_int64),
@@ -117,7 +134,14 @@ class LinearPlan:
         return float(_cabi.lib().mc_linear_plan_flops(self._h))
 
     def run(self) -> None:
+        if _PROFILE is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         _cabi.check(_cabi.lib().mc_linear_plan_run(self._h, _cabi.current_stream_ptr()), "mc_linear_plan_run")
+        _cabi.count_launch()
+        if _PROFILE is not None:
+            b.record()
+            _PROFILE.append((a, b))
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -141,6 +165,7 @@ def route_tile_masks(row_group: torch.Tensor, out: Optional[torch.Tensor] = None
         out = torch.empty(n, dtype=torch.int32, device=row_group.device)
     _cabi.check(_cabi.lib().mc_route_tile_masks(row_group.data_ptr(), M, out.data_ptr(), _cabi.current_stream_ptr()),
                 "mc_route_tile_masks")
+    _cabi.count_launch()
     return out
 
 
@@ -153,6 +178,7 @@ def silu_mul(gate: torch.Tensor, up: torch.Tensor, out: Optional[torch.Tensor] =
     _cabi.check(_cabi.lib().mc_silu_mul(g.data_ptr(), u.data_ptr(), o.data_ptr(), g.shape[0], g.shape[1], g.stride(0),
                                         u.stride(0), o.stride(0), _cabi.dtype_code(g.dtype), _cabi.current_stream_ptr()),
                 "mc_silu_mul")
+    _cabi.count_launch()
     return out
 
 

@@ -85,6 +85,7 @@ class MergePlan:
             w = _cabi.f32_array([1.0] * self.n_src)
         _cabi.check(_cabi.lib().mc_merge_plan_run(self._h, w, MODES[mode], _cabi.current_stream_ptr()),
                     "mc_merge_plan_run")
+        _cabi.count_launch()
 
     def close(self) -> None:
         if self._h:

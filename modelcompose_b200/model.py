@@ -332,8 +332,9 @@ class MultimodalLlamaForCausalLM:
         _cabi.check(_cabi.lib().mc_rmsnorm(x.data_ptr(), w.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], x.stride(0),
                                            out.stride(0), float(self.config.rms_norm_eps), _cabi.dtype_code(self.dtype),
                                            _cabi.current_stream_ptr()), "mc_rmsnorm")
+        _cabi.count_launch()
 
-    def _attention(self, ws: _Workspace, attention_mask: Optional[torch.Tensor]):
+    def _attention(self, ws: _Workspace, attention_mask: Optional[torch.Tensor], full: bool):
         cfg = self.config
         nH = cfg.num_attention_heads
         D = cfg.hidden_size // nH
@@ -342,8 +343,8 @@ class MultimodalLlamaForCausalLM:
         _cabi.check(_cabi.lib().mc_rope(ws.q.data_ptr(), ws.k.data_ptr(), cos.data_ptr(), sin.data_ptr(), ws.T, S, nH, D,
                                         ws.q.stride(0), ws.k.stride(0), _cabi.dtype_code(self.dtype),
                                         _cabi.current_stream_ptr()), "mc_rope")
+        _cabi.count_launch()
         q, k, v = (t.view(B, S, nH, D) for t in (ws.q, ws.k, ws.v))
-        full = attention_mask is None or bool(attention_mask.all())
         if full:
             try:
                 from flash_attn import flash_attn_func
@@ -375,6 +376,7 @@ class MultimodalLlamaForCausalLM:
         else:
             ws.row_group.view(B, S).copy_(modal_id)
         LN.route_tile_masks(ws.row_group, ws.mtile)
+        full = attention_mask is None or bool(attention_mask.all())  # one host sync per prefill, not per layer
         kv, hidden = [], []
         for layer, plans in zip(self.layers, ws.plans):
             if output_hidden_states:
@@ -382,7 +384,7 @@ class MultimodalLlamaForCausalLM:
             self._rmsnorm(ws.x, layer.ln1, ws.xn)
             plans["down_qkv"].run()
             plans["up_qkv"].run()
-            self._attention(ws, attention_mask)
+            self._attention(ws, attention_mask, full)
             if use_cache:
                 nH = self.config.num_attention_heads
                 kv.append((ws.k.view(B, S, nH, H // nH).transpose(1, 2).clone(), ws.v.view(B, S, nH, H // nH).transpose(1, 2).clone()))

@@ -137,6 +137,7 @@ def splice(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], labe
         io = SpliceIO(_cabi.dtype_code(dtype), H, embed_table.data_ptr(), _ptr(attention_mask), elem, _ptr(labels),
                       embeds.data_ptr(), modal_id.data_ptr(), _ptr(attn_out), _ptr(labels_out), _ptr(default_mask))
         _cabi.check(lib.mc_splice_run(plan, C.byref(io), modals, stream), "mc_splice_run")
+        _cabi.count_launch(3)  # scan + expand (plan) + gather
         nbytes = int(lib.mc_splice_plan_bytes(plan, H * embed_table.element_size()))
     finally:
         lib.mc_splice_plan_destroy(plan)

@@ -65,13 +65,46 @@ def test_decoder_layers_vs_reference_fixture(golden, key):
     compare(ws.x.view_as(x), ref["hidden_nomask"], key, "hidden (no modality mask)")
 
 
+def oracle_forward(cfg: dict, base, sd, ids, attn, feats, dtype, n_heads):
+    """CPU oracle of the whole path on 16-bit tensors: projector -> prefix/suffix -> splice -> routed layers -> logits."""
+    modal_names = MD.infer_modals(MD.MultimodalConfig.from_dict(cfg))
+    cpu = lambda t: t.detach().to("cpu", dtype)
+    proj = {}
+    for m in modal_names[1:]:
+        if m not in feats:
+            continue
+        pre = f"model.modal_projectors.{m}."
+        f = feats[m].reshape(feats[m].shape[0], -1, feats[m].shape[-1])
+        proj[m] = XO.projector_forward(cpu(f), [cpu(sd[pre + "0.weight"]), cpu(sd[pre + "2.weight"])],
+                                       [cpu(sd[pre + "0.bias"]), cpu(sd[pre + "2.bias"])])
+    pre_t = {m: cpu(sd[f"prefix_tokens.{m}"]) for m in proj}
+    suf_t = {m: cpu(sd[f"suffix_tokens.{m}"]) for m in proj}
+    am, embeds, _, masks = SO.splice(ids, attn, None, cpu(base["model.embed_tokens.weight"]),
+                                     SO.add_prefix_suffix(proj, pre_t, suf_t))
+    names, scaling, dnames = MO.effective_scaling(modal_names, cfg["lora_r"], cfg["lora_alpha"], cfg["reset_scaling_weights"])
+    layers = []
+    for li in range(cfg["num_hidden_layers"]):
+        layer = {"input_layernorm": cpu(base[f"model.layers.{li}.input_layernorm.weight"]),
+                 "post_attention_layernorm": cpu(base[f"model.layers.{li}.post_attention_layernorm.weight"])}
+        for ln in syn.LINEAR_NAMES:
+            p = f"model.layers.{li}.{ln}."
+            A = {k[len(p) + 7:-7]: cpu(v) for k, v in sd.items() if k.startswith(p + "lora_A.")}
+            Bm = {k[len(p) + 7:-7]: cpu(v) for k, v in sd.items() if k.startswith(p + "lora_B.")}
+            layer[ln.split(".")[1]] = XO.LinearParams(cpu(base[p + "weight"]), A, Bm, scaling, dnames)
+        layers.append(layer)
+    bmasks = {k: v.bool() for k, v in masks.items()}
+    ordered = {m: bmasks.get(m, torch.zeros_like(bmasks["default"])) for m in modal_names}
+    logits, _ = XO.model_forward(embeds, layers, cpu(base["model.norm.weight"]), cpu(base["lm_head.weight"]),
+                                 ordered, modal_names, n_heads, cfg["rms_norm_eps"])
+    return logits, bmasks, modal_names
+
+
 @pytest.mark.parametrize("key", list(DTYPES))
 def test_end_to_end_forward_vs_oracle(golden, key):
     """input_ids with sentinels + encoder features -> projector -> splice -> routed layers -> logits, vs the CPU oracle
     evaluated in the same 16-bit dtype."""
     dtype = DTYPES[key]
     model, run, base = tiny_model(golden, dtype)
-    sd = run["state_dict"]
     g = torch.Generator().manual_seed(9)
     B, n_text = 3, 20
     ids = syn.make_prompt_ids(B, ["vision", "audio"], n_text, 1000, seed=3, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=6)
@@ -79,34 +112,34 @@ def test_end_to_end_forward_vs_oracle(golden, key):
     attn = torch.ones_like(ids)
     out = model.forward(ids.cuda(), attn.cuda(), modal_inputs={k: v.cuda() for k, v in feats.items()})
     torch.cuda.synchronize()
-    # ---- oracle
-    proj = {}
-    for m in ("audio", "vision"):
-        pre = f"model.modal_projectors.{m}."
-        proj[m] = XO.projector_forward(feats[m], [sd[pre + "0.weight"].to(dtype), sd[pre + "2.weight"].to(dtype)],
-                                       [sd[pre + "0.bias"].to(dtype), sd[pre + "2.bias"].to(dtype)])
-    pre_t = {m: sd[f"prefix_tokens.{m}"].to(dtype) for m in proj}
-    suf_t = {m: sd[f"suffix_tokens.{m}"].to(dtype) for m in proj}
-    am, embeds, _, masks = SO.splice(ids, attn, None, base["model.embed_tokens.weight"].to(dtype),
-                                     SO.add_prefix_suffix(proj, pre_t, suf_t))
-    names, scaling, dnames = MO.effective_scaling(["default", "audio", "vision"], 8, 16, run["config"]["reset_scaling_weights"])
-    layers = []
-    for li in range(2):
-        layer = {"input_layernorm": base[f"model.layers.{li}.input_layernorm.weight"].to(dtype),
-                 "post_attention_layernorm": base[f"model.layers.{li}.post_attention_layernorm.weight"].to(dtype)}
-        for ln in syn.LINEAR_NAMES:
-            p = f"model.layers.{li}.{ln}."
-            A = {k[len(p) + 7:-7]: v.to(dtype) for k, v in sd.items() if k.startswith(p + "lora_A.")}
-            Bm = {k[len(p) + 7:-7]: v.to(dtype) for k, v in sd.items() if k.startswith(p + "lora_B.")}
-            layer[ln.split(".")[1]] = XO.LinearParams(base[p + "weight"].to(dtype), A, Bm, scaling, dnames)
-        layers.append(layer)
-    bmasks = {k: v.bool() for k, v in masks.items()}
-    ordered = {m: bmasks[m] for m in ["default", "audio", "vision"]}
-    logits, _ = XO.model_forward(embeds, layers, base["model.norm.weight"].to(dtype), base["lm_head.weight"].to(dtype),
-                                 ordered, ["default", "audio", "vision"], 4, 1e-5)
+    logits, bmasks, _ = oracle_forward(run["config"], base, run["state_dict"], ids, attn, feats, dtype, 4)
     assert out.logits.shape == logits.shape
     assert torch.equal(out.modal_id.cpu() == 1, bmasks["audio"]) and torch.equal(out.modal_id.cpu() == 2, bmasks["vision"])
     compare(out.logits, logits, key, "end-to-end logits")
+
+
+def test_full_width_layer_vs_oracle():
+    """vicuna-7B WIDTH (H 4096, I 11008, r 128, vocab 32000, 3 merged adapters at 0.333, 5+5 prefix/suffix), one decoder
+    layer, 2 requests with video + image + audio blocks of reduced length (the CPU oracle runs the reference's
+    dense-then-mask schedule, so the token count is kept where it finishes in seconds)."""
+    dev = torch.device("cuda")
+    cfg, base, sd = syn.make_composed_on_device(["audio", "vision", "video"], dev, torch.bfloat16, seed=1, layers=1)
+    model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, sd, device=dev, dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(4)
+    B = 2
+    ids = syn.make_prompt_ids(B, ["video", "vision", "audio"], 30, cfg["vocab_size"], seed=5,
+                              modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=10)
+    feats = {"audio": torch.randn(B, 40, 768, generator=g).to(torch.bfloat16),
+             "vision": torch.randn(B, 70, 1024, generator=g).to(torch.bfloat16),
+             "video": torch.randn(B, 2, 45, 1024, generator=g).to(torch.bfloat16)}
+    attn = torch.ones_like(ids)
+    out = model.forward(ids.cuda(), attn.cuda(), modal_inputs={k: v.cuda() for k, v in feats.items()})
+    torch.cuda.synchronize()
+    logits, bmasks, names = oracle_forward(cfg, base, sd, ids, attn, feats, torch.bfloat16, 32)
+    assert out.logits.shape == logits.shape
+    for i, m in enumerate(names):
+        assert torch.equal(out.modal_id.cpu() == i, bmasks[m]), m
+    compare(out.logits, logits, "torch.bfloat16", "full-width one-layer logits")
 
 
 def test_loader_from_disk_and_text_only(tmp_path, golden):
