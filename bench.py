@@ -160,6 +160,7 @@ def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; rank 0 alone works here, on every host core
     sample, desc = cpu_sample_tensors()
     from oracle import merge_oracle as MO
     nbytes = sum(t[0].numel() for t in sample) * 2 * (len(WEIGHTS) + 1)
@@ -268,8 +269,13 @@ def run_merge(args, dist, rank, world, device, barrier):
     if rank == 0:
         peak, peak_src = measured_peaks()
         achieved = my_bytes / (launch_ms * 1e-3) / 1e9
-        cpu_sample, desc = cpu_sample_tensors()
-        cpu_gbs, cpu_s, passes = cpu_merge_rate(cpu_sample, min_seconds=10.0)
+        if world == 1:
+            cpu_sample, desc = cpu_sample_tensors()
+            cpu_gbs, cpu_s, passes = cpu_merge_rate(cpu_sample, min_seconds=10.0)
+            cpu_baseline = {"value": round(cpu_gbs, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"{desc}, {passes} passes in {cpu_s:.1f} s", "host_cpus": os.cpu_count()}
+        else:
+            cpu_baseline = None  # reported at N=1 only
         line = {
             "metric": "3x7B merge GB/s", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
@@ -282,8 +288,7 @@ def run_merge(args, dist, rank, world, device, barrier):
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                          "kernel": "mc::merge_kernel<3,bf16,bf16>", "launch_ms": round(launch_ms, 4),
                          "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
-            "cpu_baseline": {"value": round(cpu_gbs, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{desc}, {passes} passes in {cpu_s:.1f} s", "host_cpus": os.cpu_count()},
+            "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": args.steps * world,
             "clocks": clocks.summary(),
@@ -579,7 +584,8 @@ def main():
     if args.workload in ("all", "prefill") and not args.no_e2e:
         pre = run_prefill(args, device, rank, world, dist, barrier, args.prefill_config)
         if rank == 0:
-            pre["cpu_baseline"] = cpu_prefill_layer_rate(args.prefill_config)
+            # CPU baseline on rank 0 at N=1 only (under torchrun the other ranks would wait on it)
+            pre["cpu_baseline"] = cpu_prefill_layer_rate(args.prefill_config) if world == 1 else None
             if args.workload == "prefill":
                 line = pre
             elif line is not None:

@@ -189,7 +189,9 @@ typedef enum mc_linear_epilogue {
   MC_LINEAR_EPI_BIAS = 1,      /* + bias[n] */
   MC_LINEAR_EPI_BIAS_GELU = 2, /* gelu_erf(acc + bias[n])  (projector builder.py:214-217) */
   MC_LINEAR_EPI_ROWMASK = 3,   /* see above */
-  MC_LINEAR_EPI_RESIDUAL = 4   /* + residual[m,n] (decoder residual adds, multimodal_llama.py:448,461) */
+  MC_LINEAR_EPI_RESIDUAL = 4,  /* + residual[m,n] (decoder residual adds, multimodal_llama.py:448,461) */
+  MC_LINEAR_EPI_SILU_MUL = 5   /* silu(residual[m,n]) * acc: `residual` holds the stored gate_proj output, the product
+                                  is the up_proj problem's result (multimodal_llama.py:381-388); may run in place */
 } mc_linear_epilogue;
 
 typedef struct mc_linear_desc {
@@ -200,7 +202,7 @@ typedef struct mc_linear_desc {
   const void* B1; int64_t ldb1; /* device [N, K1] or NULL */
   void* C; int64_t ldc;         /* device [M, N] */
   const void* bias;             /* device [N], same dtype as C, or NULL */
-  const void* residual; int64_t ldr; /* device [M, N] or NULL */
+  const void* residual; int64_t ldr; /* device [M, N] or NULL (RESIDUAL: addend; SILU_MUL: gate operand) */
   const float* col_scale;       /* device fp32 [N] (ROWMASK) or NULL */
   const uint8_t* row_group;     /* device [M] (ROWMASK) or NULL */
   const uint32_t* mtile_mask;   /* device [ceil(M/128)] or NULL (= every group present) */
@@ -212,8 +214,9 @@ typedef struct mc_linear_desc {
 typedef struct mc_linear_plan mc_linear_plan_t;
 
 /* Encodes the TMA descriptors and tile schedule of 1..MC_LINEAR_MAX_PROBLEMS problems that run as ONE launch.
- * dtype: MC_BF16 or MC_F16.  tuning: 0 = default tile, 1 = 128x128, 2 = 128x256.  The plan stays valid while the
- * pointers in `desc` do (activations are normally static per-shape buffers, so plans are built once and reused). */
+ * dtype: MC_BF16 or MC_F16.  tuning: bits 0-7 tile (0 = default, 1 = 128x128, 2 = 128x256), bits 8-15 rasterisation group
+ * override, bit 16 disables the compacted tile schedule of routed-N launches.  The plan stays valid while the pointers
+ * in `desc` do (activations are normally static per-shape buffers, so plans are built once and reused). */
 MC_API int mc_linear_plan_create(mc_linear_plan_t** plan, const mc_linear_desc_t* desc, int n_problems, int dtype, int tuning);
 MC_API int mc_linear_plan_run(const mc_linear_plan_t* plan, mc_stream_t stream);
 /* Nominal FLOPs of one run: sum of 2*M*N*(K0+K1) (skipped K1 blocks / N tiles are NOT subtracted). */

@@ -35,7 +35,8 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxProb = MC_LINEAR_MAX_PROBLEMS;
 constexpr int kThreads = 256;
-constexpr int kGroupM = 8;  // tile rasterisation: 8 M-tiles share a sweep over N (keeps the B working set in L2)
+constexpr int kMaxOwnTiles = 256;    // compact schedule: tiles one CTA may own (plan falls back to the static schedule beyond)
+constexpr int kMaxMaskTiles = 2048;  // compact schedule: M tiles whose group masks are staged in shared memory
 
 struct alignas(64) LinProblem {
   CUtensorMap tmA0, tmB0, tmA1, tmB1;
@@ -56,6 +57,8 @@ struct alignas(64) LinParams {
   LinProblem prob[kMaxProb];
   int n_prob, total_tiles, is_f16;
   unsigned int idesc;
+  int group_m;  // tile rasterisation: group_m M-tiles share a sweep over N (keeps the operand working set in L2)
+  int compact;  // 1: every CTA first compacts the (M tile, N tile) pairs that survive routing and owns every grid-th of them
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -164,16 +167,44 @@ __device__ __forceinline__ Tile decode_tile(const LinParams& P, int tile) {
   }
   const LinProblem& pr = P.prob[p];
   const int local = tile - begin;
-  const int per_group = kGroupM * pr.tiles_n;
+  const int per_group = P.group_m * pr.tiles_n;
   const int g = local / per_group, within = local % per_group;
-  const int gsize = min(kGroupM, pr.tiles_m - g * kGroupM);
+  const int gsize = min(P.group_m, pr.tiles_m - g * P.group_m);
   t.p = p;
-  t.mt = g * kGroupM + within % gsize;
+  t.mt = g * P.group_m + within % gsize;
   t.nt = within / gsize;
   t.gmask = pr.mtile_mask ? pr.mtile_mask[t.mt] : 0xffffffffu;
   t.skip = pr.ntile_mask != nullptr && (pr.ntile_mask[t.nt] & t.gmask) == 0u;
   return t;
 }
+
+// Walks the tiles this CTA owns: the static round-robin schedule, or the compacted list built in the prologue.
+struct TileIter {
+  const LinParams& P;
+  const int* own;
+  const unsigned int* mm;
+  int n_own, it;
+  __device__ __forceinline__ TileIter(const LinParams& P_, const int* own_, int n_own_, const unsigned int* mm_)
+      : P(P_), own(own_), mm(mm_), n_own(n_own_), it(0) {}
+  __device__ __forceinline__ bool next(Tile& t) {
+    if (P.compact) {
+      if (it >= n_own) return false;
+      const int packed = own[it++];
+      t.p = packed >> 28;
+      t.mt = (packed >> 10) & 0x3ffff;
+      t.nt = packed & 0x3ff;
+      t.gmask = mm[t.mt];
+      t.skip = false;
+      return true;
+    }
+    for (;;) {
+      const int tile = blockIdx.x + (it++) * gridDim.x;
+      if (tile >= P.total_tiles) return false;
+      t = decode_tile(P, tile);
+      if (!t.skip) return true;
+    }
+  }
+};
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -205,6 +236,92 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], bool is_f16) {
     }
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// One 128-row x BN-column accumulator tile: TMEM -> registers -> epilogue -> global.  Executed by the 4 epilogue warps;
+// `row` is this thread's output row, `taddr` the TMEM address of its lane quadrant and accumulator stage.
+// The RESIDUAL / SILU_MUL operand is fetched one 32-column chunk ahead so its latency hides behind the TMEM load.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16, uint32_t taddr, int row, int n0) {
+  const bool row_ok = row < pr.M;
+  const int epi = pr.epilogue;
+  const bool has_aux = (epi == MC_LINEAR_EPI_RESIDUAL || epi == MC_LINEAR_EPI_SILU_MUL) && row_ok;
+  const int rg = (epi == MC_LINEAR_EPI_ROWMASK && row_ok) ? (int)pr.row_group[row] : -1;
+  char* crow = reinterpret_cast<char*>(pr.C) + (long long)row * pr.ldc * 2;
+  const char* rrow = reinterpret_cast<const char*>(pr.residual) + (long long)row * pr.ldr * 2;
+  uint4 aux[4], aux_next[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    aux[j] = make_uint4(0u, 0u, 0u, 0u);
+    aux_next[j] = make_uint4(0u, 0u, 0u, 0u);
+    const int col = n0 + 8 * j;
+    if (has_aux && col < pr.N) aux[j] = *reinterpret_cast<const uint4*>(rrow + (long long)col * 2);
+  }
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    if (n0 + c >= pr.N) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + (uint32_t)c, v);
+    if (has_aux) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = n0 + c + 32 + 8 * j;
+        if (c + 32 < BN && col < pr.N) aux_next[j] = *reinterpret_cast<const uint4*>(rrow + (long long)col * 2);
+      }
+    }
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = n0 + c + 8 * j;
+        if (col < pr.N) {  // N % 8 == 0: the whole 8-column vector is in range
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+          if (epi == MC_LINEAR_EPI_BIAS || epi == MC_LINEAR_EPI_BIAS_GELU) {
+            float b[8];
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(pr.bias) + (long long)col * 2), is_f16, b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += b[e];
+            if (epi == MC_LINEAR_EPI_BIAS_GELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+            }
+          } else if (epi == MC_LINEAR_EPI_ROWMASK) {
+            const uint2 cg = *reinterpret_cast<const uint2*>(pr.col_group + col);
+            const float4 s0 = *reinterpret_cast<const float4*>(pr.col_scale + col);
+            const float4 s1 = *reinterpret_cast<const float4*>(pr.col_scale + col + 4);
+            const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int g = (int)(((e < 4 ? cg.x : cg.y) >> (8 * (e & 3))) & 0xffu);
+              f[e] = (g == rg) ? f[e] * s[e] : 0.0f;
+            }
+          } else if (epi == MC_LINEAR_EPI_RESIDUAL) {
+            float r[8];
+            unpack8(aux[j], is_f16, r);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += r[e];
+          } else if (epi == MC_LINEAR_EPI_SILU_MUL) {
+            // C = silu(aux) * acc with the reference's rounding points (multimodal_llama.py:381-388): aux is the stored
+            // gate_proj output; silu(gate) and up_proj are each rounded to the storage dtype before the product
+            float g[8], sg[8], up[8];
+            unpack8(aux[j], is_f16, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sg[e] = __fdividef(g[e], 1.0f + __expf(-g[e]));
+            const uint4 sgr = pack8(sg, is_f16), upr = pack8(f, is_f16);
+            unpack8(sgr, is_f16, sg);
+            unpack8(upr, is_f16, up);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = sg[e] * up[e];
+          }
+          *reinterpret_cast<uint4*>(crow + (long long)col * 2) = pack8(f, is_f16);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) aux[j] = aux_next[j];
+  }
 }
 
 template <int BN, int STAGES>
@@ -253,19 +370,54 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  __shared__ int s_own[kMaxOwnTiles];
+  __shared__ unsigned int s_mm[kMaxMaskTiles];
+  __shared__ int s_n_own;
+  if (P.compact) {
+    // Routed-N launch (LoRA down-projection): most (M tile, N tile) pairs are skipped, and a static round-robin over
+    // the full grid of pairs leaves the survivors unevenly spread.  Every CTA compacts the surviving pairs (identical
+    // order everywhere, M-major so concurrent tiles share A rows), interleaves the problems of the launch, and keeps
+    // every gridDim.x-th entry.  All problems of a compact launch share M, the N tiling and the masks (plan-checked).
+    const LinProblem& p0 = P.prob[0];
+    for (int i = threadIdx.x; i < p0.tiles_m; i += kThreads) s_mm[i] = p0.mtile_mask[i];
+    __syncthreads();
+    if (warp == 3) {
+      const int total = p0.tiles_m * p0.tiles_n;
+      int count = 0, mine = 0;
+      for (int base = 0; base < total; base += 32) {
+        const int idx = base + lane;
+        const int mt = idx / p0.tiles_n, nt = idx - mt * p0.tiles_n;
+        const bool active = idx < total && (p0.ntile_mask[nt] & s_mm[mt]) != 0u;
+        const unsigned int b = __ballot_sync(0xffffffffu, active);
+        const int j = count + __popc(b & ((1u << lane) - 1u));
+        for (int p = 0; p < P.n_prob; ++p) {
+          const bool own = active && ((j * P.n_prob + p) % (int)gridDim.x) == (int)blockIdx.x;
+          const unsigned int b2 = __ballot_sync(0xffffffffu, own);
+          if (own) {
+            const int slot = mine + __popc(b2 & ((1u << lane) - 1u));
+            if (slot < kMaxOwnTiles) s_own[slot] = (p << 28) | (mt << 10) | nt;
+          }
+          mine += __popc(b2);
+        }
+        count += __popc(b);
+      }
+      if (lane == 0) s_n_own = min(mine, kMaxOwnTiles);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_own = P.compact ? s_n_own : 0;
 
   if (warp == 0) {
     // ===== TMA producer (one thread) =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const Tile t = decode_tile(P, tile);
-        if (t.skip) continue;
+      TileIter tiles(P, s_own, n_own, s_mm);
+      Tile t;
+      while (tiles.next(t)) {
         const LinProblem& pr = P.prob[t.p];
         const int m0 = t.mt * kBM, n0 = t.nt * BN;
         for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
@@ -289,9 +441,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const Tile t = decode_tile(P, tile);
-        if (t.skip) continue;
+      TileIter tiles(P, s_own, n_own, s_mm);
+      Tile t;
+      while (tiles.next(t)) {
         const LinProblem& pr = P.prob[t.p];
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
@@ -327,63 +479,16 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
     const bool is_f16 = P.is_f16 != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const Tile t = decode_tile(P, tile);
-      if (t.skip) continue;
+    TileIter tiles(P, s_own, n_own, s_mm);
+    Tile t;
+    while (tiles.next(t)) {
       const LinProblem& pr = P.prob[t.p];
       const int row = t.mt * kBM + q * 32 + lane;
       const int n0 = t.nt * BN;
-      const bool row_ok = row < pr.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      const int rg = (pr.epilogue == MC_LINEAR_EPI_ROWMASK && row_ok) ? (int)pr.row_group[row] : -1;
-      char* crow = reinterpret_cast<char*>(pr.C) + (long long)row * pr.ldc * 2;
-      const char* rrow = pr.residual ? reinterpret_cast<const char*>(pr.residual) + (long long)row * pr.ldr * 2 : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (n0 + c >= pr.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col = n0 + c + 8 * j;
-            if (col < pr.N) {  // N % 8 == 0: the whole 8-column vector is in range
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-              if (pr.epilogue == MC_LINEAR_EPI_BIAS || pr.epilogue == MC_LINEAR_EPI_BIAS_GELU) {
-                float b[8];
-                unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(pr.bias) + (long long)col * 2), is_f16, b);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += b[e];
-                if (pr.epilogue == MC_LINEAR_EPI_BIAS_GELU) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
-                }
-              } else if (pr.epilogue == MC_LINEAR_EPI_ROWMASK) {
-                const uint2 cg = *reinterpret_cast<const uint2*>(pr.col_group + col);
-                const float4 s0 = *reinterpret_cast<const float4*>(pr.col_scale + col);
-                const float4 s1 = *reinterpret_cast<const float4*>(pr.col_scale + col + 4);
-                const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int g = (int)(((e < 4 ? cg.x : cg.y) >> (8 * (e & 3))) & 0xffu);
-                  f[e] = (g == rg) ? f[e] * s[e] : 0.0f;
-                }
-              } else if (pr.epilogue == MC_LINEAR_EPI_RESIDUAL) {
-                float r[8];
-                unpack8(*reinterpret_cast<const uint4*>(rrow + (long long)col * 2), is_f16, r);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += r[e];
-              }
-              *reinterpret_cast<uint4*>(crow + (long long)col * 2) = pack8(f, is_f16);
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(pr, is_f16, taddr, row, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -395,6 +500,220 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+
+// =====================================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair (thread-block cluster of 2 = the two SMs of a TPC) computes a 256 x 256 tile.
+// Each CTA stages its own 128 rows of A and 128 rows (N) of B per k-block (32 KB/stage instead of 48 KB for half the
+// output), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory and writes
+// both CTAs' TMEM; each CTA drains its own 128 accumulator rows.  Per output element this halves the B traffic from L2
+// and shared memory.  Used for the un-routed-N launches (base + LoRA-up linears, projector, lm_head).
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default (.release.cta) semantics: the explicit .release.cluster form costs a GPU-scope MEMBAR per k-block, and nothing
+  // this thread wrote needs to be visible to the peer (the operands travel through the async proxy / tcgen05 fences)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs of this thread completed) on the barrier at the same smem offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
+  const unsigned short mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+template <int STAGES>
+struct SmemLayout2 {
+  static constexpr int A_BYTES = kBM * kBK * 2;   // this CTA's 128 rows of the 256-row A tile
+  static constexpr int B_BYTES = 128 * kBK * 2;   // this CTA's 128 rows (N) of the 256-column B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear2_kernel(const __grid_constant__ LinParams P) {
+  using L = SmemLayout2<STAGES>;
+  constexpr int BN = 256, TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.n_prob; ++p) {
+      tma_prefetch_desc(&P.prob[p].tmA0);
+      tma_prefetch_desc(&P.prob[p].tmB0);
+      if (P.prob[p].nkb1) {
+        tma_prefetch_desc(&P.prob[p].tmA1);
+        tma_prefetch_desc(&P.prob[p].tmB1);
+      }
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer's remote arrive (leader's copy is the one used)
+      mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);   // multicast tcgen05.commit from the leader
+      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's copy
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // the pair walks tiles pair, pair + n_pairs, ...; both CTAs decode identically
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
+        Tile t = decode_tile(P, tile);
+        const LinProblem& pr = P.prob[t.p];
+        if (pr.mtile_mask) {
+          t.gmask = pr.mtile_mask[2 * t.mt];
+          if (2 * t.mt + 1 < (pr.M + kBM - 1) / kBM) t.gmask |= pr.mtile_mask[2 * t.mt + 1];
+        }
+        const int m0 = t.mt * 256 + (int)rank * 128, n0 = t.nt * BN + (int)rank * 128;
+        for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
+          const bool ext = kb >= pr.nkb0;
+          const int k = ext ? kb - pr.nkb0 : kb;
+          if (ext && pr.kb1_mask && (pr.kb1_mask[k] & t.gmask) == 0u) continue;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // both CTAs' bytes land on this barrier
+          else mbar_arrive_cluster(full_leader);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          tma_load_2d_cg2(ext ? &pr.tmA1 : &pr.tmA0, full_leader, sa, k * kBK, m0);
+          tma_load_2d_cg2(ext ? &pr.tmB1 : &pr.tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
+        Tile t = decode_tile(P, tile);
+        const LinProblem& pr = P.prob[t.p];
+        if (pr.mtile_mask) {
+          t.gmask = pr.mtile_mask[2 * t.mt];
+          if (2 * t.mt + 1 < (pr.M + kBM - 1) / kBM) t.gmask |= pr.mtile_mask[2 * t.mt + 1];
+        }
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
+          const bool ext = kb >= pr.nkb0;
+          if (ext && pr.kb1_mask && (pr.kb1_mask[kb - pr.nkb0] & t.gmask) == 0u) continue;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t a_desc = umma_smem_desc(sa), b_desc = umma_smem_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_f16_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_cg2(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_cg2(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const bool is_f16 = P.is_f16 != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
+      const Tile t = decode_tile(P, tile);
+      const LinProblem& pr = P.prob[t.p];
+      const int row = t.mt * 256 + (int)rank * 128 + q * 32 + lane;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      epilogue_tile<BN>(pr, is_f16, taddr, row, t.nt * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer can still signal its barriers or read its memory
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
 }
 
 // ---- routing helpers ------------------------------------------------------------------------------------
@@ -428,7 +747,7 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const T* __restrict__ gat
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float x = to_f32<T>(ge[e]);
-      const T s = from_f32<T>(x / (1.0f + expf(-x)));
+      const T s = from_f32<T>(__fdividef(x, 1.0f + __expf(-x)));
       oe[e] = from_f32<T>(to_f32<T>(s) * to_f32<T>(ue[e]));
     }
     *reinterpret_cast<uint4*>(out + r * ldo + c) = o;
@@ -476,6 +795,7 @@ using namespace mc;
 struct mc_linear_plan {
   LinParams params;
   int bn, grid, dtype;
+  int two_cta;  // 1: linear2_kernel (256 x 256 pair tiles)
   size_t smem_bytes;
   double flops;
   std::vector<void*> owned;  // device arrays built by the plan (group tables)
@@ -493,6 +813,22 @@ static cudaError_t launch_linear(const mc_linear_plan* p, cudaStream_t stream) {
     configured[dev] = true;
   }
   linear_kernel<BN, STAGES><<<p->grid, kThreads, L::DYN_BYTES, stream>>>(p->params);
+  return cudaGetLastError();
+}
+
+template <int STAGES>
+static cudaError_t launch_linear2(const mc_linear_plan* p, cudaStream_t stream) {
+  using L = SmemLayout2<STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(linear2_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  // the kernel carries __cluster_dims__(2, 1, 1); the grid is even
+  linear2_kernel<STAGES><<<p->grid, kThreads, L::DYN_BYTES, stream>>>(p->params);
   return cudaGetLastError();
 }
 
@@ -518,16 +854,22 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
   *out = nullptr;
   MC_REQUIRE(desc != nullptr && n_problems >= 1 && n_problems <= kMaxProb, "n_problems %d outside [1, %d]", n_problems, kMaxProb);
   MC_REQUIRE(dtype == MC_BF16 || dtype == MC_F16, "linear: dtype must be bf16 or fp16");
-  // tuning: 0 = default (BN 256 when every problem has N >= 256, else 128); 1 = force BN 128; 2 = force BN 256
+  // tuning bits 0-7: 0 = default (BN 256 when every problem has N >= 256, else 128); 1 = force BN 128; 2 = force BN 256
+  // bits 8-15: rasterisation group override; bit 16: disable the compact schedule of routed-N launches
   int bn = 256;
   for (int i = 0; i < n_problems; ++i)
     if (desc[i].N < 256) bn = 128;
-  if (tuning == 1) bn = 128;
-  if (tuning == 2) bn = 256;
+  if ((tuning & 0xff) == 1) bn = 128;
+  if ((tuning & 0xff) == 2) bn = 256;
+  // 3 = CTA-pair kernel (cta_group::2, 256 x 256 tiles); not for ROWMASK (routed-N) launches
+  const bool two = (tuning & 0xff) == 3;
+  if (two) bn = 256;
+  const int bm = two ? 256 : kBM;
   mc_linear_plan* p = new (std::nothrow) mc_linear_plan();
   if (!p) return fail(MC_ERR_NOMEM, "host allocation failed");
   memset(&p->params, 0, sizeof(p->params));
   p->bn = bn;
+  p->two_cta = two ? 1 : 0;
   p->dtype = dtype;
   p->flops = 0;
   int tile_end = 0;
@@ -550,10 +892,12 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
                    (uintptr_t)d.residual) & 15) == 0, "problem %d: operand pointers must be 16-byte aligned", i);
     PLAN_REQUIRE(d.K1 == 0 || (d.A1 && d.B1 && d.lda1 >= d.K1 && d.ldb1 >= d.K1 && d.lda1 % 8 == 0 && d.ldb1 % 8 == 0),
                  "problem %d: K1 > 0 needs A1 / B1 with valid leading dimensions", i);
-    PLAN_REQUIRE(d.epilogue >= MC_LINEAR_EPI_NONE && d.epilogue <= MC_LINEAR_EPI_RESIDUAL, "problem %d: bad epilogue %d", i, d.epilogue);
+    PLAN_REQUIRE(d.epilogue >= MC_LINEAR_EPI_NONE && d.epilogue <= MC_LINEAR_EPI_SILU_MUL, "problem %d: bad epilogue %d", i, d.epilogue);
     PLAN_REQUIRE((d.epilogue != MC_LINEAR_EPI_BIAS && d.epilogue != MC_LINEAR_EPI_BIAS_GELU) || d.bias, "problem %d: bias is NULL", i);
-    PLAN_REQUIRE(d.epilogue != MC_LINEAR_EPI_RESIDUAL || (d.residual && d.ldr >= d.N && d.ldr % 8 == 0), "problem %d: residual missing", i);
+    PLAN_REQUIRE((d.epilogue != MC_LINEAR_EPI_RESIDUAL && d.epilogue != MC_LINEAR_EPI_SILU_MUL) ||
+                     (d.residual && d.ldr >= d.N && d.ldr % 8 == 0), "problem %d: residual / gate operand missing", i);
     const bool routed_n = d.epilogue == MC_LINEAR_EPI_ROWMASK;
+    PLAN_REQUIRE(!(two && routed_n), "problem %d: the CTA-pair kernel does not take ROWMASK launches", i);
     const bool routed_k = d.K1 > 0 && d.n_groups > 0;
     PLAN_REQUIRE(!routed_n || (d.n_groups >= 1 && d.n_groups <= 32 && d.group_cols && d.row_group && d.col_scale),
                  "problem %d: ROWMASK epilogue needs n_groups in [1,32], group_cols, row_group and col_scale", i);
@@ -562,7 +906,7 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     pr.N = d.N;
     pr.nkb0 = (d.K0 + kBK - 1) / kBK;
     pr.nkb1 = (d.K1 + kBK - 1) / kBK;
-    pr.tiles_m = (d.M + kBM - 1) / kBM;
+    pr.tiles_m = (d.M + bm - 1) / bm;
     pr.tiles_n = (d.N + bn - 1) / bn;
     tile_end += pr.tiles_m * pr.tiles_n;
     pr.tile_end = tile_end;
@@ -599,9 +943,9 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
       if (e != cudaSuccess) break;
     }
     rc = encode_operand(&pr.tmA0, d.A0, d.M, d.K0, d.lda0, kBM, dtype);
-    if (rc == MC_OK) rc = encode_operand(&pr.tmB0, d.B0, d.N, d.K0, d.ldb0, bn, dtype);
+    if (rc == MC_OK) rc = encode_operand(&pr.tmB0, d.B0, d.N, d.K0, d.ldb0, two ? 128 : bn, dtype);
     if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmA1, d.A1, d.M, d.K1, d.lda1, kBM, dtype);
-    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmB1, d.B1, d.N, d.K1, d.ldb1, bn, dtype);
+    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmB1, d.B1, d.N, d.K1, d.ldb1, two ? 128 : bn, dtype);
     p->flops += 2.0 * d.M * (double)d.N * (double)(d.K0 + d.K1);
 #undef PLAN_REQUIRE
   }
@@ -612,24 +956,50 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
   }
   p->params.n_prob = n_problems;
   p->params.total_tiles = tile_end;
+  // rasterisation: when B (weights) alone overflows a good part of L2, sweep N over 32 M-tiles at a time so B streams
+  // from HBM once per 4096 rows instead of once per 1024; tuning bits 8-15 override
+  {
+    double b_bytes = 0;
+    for (int i = 0; i < n_problems; ++i) b_bytes = std::max(b_bytes, (double)desc[i].N * (desc[i].K0 + desc[i].K1) * 2.0);
+    p->params.group_m = b_bytes > 48e6 ? 32 : 8;
+    if ((tuning >> 8) & 0xff) p->params.group_m = (tuning >> 8) & 0xff;
+  }
+  // compact schedule for routed-N launches whose problems share M, N tiling and routing
+  {
+    const LinProblem& p0 = p->params.prob[0];
+    bool ok = p0.ntile_mask != nullptr && p0.mtile_mask != nullptr && p0.tiles_m <= kMaxMaskTiles && p0.tiles_n <= 1023 &&
+              !((tuning >> 16) & 1);
+    for (int i = 1; i < n_problems && ok; ++i) {
+      const LinProblem& pi = p->params.prob[i];
+      ok = pi.ntile_mask != nullptr && pi.mtile_mask == p0.mtile_mask && pi.M == p0.M && pi.N == p0.N &&
+           desc[i].n_groups == desc[0].n_groups &&
+           memcmp(desc[i].group_cols, desc[0].group_cols, sizeof(int32_t) * (desc[0].n_groups + 1)) == 0;
+    }
+    const int sms_ = sm_count();
+    if (ok && sms_ > 0 && (long long)n_problems * p0.tiles_m * p0.tiles_n > (long long)kMaxOwnTiles * sms_) ok = false;
+    p->params.compact = ok ? 1 : 0;
+  }
   p->params.is_f16 = dtype == MC_F16;
   // instruction descriptor: D = F32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12: 0 = F16, 1 = BF16), both K-major,
   // N >> 3 at bit 17, M >> 4 at bit 24
   const unsigned int fmt = dtype == MC_F16 ? 0u : 1u;
-  p->params.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(kBM >> 4) << 24);
+  p->params.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(bm >> 4) << 24);
   const int sms = sm_count();
   if (sms <= 0) {
     linear_plan_free(p);
     return fail(MC_ERR_CUDA, "no CUDA device");
   }
-  p->grid = std::min(sms, tile_end);
+  p->grid = p->params.compact ? sms : std::min(sms, tile_end);
+  if (two) p->grid = std::min(sms & ~1, 2 * tile_end);
   *out = p;
   return MC_OK;
 }
 
 extern "C" int mc_linear_plan_run(const mc_linear_plan_t* p, mc_stream_t stream) {
   MC_REQUIRE(p != nullptr, "plan is NULL");
-  cudaError_t e = p->bn == 256 ? launch_linear<256, 4>(p, (cudaStream_t)stream) : launch_linear<128, 6>(p, (cudaStream_t)stream);
+  cudaError_t e = p->two_cta   ? launch_linear2<6>(p, (cudaStream_t)stream)
+                  : p->bn == 256 ? launch_linear<256, 4>(p, (cudaStream_t)stream)
+                                 : launch_linear<128, 6>(p, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(MC_ERR_CUDA, "linear launch failed: %s", cudaGetErrorString(e));
   return MC_OK;
 }

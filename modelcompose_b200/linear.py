@@ -16,7 +16,7 @@ import torch
 
 from . import _cabi
 
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_ROWMASK, EPI_RESIDUAL = 0, 1, 2, 3, 4
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_ROWMASK, EPI_RESIDUAL, EPI_SILU_MUL = 0, 1, 2, 3, 4, 5
 MAX_PROBLEMS = 4
 TILE_M = 128
 K_BLOCK = 64

@@ -17,6 +17,7 @@ multimodal_arch.py:231-243.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -27,6 +28,9 @@ from . import linear as LN
 from . import splice as SP
 
 ADAPTER_ORDER = ("audio", "vision", "video", "point")
+# kernel variant of the base + LoRA-up launches (mc_linear_plan_create `tuning`): 0 = 128x256 single-CTA tiles (default),
+# 3 = 256x256 CTA-pair tiles (cta_group::2).  Development switch; both are parity-tested.
+UP_TUNING = int(os.environ.get("MC_LINEAR_UP_TUNING", "0"))
 
 
 class MultimodalConfig:
@@ -153,7 +157,7 @@ class _Workspace:
         self.xn = buf(T, H)
         self.q, self.k, self.v, self.attn = buf(T, H), buf(T, H), buf(T, H), buf(T, H)
         self.t = [buf(T, R) for _ in range(3)]
-        self.gate, self.up = buf(T, I), buf(T, I)
+        self.gate = buf(T, I)
         self.logits = buf(T, V)
         self.row_group = torch.zeros(T, dtype=torch.uint8, device=dev)
         self.mtile = torch.zeros((T + LN.TILE_M - 1) // LN.TILE_M, dtype=torch.int32, device=dev)
@@ -165,13 +169,14 @@ class _Workspace:
     def _down(self, src, layer: _Layer, names, tbufs):
         return LN.LinearPlan([LN.Problem(src, layer.ad[n].A_all, t, col_scale=layer.ad[n].col_scale, row_group=self.row_group,
                                          mtile_mask=self.mtile, group_cols=layer.ad[n].group_cols, epilogue=LN.EPI_ROWMASK)
-                              for n, t in zip(names, tbufs)])
+                              for n, t in zip(names, tbufs)], tuning=1)  # 128x128 tiles: one routing group per N tile
 
-    def _up(self, src, layer: _Layer, names, tbufs, outs, residual=None):
+    def _up(self, src, layer: _Layer, names, tbufs, outs, residual=None, epilogue=None):
+        if epilogue is None:
+            epilogue = LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE
         return LN.LinearPlan([LN.Problem(src, layer.W[n], o, A1=t, B1=layer.ad[n].B_all, mtile_mask=self.mtile,
-                                         group_cols=layer.ad[n].group_cols, residual=residual,
-                                         epilogue=LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE)
-                              for n, t, o in zip(names, tbufs, outs)])
+                                         group_cols=layer.ad[n].group_cols, residual=residual, epilogue=epilogue)
+                              for n, t, o in zip(names, tbufs, outs)], tuning=UP_TUNING)
 
     def _layer_plans(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
         qkv, gu = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
@@ -181,7 +186,9 @@ class _Workspace:
             "down_o": self._down(self.attn, layer, ("o_proj",), self.t[:1]),
             "up_o": self._up(self.attn, layer, ("o_proj",), self.t[:1], (self.x,), residual=self.x),
             "down_gu": self._down(self.xn, layer, gu, self.t[:2]),
-            "up_gu": self._up(self.xn, layer, gu, self.t[:2], (self.gate, self.up)),
+            # gate first, then up with the SiLU·mul folded into its epilogue (act overwrites the gate buffer)
+            "up_g": self._up(self.xn, layer, gu[:1], self.t[:1], (self.gate,)),
+            "up_u": self._up(self.xn, layer, gu[1:], self.t[1:2], (self.gate,), residual=self.gate, epilogue=LN.EPI_SILU_MUL),
             "down_d": self._down(self.gate, layer, ("down_proj",), self.t[:1]),
             "up_d": self._up(self.gate, layer, ("down_proj",), self.t[:1], (self.x,), residual=self.x),
         }
@@ -392,8 +399,8 @@ class MultimodalLlamaForCausalLM:
             plans["up_o"].run()
             self._rmsnorm(ws.x, layer.ln2, ws.xn)
             plans["down_gu"].run()
-            plans["up_gu"].run()
-            LN.silu_mul(ws.gate, ws.up, ws.gate)
+            plans["up_g"].run()
+            plans["up_u"].run()
             plans["down_d"].run()
             plans["up_d"].run()
         self._rmsnorm(ws.x, self.norm, ws.xn)

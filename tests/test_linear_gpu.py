@@ -33,7 +33,9 @@ def rnd(shape, dtype, seed, std=1.0):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("M,N,K,tuning", [(1, 8, 8, 0), (128, 256, 64, 0), (129, 264, 72, 0), (48, 192, 256, 0), (300, 136, 688, 1),
-                                          (1000, 1000, 1000, 2), (513, 4096, 384, 0), (960, 688, 256, 0), (77, 32000, 256, 0)])
+                                          (1000, 1000, 1000, 2), (513, 4096, 384, 0), (960, 688, 256, 0), (77, 32000, 256, 0),
+                                          # CTA-pair kernel (cta_group::2)
+                                          (1, 256, 64, 3), (300, 264, 72, 3), (1000, 1000, 1000, 3), (2100, 4096, 512, 3)])
 def test_plain_linear(dtype, M, N, K, tuning):
     A, B = rnd((M, K), dtype, 1), rnd((N, K), dtype, 2, std=0.05)
     C = torch.full((M, N), 9.0, dtype=dtype, device="cuda")
@@ -62,6 +64,58 @@ def test_strided_views_and_epilogues(dtype):
     check(x, ref + res.float(), dtype, "residual in place")
 
 
+def test_compact_schedule_multi_problem():
+    """Three ROWMASK problems in one launch (q/k/v down-projections) under the compacted tile schedule."""
+    dtype, T, in_f, r = torch.bfloat16, 3000, 256, 128
+    modal_names = ["default", "audio", "vision", "video"]
+    dnames = [f"default-{m}" for m in modal_names[1:]]
+    mid = make_modal_id(T, 11, 4)
+    x = rnd((T, in_f), dtype, 1).cuda()
+    rg = mid.cuda()
+    mt = LN.route_tile_masks(rg)
+    probs, refs = [], []
+    for j in range(3):
+        A = {n: rnd((r, in_f), dtype, 100 * j + i, 0.1) for i, n in enumerate(modal_names[1:] + dnames)}
+        Bm = {n: rnd((64, r), dtype, 100 * j + 50 + i, 0.1) for i, n in enumerate(A)}
+        scaling = {n: 1.0 + 0.25 * i for i, n in enumerate(A)}
+        pk = LN.pack_adapters({k: v.cuda() for k, v in A.items()}, {k: v.cuda() for k, v in Bm.items()}, scaling, modal_names,
+                              dnames, in_f, 64, dtype, torch.device("cuda"))
+        Tb = torch.full((T, pk.A_all.shape[0]), float("nan"), dtype=dtype, device="cuda")
+        probs.append(LN.Problem(x, pk.A_all, Tb, col_scale=pk.col_scale, row_group=rg, mtile_mask=mt, group_cols=pk.group_cols,
+                                epilogue=LN.EPI_ROWMASK))
+        full = (x.float() @ pk.A_all.float().t()) * pk.col_scale[None]
+        colg = torch.zeros(pk.A_all.shape[0], dtype=torch.long)
+        for g in range(4):
+            colg[pk.group_cols[g]:pk.group_cols[g + 1]] = g
+        refs.append((full.cpu() * (colg[None] == mid.long()[:, None]), colg))
+    LN.LinearPlan(probs, tuning=1).run()
+    torch.cuda.synchronize()
+    for pr, (ref, colg) in zip(probs, refs):
+        got = pr.C.float().cpu()
+        own = colg[None] == mid.long()[:, None]
+        check(torch.where(own, got, torch.zeros_like(got)), ref, dtype, "compact multi-problem")
+        # columns of a group present in the row's 128-row tile but not the row's own are written as exact zeros
+        tile_groups = torch.stack([torch.stack([(mid[t * 128:(t + 1) * 128] == g).any() for g in range(4)]) for t in range((T + 127) // 128)])
+        present = tile_groups[torch.arange(T) // 128][:, colg]
+        assert (got[present & ~own] == 0).all()
+
+
+def test_silu_mul_epilogue_matches_separate_ops():
+    dtype = torch.bfloat16
+    M, N, K = 300, 688, 256
+    x, Wg, Wu = rnd((M, K), dtype, 1).cuda(), rnd((N, K), dtype, 2, 0.2).cuda(), rnd((N, K), dtype, 3, 0.2).cuda()
+    gate, up = torch.empty((M, N), dtype=dtype, device="cuda"), torch.empty((M, N), dtype=dtype, device="cuda")
+    LN.LinearPlan([LN.Problem(x, Wg, gate), LN.Problem(x, Wu, up)]).run()
+    want = LN.silu_mul(gate, up)
+    act = gate.clone()
+    LN.LinearPlan([LN.Problem(x, Wu, act, residual=act, epilogue=LN.EPI_SILU_MUL)]).run()  # in place over the gate buffer
+    torch.cuda.synchronize()
+    assert torch.equal(act, want)
+    ref = torch.nn.functional.silu(gate.cpu()) * up.cpu()
+    d = (act.cpu().float() - ref.float()).abs()
+    assert (d <= 2 ** -6 * ref.float().abs() + 1e-7).all() and (d > 0).float().mean().item() < 0.01
+
+
 def test_k_extension_unrouted():
     dtype = torch.bfloat16
     M, N, K0, K1 = 260, 512, 192, 128
@@ -85,8 +139,10 @@ def make_modal_id(T, seed, n_groups, runs=True):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("T,in_f,out_f,r,runs", [(1000, 256, 512, 8, True), (700, 688, 256, 8, False), (1500, 512, 1024, 128, True)])
-def test_routed_lora_linear_vs_oracle(dtype, T, in_f, out_f, r, runs):
+@pytest.mark.parametrize("down_tuning", [0, 1, 1 | (1 << 16)])  # default tile / 128x128 compact schedule / 128x128 static
+@pytest.mark.parametrize("T,in_f,out_f,r,runs", [(1000, 256, 512, 8, True), (700, 688, 256, 8, False), (1500, 512, 1024, 128, True),
+                                                 (40000, 256, 256, 128, True)])
+def test_routed_lora_linear_vs_oracle(dtype, T, in_f, out_f, r, runs, down_tuning):
     """LocalLoraLinear.forward + masked-sum routing (oracle, fp32 on the same 16-bit values) vs the two routed launches."""
     modal_names = ["default", "audio", "vision", "video"]
     dnames = [f"default-{m}" for m in modal_names[1:]]
@@ -114,7 +170,7 @@ def test_routed_lora_linear_vs_oracle(dtype, T, in_f, out_f, r, runs):
     Tb = torch.full((T, pk.A_all.shape[0]), float("nan"), dtype=dtype, device="cuda")  # skipped tiles must never be read
     y = torch.empty((T, out_f), dtype=dtype, device="cuda")
     LN.LinearPlan([LN.Problem(xd, pk.A_all, Tb, col_scale=pk.col_scale, row_group=rg, mtile_mask=mt, group_cols=pk.group_cols,
-                              epilogue=LN.EPI_ROWMASK)]).run()
+                              epilogue=LN.EPI_ROWMASK)], tuning=down_tuning).run()
     LN.LinearPlan([LN.Problem(xd, W.cuda(), y, A1=Tb, B1=pk.B_all, mtile_mask=mt, group_cols=pk.group_cols)]).run()
     torch.cuda.synchronize()
     assert not torch.isnan(y).any()

@@ -62,13 +62,20 @@ def main():
     ok &= case(4096, 4096, 4096, name="4096^3")
     ok &= case(4096, 4096, 4096, dtype=torch.float16, name="4096^3 fp16")
     ok &= case(300, 136, 72, tuning=1, name="ragged small BN=128")
+    if "--two-cta" in sys.argv:
+        ok &= case(256, 256, 64, tuning=3, name="2-CTA one k-block")
+        ok &= case(256, 256, 512, tuning=3, name="2-CTA 8 k-blocks")
+        ok &= case(512, 768, 256, tuning=3, name="2-CTA 2x3 tiles")
+        ok &= case(1000, 1000, 1000, tuning=3, name="2-CTA ragged 1000^3")
+        ok &= case(4096, 4096, 4096, tuning=3, name="2-CTA 4096^3")
+        ok &= case(300, 264, 72, tuning=3, name="2-CTA ragged small")
     print("ALL OK" if ok else "FAILURES", flush=True)
     # quick timing
     for (M, N, K) in [(8192, 8192, 8192), (30720, 4096, 4096), (30720, 11008, 4096), (30720, 4096, 11008)]:
         A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
         B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
         Cm = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        for tuning in (2, 1):
+        for tuning in ((3, 2) if "--two-cta" in sys.argv else (2, 1)):
             plan = LN.LinearPlan([LN.Problem(A, B, Cm)], tuning=tuning)
             for _ in range(3):
                 plan.run()
@@ -80,7 +87,7 @@ def main():
             b.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b) / 10
-            print(f"timing M{M} N{N} K{K} BN={'256' if tuning == 2 else '128'}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+            print(f"timing M{M} N{N} K{K} tuning={tuning}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(3):
             torch.matmul(A, B.t(), out=Cm)
