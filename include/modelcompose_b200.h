@@ -235,13 +235,14 @@ MC_API int mc_silu_mul(const void* gate, const void* up, void* out, int64_t rows
  *   mc_rmsnorm : LlamaRMSNorm (used at :405-406,:441,:455,:603) — fp32 variance, x*rsqrt(var+eps) rounded to the
  *                storage dtype, then weight * that, rounded again.
  *   mc_rope    : apply_rotary_pos_emb (:281-282) in place on q and k viewed as [tokens, n_heads, head_dim];
- *                cos/sin tables [>= seq_len, head_dim] in the storage dtype; position of token t is t % seq_len
- *                (prefill: position_ids = arange(seq_len), :526-533).
+ *                cos/sin tables [>= pos_offset + seq_len, head_dim] in the storage dtype; position of token t is
+ *                pos_offset + t % seq_len (prefill: position_ids = arange(seq_len), :526-533; decode step: seq_len 1,
+ *                pos_offset = past length).
  * ---------------------------------------------------------------------------------------------- */
 MC_API int mc_rmsnorm(const void* x, const void* weight, void* out, int64_t rows, int hidden, int64_t ldx, int64_t ldo,
                float eps, int dtype, mc_stream_t stream);
-MC_API int mc_rope(void* q, void* k, const void* cos_table, const void* sin_table, int64_t tokens, int seq_len, int n_heads,
-            int head_dim, int64_t ldq, int64_t ldk, int dtype, mc_stream_t stream);
+MC_API int mc_rope(void* q, void* k, const void* cos_table, const void* sin_table, int64_t tokens, int seq_len, int pos_offset,
+            int n_heads, int head_dim, int64_t ldq, int64_t ldk, int dtype, mc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ SIGNATURES = {
     "mc_route_tile_masks": (_i, [_vp, _i, _vp, _vp]),
     "mc_silu_mul": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _i64, _i, _vp]),
     "mc_rmsnorm": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, C.c_float, _i, _vp]),
-    "mc_rope": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i64, _i64, _i, _vp]),
+    "mc_rope": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i64, _i64, _i, _vp]),
 }
 
 

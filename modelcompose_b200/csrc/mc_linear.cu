@@ -504,11 +504,11 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
 
 
 // =====================================================================================================================
-// 2-CTA variant (cta_group::2): a CTA pair (thread-block cluster of 2 = the two SMs of a TPC) computes a 256 x 256 tile.
-// Each CTA stages its own 128 rows of A and 128 rows (N) of B per k-block (32 KB/stage instead of 48 KB for half the
-// output), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory and writes
-// both CTAs' TMEM; each CTA drains its own 128 accumulator rows.  Per output element this halves the B traffic from L2
-// and shared memory.  Used for the un-routed-N launches (base + LoRA-up linears, projector, lm_head).
+// 2-CTA variant (cta_group::2): a CTA pair (thread-block cluster of 2 = the two SMs of a TPC) computes a 512 x 256 tile.
+// The leader CTA issues tcgen05.mma.cta_group::2 (M = 256: 128 rows from each CTA), which reads both CTAs' shared memory
+// (each CTA holds its own A rows and HALF of the B tile) and writes both CTAs' TMEM; each CTA drains its own accumulator
+// rows.  Barriers: TMA bytes of both CTAs complete on the leader's `full` barrier, tcgen05.commit multicasts to both
+// CTAs' `empty` / `tfull` barriers, both epilogues arrive on the leader's `tempty`.  For un-routed-N launches.
 // =====================================================================================================================
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -563,18 +563,37 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
                : "memory");
 }
 
+constexpr int kThreads2 = 384;  // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant, one per accumulator half)
+
 template <int STAGES>
 struct SmemLayout2 {
-  static constexpr int A_BYTES = kBM * kBK * 2;   // this CTA's 128 rows of the 256-row A tile
-  static constexpr int B_BYTES = 128 * kBK * 2;   // this CTA's 128 rows (N) of the 256-column B tile
+  static constexpr int A_HALF = kBM * kBK * 2;     // 128 rows x 64
+  static constexpr int A_BYTES = 2 * A_HALF;       // this CTA's 256 rows of the 512-row pair tile
+  static constexpr int B_BYTES = 128 * kBK * 2;    // this CTA's 128 rows (N) of the 256-column B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 2) * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
+// groups present in the rows the pair's MMA for accumulator half h touches: 128 rows of the leader and 128 of the peer
+__device__ __forceinline__ unsigned int pair_half_mask(const LinProblem& pr, int mt, int h) {
+  if (!pr.mtile_mask) return 0xffffffffu;
+  const int n128 = (pr.M + kBM - 1) / kBM;
+  const int t0 = mt * 4 + h, t1 = mt * 4 + 2 + h;
+  unsigned int m = 0;
+  if (t0 < n128) m |= pr.mtile_mask[t0];
+  if (t1 < n128) m |= pr.mtile_mask[t1];
+  return m;
+}
+
+// Pair tile 512 x 256: each CTA owns 256 rows (two 128-row accumulator halves, 2 x 256 TMEM columns = all of TMEM) and
+// stages A[256 x 64] + B[128 x 64] = 48 KB per k-block; per k-block the leader issues 2 x 4 tcgen05.mma.cta_group::2
+// (M 256 = 128 rows of each CTA, N 256, K 16).  Shared-memory traffic per SM drops to ~94 B/cycle at full tensor rate
+// (single-CTA 128x256 tiles need ~190 B/cycle), which is what lifts the tensor pipe above the ~80 % the other tilings
+// plateau at.  The accumulator is single-buffered (TMEM is full): the epilogue of a tile is not overlapped with MMAs.
 template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear2_kernel(const __grid_constant__ LinParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear2_kernel(const __grid_constant__ LinParams P) {
   using L = SmemLayout2<STAGES>;
   constexpr int BN = 256, TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -582,8 +601,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear2
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
@@ -601,13 +620,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear2
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer's remote arrive (leader's copy is the one used)
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer's remote arrive (the leader's copy is the one used)
       mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit from the leader
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull_bar[a], 1);   // multicast tcgen05.commit from the leader
-      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's copy
-    }
+    mbar_init(tfull_bar, 1);     // multicast tcgen05.commit from the leader
+    mbar_init(tempty_bar, 16);   // 8 epilogue warps x 2 CTAs arrive on the leader's copy
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
@@ -623,17 +640,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear2
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-        Tile t = decode_tile(P, tile);
+        const Tile t = decode_tile(P, tile);
         const LinProblem& pr = P.prob[t.p];
-        if (pr.mtile_mask) {
-          t.gmask = pr.mtile_mask[2 * t.mt];
-          if (2 * t.mt + 1 < (pr.M + kBM - 1) / kBM) t.gmask |= pr.mtile_mask[2 * t.mt + 1];
-        }
-        const int m0 = t.mt * 256 + (int)rank * 128, n0 = t.nt * BN + (int)rank * 128;
+        const unsigned int gmask = pair_half_mask(pr, t.mt, 0) | pair_half_mask(pr, t.mt, 1);
+        const int m0 = t.mt * 512 + (int)rank * 256, n0 = t.nt * BN + (int)rank * 128;
         for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
           const bool ext = kb >= pr.nkb0;
           const int k = ext ? kb - pr.nkb0 : kb;
-          if (ext && pr.kb1_mask && (pr.kb1_mask[k] & t.gmask) == 0u) continue;
+          if (ext && pr.kb1_mask && (pr.kb1_mask[k] & gmask) == 0u) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // both CTAs' bytes land on this barrier
@@ -650,30 +664,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear2
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      int stage = 0;
+      uint32_t phase = 0, t_phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-        Tile t = decode_tile(P, tile);
+        const Tile t = decode_tile(P, tile);
         const LinProblem& pr = P.prob[t.p];
-        if (pr.mtile_mask) {
-          t.gmask = pr.mtile_mask[2 * t.mt];
-          if (2 * t.mt + 1 < (pr.M + kBM - 1) / kBM) t.gmask |= pr.mtile_mask[2 * t.mt + 1];
-        }
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        const unsigned int hmask[2] = {pair_half_mask(pr, t.mt, 0), pair_half_mask(pr, t.mt, 1)};
+        mbar_wait(tempty_bar, t_phase ^ 1u);  // both CTAs' epilogues have drained the previous tile
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        uint32_t accumulate = 0;
+        uint32_t accumulate[2] = {0u, 0u};
         for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
           const bool ext = kb >= pr.nkb0;
-          if (ext && pr.kb1_mask && (pr.kb1_mask[kb - pr.nkb0] & t.gmask) == 0u) continue;
+          const unsigned int kbm = (ext && pr.kb1_mask) ? pr.kb1_mask[kb - pr.nkb0] : 0xffffffffu;
+          if ((kbm & (hmask[0] | hmask[1])) == 0u) continue;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint64_t a_desc = umma_smem_desc(sa), b_desc = umma_smem_desc(sa + L::A_BYTES);
+          const uint64_t b_desc = umma_smem_desc(sa + L::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            umma_f16_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate);
-            accumulate = 1;
+          for (int h = 0; h < 2; ++h) {
+            if ((kbm & hmask[h]) == 0u) continue;  // this half's rows carry none of the k-block's adapter group
+            const uint64_t a_desc = umma_smem_desc(sa + h * L::A_HALF);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              umma_f16_cg2(tmem_base + (uint32_t)(h * BN), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate[h]);
+              accumulate[h] = 1;
+            }
           }
           umma_commit_cg2(&empty_bar[stage]);
           if (++stage == STAGES) {
@@ -681,32 +697,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear2
             phase ^= 1u;
           }
         }
-        umma_commit_cg2(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        umma_commit_cg2(tfull_bar);
+        t_phase ^= 1u;
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int q = warp & 3, h = (warp - 4) >> 2;
     const bool is_f16 = P.is_f16 != 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t t_phase = 0;
     for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
       const Tile t = decode_tile(P, tile);
       const LinProblem& pr = P.prob[t.p];
-      const int row = t.mt * 256 + (int)rank * 128 + q * 32 + lane;
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      const int row = t.mt * 512 + (int)rank * 256 + h * 128 + q * 32 + lane;
+      mbar_wait(tfull_bar, t_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN);
       epilogue_tile<BN>(pr, is_f16, taddr, row, t.nt * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (rank == 0) mbar_arrive(&tempty_bar[acc]);
-        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        if (rank == 0) mbar_arrive(tempty_bar);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(tempty_bar), 0));
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      t_phase ^= 1u;
     }
   }
   tc_fence_before();
@@ -795,7 +808,7 @@ using namespace mc;
 struct mc_linear_plan {
   LinParams params;
   int bn, grid, dtype;
-  int two_cta;  // 1: linear2_kernel (256 x 256 pair tiles)
+  int two_cta;  // 1: linear2_kernel (512 x 256 pair tiles)
   size_t smem_bytes;
   double flops;
   std::vector<void*> owned;  // device arrays built by the plan (group tables)
@@ -828,7 +841,7 @@ static cudaError_t launch_linear2(const mc_linear_plan* p, cudaStream_t stream) 
     configured[dev] = true;
   }
   // the kernel carries __cluster_dims__(2, 1, 1); the grid is even
-  linear2_kernel<STAGES><<<p->grid, kThreads, L::DYN_BYTES, stream>>>(p->params);
+  linear2_kernel<STAGES><<<p->grid, kThreads2, L::DYN_BYTES, stream>>>(p->params);
   return cudaGetLastError();
 }
 
@@ -861,10 +874,10 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     if (desc[i].N < 256) bn = 128;
   if ((tuning & 0xff) == 1) bn = 128;
   if ((tuning & 0xff) == 2) bn = 256;
-  // 3 = CTA-pair kernel (cta_group::2, 256 x 256 tiles); not for ROWMASK (routed-N) launches
+  // 3 = CTA-pair kernel (cta_group::2, 512 x 256 pair tiles); not for ROWMASK (routed-N) launches
   const bool two = (tuning & 0xff) == 3;
   if (two) bn = 256;
-  const int bm = two ? 256 : kBM;
+  const int bm = two ? 512 : kBM;
   mc_linear_plan* p = new (std::nothrow) mc_linear_plan();
   if (!p) return fail(MC_ERR_NOMEM, "host allocation failed");
   memset(&p->params, 0, sizeof(p->params));
@@ -942,9 +955,9 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
       }
       if (e != cudaSuccess) break;
     }
-    rc = encode_operand(&pr.tmA0, d.A0, d.M, d.K0, d.lda0, kBM, dtype);
+    rc = encode_operand(&pr.tmA0, d.A0, d.M, d.K0, d.lda0, two ? 256 : kBM, dtype);
     if (rc == MC_OK) rc = encode_operand(&pr.tmB0, d.B0, d.N, d.K0, d.ldb0, two ? 128 : bn, dtype);
-    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmA1, d.A1, d.M, d.K1, d.lda1, kBM, dtype);
+    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmA1, d.A1, d.M, d.K1, d.lda1, two ? 256 : kBM, dtype);
     if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmB1, d.B1, d.N, d.K1, d.ldb1, two ? 128 : bn, dtype);
     p->flops += 2.0 * d.M * (double)d.N * (double)(d.K0 + d.K1);
 #undef PLAN_REQUIRE
@@ -983,7 +996,7 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
   // instruction descriptor: D = F32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12: 0 = F16, 1 = BF16), both K-major,
   // N >> 3 at bit 17, M >> 4 at bit 24
   const unsigned int fmt = dtype == MC_F16 ? 0u : 1u;
-  p->params.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)(bm >> 4) << 24);
+  p->params.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(bn >> 3) << 17) | ((unsigned)((two ? 256 : kBM) >> 4) << 24);
   const int sms = sm_count();
   if (sms <= 0) {
     linear_plan_free(p);
@@ -997,7 +1010,7 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
 
 extern "C" int mc_linear_plan_run(const mc_linear_plan_t* p, mc_stream_t stream) {
   MC_REQUIRE(p != nullptr, "plan is NULL");
-  cudaError_t e = p->two_cta   ? launch_linear2<6>(p, (cudaStream_t)stream)
+  cudaError_t e = p->two_cta   ? launch_linear2<4>(p, (cudaStream_t)stream)
                   : p->bn == 256 ? launch_linear<256, 4>(p, (cudaStream_t)stream)
                                  : launch_linear<128, 6>(p, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(MC_ERR_CUDA, "linear launch failed: %s", cudaGetErrorString(e));

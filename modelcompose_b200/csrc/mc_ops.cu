@@ -57,7 +57,7 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256)
 rope_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ cos_t, const T* __restrict__ sin_t,
-            long long tokens, int seq_len, int n_heads, int head_dim, long long ldq, long long ldk) {
+            long long tokens, int seq_len, int pos_offset, int n_heads, int head_dim, long long ldq, long long ldk) {
   const int half = head_dim >> 1;
   const int vec_per_head = half >> 3;
   const long long per_token = (long long)2 * n_heads * vec_per_head;  // q heads then k heads
@@ -69,7 +69,7 @@ rope_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ cos_t, c
     if (is_k) r -= n_heads * vec_per_head;
     const int head = r / vec_per_head, v = r % vec_per_head;
     T* base = (is_k ? k + t * ldk : q + t * ldq) + head * head_dim + v * 8;
-    const int pos = (int)(t % seq_len);
+    const int pos = pos_offset + (int)(t % seq_len);
     const T* cr = cos_t + (long long)pos * head_dim + v * 8;
     const T* sr = sin_t + (long long)pos * head_dim + v * 8;
     const uint4 lo = *reinterpret_cast<const uint4*>(base);
@@ -123,11 +123,12 @@ extern "C" int mc_rmsnorm(const void* x, const void* weight, void* out, int64_t 
   return MC_OK;
 }
 
-extern "C" int mc_rope(void* q, void* k, const void* cos_table, const void* sin_table, int64_t tokens, int seq_len, int n_heads,
-                       int head_dim, int64_t ldq, int64_t ldk, int dtype, mc_stream_t stream) {
+extern "C" int mc_rope(void* q, void* k, const void* cos_table, const void* sin_table, int64_t tokens, int seq_len, int pos_offset,
+                       int n_heads, int head_dim, int64_t ldq, int64_t ldk, int dtype, mc_stream_t stream) {
   MC_REQUIRE(q && k && cos_table && sin_table, "rope: NULL pointer");
   MC_REQUIRE(dtype == MC_BF16 || dtype == MC_F16, "rope: dtype must be bf16 or fp16");
-  MC_REQUIRE(tokens >= 0 && seq_len >= 1 && n_heads >= 1 && head_dim >= 16 && head_dim % 16 == 0, "rope: head_dim must be a multiple of 16");
+  MC_REQUIRE(tokens >= 0 && seq_len >= 1 && pos_offset >= 0 && n_heads >= 1 && head_dim >= 16 && head_dim % 16 == 0,
+             "rope: head_dim must be a multiple of 16");
   MC_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0, "rope: leading dimensions must be multiples of 8");
   MC_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)cos_table | (uintptr_t)sin_table) & 15) == 0, "rope: pointers must be 16-byte aligned");
   if (tokens == 0) return MC_OK;
@@ -137,10 +138,10 @@ extern "C" int mc_rope(void* q, void* k, const void* cos_table, const void* sin_
   const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
   if (dtype == MC_BF16)
     rope_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)q, (__nv_bfloat16*)k, (const __nv_bfloat16*)cos_table,
-                                                                      (const __nv_bfloat16*)sin_table, tokens, seq_len, n_heads, head_dim, ldq, ldk);
+                                                                      (const __nv_bfloat16*)sin_table, tokens, seq_len, pos_offset, n_heads, head_dim, ldq, ldk);
   else
     rope_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((__half*)q, (__half*)k, (const __half*)cos_table, (const __half*)sin_table,
-                                                                tokens, seq_len, n_heads, head_dim, ldq, ldk);
+                                                                tokens, seq_len, pos_offset, n_heads, head_dim, ldq, ldk);
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
 }

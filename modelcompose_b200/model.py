@@ -142,6 +142,35 @@ class _Layer:
     ln2: torch.Tensor = None
 
 
+class KVCache:
+    """Key/value cache of one batch: per layer ``[B, capacity, heads, head_dim]`` (keys stored after RoPE, as
+    transformers 4.31 caches them, multimodal_llama.py:284-289).  Returned as ``past_key_values`` when ``use_cache``."""
+
+    def __init__(self, n_layers: int, B: int, capacity: int, n_heads: int, head_dim: int, dtype, device):
+        self.k = [torch.empty((B, capacity, n_heads, head_dim), dtype=dtype, device=device) for _ in range(n_layers)]
+        self.v = [torch.empty((B, capacity, n_heads, head_dim), dtype=dtype, device=device) for _ in range(n_layers)]
+        self.length = 0
+        self.capacity = capacity
+
+    def grow(self, capacity: int) -> None:
+        for lst in (self.k, self.v):
+            for i, t in enumerate(lst):
+                n = torch.empty((t.shape[0], capacity) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+                n[:, :self.length].copy_(t[:, :self.length])
+                lst[i] = n
+        self.capacity = capacity
+
+    def legacy(self):
+        """transformers-4.31 layout: tuple over layers of (k, v) ``[B, heads, length, head_dim]`` views."""
+        return tuple((k[:, :self.length].transpose(1, 2), v[:, :self.length].transpose(1, 2)) for k, v in zip(self.k, self.v))
+
+    def __len__(self):
+        return len(self.k)
+
+    def __getitem__(self, i):
+        return self.legacy()[i]
+
+
 class _Workspace:
     """Static activation buffers and launch plans for one (batch, padded length) shape."""
 
@@ -150,6 +179,8 @@ class _Workspace:
         T, H, I, V = B * S, cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
         R = model.rank_total
         self.B, self.S, self.T = B, S, T
+        # a decode step has at most 128 rows: 128x128 tiles double the number of CTAs streaming the weights
+        self.up_tuning = 1 if T <= LN.TILE_M else UP_TUNING
 
         def buf(*shape, dtype=dt):
             return torch.empty(shape, dtype=dtype, device=dev)
@@ -164,7 +195,7 @@ class _Workspace:
         self.plans: List[Dict[str, LN.LinearPlan]] = []
         for layer in model.layers:
             self.plans.append(self._layer_plans(layer))
-        self.lm_head = LN.LinearPlan([LN.Problem(self.xn, model.lm_head, self.logits)])
+        self.lm_head = LN.LinearPlan([LN.Problem(self.xn, model.lm_head, self.logits)], tuning=1 if T <= LN.TILE_M else 0)
 
     def _down(self, src, layer: _Layer, names, tbufs):
         return LN.LinearPlan([LN.Problem(src, layer.ad[n].A_all, t, col_scale=layer.ad[n].col_scale, row_group=self.row_group,
@@ -176,7 +207,7 @@ class _Workspace:
             epilogue = LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE
         return LN.LinearPlan([LN.Problem(src, layer.W[n], o, A1=t, B1=layer.ad[n].B_all, mtile_mask=self.mtile,
                                          group_cols=layer.ad[n].group_cols, residual=residual, epilogue=epilogue)
-                              for n, t, o in zip(names, tbufs, outs)], tuning=UP_TUNING)
+                              for n, t, o in zip(names, tbufs, outs)], tuning=self.up_tuning)
 
     def _layer_plans(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
         qkv, gu = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
@@ -253,6 +284,7 @@ class MultimodalLlamaForCausalLM:
         # prefix / suffix tokens (multimodal_llama.py:634-649): zeros unless the checkpoint carries them
         self.prefix_tokens = self._local_tokens(sd, "prefix", config.local_prefix_tokens)
         self.suffix_tokens = self._local_tokens(sd, "suffix", config.local_suffix_tokens)
+        self._attn_backend: Optional[str] = os.environ.get("MC_ATTENTION_BACKEND") or None
         self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._ws: Dict[Tuple[int, int], _Workspace] = {}
         self._proj_cache: Dict[tuple, tuple] = {}
@@ -341,40 +373,93 @@ class MultimodalLlamaForCausalLM:
                                            _cabi.current_stream_ptr()), "mc_rmsnorm")
         _cabi.count_launch()
 
-    def _attention(self, ws: _Workspace, attention_mask: Optional[torch.Tensor], full: bool):
+    def _causal_attention(self, q, k, v, scale):
+        """Stock-library causal attention on [B, S, heads, D].  Preference order measured on B200
+        (tools/bench_attention_lib.py): cuDNN fused attention through torch SDPA (0.36 ms at C3 shapes), flash-attn 2
+        (0.86 ms), torch's default SDPA choice.  The first backend that works is remembered."""
+        F = torch.nn.functional
+        order = [self._attn_backend] if self._attn_backend else ["cudnn", "flash_attn", "sdpa"]
+        last_err = None
+        for name in order:
+            try:
+                if name == "cudnn":
+                    from torch.nn.attention import SDPBackend, sdpa_kernel
+                    with sdpa_kernel([SDPBackend.CUDNN_ATTENTION]):
+                        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                           is_causal=True, scale=scale).transpose(1, 2)
+                elif name == "flash_attn":
+                    from flash_attn import flash_attn_func
+                    o = flash_attn_func(q, k, v, causal=True, softmax_scale=scale)
+                else:
+                    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                       is_causal=True, scale=scale).transpose(1, 2)
+                self._attn_backend = name
+                return o
+            except (ImportError, RuntimeError) as e:
+                last_err = e
+        raise RuntimeError(f"no causal attention backend available: {last_err}")
+
+    def _attention(self, ws: _Workspace, attention_mask: Optional[torch.Tensor], full: bool,
+                   cache: Optional[KVCache] = None, layer_idx: int = 0, past: int = 0):
+        """RoPE + causal attention of one layer.  ``past`` > 0 is the decode step: the new keys/values are appended to
+        ``cache`` and the queries attend to everything cached (multimodal_llama.py:274-312 with past_key_value)."""
         cfg = self.config
         nH = cfg.num_attention_heads
         D = cfg.hidden_size // nH
         B, S = ws.B, ws.S
-        cos, sin = self._rope_tables(S)
-        _cabi.check(_cabi.lib().mc_rope(ws.q.data_ptr(), ws.k.data_ptr(), cos.data_ptr(), sin.data_ptr(), ws.T, S, nH, D,
+        cos, sin = self._rope_tables(past + S)
+        _cabi.check(_cabi.lib().mc_rope(ws.q.data_ptr(), ws.k.data_ptr(), cos.data_ptr(), sin.data_ptr(), ws.T, S, past, nH, D,
                                         ws.q.stride(0), ws.k.stride(0), _cabi.dtype_code(self.dtype),
                                         _cabi.current_stream_ptr()), "mc_rope")
         _cabi.count_launch()
         q, k, v = (t.view(B, S, nH, D) for t in (ws.q, ws.k, ws.v))
-        if full:
-            try:
-                from flash_attn import flash_attn_func
-                o = flash_attn_func(q, k, v, causal=True, softmax_scale=1.0 / math.sqrt(D))
-            except (ImportError, RuntimeError):
-                o = torch.nn.functional.scaled_dot_product_attention(
-                    q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True).transpose(1, 2)
+        if cache is not None:
+            cache.k[layer_idx][:, past:past + S].copy_(k)
+            cache.v[layer_idx][:, past:past + S].copy_(v)
+        F = torch.nn.functional
+        if past > 0:
+            kk, vv = cache.k[layer_idx][:, :past + S], cache.v[layer_idx][:, :past + S]
+            mask = None
+            if not full or S > 1:
+                neg = torch.finfo(self.dtype).min
+                mask = torch.zeros((B, 1, S, past + S), dtype=self.dtype, device=self.device)
+                if S > 1:
+                    mask = mask + torch.full((S, past + S), neg, dtype=self.dtype, device=self.device).triu(past + 1)[None, None]
+                if not full:
+                    mask = (mask + (~attention_mask.bool())[:, None, None, :].to(self.dtype) * neg).clamp_min(neg)
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), attn_mask=mask,
+                                               scale=1.0 / math.sqrt(D)).transpose(1, 2)
+        elif full:
+            o = self._causal_attention(q, k, v, 1.0 / math.sqrt(D))
         else:
             # padded batch: additive mask as transformers 4.31 _prepare_decoder_attention_mask builds it (:543-545)
             neg = torch.finfo(self.dtype).min
             causal = torch.full((S, S), neg, dtype=self.dtype, device=self.device).triu(1)[None, None]
             pad = (~attention_mask.bool())[:, None, None, :].to(self.dtype) * neg
-            o = torch.nn.functional.scaled_dot_product_attention(
-                q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=(causal + pad).clamp_min(neg)).transpose(1, 2)
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                               attn_mask=(causal + pad).clamp_min(neg)).transpose(1, 2)
         ws.attn.view(B, S, nH, D).copy_(o)
 
     def prefill(self, inputs_embeds: torch.Tensor, modal_id: Optional[torch.Tensor], attention_mask=None,
-                use_cache: bool = False, output_hidden_states: bool = False):
-        """MultimodalLlamaModel.forward + lm_head (:488-619, :720) on spliced embeddings; returns (logits, kv, hidden)."""
+                use_cache: bool = False, output_hidden_states: bool = False, past_key_values: Optional[KVCache] = None):
+        """MultimodalLlamaModel.forward + lm_head (:488-619, :720) on (spliced) embeddings; returns (logits, cache, hidden).
+        With ``past_key_values`` this is the decode step: ``inputs_embeds`` holds the new token(s) only, every row takes
+        the default adapter (``modal_id`` None — the reference drops the modality masks when a cache is present, :436-438)."""
         B, S, H = inputs_embeds.shape
+        cfg = self.config
+        nH = cfg.num_attention_heads
+        cache, past = past_key_values, 0
+        if cache is not None:
+            past = cache.length
+            if past + S > cache.capacity:
+                cache.grow(max(past + S, cache.capacity * 2))
+        elif use_cache:
+            cache = KVCache(len(self.layers), B, S + 128, nH, H // nH, self.dtype, self.device)
         key = (B, S)
         if key not in self._ws:
-            self._ws.clear()  # one resident shape: the buffers are GBs at 7B width
+            if S > 1:
+                for k_ in [k_ for k_ in self._ws if k_[1] > 1]:  # one resident prefill shape: its buffers are GBs at 7B width
+                    del self._ws[k_]
             self._ws[key] = _Workspace(self, B, S)
         ws = self._ws[key]
         ws.x.view(B, S, H).copy_(inputs_embeds)
@@ -383,18 +468,15 @@ class MultimodalLlamaForCausalLM:
         else:
             ws.row_group.view(B, S).copy_(modal_id)
         LN.route_tile_masks(ws.row_group, ws.mtile)
-        full = attention_mask is None or bool(attention_mask.all())  # one host sync per prefill, not per layer
-        kv, hidden = [], []
-        for layer, plans in zip(self.layers, ws.plans):
+        full = attention_mask is None or bool(attention_mask.all())  # one host sync per call, not per layer
+        hidden = []
+        for li, (layer, plans) in enumerate(zip(self.layers, ws.plans)):
             if output_hidden_states:
                 hidden.append(ws.x.view(B, S, H).clone())
             self._rmsnorm(ws.x, layer.ln1, ws.xn)
             plans["down_qkv"].run()
             plans["up_qkv"].run()
-            self._attention(ws, attention_mask, full)
-            if use_cache:
-                nH = self.config.num_attention_heads
-                kv.append((ws.k.view(B, S, nH, H // nH).transpose(1, 2).clone(), ws.v.view(B, S, nH, H // nH).transpose(1, 2).clone()))
+            self._attention(ws, attention_mask, full, cache, li, past)
             plans["down_o"].run()
             plans["up_o"].run()
             self._rmsnorm(ws.x, layer.ln2, ws.xn)
@@ -403,20 +485,33 @@ class MultimodalLlamaForCausalLM:
             plans["up_u"].run()
             plans["down_d"].run()
             plans["up_d"].run()
+        if cache is not None:
+            cache.length = past + S
         self._rmsnorm(ws.x, self.norm, ws.xn)
         if output_hidden_states:
             hidden.append(ws.xn.view(B, S, H).clone())
         ws.lm_head.run()
-        return ws.logits.view(B, S, -1), (kv if use_cache else None), (tuple(hidden) if output_hidden_states else None)
+        return ws.logits.view(B, S, -1), cache, (tuple(hidden) if output_hidden_states else None)
 
     def forward(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
                 use_cache=None, output_attentions=None, output_hidden_states=None, modal_inputs=None, return_dict=None):
-        """Reference signature (multimodal_llama.py:676-688).  Prefill only: the decode step (default adapter, KV cache)
-        is SURVEY §8(f) item 2 and raises NotImplementedError."""
+        """Reference signature (multimodal_llama.py:676-688).  ``past_key_values`` (a ``KVCache`` returned by an earlier
+        call with ``use_cache=True``) selects the decode step: new tokens only, default adapter, no splice (:290-293)."""
         if output_attentions:
             raise NotImplementedError("attention probabilities are never materialised on this path")
-        if past_key_values is not None or (input_ids is not None and input_ids.shape[1] == 1 and modal_inputs is not None):
-            raise NotImplementedError("decode step with past_key_values is not part of the prefill hot path (SURVEY §8(f))")
+        if past_key_values is not None:
+            if not isinstance(past_key_values, KVCache):
+                raise TypeError("past_key_values must be the KVCache a previous forward(use_cache=True) returned")
+            if input_ids is None:
+                raise ValueError("the decode step takes input_ids")
+            ids = input_ids.to(self.device)
+            if attention_mask is not None and modal_inputs is not None and ids.shape[1] == 1:
+                # multimodal_arch.py:291-292: the mask is rebuilt as all ones over past + 1
+                attention_mask = torch.ones((ids.shape[0], past_key_values.length + 1), dtype=attention_mask.dtype, device=self.device)
+            r = SP.splice(ids, None, None, self.embed_tokens, {})  # embedding lookup of the new tokens
+            logits, kv, hidden = self.prefill(r.inputs_embeds, None, attention_mask, True, bool(output_hidden_states), past_key_values)
+            out = CausalLMOutputWithPast(logits=logits, past_key_values=kv, hidden_states=hidden)
+            return (logits, kv) if return_dict is False else out
         modal_id = None
         if input_ids is not None:
             feats = self.project_modal_features(modal_inputs) if modal_inputs else {}
@@ -447,3 +542,46 @@ class MultimodalLlamaForCausalLM:
         return out
 
     __call__ = forward
+
+    @torch.no_grad()
+    def generate(self, input_ids, modal_inputs=None, attention_mask=None, max_new_tokens: int = 128, do_sample: bool = False,
+                 temperature: float = 1.0, top_p: Optional[float] = None, use_cache: bool = True, eos_token_id: Optional[int] = None,
+                 pad_token_id: Optional[int] = None, generator: Optional[torch.Generator] = None, **_):
+        """Greedy / nucleus decoding with the call shape of the reference's eval loop
+        (``model.generate(input_ids, modal_inputs=..., do_sample=..., temperature=..., top_p=..., max_new_tokens=...,
+        use_cache=True)``, modelcompose/eval/model_multimodal_qa_loader.py:93-102).  Returns ``[B, S + new]`` ids: the
+        prompt (sentinels included, as HF returns it) followed by the generated tokens."""
+        ids = input_ids.to(self.device)
+        B = ids.shape[0]
+        if attention_mask is None:
+            attention_mask = torch.ones_like(ids)
+        out = self.forward(ids, attention_mask.to(self.device), modal_inputs=modal_inputs, use_cache=True)
+        cache = out.past_key_values
+        logits = out.logits[:, -1, :]
+        done = torch.zeros(B, dtype=torch.bool, device=self.device)
+        pad = pad_token_id if pad_token_id is not None else (eos_token_id if eos_token_id is not None else 0)
+        new_tokens = []
+        for step in range(max_new_tokens):
+            if do_sample and temperature > 0:
+                probs = torch.softmax(logits.float() / temperature, dim=-1)
+                if top_p is not None and top_p < 1.0:
+                    sp, si = probs.sort(dim=-1, descending=True)
+                    keep = sp.cumsum(-1) - sp < top_p
+                    sp = sp * keep
+                    probs = torch.zeros_like(probs).scatter_(1, si, sp)
+                    probs = probs / probs.sum(-1, keepdim=True)
+                nxt = torch.multinomial(probs, 1, generator=generator).squeeze(1)
+            else:
+                nxt = logits.argmax(-1)
+            nxt = torch.where(done, torch.full_like(nxt, pad), nxt)
+            new_tokens.append(nxt)
+            if eos_token_id is not None:
+                done = done | (nxt == eos_token_id)
+                if bool(done.all()):
+                    break
+            if step + 1 == max_new_tokens:
+                break
+            step_mask = torch.ones((B, cache.length + 1), dtype=attention_mask.dtype, device=self.device)
+            o = self.forward(nxt[:, None], step_mask, past_key_values=cache, use_cache=True)
+            logits = o.logits[:, -1, :]
+        return torch.cat([ids, torch.stack(new_tokens, dim=1)], dim=1)

@@ -246,12 +246,17 @@ def test_rowwise_glue_bit_exact_vs_oracle(dtype):
     q, k = rnd((Bn * S, H), dtype, 3), rnd((Bn * S, H), dtype, 4)
     cos, sin = XO.rope_cos_sin(D, 64, dtype)
     qd, kd, cos_d, sin_d = q.cuda(), k.cuda(), cos.cuda(), sin.cuda()
-    _cabi.check(lib.mc_rope(qd.data_ptr(), kd.data_ptr(), cos_d.data_ptr(), sin_d.data_ptr(), Bn * S, S, nH, D, H, H,
+    _cabi.check(lib.mc_rope(qd.data_ptr(), kd.data_ptr(), cos_d.data_ptr(), sin_d.data_ptr(), Bn * S, S, 0, nH, D, H, H,
                             code, st), "rope")
     pos = torch.arange(S)[None].expand(Bn, S)
     qr, kr = XO.apply_rope(q.view(Bn, S, nH, D).transpose(1, 2), k.view(Bn, S, nH, D).transpose(1, 2), cos, sin, pos)
     assert torch.equal(qd.cpu().view(Bn, S, nH, D).transpose(1, 2), qr)
     assert torch.equal(kd.cpu().view(Bn, S, nH, D).transpose(1, 2), kr)
+    # decode-step form: one token per sequence at position 9
+    q1, k1 = q.view(Bn, S, H)[:, 9].contiguous(), k.view(Bn, S, H)[:, 9].contiguous()
+    q1d, k1d = q1.cuda(), k1.cuda()
+    _cabi.check(lib.mc_rope(q1d.data_ptr(), k1d.data_ptr(), cos_d.data_ptr(), sin_d.data_ptr(), Bn, 1, 9, nH, D, H, H, code, st), "rope")
+    assert torch.equal(q1d.cpu().view(Bn, nH, D), qr[:, :, 9]) and torch.equal(k1d.cpu().view(Bn, nH, D), kr[:, :, 9])
     # silu * mul
     g_, u_ = rnd((T, 688), dtype, 5, 2.0), rnd((T, 688), dtype, 6)
     got = LN.silu_mul(g_.cuda(), u_.cuda()).cpu()

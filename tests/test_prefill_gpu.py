@@ -160,5 +160,41 @@ def test_loader_from_disk_and_text_only(tmp_path, golden):
     assert out.logits.shape == (2, 17, 1000) and torch.isfinite(out.logits).all()
     with pytest.raises(NotImplementedError):
         BD.load_pretrained_model(odir, bdir, "llava-thing")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):
         model.forward(ids[:, :1], torch.ones_like(ids), past_key_values=[()])
+
+
+@pytest.mark.parametrize("key", list(DTYPES))
+def test_decode_step_and_generate(golden, key):
+    """Decode steps (KV cache, default adapter only: multimodal_llama.py:436-438, multimodal_arch.py:290-293) must agree
+    with a from-scratch prefill of the extended sequence, which is itself checked against the oracle above."""
+    dtype = DTYPES[key]
+    model, run, base = tiny_model(golden, dtype)
+    g = torch.Generator().manual_seed(21)
+    B = 3
+    ids = syn.make_prompt_ids(B, ["vision", "audio"], 9, 1000, seed=8, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=4)
+    feats = {"audio": torch.randn(B, 6, 48, generator=g).to(dtype).cuda(), "vision": torch.randn(B, 11, 64, generator=g).to(dtype).cuda()}
+    new = 6
+    out_ids = model.generate(ids.cuda(), modal_inputs=feats, max_new_tokens=new, do_sample=False)
+    assert out_ids.shape == (B, ids.shape[1] + new) and torch.equal(out_ids[:, :ids.shape[1]].cpu(), ids)
+    # teacher forcing: one prefill over prompt + generated tokens
+    full = model.forward(out_ids, torch.ones_like(out_ids), modal_inputs=feats)
+    Sp = full.logits.shape[1]
+    for i in range(new):
+        step_logits = full.logits[:, Sp - new + i - 1, :].float()
+        tok = out_ids[:, ids.shape[1] + i]
+        top = step_logits.max(-1).values
+        chosen = step_logits.gather(1, tok[:, None]).squeeze(1)
+        assert ((top - chosen) <= MAXABS[key] * step_logits.abs().max()).all(), (i, top, chosen)
+    # explicit decode-step logits vs the prefill logits at the same position
+    o1 = model.forward(ids.cuda(), torch.ones_like(ids).cuda(), modal_inputs=feats, use_cache=True)
+    cache = o1.past_key_values
+    assert isinstance(cache, MD.KVCache) and cache.length == o1.logits.shape[1] and len(cache.legacy()) == 2
+    t1 = out_ids[:, ids.shape[1]:ids.shape[1] + 1]
+    o2 = model.forward(t1, torch.ones((B, cache.length + 1), dtype=torch.int64, device="cuda"), past_key_values=cache, modal_inputs=feats)
+    assert cache.length == o1.logits.shape[1] + 1 and o2.logits.shape == (B, 1, 1000)
+    compare(o2.logits[:, 0], full.logits[:, Sp - new, :], key, "decode-step logits vs prefill of the extended sequence")
+    # sampling path runs and respects eos
+    s_ids = model.generate(ids.cuda(), modal_inputs=feats, max_new_tokens=4, do_sample=True, temperature=0.7, top_p=0.9,
+                           generator=torch.Generator(device="cuda").manual_seed(0), eos_token_id=int(out_ids[0, ids.shape[1]]))
+    assert s_ids.shape[0] == B and ids.shape[1] < s_ids.shape[1] <= ids.shape[1] + 4

@@ -63,9 +63,9 @@ def main():
     ok &= case(4096, 4096, 4096, dtype=torch.float16, name="4096^3 fp16")
     ok &= case(300, 136, 72, tuning=1, name="ragged small BN=128")
     if "--two-cta" in sys.argv:
-        ok &= case(256, 256, 64, tuning=3, name="2-CTA one k-block")
-        ok &= case(256, 256, 512, tuning=3, name="2-CTA 8 k-blocks")
-        ok &= case(512, 768, 256, tuning=3, name="2-CTA 2x3 tiles")
+        ok &= case(512, 256, 64, tuning=3, name="2-CTA one k-block")
+        ok &= case(512, 256, 512, tuning=3, name="2-CTA 8 k-blocks")
+        ok &= case(1024, 768, 256, tuning=3, name="2-CTA 2x3 tiles")
         ok &= case(1000, 1000, 1000, tuning=3, name="2-CTA ragged 1000^3")
         ok &= case(4096, 4096, 4096, tuning=3, name="2-CTA 4096^3")
         ok &= case(300, 264, 72, tuning=3, name="2-CTA ragged small")
