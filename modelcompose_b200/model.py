@@ -504,7 +504,7 @@ class MultimodalLlamaForCausalLM:
                 raise TypeError("past_key_values must be the KVCache a previous forward(use_cache=True) returned")
             if input_ids is None:
                 raise ValueError("the decode step takes input_ids")
-            ids = input_ids.to(self.device)
+            ids = input_ids.to(self.device).contiguous()
             if attention_mask is not None and modal_inputs is not None and ids.shape[1] == 1:
                 # multimodal_arch.py:291-292: the mask is rebuilt as all ones over past + 1
                 attention_mask = torch.ones((ids.shape[0], past_key_values.length + 1), dtype=attention_mask.dtype, device=self.device)
@@ -517,8 +517,9 @@ class MultimodalLlamaForCausalLM:
             feats = self.project_modal_features(modal_inputs) if modal_inputs else {}
             pre = {m: self.prefix_tokens[m] for m in feats} if self.prefix_tokens is not None else None
             suf = {m: self.suffix_tokens[m] for m in feats} if self.suffix_tokens is not None else None
-            r = SP.splice(input_ids.to(self.device), None if attention_mask is None else attention_mask.to(self.device),
-                          None if labels is None else labels.to(self.device), self.embed_tokens, feats, pre, suf,
+            r = SP.splice(input_ids.to(self.device).contiguous(),
+                          None if attention_mask is None else attention_mask.to(self.device).contiguous(),
+                          None if labels is None else labels.to(self.device).contiguous(), self.embed_tokens, feats, pre, suf,
                           list(modal_inputs.keys()) if modal_inputs else None)
             inputs_embeds, attention_mask, labels = r.inputs_embeds, r.attention_mask, r.labels
             if r.modal_names:
