@@ -95,6 +95,20 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def measured_traffic(key_prefix: str, world: int):
+    """DRAM bytes per launch from the committed ncu --set full capture of this kernel (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    want = "N=1" if world == 1 else ("1/8 shard" if world == 8 else None)
+    for k, v in d.items():
+        if want and k.startswith(key_prefix) and want in k:
+            return v["dram_bytes"]
+    return None
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -285,7 +299,8 @@ def run_merge(args, dist, rank, world, device, barrier):
                        "algorithmic_bytes": total_bytes, "l2": "inputs larger than L2 (%.2f GB per GPU vs 0.13 GB)" % (my_bytes / 1e9),
                        "tuning": args.tuning},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic("merge_kernel<3,bf16,bf16>", world),
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/traffic.json)", "peak_source": peak_src,
                          "kernel": "mc::merge_kernel<3,bf16,bf16>", "launch_ms": round(launch_ms, 4),
                          "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
             "cpu_baseline": cpu_baseline,

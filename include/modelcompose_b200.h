@@ -145,11 +145,13 @@ typedef struct mc_splice_io {
 
 typedef struct mc_splice_plan mc_splice_plan_t;
 
-/* Scans input_ids (device, int64 [B, S]) on the GPU: output offsets, batch-global block cursors, padded length.
- * Synchronises `stream` once (the output shape depends on the data).  Fails with MC_ERR_INVALID where the
+/* Allocates the plan's tables for batches of shape [B, S] with this modality geometry (pointers in `modals` are
+ * ignored here).  Reusable: scan + run it for every batch of that shape; nothing is allocated in steady state. */
+MC_API int mc_splice_plan_create(mc_splice_plan_t** plan, int B, int S, int vocab, const mc_splice_modal_t* modals, int n_modal);
+/* Scans input_ids (device, int64 [B, S]) on the GPU: output offsets, batch-global block cursors, padded length, row
+ * descriptors.  Synchronises `stream` once (the output shape depends on the data).  Fails with MC_ERR_INVALID where the
  * reference raises (unknown negative id, id >= vocab, sentinel without a feature block left). */
-MC_API int mc_splice_plan_create(mc_splice_plan_t** plan, const int64_t* d_input_ids, int B, int S, int vocab,
-                          const mc_splice_modal_t* modals, int n_modal, mc_stream_t stream);
+MC_API int mc_splice_plan_scan(mc_splice_plan_t* plan, const int64_t* d_input_ids, mc_stream_t stream);
 /* max_len / min_len over the batch (ragged iff they differ), per-sample lengths (B ints, may be NULL) and
  * feature blocks consumed per modality (MC_SPLICE_MAX_MODAL ints, may be NULL). */
 MC_API int mc_splice_plan_info(const mc_splice_plan_t* plan, int* max_len, int* min_len, int32_t* out_len,
@@ -190,8 +192,10 @@ typedef enum mc_linear_epilogue {
   MC_LINEAR_EPI_BIAS_GELU = 2, /* gelu_erf(acc + bias[n])  (projector builder.py:214-217) */
   MC_LINEAR_EPI_ROWMASK = 3,   /* see above */
   MC_LINEAR_EPI_RESIDUAL = 4,  /* + residual[m,n] (decoder residual adds, multimodal_llama.py:448,461) */
-  MC_LINEAR_EPI_SILU_MUL = 5   /* silu(residual[m,n]) * acc: `residual` holds the stored gate_proj output, the product
+  MC_LINEAR_EPI_SILU_MUL = 5,  /* silu(residual[m,n]) * acc: `residual` holds the stored gate_proj output, the product
                                   is the up_proj problem's result (multimodal_llama.py:381-388); may run in place */
+  MC_LINEAR_EPI_ROPE = 6       /* rotary embedding of the q / k projection outputs (multimodal_llama.py:281-282), same
+                                  rounding points as mc_rope; head_dim in {64,128,256} dividing N and the N tile */
 } mc_linear_epilogue;
 
 typedef struct mc_linear_desc {
@@ -209,6 +213,11 @@ typedef struct mc_linear_desc {
   const int32_t* group_cols;    /* HOST [n_groups + 1] or NULL */
   int32_t n_groups;
   int32_t epilogue;             /* mc_linear_epilogue */
+  const void* rope_cos;         /* ROPE: device cos / sin tables [positions, rope_head_dim], same dtype as C */
+  const void* rope_sin;
+  const int32_t* rope_pos;      /* ROPE: device scalar, position of the first row of every sequence (NULL = 0) */
+  int32_t rope_seq_len;         /* ROPE: row m is token (rope_pos + m % rope_seq_len) of its sequence */
+  int32_t rope_head_dim;
 } mc_linear_desc_t;
 
 typedef struct mc_linear_plan mc_linear_plan_t;

@@ -34,7 +34,8 @@ SIGNATURES = {
     "mc_merge_tensors": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), C.POINTER(C.c_float), _i, _i, _i, _vp]),
     "mc_merge_host": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), C.POINTER(C.c_float), _i, _i, _i, _sz]),
     # structs are passed as void* (modelcompose_b200.splice defines the ctypes.Structure mirrors)
-    "mc_splice_plan_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i, _vp, _i, _vp]),
+    "mc_splice_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp, _i]),
+    "mc_splice_plan_scan": (_i, [_vp, _vp, _vp]),
     "mc_splice_plan_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), _vp, _vp]),
     "mc_splice_plan_bytes": (_i64, [_vp, _i]),
     "mc_splice_run": (_i, [_vp, _vp, _vp, _vp]),

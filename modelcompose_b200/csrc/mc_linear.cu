@@ -49,8 +49,12 @@ struct alignas(64) LinProblem {
   const unsigned int* ntile_mask;
   const unsigned int* kb1_mask;
   const void* residual;
+  const void* rope_cos;  // ROPE epilogue: cos / sin tables [positions, head_dim] in the storage dtype
+  const void* rope_sin;
+  const int* rope_pos;   // device scalar: position of the first row of every sequence (NULL = 0)
   long long ldc, ldr;
   int M, N, nkb0, nkb1, tiles_m, tiles_n, tile_end, epilogue;
+  int rope_seq_len, rope_head_dim;
 };
 
 struct alignas(64) LinParams {
@@ -249,6 +253,69 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
   const int rg = (epi == MC_LINEAR_EPI_ROWMASK && row_ok) ? (int)pr.row_group[row] : -1;
   char* crow = reinterpret_cast<char*>(pr.C) + (long long)row * pr.ldc * 2;
   const char* rrow = reinterpret_cast<const char*>(pr.residual) + (long long)row * pr.ldr * 2;
+  if (epi == MC_LINEAR_EPI_ROPE) {
+    // apply_rotary_pos_emb fused behind the q / k projections (multimodal_llama.py:281-282): the projection output is
+    // rounded to the storage dtype first, then q*cos + rotate_half(q)*sin with every product and the sum rounded, exactly
+    // the op sequence of rope_kernel / the eager reference.  A tile holds BN / head_dim whole heads.
+    const int D = pr.rope_head_dim, half = D >> 1;
+    const int pos = (pr.rope_pos ? *pr.rope_pos : 0) + row % pr.rope_seq_len;
+    const char* cosr = reinterpret_cast<const char*>(pr.rope_cos) + (long long)pos * D * 2;
+    const char* sinr = reinterpret_cast<const char*>(pr.rope_sin) + (long long)pos * D * 2;
+#pragma unroll 1
+    for (int h0 = 0; h0 < BN; h0 += D) {
+      if (n0 + h0 >= pr.N) break;  // warp-uniform (N is a multiple of head_dim)
+#pragma unroll 1
+      for (int c = 0; c < half; c += 32) {
+        uint32_t lo[32], hi[32];
+        tmem_ld_32x32(taddr + (uint32_t)(h0 + c), lo);
+        tmem_ld_32x32(taddr + (uint32_t)(h0 + half + c), hi);
+        uint4 cv[4], sv[4];
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            cv[j] = *reinterpret_cast<const uint4*>(cosr + (c + 8 * j) * 2);
+            sv[j] = *reinterpret_cast<const uint4*>(sinr + (c + 8 * j) * 2);
+          }
+        }
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x1[8], x2[8], cs[8], sn[8], o1[8], o2[8], p1[8], p2[8], p3[8], p4[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              x1[e] = __uint_as_float(lo[8 * j + e]);
+              x2[e] = __uint_as_float(hi[8 * j + e]);
+            }
+            unpack8(pack8(x1, is_f16), is_f16, x1);  // the linear's output, rounded to the storage dtype
+            unpack8(pack8(x2, is_f16), is_f16, x2);
+            unpack8(cv[j], is_f16, cs);
+            unpack8(sv[j], is_f16, sn);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              p1[e] = x1[e] * cs[e];
+              p2[e] = -x2[e] * sn[e];
+              p3[e] = x2[e] * cs[e];
+              p4[e] = x1[e] * sn[e];
+            }
+            unpack8(pack8(p1, is_f16), is_f16, p1);
+            unpack8(pack8(p2, is_f16), is_f16, p2);
+            unpack8(pack8(p3, is_f16), is_f16, p3);
+            unpack8(pack8(p4, is_f16), is_f16, p4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              o1[e] = p1[e] + p2[e];
+              o2[e] = p3[e] + p4[e];
+            }
+            const int col = n0 + h0 + c + 8 * j;
+            *reinterpret_cast<uint4*>(crow + (long long)col * 2) = pack8(o1, is_f16);
+            *reinterpret_cast<uint4*>(crow + (long long)(col + half) * 2) = pack8(o2, is_f16);
+          }
+        }
+      }
+    }
+    return;
+  }
   uint4 aux[4], aux_next[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -905,7 +972,12 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
                    (uintptr_t)d.residual) & 15) == 0, "problem %d: operand pointers must be 16-byte aligned", i);
     PLAN_REQUIRE(d.K1 == 0 || (d.A1 && d.B1 && d.lda1 >= d.K1 && d.ldb1 >= d.K1 && d.lda1 % 8 == 0 && d.ldb1 % 8 == 0),
                  "problem %d: K1 > 0 needs A1 / B1 with valid leading dimensions", i);
-    PLAN_REQUIRE(d.epilogue >= MC_LINEAR_EPI_NONE && d.epilogue <= MC_LINEAR_EPI_SILU_MUL, "problem %d: bad epilogue %d", i, d.epilogue);
+    PLAN_REQUIRE(d.epilogue >= MC_LINEAR_EPI_NONE && d.epilogue <= MC_LINEAR_EPI_ROPE, "problem %d: bad epilogue %d", i, d.epilogue);
+    PLAN_REQUIRE(d.epilogue != MC_LINEAR_EPI_ROPE ||
+                     (d.rope_cos && d.rope_sin && d.rope_seq_len >= 1 && d.rope_head_dim >= 64 && d.rope_head_dim % 64 == 0 &&
+                      bn % d.rope_head_dim == 0 && d.N % d.rope_head_dim == 0 &&
+                      (((uintptr_t)d.rope_cos | (uintptr_t)d.rope_sin) & 15) == 0),
+                 "problem %d: ROPE epilogue needs cos/sin tables, seq_len >= 1 and a head_dim in {64, 128, 256} dividing N and the tile", i);
     PLAN_REQUIRE((d.epilogue != MC_LINEAR_EPI_BIAS && d.epilogue != MC_LINEAR_EPI_BIAS_GELU) || d.bias, "problem %d: bias is NULL", i);
     PLAN_REQUIRE((d.epilogue != MC_LINEAR_EPI_RESIDUAL && d.epilogue != MC_LINEAR_EPI_SILU_MUL) ||
                      (d.residual && d.ldr >= d.N && d.ldr % 8 == 0), "problem %d: residual / gate operand missing", i);
@@ -929,6 +1001,11 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     pr.bias = d.bias;
     pr.residual = d.residual;
     pr.ldr = d.ldr;
+    pr.rope_cos = d.rope_cos;
+    pr.rope_sin = d.rope_sin;
+    pr.rope_pos = d.rope_pos;
+    pr.rope_seq_len = d.rope_seq_len;
+    pr.rope_head_dim = d.rope_head_dim;
     pr.col_scale = d.col_scale;
     pr.row_group = d.row_group;
     pr.mtile_mask = d.mtile_mask;

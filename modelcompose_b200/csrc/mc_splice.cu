@@ -6,6 +6,8 @@
 //
 // The reference walks every sample on the host (a device sync per sentinel search) and issues
 // O(batch x segments) tiny embed/cat/full kernels.  Here the work is three launches:
+// (mc_splice_plan_scan = launches 1 + 2 and one stream sync; mc_splice_run = launch 3; a plan is reusable across
+// batches of the same [B, S] and modality geometry and allocates nothing in steady state)
 //   1. splice_scan_kernel    one CTA per sample: output offset of every input token (block scan),
 //                            per-sample sentinel counts; the last CTA to finish turns the counts into
 //                            the batch-global per-modality cursors (:302,:365), the padded length and
@@ -285,35 +287,30 @@ struct mc_splice_plan {
   SpliceHeader* d_hdr;
   unsigned int* d_done;
   int4* d_desc;
+  char* d_arena;     // one allocation behind the seven small tables above
+  size_t desc_rows;  // capacity of d_desc (grow-only)
+  bool scanned;
   std::vector<int> out_len;
   int total_blocks[kMaxModal];
 };
 
 static void splice_plan_free(mc_splice_plan* p) {
   if (!p) return;
-  cudaFree(p->d_tok_off);
-  cudaFree(p->d_tok_blk);
-  cudaFree(p->d_out_len);
-  cudaFree(p->d_cnt);
-  cudaFree(p->d_base);
-  cudaFree(p->d_hdr);
-  cudaFree(p->d_done);
+  cudaFree(p->d_arena);
   cudaFree(p->d_desc);
   delete p;
 }
 
-extern "C" int mc_splice_plan_create(mc_splice_plan_t** out, const int64_t* d_input_ids, int B, int S, int vocab,
-                                     const mc_splice_modal_t* modals, int n_modal, mc_stream_t stream_) {
+extern "C" int mc_splice_plan_create(mc_splice_plan_t** out, int B, int S, int vocab, const mc_splice_modal_t* modals,
+                                     int n_modal) {
   MC_REQUIRE(out != nullptr, "plan out-pointer is NULL");
   *out = nullptr;
   MC_REQUIRE(B >= 1 && S >= 1, "empty batch (B=%d, S=%d)", B, S);
   MC_REQUIRE(S < kSearchLimit, "S=%d: the reference stops matching sentinels at index %d (multimodal_arch.py:278)", S,
              kSearchLimit);
-  MC_REQUIRE(d_input_ids != nullptr, "input_ids is NULL");
   MC_REQUIRE(vocab >= 1, "vocab < 1");
   MC_REQUIRE(n_modal >= 0 && n_modal <= kMaxModal && (n_modal == 0 || modals), "n_modal %d outside [0, %d]", n_modal,
              kMaxModal);
-  cudaStream_t stream = (cudaStream_t)stream_;
   mc_splice_plan* p = new (std::nothrow) mc_splice_plan();
   if (!p) return fail(MC_ERR_NOMEM, "host allocation failed");
   memset(&p->dev, 0, sizeof(p->dev));
@@ -333,61 +330,74 @@ extern "C" int mc_splice_plan_create(mc_splice_plan_t** out, const int64_t* d_in
   p->d_hdr = nullptr;
   p->d_done = nullptr;
   p->d_desc = nullptr;
+  p->d_arena = nullptr;
+  p->desc_rows = 0;
+  p->scanned = false;
+  p->max_len = p->min_len = 0;
   cudaError_t e = cudaGetDevice(&p->device);
   const size_t nt = (size_t)B * S;
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_tok_off, nt * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_tok_blk, nt * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_out_len, (size_t)B * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_cnt, (size_t)B * kMaxModal * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_base, (size_t)B * kMaxModal * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_hdr, sizeof(SpliceHeader));
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_done, sizeof(unsigned int));
+  auto up16 = [](size_t n) { return (n + 15) & ~(size_t)15; };
+  const size_t o_off = 0, o_blk = o_off + up16(nt * sizeof(int)), o_len = o_blk + up16(nt * sizeof(int)),
+               o_cnt = o_len + up16((size_t)B * sizeof(int)), o_base = o_cnt + up16((size_t)B * kMaxModal * sizeof(int)),
+               o_hdr = o_base + up16((size_t)B * kMaxModal * sizeof(int)), o_done = o_hdr + up16(sizeof(SpliceHeader)),
+               arena_bytes = o_done + 16;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_arena, arena_bytes);
+  if (e != cudaSuccess) {
+    splice_plan_free(p);
+    return fail(MC_ERR_CUDA, "splice plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  p->d_tok_off = reinterpret_cast<int*>(p->d_arena + o_off);
+  p->d_tok_blk = reinterpret_cast<int*>(p->d_arena + o_blk);
+  p->d_out_len = reinterpret_cast<int*>(p->d_arena + o_len);
+  p->d_cnt = reinterpret_cast<int*>(p->d_arena + o_cnt);
+  p->d_base = reinterpret_cast<int*>(p->d_arena + o_base);
+  p->d_hdr = reinterpret_cast<SpliceHeader*>(p->d_arena + o_hdr);
+  p->d_done = reinterpret_cast<unsigned int*>(p->d_arena + o_done);
+  p->out_len.assign(B, 0);
+  *out = p;
+  return MC_OK;
+}
+
+extern "C" int mc_splice_plan_scan(mc_splice_plan_t* p, const int64_t* d_input_ids, mc_stream_t stream_) {
+  MC_REQUIRE(p != nullptr, "plan is NULL");
+  MC_REQUIRE(d_input_ids != nullptr, "input_ids is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int B = p->dev.B, S = p->dev.S;
+  const size_t nt = (size_t)B * S;
+  p->scanned = false;
   SpliceHeader h0;
   memset(&h0, 0, sizeof(h0));
   h0.error_b = 0x7fffffff;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_hdr, &h0, sizeof(h0), cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(p->d_done, 0, sizeof(unsigned int), stream);
-  if (e == cudaSuccess) {
-    splice_scan_kernel<<<B, kScanThreads, 0, stream>>>(p->dev, (const long long*)d_input_ids, p->d_tok_off, p->d_tok_blk,
-                                                       p->d_out_len, p->d_cnt, p->d_base, p->d_hdr, p->d_done);
-    e = cudaGetLastError();
-  }
+  MC_CUDA_OK(cudaMemcpyAsync(p->d_hdr, &h0, sizeof(h0), cudaMemcpyHostToDevice, stream));
+  MC_CUDA_OK(cudaMemsetAsync(p->d_done, 0, sizeof(unsigned int), stream));
+  splice_scan_kernel<<<B, kScanThreads, 0, stream>>>(p->dev, (const long long*)d_input_ids, p->d_tok_off, p->d_tok_blk,
+                                                     p->d_out_len, p->d_cnt, p->d_base, p->d_hdr, p->d_done);
+  MC_CUDA_OK(cudaGetLastError());
   SpliceHeader h;
-  p->out_len.resize(B);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, p->d_hdr, sizeof(h), cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->out_len.data(), p->d_out_len, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the output shape depends on the data: one sync per batch
-  if (e != cudaSuccess) {
-    splice_plan_free(p);
-    return fail(MC_ERR_CUDA, "splice plan failed: %s", cudaGetErrorString(e));
-  }
-  if (h.error & MC_SPLICE_ERR_BAD_TOKEN) {
-    int b = h.error_b;
-    splice_plan_free(p);
-    return fail(MC_ERR_INVALID, "sample %d holds a token id that is neither in [0, vocab) nor a configured modality sentinel", b);
-  }
-  if (h.error & MC_SPLICE_ERR_CURSOR) {
-    splice_plan_free(p);
-    return fail(MC_ERR_INVALID, "more modality sentinels in the batch than feature blocks supplied");
-  }
+  MC_CUDA_OK(cudaMemcpyAsync(&h, p->d_hdr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  MC_CUDA_OK(cudaMemcpyAsync(p->out_len.data(), p->d_out_len, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  MC_CUDA_OK(cudaStreamSynchronize(stream));  // the output shape depends on the data: one sync per batch
+  if (h.error & MC_SPLICE_ERR_BAD_TOKEN)
+    return fail(MC_ERR_INVALID, "sample %d holds a token id that is neither in [0, vocab) nor a configured modality sentinel", h.error_b);
+  if (h.error & MC_SPLICE_ERR_CURSOR) return fail(MC_ERR_INVALID, "more modality sentinels in the batch than feature blocks supplied");
   p->max_len = h.max_len;
   p->min_len = h.min_len;
   memcpy(p->total_blocks, h.total_blocks, sizeof(p->total_blocks));
   const size_t n_rows = (size_t)B * p->max_len;
-  if (n_rows) {
-    e = cudaMalloc(&p->d_desc, n_rows * sizeof(int4));
-    if (e == cudaSuccess) {
-      const long long threads = (long long)nt * 32;
-      splice_expand_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-          p->dev, (const long long*)d_input_ids, p->d_tok_off, p->d_tok_blk, p->d_out_len, p->d_base, p->d_hdr, p->d_desc);
-      e = cudaGetLastError();
-    }
-    if (e != cudaSuccess) {
-      splice_plan_free(p);
-      return fail(MC_ERR_CUDA, "splice expand failed: %s", cudaGetErrorString(e));
-    }
+  if (n_rows > p->desc_rows) {  // grow-only: steady-state batches of one shape never allocate
+    if (p->d_desc) MC_CUDA_OK(cudaFree(p->d_desc));
+    p->d_desc = nullptr;
+    p->desc_rows = 0;
+    MC_CUDA_OK(cudaMalloc((void**)&p->d_desc, n_rows * sizeof(int4)));
+    p->desc_rows = n_rows;
   }
-  *out = p;
+  if (n_rows) {
+    const long long threads = (long long)nt * 32;
+    splice_expand_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        p->dev, (const long long*)d_input_ids, p->d_tok_off, p->d_tok_blk, p->d_out_len, p->d_base, p->d_hdr, p->d_desc);
+    MC_CUDA_OK(cudaGetLastError());
+  }
+  p->scanned = true;
   return MC_OK;
 }
 
@@ -409,6 +419,7 @@ extern "C" int64_t mc_splice_plan_bytes(const mc_splice_plan_t* p, int row_bytes
 extern "C" int mc_splice_run(const mc_splice_plan_t* p, const mc_splice_io_t* io, const mc_splice_modal_t* modals,
                              mc_stream_t stream) {
   MC_REQUIRE(p != nullptr && io != nullptr, "NULL plan / io");
+  MC_REQUIRE(p->scanned, "mc_splice_plan_scan has not succeeded on this plan");
   MC_REQUIRE(dtype_valid(io->dtype), "bad dtype");
   MC_REQUIRE(io->hidden >= 1, "hidden < 1");
   const long long row_bytes = (long long)io->hidden * (long long)dtype_size(io->dtype);

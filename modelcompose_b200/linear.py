@@ -16,7 +16,7 @@ import torch
 
 from . import _cabi
 
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_ROWMASK, EPI_RESIDUAL, EPI_SILU_MUL = 0, 1, 2, 3, 4, 5
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_ROWMASK, EPI_RESIDUAL, EPI_SILU_MUL, EPI_ROPE = 0, 1, 2, 3, 4, 5, 6
 MAX_PROBLEMS = 4
 TILE_M = 128
 K_BLOCK = 64
@@ -46,7 +46,8 @@ class LinearDesc(C.Structure):
                 ("C", C.c_void_p), ("ldc", C.c_int64), ("bias", C.c_void_p), ("residual", C.c_void_p),
                 ("ldr", C.c_int64), ("col_scale", C.c_void_p), ("row_group", C.c_void_p),
                 ("mtile_mask", C.c_void_p), ("group_cols", C.POINTER(C.c_int32)), ("n_groups", C.c_int32),
-                ("epilogue", C.c_int32)]
+                ("epilogue", C.c_int32), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_pos", C.c_void_p),
+                ("rope_seq_len", C.c_int32), ("rope_head_dim", C.c_int32)]
 
 
 def _mat(t: torch.Tensor, what: str, dtype=None):
@@ -74,6 +75,7 @@ class Problem:
     mtile_mask: Optional[torch.Tensor] = None  # int32 [ceil(M/128)]
     group_cols: Optional[Sequence[int]] = None
     epilogue: int = EPI_NONE
+    rope: Optional[tuple] = None               # EPI_ROPE: (cos table, sin table, int32 position scalar or None, seq_len, head_dim)
 
 
 class LinearPlan:
@@ -124,6 +126,13 @@ class LinearPlan:
                 self._keep.append(arr)
                 d.group_cols, d.n_groups = arr, len(p.group_cols) - 1
             d.epilogue = p.epilogue
+            if p.rope is not None:
+                cos, sin, pos, seq_len, head_dim = p.rope
+                if cos.dtype != dtype or sin.dtype != dtype or not cos.is_cuda or cos.shape[-1] != head_dim:
+                    raise ValueError(f"problem {i}: rope tables must be CUDA {dtype} [positions, head_dim]")
+                d.rope_cos, d.rope_sin = cos.data_ptr(), sin.data_ptr()
+                d.rope_pos = None if pos is None else pos.data_ptr()
+                d.rope_seq_len, d.rope_head_dim = int(seq_len), int(head_dim)
             self._keep.append(p)
         self._h = C.c_void_p()
         _cabi.check(_cabi.lib().mc_linear_plan_create(C.byref(self._h), descs, len(problems), _cabi.dtype_code(dtype), tuning),

@@ -31,6 +31,7 @@ ADAPTER_ORDER = ("audio", "vision", "video", "point")
 # kernel variant of the base + LoRA-up launches (mc_linear_plan_create `tuning`): 0 = 128x256 single-CTA tiles (default),
 # 3 = 256x256 CTA-pair tiles (cta_group::2).  Development switch; both are parity-tested.
 UP_TUNING = int(os.environ.get("MC_LINEAR_UP_TUNING", "0"))
+FUSE_ROPE = os.environ.get("MC_FUSE_ROPE", "1") != "0"  # development switch: 0 = separate mc_rope launch
 
 
 class MultimodalConfig:
@@ -191,6 +192,12 @@ class _Workspace:
         self.gate = buf(T, I)
         self.logits = buf(T, V)
         self.row_group = torch.zeros(T, dtype=torch.uint8, device=dev)
+        # RoPE rides in the q / k projection epilogue when a tile holds whole heads; otherwise mc_rope runs after it
+        D = H // cfg.num_attention_heads
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pos_value = 0
+        self.rope_fused = FUSE_ROPE and D in (64, 128, 256) and (128 if T <= LN.TILE_M or H < 256 else 256) % D == 0
+        self.rope = (model._rope[0], model._rope[1], self.pos, S, D) if self.rope_fused else None
         self.mtile = torch.zeros((T + LN.TILE_M - 1) // LN.TILE_M, dtype=torch.int32, device=dev)
         self.plans: List[Dict[str, LN.LinearPlan]] = []
         for layer in model.layers:
@@ -205,9 +212,13 @@ class _Workspace:
     def _up(self, src, layer: _Layer, names, tbufs, outs, residual=None, epilogue=None):
         if epilogue is None:
             epilogue = LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE
-        return LN.LinearPlan([LN.Problem(src, layer.W[n], o, A1=t, B1=layer.ad[n].B_all, mtile_mask=self.mtile,
-                                         group_cols=layer.ad[n].group_cols, residual=residual, epilogue=epilogue)
-                              for n, t, o in zip(names, tbufs, outs)], tuning=self.up_tuning)
+        probs = []
+        for n, t, o in zip(names, tbufs, outs):
+            rope = self.rope if n in ("q_proj", "k_proj") else None
+            probs.append(LN.Problem(src, layer.W[n], o, A1=t, B1=layer.ad[n].B_all, mtile_mask=self.mtile,
+                                    group_cols=layer.ad[n].group_cols, residual=residual,
+                                    epilogue=LN.EPI_ROPE if rope is not None else epilogue, rope=rope))
+        return LN.LinearPlan(probs, tuning=self.up_tuning)
 
     def _layer_plans(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
         qkv, gu = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
@@ -285,8 +296,8 @@ class MultimodalLlamaForCausalLM:
         self.prefix_tokens = self._local_tokens(sd, "prefix", config.local_prefix_tokens)
         self.suffix_tokens = self._local_tokens(sd, "suffix", config.local_suffix_tokens)
         self._attn_backend: Optional[str] = os.environ.get("MC_ATTENTION_BACKEND") or None
-        self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._ws: Dict[Tuple[int, int], _Workspace] = {}
+        self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._proj_cache: Dict[tuple, tuple] = {}
 
     # ------------------------------------------------------------------------------------------ construction helpers
@@ -305,9 +316,12 @@ class MultimodalLlamaForCausalLM:
         return out
 
     def _rope_tables(self, seq_len: int):
-        """transformers 4.31 LlamaRotaryEmbedding: fp32 cache built on the host, cast to the model dtype on use."""
+        """transformers 4.31 LlamaRotaryEmbedding: fp32 cache built on the host, cast to the model dtype on use.  The
+        tables are referenced by the launch plans, so they only ever grow (in 4096-position steps) and growing drops the
+        cached workspaces."""
         n = max(seq_len, self.config.max_position_embeddings)
         if self._rope is None or self._rope[0].shape[0] < n:
+            n = (n + 4095) // 4096 * 4096
             D = self.config.hidden_size // self.config.num_attention_heads
             base = float(getattr(self.config, "rope_theta", 10000.0) or 10000.0)
             inv_freq = 1.0 / (base ** (torch.arange(0, D, 2).float() / D))
@@ -316,6 +330,7 @@ class MultimodalLlamaForCausalLM:
             emb = torch.cat((freqs, freqs), dim=-1)
             self._rope = (emb.cos().to(self.dtype).to(self.device).contiguous(),
                           emb.sin().to(self.dtype).to(self.device).contiguous())
+            self._ws.clear()
         return self._rope
 
     def get_model(self):
@@ -407,11 +422,12 @@ class MultimodalLlamaForCausalLM:
         nH = cfg.num_attention_heads
         D = cfg.hidden_size // nH
         B, S = ws.B, ws.S
-        cos, sin = self._rope_tables(past + S)
-        _cabi.check(_cabi.lib().mc_rope(ws.q.data_ptr(), ws.k.data_ptr(), cos.data_ptr(), sin.data_ptr(), ws.T, S, past, nH, D,
-                                        ws.q.stride(0), ws.k.stride(0), _cabi.dtype_code(self.dtype),
-                                        _cabi.current_stream_ptr()), "mc_rope")
-        _cabi.count_launch()
+        if not ws.rope_fused:
+            cos, sin = self._rope
+            _cabi.check(_cabi.lib().mc_rope(ws.q.data_ptr(), ws.k.data_ptr(), cos.data_ptr(), sin.data_ptr(), ws.T, S, past, nH, D,
+                                            ws.q.stride(0), ws.k.stride(0), _cabi.dtype_code(self.dtype),
+                                            _cabi.current_stream_ptr()), "mc_rope")
+            _cabi.count_launch()
         q, k, v = (t.view(B, S, nH, D) for t in (ws.q, ws.k, ws.v))
         if cache is not None:
             cache.k[layer_idx][:, past:past + S].copy_(k)
@@ -455,6 +471,7 @@ class MultimodalLlamaForCausalLM:
                 cache.grow(max(past + S, cache.capacity * 2))
         elif use_cache:
             cache = KVCache(len(self.layers), B, S + 128, nH, H // nH, self.dtype, self.device)
+        self._rope_tables(past + S)  # before the workspace: its plans point at the tables
         key = (B, S)
         if key not in self._ws:
             if S > 1:
@@ -463,6 +480,9 @@ class MultimodalLlamaForCausalLM:
             self._ws[key] = _Workspace(self, B, S)
         ws = self._ws[key]
         ws.x.view(B, S, H).copy_(inputs_embeds)
+        if ws.pos_value != past:
+            ws.pos.fill_(past)
+            ws.pos_value = past
         if modal_id is None:
             ws.row_group.zero_()
         else:

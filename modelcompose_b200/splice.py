@@ -46,6 +46,32 @@ class SpliceResult:
     algorithmic_bytes: int
 
 
+# Reusable plans, keyed by device and batch geometry (a plan owns a few KB..MB of device tables and allocates nothing
+# in steady state).  A handful of shapes are live at a time (one prefill shape, one decode shape).
+_PLANS: "OrderedDict[tuple, C.c_void_p]" = None
+_MAX_PLANS = 8
+
+
+def _plan_for(device, B, S, V, modals, n_modal) -> C.c_void_p:
+    global _PLANS
+    from collections import OrderedDict
+    if _PLANS is None:
+        _PLANS = OrderedDict()
+    key = (device.index, B, S, V, tuple((int(modals[i].sentinel), modals[i].n_blocks, modals[i].n_rows, modals[i].n_prefix,
+                                          modals[i].n_suffix) for i in range(n_modal)))
+    plan = _PLANS.get(key)
+    if plan is None:
+        plan = C.c_void_p()
+        _cabi.check(_cabi.lib().mc_splice_plan_create(C.byref(plan), B, S, V, modals, n_modal), "mc_splice_plan_create")
+        _PLANS[key] = plan
+        while len(_PLANS) > _MAX_PLANS:
+            _, old = _PLANS.popitem(last=False)
+            _cabi.lib().mc_splice_plan_destroy(old)
+    else:
+        _PLANS.move_to_end(key)
+    return plan
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -105,42 +131,38 @@ def splice(input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor], labe
         modals[i].features, modals[i].prefix, modals[i].suffix = _ptr(f), _ptr(pre), _ptr(suf)
 
     stream = _cabi.current_stream_ptr()
-    plan = C.c_void_p()
-    _cabi.check(lib.mc_splice_plan_create(C.byref(plan), input_ids.data_ptr(), B, S, V, modals, len(names), stream),
-                "mc_splice_plan_create")
-    try:
-        max_len, min_len = C.c_int(), C.c_int()
-        out_len = (C.c_int32 * B)()
-        used = (C.c_int32 * MAX_MODAL)()
-        _cabi.check(lib.mc_splice_plan_info(plan, C.byref(max_len), C.byref(min_len), out_len, used), "mc_splice_plan_info")
-        Sp = max_len.value
-        if min_len.value != Sp and labels is None:
-            # the reference binds `_new_labels` only under `if labels is not None` (multimodal_arch.py:414-429)
-            raise UnboundLocalError("cannot access local variable '_new_labels' where it is not associated with a value "
-                                    "(ragged batch with labels=None, reference multimodal_arch.py:414-429)")
-        any_sentinel = any(used[i] > 0 for i in range(len(names)))
-        mask_names = list(names)
-        if modal_input_keys is not None and any_sentinel:
-            mask_names = [m for m in names if m in set(modal_input_keys)]
-            if len(mask_names) != len(names) and any(n == S for n in out_len):
-                raise ValueError("a batch mixing sentinel-free samples with a partial modal_inputs dict has no "
-                                 "consistent mask shape in the reference (multimodal_arch.py:323-342,452)")
-        dev = input_ids.device
-        embeds = torch.empty((B, Sp, H), dtype=dtype, device=dev)
-        modal_id = torch.empty((B, Sp), dtype=torch.uint8, device=dev)
-        attn_out = torch.empty((B, Sp), dtype=mask_dtype, device=dev) if attention_mask is not None else None
-        labels_out = torch.empty((B, Sp), dtype=torch.int64, device=dev) if labels is not None else None
-        masks = {m: torch.empty((B, Sp), dtype=mask_dtype, device=dev) for m in mask_names}
-        default_mask = torch.empty((B, Sp), dtype=torch.bool, device=dev) if masks else None
-        for i, m in enumerate(names):
-            modals[i].mask_out = _ptr(masks.get(m))
-        io = SpliceIO(_cabi.dtype_code(dtype), H, embed_table.data_ptr(), _ptr(attention_mask), elem, _ptr(labels),
-                      embeds.data_ptr(), modal_id.data_ptr(), _ptr(attn_out), _ptr(labels_out), _ptr(default_mask))
-        _cabi.check(lib.mc_splice_run(plan, C.byref(io), modals, stream), "mc_splice_run")
-        _cabi.count_launch(3)  # scan + expand (plan) + gather
-        nbytes = int(lib.mc_splice_plan_bytes(plan, H * embed_table.element_size()))
-    finally:
-        lib.mc_splice_plan_destroy(plan)
+    plan = _plan_for(input_ids.device, B, S, V, modals, len(names))
+    _cabi.check(lib.mc_splice_plan_scan(plan, input_ids.data_ptr(), stream), "mc_splice_plan_scan")
+    max_len, min_len = C.c_int(), C.c_int()
+    out_len = (C.c_int32 * B)()
+    used = (C.c_int32 * MAX_MODAL)()
+    _cabi.check(lib.mc_splice_plan_info(plan, C.byref(max_len), C.byref(min_len), out_len, used), "mc_splice_plan_info")
+    Sp = max_len.value
+    if min_len.value != Sp and labels is None:
+        # the reference binds `_new_labels` only under `if labels is not None` (multimodal_arch.py:414-429)
+        raise UnboundLocalError("cannot access local variable '_new_labels' where it is not associated with a value "
+                                "(ragged batch with labels=None, reference multimodal_arch.py:414-429)")
+    any_sentinel = any(used[i] > 0 for i in range(len(names)))
+    mask_names = list(names)
+    if modal_input_keys is not None and any_sentinel:
+        mask_names = [m for m in names if m in set(modal_input_keys)]
+        if len(mask_names) != len(names) and any(n == S for n in out_len):
+            raise ValueError("a batch mixing sentinel-free samples with a partial modal_inputs dict has no "
+                             "consistent mask shape in the reference (multimodal_arch.py:323-342,452)")
+    dev = input_ids.device
+    embeds = torch.empty((B, Sp, H), dtype=dtype, device=dev)
+    modal_id = torch.empty((B, Sp), dtype=torch.uint8, device=dev)
+    attn_out = torch.empty((B, Sp), dtype=mask_dtype, device=dev) if attention_mask is not None else None
+    labels_out = torch.empty((B, Sp), dtype=torch.int64, device=dev) if labels is not None else None
+    masks = {m: torch.empty((B, Sp), dtype=mask_dtype, device=dev) for m in mask_names}
+    default_mask = torch.empty((B, Sp), dtype=torch.bool, device=dev) if masks else None
+    for i, m in enumerate(names):
+        modals[i].mask_out = _ptr(masks.get(m))
+    io = SpliceIO(_cabi.dtype_code(dtype), H, embed_table.data_ptr(), _ptr(attention_mask), elem, _ptr(labels),
+                  embeds.data_ptr(), modal_id.data_ptr(), _ptr(attn_out), _ptr(labels_out), _ptr(default_mask))
+    _cabi.check(lib.mc_splice_run(plan, C.byref(io), modals, stream), "mc_splice_run")
+    _cabi.count_launch(3)  # scan + expand (plan) + gather
+    nbytes = int(lib.mc_splice_plan_bytes(plan, H * embed_table.element_size()))
     del keep
     out_masks = None
     if masks:

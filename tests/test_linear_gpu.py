@@ -116,6 +116,33 @@ def test_silu_mul_epilogue_matches_separate_ops():
     assert (d <= 2 ** -6 * ref.float().abs() + 1e-7).all() and (d > 0).float().mean().item() < 0.01
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("D,tuning", [(128, 0), (64, 0), (64, 1), (128, 3)])
+def test_rope_epilogue_bit_exact_vs_separate_kernel(dtype, D, tuning):
+    """q/k projection with RoPE in the epilogue == projection followed by mc_rope == oracle apply_rope on the rounded projection."""
+    Bn, S, nH, K = 3, 50, 4, 192
+    H = nH * D
+    x, W = rnd((Bn * S, K), dtype, 1).cuda(), rnd((H, K), dtype, 2, 0.1).cuda()
+    cos, sin = XO.rope_cos_sin(D, 128, dtype)
+    cos_d, sin_d = cos.cuda(), sin.cuda()
+    pos = torch.tensor([7], dtype=torch.int32, device="cuda")
+    plain = torch.empty((Bn * S, H), dtype=dtype, device="cuda")
+    LN.LinearPlan([LN.Problem(x, W, plain)], tuning=tuning).run()
+    fused = torch.empty_like(plain)
+    LN.LinearPlan([LN.Problem(x, W, fused, epilogue=LN.EPI_ROPE, rope=(cos_d, sin_d, pos, S, D))], tuning=tuning).run()
+    torch.cuda.synchronize()
+    q = plain.cpu().view(Bn, S, nH, D).transpose(1, 2)
+    position_ids = (7 + torch.arange(S))[None].expand(Bn, S)
+    want, _ = XO.apply_rope(q, q, cos, sin, position_ids)
+    assert torch.equal(fused.cpu().view(Bn, S, nH, D).transpose(1, 2), want)
+    sep, dummy = plain.clone(), plain.clone()
+    lib = _cabi.lib()
+    _cabi.check(lib.mc_rope(sep.data_ptr(), dummy.data_ptr(), cos_d.data_ptr(), sin_d.data_ptr(), Bn * S, S, 7, nH, D, H, H,
+                            _cabi.dtype_code(dtype), _cabi.current_stream_ptr()), "rope")
+    torch.cuda.synchronize()
+    assert torch.equal(sep, fused)
+
+
 def test_k_extension_unrouted():
     dtype = torch.bfloat16
     M, N, K0, K1 = 260, 512, 192, 128
