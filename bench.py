@@ -368,6 +368,77 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             "timer": "host wall clock around the synchronous call, max over ranks"}
 
 
+# ------------------------------------------------------------------------------------------------ TIES workload
+def run_ties(device, steps: int = 10, K: int = 20, func: str = "mean"):
+    """TIES merge (`--strategy ties-mean -K 20`, reference ties_merging.py:161-179) of the shared `default` adapters of
+    three vicuna-7B DAMC checkpoints: 3 sources x 448 LoRA tensors = 319,815,680 bf16 elements per source, N(0, 0.02) /
+    U(+-1/sqrt(in)) random init on the device.  One GPU (the trim threshold and the majority sign are global statistics).
+    Parity outside the timed region: exact rank of every threshold (torch counts on the device) and three tensors
+    re-derived by the CPU oracle from those statistics."""
+    from modelcompose_b200 import merge as M
+    from modelcompose_b200 import synthetic as syn
+    from oracle import ties_oracle as TO
+    llama, r = syn.VICUNA_7B, 128
+    shapes = []
+    for _ in range(llama["num_hidden_layers"]):
+        for name in syn.LINEAR_NAMES:
+            out_f, in_f = syn.linear_shape(llama, name)
+            shapes += [(r, in_f), (out_f, r)]
+    srcs = []
+    for s in range(3):
+        g = torch.Generator(device=device).manual_seed(3000 + s)
+        lst = []
+        for (a, b) in shapes:
+            if a == r:   # lora_A ~ U(+-1/sqrt(in)) (peft init)
+                t = (torch.rand((a, b), generator=g, device=device) * 2 - 1) / (b ** 0.5)
+            else:        # lora_B ~ N(0, 0.02)
+                t = torch.randn((a, b), generator=g, device=device) * 0.02
+            lst.append(t.to(torch.bfloat16))
+        srcs.append(lst)
+    outs = [torch.empty(sh, dtype=torch.float32 if func == "mean" else torch.bfloat16, device=device) for sh in shapes]
+    plan = M.TiesPlan(srcs, outs)
+    for _ in range(3):
+        plan.run(K, func)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        plan.run(K, func)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    st = plan.stats()
+    d, k = plan.elements, M.ties_kth_rank(plan.elements, K)
+    for s in range(3):
+        thr = st["thresholds"][s]
+        below = sum(int((t.abs().float() < thr).sum()) for t in srcs[s])
+        upto = sum(int((t.abs().float() <= thr).sum()) for t in srcs[s])
+        if not below < k <= upto:
+            raise SystemExit(f"PARITY FAILURE: TIES threshold of source {s} is not the k-th smallest magnitude")
+    if st["n_pos"] + st["n_neg"] + st["n_zero"] + st["n_ambiguous"] != d or st["majority"] != (st["n_pos"] > st["n_neg"]) - (st["n_pos"] < st["n_neg"]):
+        raise SystemExit("PARITY FAILURE: TIES sign census inconsistent")
+    for j in (0, 1, len(shapes) - 1):
+        flat = torch.stack([srcs[s][j].cpu().reshape(-1) for s in range(3)])
+        want = TO.merge_given_statistics(flat, st["thresholds"], st["majority"], func)
+        got = outs[j].cpu().reshape(-1)
+        if got.dtype != want.dtype or not torch.equal(got.view(torch.int32 if got.dtype == torch.float32 else torch.int16),
+                                                     want.view(torch.int32 if want.dtype == torch.float32 else torch.int16)):
+            raise SystemExit(f"PARITY FAILURE: TIES output tensor {j} differs from the oracle")
+    peak, peak_src = measured_peaks()
+    gbs = plan.algorithmic_bytes / (ms * 1e-3) / 1e9
+    res = {"metric": "TIES merge GB/s (ties-%s, K=%d)" % (func, K), "value": round(gbs, 1), "unit": "GB/s", "n_gpus": 1, "steps": steps,
+           "ms_per_step": round(ms, 4), "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": "ties-%s of the `default` LoRA adapters of 3 vicuna-7B DAMC checkpoints" % func, "tensors": len(shapes),
+                      "elements_per_source": d, "algorithmic_bytes": plan.algorithmic_bytes,
+                      "passes": "1 counting pass + 1 merge pass over 3 sources, fp32 output"},
+           "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
+                        "traffic": None, "peak_source": peak_src, "kernel": "whole mc_ties_plan_run (sample, bracket, count, select, merge, fix-up)"},
+           "stats": st, "gpu_launches": 11 * steps}
+    del plan, srcs, outs
+    torch.cuda.empty_cache()
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ prefill workload
 PREFILL_CONFIGS = {
     # name: (BASELINE config, requests per GPU, merged adapters (infer_modals order), modalities in every request, text tokens)
@@ -577,7 +648,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "merge", "prefill"],
+    ap.add_argument("--workload", default="all", choices=["all", "merge", "prefill", "ties"],
                     help="all (default): the merge line (BASELINE config 2) carrying the prefill result under \"prefill\"; "
                          "merge / prefill: that workload alone as the primary line")
     ap.add_argument("--prefill-config", default="c3", choices=sorted(PREFILL_CONFIGS))
@@ -594,8 +665,17 @@ def main():
     args.warmup = max(args.warmup, 3)
     dist, rank, world, device, barrier = setup_dist(args)
     line = None
+    if args.workload == "ties":
+        if rank == 0:
+            print(json.dumps(run_ties(device)), flush=True)
+        if world > 1:
+            barrier()
+            dist.destroy_process_group()
+        return
     if args.workload in ("all", "merge"):
         line = run_merge(args, dist, rank, world, device, barrier)
+        if line is not None and world == 1 and not args.no_e2e:
+            line["ties"] = run_ties(device)  # the other merge strategy family of the CLI, one GPU
     if args.workload in ("all", "prefill") and not args.no_e2e:
         pre = run_prefill(args, device, rank, world, dist, barrier, args.prefill_config)
         if rank == 0:

@@ -103,6 +103,64 @@ MC_API int mc_merge_host(int n_tensors, int n_src, const void* const* h_src, voi
 
 
 /* ------------------------------------------------------------------------------------------------
+ * TIES merge (trim, elect sign, disjoint merge) — the `ties-{sum,mean,max}`, `convert-drop-*` strategies
+ *
+ * Replaces scripts/model_composition/ties_merging.py:88-179 (topk_values_mask, resolve_sign, resolve_zero_signs,
+ * disjoint_merge, ties_merging) as called by do_merging (:182-222) from
+ * scripts/model_composition/merge_unimodal_modelcompose.py:59-64,75-85.  The reference flattens every source into one
+ * vector (sorted keys) and runs torch ops over the [n_src, d] matrix; here the tensors stay where they are (pointer
+ * table, as the merge plan) because every step is either elementwise or a global statistic:
+ *   trim   thr_s = k-th smallest |x| of source s over ALL its tensors, exact: bf16 / fp16 — a 1/32 sample brackets the
+ *          rank, one streaming pass counts the keys below the bracket and histograms the few bins inside it (a miss
+ *          falls back to a full 2^15-bin histogram pass); fp32 — radix select, three histogram passes of 11+10+10 bits;
+ *          m = x * (|x| >= thr_s)
+ *   elect  sgn = sign(round_src(sum_s m_s)); elements whose sum is 0 take the majority sign = sign(#pos - #neg), one
+ *          scalar over all elements
+ *   merge  entries whose sign agrees with sgn are kept, then  SUM: round_src(sum kept)
+ *          MEAN: float32( round_src(sum kept) ) / max(#kept != 0, 1)   (dst is float32: torch promotes bf16 / float32)
+ *          MAX : round_src(max |kept|) * sgn                           (-0 where sgn = -1 and nothing is kept)
+ * The majority sign is only known after a full pass, so the merge pass runs with the speculative majority +1 while
+ * taking the census and listing the elements whose survivors cancel exactly (the only ones that depend on it); if the
+ * majority turns out different those elements are recomputed from the list.  A dense second merge pass runs only when
+ * the list overflows (2^20 entries) or for MAX with a negative majority (every element without survivors becomes -0).
+ * Everything is enqueued on the stream; nothing synchronises.  Bit-identical to the reference's CPU torch result for finite inputs.
+ * dst dtype: float32 for MC_TIES_MEAN, the source dtype otherwise.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum mc_ties_func { MC_TIES_SUM = 0, MC_TIES_MEAN = 1, MC_TIES_MAX = 2 } mc_ties_func;
+
+typedef struct mc_ties_stats {
+  float threshold[MC_MERGE_MAX_SRC]; /* k-th smallest |x| per source */
+  int64_t n_pos, n_neg;              /* elements whose elected sign is + / - before zeros are resolved */
+  int64_t n_zero;                    /* elements where no source survives the trim */
+  int64_t n_ambiguous;               /* elements whose survivors cancel exactly */
+  int32_t majority;                  /* sign(n_pos - n_neg) */
+  int32_t full_select_ran;           /* 1: thresholds came from the full-range histogram passes (fp32, small inputs, or the
+                                        sampled bracket missed); 0: from the sampled bracket + one counting pass */
+  int32_t fix_pass_ran;              /* 0: speculative outputs were final; 1: the listed majority-dependent elements were
+                                        recomputed; 2: dense second merge pass */
+} mc_ties_stats_t;
+
+typedef struct mc_ties_plan mc_ties_plan_t;
+
+/* Pointer / chunk tables as mc_merge_plan_create (src[s * n_tensors + t], dst[t], numel[t]); dst_dtype must be MC_F32
+ * when the plan will run MC_TIES_MEAN and src_dtype otherwise (checked at run).  Synchronous. */
+MC_API int mc_ties_plan_create(mc_ties_plan_t** plan, int n_tensors, int n_src, const void* const* src, void* const* dst,
+                        const int64_t* numel, int src_dtype, int dst_dtype);
+/* Enqueues the whole TIES merge.  kth = 1-based rank (ascending magnitude) of the smallest kept element among the
+ * plan's total element count d: the reference's `d - int(d * K)` (ties_merging.py:89-96); 1 <= kth <= d. */
+MC_API int mc_ties_plan_run(const mc_ties_plan_t* plan, int64_t kth, int func, mc_stream_t stream);
+/* Synchronises `stream` and reports the thresholds / census of the last run. */
+MC_API int mc_ties_plan_stats(const mc_ties_plan_t* plan, mc_ties_stats_t* out, mc_stream_t stream);
+/* Algorithmic bytes of one run without the fix pass: (select passes + 1) reads of every source + one write of dst. */
+MC_API int64_t mc_ties_plan_bytes(const mc_ties_plan_t* plan);
+MC_API int64_t mc_ties_plan_elements(const mc_ties_plan_t* plan);
+MC_API int mc_ties_plan_destroy(mc_ties_plan_t* plan);
+/* Host-buffer form used by the merge CLI: copies every source to the device (all of them must be resident for the two
+ * global statistics), runs the plan and copies the result back; returns when h_dst is complete.  stats may be NULL. */
+MC_API int mc_ties_host(int n_tensors, int n_src, const void* const* h_src, void* const* h_dst, const int64_t* numel,
+                 int64_t kth, int func, int src_dtype, mc_ties_stats_t* stats);
+
+/* ------------------------------------------------------------------------------------------------
  * Modality-token splice
  *
  * Replaces modelcompose/model/multimodal_arch.py:287-459 (prepare_inputs_labels_for_multimodal), its helper
@@ -218,12 +276,16 @@ typedef struct mc_linear_desc {
   const int32_t* rope_pos;      /* ROPE: device scalar, position of the first row of every sequence (NULL = 0) */
   int32_t rope_seq_len;         /* ROPE: row m is token (rope_pos + m % rope_seq_len) of its sequence */
   int32_t rope_head_dim;
+  const int32_t* c_rowmap;      /* device [M] or NULL: row m of the problem is written to row c_rowmap[m] of C (a permutation:
+                                   activations kept in modality-major row order scatter back to sequence order for
+                                   attention / the logits); ROPE takes the token position from the mapped row */
 } mc_linear_desc_t;
 
 typedef struct mc_linear_plan mc_linear_plan_t;
 
 /* Encodes the TMA descriptors and tile schedule of 1..MC_LINEAR_MAX_PROBLEMS problems that run as ONE launch.
- * dtype: MC_BF16 or MC_F16.  tuning: bits 0-7 tile (0 = default, 1 = 128x128, 2 = 128x256), bits 8-15 rasterisation group
+ * dtype: MC_BF16 or MC_F16.  tuning: bits 0-7 tile (0 = default, 1 = 128x128, 2 = 128x256, 3 = CTA pair 512x256,
+ * 4 = CTA pair 256x256 with overlapped epilogue; 3 and 4 not for ROWMASK launches), bits 8-15 rasterisation group
  * override, bit 16 disables the compacted tile schedule of routed-N launches.  The plan stays valid while the pointers
  * in `desc` do (activations are normally static per-shape buffers, so plans are built once and reused). */
 MC_API int mc_linear_plan_create(mc_linear_plan_t** plan, const mc_linear_desc_t* desc, int n_problems, int dtype, int tuning);
@@ -248,6 +310,10 @@ MC_API int mc_silu_mul(const void* gate, const void* up, void* out, int64_t rows
  *                pos_offset + t % seq_len (prefill: position_ids = arange(seq_len), :526-533; decode step: seq_len 1,
  *                pos_offset = past length).
  * ---------------------------------------------------------------------------------------------- */
+/* dst[i, :] = src[index[i], :] for i < rows (bit-exact row copy, 128-bit accesses; row_bytes % 16 == 0).  Used to put the
+ * spliced embeddings / the attention output into the modality-major row order the routed linears run in, and back. */
+MC_API int mc_gather_rows(const void* src, int64_t ld_src_bytes, void* dst, int64_t ld_dst_bytes, const int32_t* index,
+                   int64_t rows, int row_bytes, mc_stream_t stream);
 MC_API int mc_rmsnorm(const void* x, const void* weight, void* out, int64_t rows, int hidden, int64_t ldx, int64_t ldo,
                float eps, int dtype, mc_stream_t stream);
 MC_API int mc_rope(void* q, void* k, const void* cos_table, const void* sin_table, int64_t tokens, int seq_len, int pos_offset,

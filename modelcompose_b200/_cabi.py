@@ -16,6 +16,7 @@ MC_OK = 0
 MC_F32, MC_F16, MC_BF16 = 0, 1, 2
 MC_MERGE_WEIGHTED, MC_MERGE_REF_SUM, MC_MERGE_REF_MEAN = 0, 1, 2
 MC_MERGE_MAX_SRC = 8
+MC_TIES_SUM, MC_TIES_MEAN, MC_TIES_MAX = 0, 1, 2
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmodelcompose_b200.so")
 
@@ -33,6 +34,13 @@ SIGNATURES = {
     "mc_merge_plan_destroy": (_i, [_vp]),
     "mc_merge_tensors": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), C.POINTER(C.c_float), _i, _i, _i, _vp]),
     "mc_merge_host": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), C.POINTER(C.c_float), _i, _i, _i, _sz]),
+    "mc_ties_plan_create": (_i, [C.POINTER(_vp), _i, _i, _pp, _pp, C.POINTER(_i64), _i, _i]),
+    "mc_ties_plan_run": (_i, [_vp, _i64, _i, _vp]),
+    "mc_ties_plan_stats": (_i, [_vp, _vp, _vp]),
+    "mc_ties_plan_bytes": (_i64, [_vp]),
+    "mc_ties_plan_elements": (_i64, [_vp]),
+    "mc_ties_plan_destroy": (_i, [_vp]),
+    "mc_ties_host": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), _i64, _i, _i, _vp]),
     # structs are passed as void* (modelcompose_b200.splice defines the ctypes.Structure mirrors)
     "mc_splice_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp, _i]),
     "mc_splice_plan_scan": (_i, [_vp, _vp, _vp]),
@@ -46,9 +54,16 @@ SIGNATURES = {
     "mc_linear_plan_destroy": (_i, [_vp]),
     "mc_route_tile_masks": (_i, [_vp, _i, _vp, _vp]),
     "mc_silu_mul": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _i64, _i, _vp]),
+    "mc_gather_rows": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp]),
     "mc_rmsnorm": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, C.c_float, _i, _vp]),
     "mc_rope": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i64, _i64, _i, _vp]),
 }
+
+
+class TiesStats(C.Structure):
+    """mirror of mc_ties_stats_t"""
+    _fields_ = [("threshold", C.c_float * MC_MERGE_MAX_SRC), ("n_pos", C.c_int64), ("n_neg", C.c_int64), ("n_zero", C.c_int64),
+                ("n_ambiguous", C.c_int64), ("majority", C.c_int32), ("full_select_ran", C.c_int32), ("fix_pass_ran", C.c_int32)]
 
 
 class McError(RuntimeError):

@@ -31,6 +31,9 @@ def translation_units():
         if f == "mc_merge_inst.cu":
             for k in range(7):
                 tus.append((f, f"mc_merge_inst_{k}.o", [f"-DMC_PAIR={k}"]))
+        elif f == "mc_ties_inst.cu":
+            for k in range(3):
+                tus.append((f, f"mc_ties_inst_{k}.o", [f"-DMC_TIES_DT={k}"]))
         else:
             tus.append((f, f[:-3] + ".o", []))
     return tus

@@ -52,6 +52,7 @@ struct alignas(64) LinProblem {
   const void* rope_cos;  // ROPE epilogue: cos / sin tables [positions, head_dim] in the storage dtype
   const void* rope_sin;
   const int* rope_pos;   // device scalar: position of the first row of every sequence (NULL = 0)
+  const int* c_rowmap;   // output row of problem row m (NULL = m): scatters a modality-major row order back to sequence order
   long long ldc, ldr;
   int M, N, nkb0, nkb1, tiles_m, tiles_n, tile_end, epilogue;
   int rope_seq_len, rope_head_dim;
@@ -251,14 +252,15 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
   const int epi = pr.epilogue;
   const bool has_aux = (epi == MC_LINEAR_EPI_RESIDUAL || epi == MC_LINEAR_EPI_SILU_MUL) && row_ok;
   const int rg = (epi == MC_LINEAR_EPI_ROWMASK && row_ok) ? (int)pr.row_group[row] : -1;
-  char* crow = reinterpret_cast<char*>(pr.C) + (long long)row * pr.ldc * 2;
+  const int orow = (pr.c_rowmap && row_ok) ? pr.c_rowmap[row] : row;  // where this row lands in C (and its token index)
+  char* crow = reinterpret_cast<char*>(pr.C) + (long long)orow * pr.ldc * 2;
   const char* rrow = reinterpret_cast<const char*>(pr.residual) + (long long)row * pr.ldr * 2;
   if (epi == MC_LINEAR_EPI_ROPE) {
     // apply_rotary_pos_emb fused behind the q / k projections (multimodal_llama.py:281-282): the projection output is
     // rounded to the storage dtype first, then q*cos + rotate_half(q)*sin with every product and the sum rounded, exactly
     // the op sequence of rope_kernel / the eager reference.  A tile holds BN / head_dim whole heads.
     const int D = pr.rope_head_dim, half = D >> 1;
-    const int pos = (pr.rope_pos ? *pr.rope_pos : 0) + row % pr.rope_seq_len;
+    const int pos = (pr.rope_pos ? *pr.rope_pos : 0) + orow % pr.rope_seq_len;
     const char* cosr = reinterpret_cast<const char*>(pr.rope_cos) + (long long)pos * D * 2;
     const char* sinr = reinterpret_cast<const char*>(pr.rope_sin) + (long long)pos * D * 2;
 #pragma unroll 1
@@ -796,6 +798,171 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
   if (warp == 2) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
 }
 
+// =====================================================================================================================
+// CTA-pair variant with overlapped epilogue: a pair computes a 256 x 256 tile (cta_group::2, M = 256: 128 rows per CTA).
+// Each CTA stages its own A rows [128 x 64] and HALF of the B tile [128 x 64] = 32 KB per k-block (6-stage ring), so the
+// tensor cores read 2/3 of the shared-memory bytes per MMA of the single-CTA kernel and B crosses L2 -> SM once per
+// pair instead of once per CTA.  One accumulator is 256 TMEM columns: the 512 columns hold TWO, and the epilogue of
+// tile i (4 warps per CTA) overlaps the MMAs of tile i + 1 exactly as in linear_kernel.  LoRA k-blocks are skipped on the
+// union of the groups of the pair's two 128-row tiles (pure tiles in the modality-major row order).
+// =====================================================================================================================
+template <int STAGES>
+struct SmemLayout3 {
+  static constexpr int A_BYTES = kBM * kBK * 2;   // this CTA's 128 rows
+  static constexpr int B_BYTES = 128 * kBK * 2;   // this CTA's 128 (of 256) B rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+__device__ __forceinline__ unsigned int pair256_mask(const LinProblem& pr, int mt) {
+  if (!pr.mtile_mask) return 0xffffffffu;
+  const int n128 = (pr.M + kBM - 1) / kBM;
+  unsigned int m = pr.mtile_mask[2 * mt];
+  if (2 * mt + 1 < n128) m |= pr.mtile_mask[2 * mt + 1];
+  return m;
+}
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3_kernel(const __grid_constant__ LinParams P) {
+  using L = SmemLayout3<STAGES>;
+  constexpr int BN = 256, TMEM_COLS = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < P.n_prob; ++p) {
+      tma_prefetch_desc(&P.prob[p].tmA0);
+      tma_prefetch_desc(&P.prob[p].tmB0);
+      if (P.prob[p].nkb1) {
+        tma_prefetch_desc(&P.prob[p].tmA1);
+        tma_prefetch_desc(&P.prob[p].tmB1);
+      }
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer's remote arrive (the leader's copy is the one used)
+      mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);   // multicast tcgen05.commit from the leader
+      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's copy
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread per CTA): own A rows + own half of B, bytes complete on the leader's barrier =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
+        const Tile t = decode_tile(P, tile);
+        const LinProblem& pr = P.prob[t.p];
+        const unsigned int gmask = pair256_mask(pr, t.mt);
+        const int m0 = t.mt * 256 + (int)rank * 128, n0 = t.nt * BN + (int)rank * 128;
+        for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
+          const bool ext = kb >= pr.nkb0;
+          const int k = ext ? kb - pr.nkb0 : kb;
+          if (ext && pr.kb1_mask && (pr.kb1_mask[k] & gmask) == 0u) continue;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          else mbar_arrive_cluster(full_leader);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          tma_load_2d_cg2(ext ? &pr.tmA1 : &pr.tmA0, full_leader, sa, k * kBK, m0);
+          tma_load_2d_cg2(ext ? &pr.tmB1 : &pr.tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread of the leader CTA) =====
+    if (lane == 0 && rank == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
+        const Tile t = decode_tile(P, tile);
+        const LinProblem& pr = P.prob[t.p];
+        const unsigned int gmask = pair256_mask(pr, t.mt);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
+          const bool ext = kb >= pr.nkb0;
+          if (ext && pr.kb1_mask && (pr.kb1_mask[kb - pr.nkb0] & gmask) == 0u) continue;
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t a_desc = umma_smem_desc(sa), b_desc = umma_smem_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_f16_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_cg2(&empty_bar[stage]);  // frees the stage in both CTAs once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_cg2(&tfull_bar[acc]);  // accumulator complete -> both CTAs' epilogues
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: each CTA drains its own 128 accumulator rows =====
+    const int q = warp & 3;
+    const bool is_f16 = P.is_f16 != 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
+      const Tile t = decode_tile(P, tile);
+      const LinProblem& pr = P.prob[t.p];
+      const int row = t.mt * 256 + (int)rank * 128 + q * 32 + lane;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      epilogue_tile<BN>(pr, is_f16, taddr, row, t.nt * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer can still signal its barriers or read its memory
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+}
+
 // ---- routing helpers ------------------------------------------------------------------------------------
 // mask[t] = OR over the rows of 128-row tile t of (1 << group[row])
 __global__ void route_tile_mask_kernel(const unsigned char* __restrict__ group, int M, unsigned int* __restrict__ mask, int n_tiles) {
@@ -875,7 +1042,7 @@ using namespace mc;
 struct mc_linear_plan {
   LinParams params;
   int bn, grid, dtype;
-  int two_cta;  // 1: linear2_kernel (512 x 256 pair tiles)
+  int two_cta;  // 1: linear2_kernel (512 x 256 pair tiles); 2: linear3_kernel (256 x 256 pair tiles, overlapped epilogue)
   size_t smem_bytes;
   double flops;
   std::vector<void*> owned;  // device arrays built by the plan (group tables)
@@ -912,6 +1079,21 @@ static cudaError_t launch_linear2(const mc_linear_plan* p, cudaStream_t stream) 
   return cudaGetLastError();
 }
 
+template <int STAGES>
+static cudaError_t launch_linear3(const mc_linear_plan* p, cudaStream_t stream) {
+  using L = SmemLayout3<STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(linear3_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    if (e != cudaSuccess) return e;
+    configured[dev] = true;
+  }
+  linear3_kernel<STAGES><<<p->grid, kThreads, L::DYN_BYTES, stream>>>(p->params);
+  return cudaGetLastError();
+}
+
 static void linear_plan_free(mc_linear_plan* p) {
   if (!p) return;
   for (void* d : p->owned) cudaFree(d);
@@ -941,15 +1123,18 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     if (desc[i].N < 256) bn = 128;
   if ((tuning & 0xff) == 1) bn = 128;
   if ((tuning & 0xff) == 2) bn = 256;
-  // 3 = CTA-pair kernel (cta_group::2, 512 x 256 pair tiles); not for ROWMASK (routed-N) launches
-  const bool two = (tuning & 0xff) == 3;
+  // 3 = CTA-pair kernel (cta_group::2, 512 x 256 pair tiles), 4 = CTA-pair kernel with 256 x 256 pair tiles and an
+  // overlapped epilogue; neither takes ROWMASK (routed-N) launches
+  const int pair_mode = (tuning & 0xff) == 3 ? 1 : ((tuning & 0xff) == 4 ? 2 : 0);
+  const bool two = pair_mode != 0;
   if (two) bn = 256;
-  const int bm = two ? 512 : kBM;
+  const int bm = pair_mode == 1 ? 512 : (pair_mode == 2 ? 256 : kBM);
+  const int a_box = pair_mode == 1 ? 256 : kBM;
   mc_linear_plan* p = new (std::nothrow) mc_linear_plan();
   if (!p) return fail(MC_ERR_NOMEM, "host allocation failed");
   memset(&p->params, 0, sizeof(p->params));
   p->bn = bn;
-  p->two_cta = two ? 1 : 0;
+  p->two_cta = pair_mode;
   p->dtype = dtype;
   p->flops = 0;
   int tile_end = 0;
@@ -1006,6 +1191,7 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     pr.rope_pos = d.rope_pos;
     pr.rope_seq_len = d.rope_seq_len;
     pr.rope_head_dim = d.rope_head_dim;
+    pr.c_rowmap = d.c_rowmap;
     pr.col_scale = d.col_scale;
     pr.row_group = d.row_group;
     pr.mtile_mask = d.mtile_mask;
@@ -1032,9 +1218,9 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
       }
       if (e != cudaSuccess) break;
     }
-    rc = encode_operand(&pr.tmA0, d.A0, d.M, d.K0, d.lda0, two ? 256 : kBM, dtype);
+    rc = encode_operand(&pr.tmA0, d.A0, d.M, d.K0, d.lda0, a_box, dtype);
     if (rc == MC_OK) rc = encode_operand(&pr.tmB0, d.B0, d.N, d.K0, d.ldb0, two ? 128 : bn, dtype);
-    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmA1, d.A1, d.M, d.K1, d.lda1, two ? 256 : kBM, dtype);
+    if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmA1, d.A1, d.M, d.K1, d.lda1, a_box, dtype);
     if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmB1, d.B1, d.N, d.K1, d.ldb1, two ? 128 : bn, dtype);
     p->flops += 2.0 * d.M * (double)d.N * (double)(d.K0 + d.K1);
 #undef PLAN_REQUIRE
@@ -1087,7 +1273,8 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
 
 extern "C" int mc_linear_plan_run(const mc_linear_plan_t* p, mc_stream_t stream) {
   MC_REQUIRE(p != nullptr, "plan is NULL");
-  cudaError_t e = p->two_cta   ? launch_linear2<4>(p, (cudaStream_t)stream)
+  cudaError_t e = p->two_cta == 1 ? launch_linear2<4>(p, (cudaStream_t)stream)
+                  : p->two_cta == 2 ? launch_linear3<6>(p, (cudaStream_t)stream)
                   : p->bn == 256 ? launch_linear<256, 4>(p, (cudaStream_t)stream)
                                  : launch_linear<128, 6>(p, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(MC_ERR_CUDA, "linear launch failed: %s", cudaGetErrorString(e));

@@ -99,9 +99,46 @@ rope_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ cos_t, c
   }
 }
 
+// dst[i] = src[index[i]]: one warp per row, four 128-bit loads in flight per lane
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const char* __restrict__ src, long long ld_src, char* __restrict__ dst, long long ld_dst,
+                   const int* __restrict__ index, long long rows, int n_vec) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const Vec<16>* s = reinterpret_cast<const Vec<16>*>(src + (long long)index[row] * ld_src);
+    Vec<16>* d = reinterpret_cast<Vec<16>*>(dst + row * ld_dst);
+    int i = lane;
+    for (; i + 96 < n_vec; i += 128) {
+      const Vec<16> a = ld_stream(s + i), b = ld_stream(s + i + 32), c = ld_stream(s + i + 64), e = ld_stream(s + i + 96);
+      d[i] = a;
+      d[i + 32] = b;
+      d[i + 64] = c;
+      d[i + 96] = e;
+    }
+    for (; i < n_vec; i += 32) d[i] = ld_stream(s + i);
+  }
+}
+
 }  // namespace mc
 
 using namespace mc;
+
+extern "C" int mc_gather_rows(const void* src, int64_t ld_src_bytes, void* dst, int64_t ld_dst_bytes, const int32_t* index,
+                              int64_t rows, int row_bytes, mc_stream_t stream) {
+  MC_REQUIRE(src && dst && index, "gather_rows: NULL pointer");
+  MC_REQUIRE(rows >= 0 && row_bytes >= 16 && row_bytes % 16 == 0 && ld_src_bytes % 16 == 0 && ld_dst_bytes % 16 == 0,
+             "gather_rows: row_bytes and leading dimensions must be multiples of 16 bytes");
+  MC_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "gather_rows: pointers must be 16-byte aligned");
+  if (rows == 0) return MC_OK;
+  const int sms = sm_count();
+  MC_REQUIRE(sms > 0, "no CUDA device");
+  const int grid = (int)std::min<long long>((rows + 7) / 8, (long long)sms * 32);
+  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const char*)src, ld_src_bytes, (char*)dst, ld_dst_bytes, index, rows,
+                                                             row_bytes / 16);
+  MC_CUDA_OK(cudaGetLastError());
+  return MC_OK;
+}
 
 extern "C" int mc_rmsnorm(const void* x, const void* weight, void* out, int64_t rows, int hidden, int64_t ldx, int64_t ldo,
                           float eps, int dtype, mc_stream_t stream) {

@@ -1,0 +1,692 @@
+// TIES merge: exact magnitude top-k trim, sign election, disjoint merge — multi-tensor, all on one stream.
+//
+// Replaces (reference paths): scripts/model_composition/ties_merging.py:88-179 as driven by do_merging (:182-222) and
+// scripts/model_composition/merge_unimodal_modelcompose.py:59-64,75-85 (`ties-*`, `convert-drop-*`).
+//
+// Roofline: HBM.  Every pass streams the sources once with 128-bit L1::no_allocate loads:
+//   select   1 pass (bf16 / fp16: 2^15 shared-memory bins cover the whole magnitude) or 3 passes (fp32: 11+10+10 bits)
+//            ties_hist_kernel -> ties_select_kernel (one CTA per source walks the histogram to the k-th bin)
+//   merge    ties_merge_kernel, speculative majority +1, census of elected signs (mc_ties_kernels.cuh)
+//   fix      ties_finalize_kernel decides: nothing / ties_fix_kernel over the listed majority-dependent elements / a dense
+//            re-merge (list overflow, or MAX with a negative majority); the unused kernels exit at once
+// Algorithmic bytes per element = (passes + 1) * n_src * sizeof(src) + sizeof(dst)  (bf16, 3 sources, sum: 14 B).
+#include <algorithm>
+#include <vector>
+
+#include "mc_ties_kernels.cuh"
+
+namespace mc {
+
+template <typename S>
+__device__ __forceinline__ unsigned int magnitude_key(S v);
+template <>
+__device__ __forceinline__ unsigned int magnitude_key<float>(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+template <>
+__device__ __forceinline__ unsigned int magnitude_key<__half>(__half v) { return (unsigned int)(__half_as_ushort(v) & 0x7fffu); }
+template <>
+__device__ __forceinline__ unsigned int magnitude_key<__nv_bfloat16>(__nv_bfloat16 v) {
+  return (unsigned int)(__bfloat16_as_ushort(v) & 0x7fffu);
+}
+
+// Histogram of digit ((key >> shift) & (2^bits - 1)) over the elements of source blockIdx.y whose higher key bits equal
+// the prefix found by the earlier passes.  One shared-memory histogram per CTA (<= 128 KB), flushed with 64-bit global
+// atomics; CTAs take super-chunks of 4 chunks so every thread has four 128-bit loads in flight.
+template <typename S>
+__global__ void __launch_bounds__(kTiesHistThreads, 1)
+ties_hist_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, const TiesState* __restrict__ st,
+                 unsigned long long* __restrict__ ghist, int shift, int bits, int hi_shift) {
+  extern __shared__ unsigned int s_hist[];
+  constexpr int E = 16 / sizeof(S);
+  constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
+  constexpr int SUPER = 4;
+  static_assert(CHUNK == kTiesHistThreads * E, "chunk geometry");
+  if (!st->need_full) return;  // the sampled bracket already produced the thresholds
+  const int src = blockIdx.y;
+  const int nbins = 1 << bits;
+  const unsigned int dmask = (unsigned int)nbins - 1u;
+  const unsigned int prefix = st->prefix[src];
+  for (int i = threadIdx.x; i < nbins; i += kTiesHistThreads) s_hist[i] = 0u;
+  __syncthreads();
+  const int nsuper = (nchunks + SUPER - 1) / SUPER;
+  for (int sc = blockIdx.x; sc < nsuper; sc += gridDim.x) {
+    Vec<16> v[SUPER];
+    bool fast[SUPER];
+#pragma unroll
+    for (int j = 0; j < SUPER; ++j) {
+      const int c = sc * SUPER + j;
+      fast[j] = false;
+      if (c < nchunks) {
+        const MergeChunk ch = chunks[c];
+        const MergeSeg* sg = segs + ch.seg;
+        const long long base = (long long)ch.idx * CHUNK;
+        if (sg->aligned && sg->numel - base >= CHUNK) {
+          fast[j] = true;
+          v[j] = ld_stream(reinterpret_cast<const Vec<16>*>(reinterpret_cast<const S*>(sg->src[src]) + base) + threadIdx.x);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < SUPER; ++j) {
+      const int c = sc * SUPER + j;
+      if (c >= nchunks) break;
+      if (fast[j]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const unsigned int key = magnitude_key<S>(reinterpret_cast<const S*>(&v[j])[e]);
+          if ((key >> hi_shift) == prefix) atomicAdd(&s_hist[(key >> shift) & dmask], 1u);
+        }
+      } else {
+        const MergeChunk ch = chunks[c];
+        const MergeSeg* sg = segs + ch.seg;
+        const long long base = (long long)ch.idx * CHUNK;
+        const long long n = min((long long)CHUNK, sg->numel - base);
+        for (long long i = threadIdx.x; i < n; i += kTiesHistThreads) {
+          const unsigned int key = magnitude_key<S>(reinterpret_cast<const S*>(sg->src[src])[base + i]);
+          if ((key >> hi_shift) == prefix) atomicAdd(&s_hist[(key >> shift) & dmask], 1u);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long* gh = ghist + (size_t)src * nbins;
+  for (int i = threadIdx.x; i < nbins; i += kTiesHistThreads) {
+    const unsigned int c = s_hist[i];
+    if (c) atomicAdd(gh + i, (unsigned long long)c);
+  }
+}
+
+__global__ void ties_init_kernel(TiesState* st, unsigned long long kth, int n_src, int need_full) {
+  const int i = threadIdx.x;
+  if (i < MC_MERGE_MAX_SRC) {
+    st->k_rem[i] = i < n_src ? kth : 0ull;
+    st->prefix[i] = 0u;
+    st->thr[i] = 0.0f;
+    st->win_lo[i] = 0u;
+    st->win_hi[i] = 0u;
+    st->below[i] = 0ull;
+  }
+  if (i == 0) st->need_full = need_full;
+  if (i == 0) {
+    st->n_pos = st->n_neg = st->n_zero = st->n_amb = 0ull;
+    st->majority = 1;
+    st->need_fix = 0;
+    st->fix_count = 0u;
+  }
+}
+
+// One CTA per source: find the bin holding rank k_rem, append it to the prefix, clear the histogram for the next pass.
+// `key_kind` on the last pass turns the finished key into the threshold value: 0 fp32 bits, 1 fp16 bits, 2 bf16 bits.
+__global__ void __launch_bounds__(1024) ties_select_kernel(unsigned long long* __restrict__ ghist, TiesState* st, int bits, int last, int key_kind) {
+  __shared__ unsigned long long s_part[1024];
+  if (!st->need_full) return;
+  const int src = blockIdx.x, tid = threadIdx.x;
+  const int nbins = 1 << bits;
+  const int per = nbins >= 1024 ? nbins / 1024 : 1;
+  unsigned long long* gh = ghist + (size_t)src * nbins;
+  const int b0 = tid * per;
+  unsigned long long local = 0ull;
+  if (b0 < nbins)
+    for (int i = 0; i < per; ++i) local += gh[b0 + i];
+  s_part[tid] = local;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan over the per-thread partial sums
+    const unsigned long long add = tid >= off ? s_part[tid - off] : 0ull;
+    __syncthreads();
+    s_part[tid] += add;
+    __syncthreads();
+  }
+  const unsigned long long k = st->k_rem[src];
+  const unsigned long long incl = s_part[tid], excl = incl - local;
+  if (b0 < nbins && excl < k && k <= incl) {
+    unsigned long long cum = excl;
+    int b = b0;
+    for (int i = 0; i < per; ++i) {
+      const unsigned long long c = gh[b0 + i];
+      if (cum + c >= k) {
+        b = b0 + i;
+        break;
+      }
+      cum += c;
+    }
+    const unsigned int key = (st->prefix[src] << bits) | (unsigned int)b;
+    st->prefix[src] = key;
+    st->k_rem[src] = k - cum;
+    if (last) {
+      float thr;
+      if (key_kind == 0) thr = __uint_as_float(key);
+      else if (key_kind == 1) thr = __half2float(__ushort_as_half((unsigned short)key));
+      else thr = __uint_as_float(key << 16);
+      st->thr[src] = thr;
+    }
+  }
+  __syncthreads();
+  if (b0 < nbins)
+    for (int i = 0; i < per; ++i) gh[b0 + i] = 0ull;
+}
+
+// ---- sampled bracket (bf16 / fp16) --------------------------------------------------------------------------------
+// A full-range shared-memory histogram costs one atomic per element (2.9 TB/s measured).  Instead: (1) histogram a 1/32
+// sample (one 512-byte granule of every chunk), (2) bracket the k-th magnitude between the sample quantiles k/d -/+ 6 sigma,
+// (3) stream everything once counting the keys below the bracket and histogramming only the keys inside it (a handful of
+// bins), (4) pick the exact bin.  If the rank falls outside the bracket (or the bracket is wider than the window) the
+// full-range passes run instead, so the result is always exact.
+template <typename S>
+__device__ __forceinline__ float key_to_float(unsigned int key);
+template <>
+__device__ __forceinline__ float key_to_float<__half>(unsigned int key) { return __half2float(__ushort_as_half((unsigned short)key)); }
+template <>
+__device__ __forceinline__ float key_to_float<__nv_bfloat16>(unsigned int key) { return __uint_as_float(key << 16); }
+template <>
+__device__ __forceinline__ float key_to_float<float>(unsigned int key) { return __uint_as_float(key); }
+
+template <typename S>
+__global__ void __launch_bounds__(kTiesHistThreads, 1)
+ties_sample_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, const TiesState* __restrict__ st,
+                   unsigned long long* __restrict__ ghist) {
+  extern __shared__ unsigned int s_hist[];
+  if (st->need_full) return;
+  constexpr int E = 16 / sizeof(S);
+  constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
+  constexpr int NB = 1 << 15;
+  const int src = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NB; i += kTiesHistThreads) s_hist[i] = 0u;
+  __syncthreads();
+  for (int c0 = blockIdx.x * 32; c0 < nchunks; c0 += gridDim.x * 32) {
+    const int c = c0 + warp;
+    if (c >= nchunks) continue;
+    const MergeChunk ch = chunks[c];
+    const MergeSeg* sg = segs + ch.seg;
+    const long long base = (long long)ch.idx * CHUNK;
+    const long long n = min((long long)CHUNK, sg->numel - base);
+    const int granule = (int)(((unsigned int)c * 7u) % (unsigned int)kTiesSampleEvery);  // which 512 B of the chunk
+    const long long first = (long long)(granule * 32 + lane) * E;
+    const S* p = reinterpret_cast<const S*>(sg->src[src]) + base;
+    if (sg->aligned && first + E <= n) {
+      const Vec<16> v = ld_stream(reinterpret_cast<const Vec<16>*>(p + first));
+#pragma unroll
+      for (int e = 0; e < E; ++e) atomicAdd(&s_hist[magnitude_key<S>(reinterpret_cast<const S*>(&v)[e])], 1u);
+    } else {
+      for (long long i = first; i < min(first + E, n); ++i) atomicAdd(&s_hist[magnitude_key<S>(p[i])], 1u);
+    }
+  }
+  __syncthreads();
+  unsigned long long* gh = ghist + (size_t)src * NB;
+  for (int i = threadIdx.x; i < NB; i += kTiesHistThreads) {
+    const unsigned int c = s_hist[i];
+    if (c) atomicAdd(gh + i, (unsigned long long)c);
+  }
+}
+
+// One CTA per source over the 2^15-bin sample histogram: bins holding the sample ranks t - margin and t + margin, where
+// t = k * n_sample / d.  Clears the histogram for the counting pass.
+__global__ void __launch_bounds__(1024) ties_bracket_kernel(unsigned long long* __restrict__ ghist, TiesState* st, unsigned long long kth,
+                                                            unsigned long long d_total) {
+  extern __shared__ unsigned int s_cnt[];  // 2^15 sample counts, padded (+1 word per 32) so a thread's 32 bins are conflict-free
+  __shared__ unsigned long long s_part[1024];
+  __shared__ unsigned int s_lo, s_hi;
+  if (st->need_full) return;
+  constexpr int NB = 1 << 15, PER = NB / 1024;
+  const int src = blockIdx.x, tid = threadIdx.x;
+  unsigned long long* gh = ghist + (size_t)src * NB;
+  for (int b = tid; b < NB; b += 1024) {  // coalesced read, cleared for the counting pass on the way
+    s_cnt[b + (b >> 5)] = (unsigned int)gh[b];
+    gh[b] = 0ull;
+  }
+  if (tid == 0) {
+    s_lo = 0u;
+    s_hi = (unsigned int)NB - 1u;
+  }
+  __syncthreads();
+  unsigned long long local = 0ull;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) local += s_cnt[tid * (PER + 1) + i];
+  s_part[tid] = local;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const unsigned long long add = tid >= off ? s_part[tid - off] : 0ull;
+    __syncthreads();
+    s_part[tid] += add;
+    __syncthreads();
+  }
+  const float n_s = (float)s_part[1023];
+  const float q = (float)((double)kth / (double)d_total);
+  const float t = q * n_s, margin = 6.0f * sqrtf(n_s * q * (1.0f - q)) + 64.0f;
+  const float r_lo = t - margin, r_hi = t + margin;  // sample ranks (1-based) that bracket the k-th element
+  unsigned long long cum = s_part[tid] - local;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const unsigned int c = s_cnt[tid * (PER + 1) + i];
+    const float before = (float)cum, after = (float)(cum + c);
+    if (c) {
+      if (r_lo >= 1.0f && before < r_lo && r_lo <= after) s_lo = (unsigned int)(tid * PER + i);
+      if (r_hi <= n_s && before < r_hi && r_hi <= after) s_hi = (unsigned int)(tid * PER + i);
+    }
+    cum += c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // a bracket wider than the window is clipped: the select notices if the rank lies beyond it and asks for the full passes
+    st->win_lo[src] = s_lo;
+    st->win_hi[src] = min(s_hi, s_lo + (unsigned int)kTiesWindowBins - 1u);
+    if (n_s < 1.0f) atomicExch(&st->need_full, 1);
+  }
+}
+
+// The streaming pass: keys below the bracket are counted, keys inside it histogrammed (a few bins, rarely hit).
+template <typename S>
+__global__ void __launch_bounds__(kTiesCountThreads, 2)
+ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, TiesState* st,
+                  unsigned long long* __restrict__ ghist) {
+  __shared__ unsigned int s_win[kTiesWindowBins];
+  __shared__ unsigned int s_below;
+  if (st->need_full) return;
+  constexpr int E = 16 / sizeof(S);
+  constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
+  constexpr int VPT = 2, PAIR = 4;  // one chunk = 512 threads x 2 vectors; four chunks (eight 128-bit loads per thread) per iteration
+  static_assert(CHUNK == kTiesCountThreads * VPT * E, "chunk geometry");
+  const int src = blockIdx.y;
+  const unsigned int lo = st->win_lo[src], span = st->win_hi[src] - lo;
+  for (int i = threadIdx.x; i <= (int)span; i += kTiesCountThreads) s_win[i] = 0u;
+  if (threadIdx.x == 0) s_below = 0u;
+  __syncthreads();
+  static_assert(sizeof(S) == 2, "the counting pass packs two 16-bit keys per word");
+  const unsigned int lo2 = lo | (lo << 16), hi2 = (lo + span) | ((lo + span) << 16) | 0x80008000u;
+  unsigned int below = 0u, ge_acc = 0u, n_fast = 0u;  // ge_acc = 128 x (#keys >= lo) over the n_fast vector-path elements
+  unsigned long long below_total = 0ull;
+  for (int c0 = blockIdx.x * PAIR; c0 < nchunks; c0 += gridDim.x * PAIR) {
+    Vec<16> v[PAIR][VPT];
+    bool fast[PAIR];
+#pragma unroll
+    for (int j = 0; j < PAIR; ++j) {
+      const int c = c0 + j;
+      fast[j] = false;
+      if (c < nchunks) {
+        const MergeChunk ch = chunks[c];
+        const MergeSeg* sg = segs + ch.seg;
+        const long long base = (long long)ch.idx * CHUNK;
+        if (sg->aligned && sg->numel - base >= CHUNK) {
+          fast[j] = true;
+          const Vec<16>* p = reinterpret_cast<const Vec<16>*>(reinterpret_cast<const S*>(sg->src[src]) + base) + threadIdx.x;
+#pragma unroll
+          for (int u = 0; u < VPT; ++u) v[j][u] = ld_stream(p + u * kTiesCountThreads);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PAIR; ++j) {
+      const int c = c0 + j;
+      if (c >= nchunks) break;
+      if (fast[j]) {
+        // two 15-bit keys per 32-bit word: (0x8000 | key) - lo keeps bit 15 iff key >= lo, (0x8000 | hi) - key keeps it iff
+        // key <= hi (no borrow crosses the halves); the flag bytes (0x80) are summed with one dp4a per word
+#pragma unroll
+        for (int u = 0; u < VPT; ++u) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const unsigned int keys = v[j][u].w[w] & 0x7fff7fffu;
+            const unsigned int ge = ((keys | 0x80008000u) - lo2) & 0x80008000u;
+            ge_acc = __dp4a(ge, 0x01010101u, ge_acc);
+            const unsigned int in = ge & (hi2 - keys);
+            if (in) {
+              if (in & 0x00008000u) atomicAdd(&s_win[(keys & 0xffffu) - lo], 1u);
+              if (in & 0x80000000u) atomicAdd(&s_win[(keys >> 16) - lo], 1u);
+            }
+          }
+        }
+        n_fast += (unsigned int)(VPT * E);
+      } else {
+        const MergeChunk ch = chunks[c];
+        const MergeSeg* sg = segs + ch.seg;
+        const long long base = (long long)ch.idx * CHUNK;
+        const long long n = min((long long)CHUNK, sg->numel - base);
+        for (long long i = threadIdx.x; i < n; i += kTiesCountThreads) {
+          const unsigned int key = magnitude_key<S>(reinterpret_cast<const S*>(sg->src[src])[base + i]);
+          below += key < lo ? 1u : 0u;
+          if (key - lo <= span) atomicAdd(&s_win[key - lo], 1u);
+        }
+      }
+    }
+    if (n_fast > (1u << 24)) {  // keep the 32-bit per-thread counters (ge_acc counts in units of 128) from wrapping
+      below_total += below + (n_fast - (ge_acc >> 7));
+      below = ge_acc = n_fast = 0u;
+    }
+  }
+  below_total += below + (n_fast - (ge_acc >> 7));
+  // block reduction of the below-counts (64-bit), then one global atomic per CTA
+  unsigned long long x = below_total;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+  __shared__ unsigned long long s_red[kTiesCountThreads / 32];
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0ull;
+    for (int w = 0; w < kTiesCountThreads / 32; ++w) tot += s_red[w];
+    if (tot) atomicAdd(&st->below[src], tot);
+  }
+  unsigned long long* gh = ghist + (size_t)src * (1 << 15) + lo;
+  for (int i = threadIdx.x; i <= (int)span; i += kTiesCountThreads) {
+    const unsigned int cnt = s_win[i];
+    if (cnt) atomicAdd(gh + i, (unsigned long long)cnt);
+  }
+}
+
+// One CTA per source: the bin of the bracket that holds rank k - below; a rank outside the bracket requests the full passes.
+template <typename S>
+__global__ void __launch_bounds__(1024) ties_window_select_kernel(unsigned long long* __restrict__ ghist, TiesState* st, unsigned long long kth) {
+  __shared__ int s_miss;
+  const int src = blockIdx.x, tid = threadIdx.x;
+  // need_full may be raised by another source's CTA of this launch: every CTA still cleans its own bins
+  const bool active = st->need_full == 0;
+  const unsigned int lo = st->win_lo[src], hi = st->win_hi[src];
+  unsigned long long* gh = ghist + (size_t)src * (1 << 15);
+  if (tid == 0) s_miss = 0;
+  __syncthreads();
+  if (active && tid == 0) {
+    const unsigned long long below = st->below[src];
+    bool found = false;
+    if (kth > below) {
+      unsigned long long cum = below;
+      for (unsigned int b = lo; b <= hi; ++b) {
+        cum += gh[b];
+        if (cum >= kth) {
+          st->thr[src] = key_to_float<S>(b);
+          found = true;
+          break;
+        }
+      }
+    }
+    if (!found) s_miss = 1;
+  }
+  __syncthreads();
+  for (unsigned int b = lo + tid; b <= hi; b += 1024) gh[b] = 0ull;
+  if (tid == 0 && s_miss) atomicExch(&st->need_full, 1);
+}
+
+__global__ void ties_finalize_kernel(TiesState* st, int func, unsigned long long total) {
+  const unsigned long long p = st->n_pos, n = st->n_neg;
+  st->n_zero = total - p - n - st->n_amb;
+  const int majority = p > n ? 1 : (p < n ? -1 : 0);
+  st->majority = majority;
+  // the speculative pass used +1: wrong wherever survivors cancel exactly (listed: sparse fix-up), and MAX writes
+  // -0 (0 * -1) into every element without survivors when the majority is negative (dense re-merge)
+  int fix = 0;
+  if (majority != 1) {
+    if (func == MC_TIES_MAX && majority == -1 && st->n_zero > 0ull) fix = 2;
+    else if (st->n_amb > 0ull) fix = st->fix_count <= kTiesFixCapacity ? 1 : 2;
+  }
+  st->need_fix = fix;
+}
+
+static TiesKernels pick_ties(int sdt, int n_src, int func) {
+  if (sdt == MC_BF16) return pick_ties_bf16(n_src, func);
+  if (sdt == MC_F16) return pick_ties_f16(n_src, func);
+  if (sdt == MC_F32) return pick_ties_f32(n_src, func);
+  return TiesKernels{nullptr, nullptr};
+}
+
+}  // namespace mc
+
+using namespace mc;
+
+struct mc_ties_plan {
+  int n_src, src_dtype, dst_dtype, device, sms;
+  int nsegs, nchunks;
+  long long total_elems;
+  MergeSeg* d_segs;
+  MergeChunk* d_chunks;
+  TiesState* d_state;
+  unsigned long long* d_hist;  // n_src x 2^15 bins
+  unsigned long long* d_fix;   // kTiesFixCapacity entries
+};
+
+static const int kHistBinsMax = 1 << 15;
+
+extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_src, const void* const* src, void* const* dst,
+                                   const int64_t* numel, int src_dtype, int dst_dtype) {
+  MC_REQUIRE(out != nullptr, "plan out-pointer is NULL");
+  *out = nullptr;
+  MC_REQUIRE(n_tensors >= 0, "n_tensors < 0");
+  MC_REQUIRE(n_src >= 1 && n_src <= MC_MERGE_MAX_SRC, "n_src %d outside [1, %d]", n_src, MC_MERGE_MAX_SRC);
+  MC_REQUIRE(dtype_valid(src_dtype) && dtype_valid(dst_dtype), "bad dtype");
+  MC_REQUIRE(dst_dtype == src_dtype || dst_dtype == MC_F32, "dst dtype must be the source dtype (sum / max) or float32 (mean)");
+  MC_REQUIRE(n_tensors == 0 || (src && dst && numel), "NULL table");
+  const size_t ss = dtype_size(src_dtype), ds = dtype_size(dst_dtype);
+  const long long CHUNK = kTiesChunkBytes / (long long)ss;
+  std::vector<MergeSeg> segs;
+  for (int t = 0; t < n_tensors; ++t) {
+    MC_REQUIRE(numel[t] >= 0, "numel[%d] < 0", t);
+    if (numel[t] == 0) continue;
+    MergeSeg s{};
+    for (int k = 0; k < n_src; ++k) {
+      s.src[k] = src[(size_t)k * n_tensors + t];
+      MC_REQUIRE(s.src[k] != nullptr, "src[%d][%d] is NULL", k, t);
+    }
+    s.dst = dst[t];
+    MC_REQUIRE(s.dst != nullptr, "dst[%d] is NULL", t);
+    s.numel = numel[t];
+    bool fused = false;
+    if (!segs.empty()) {
+      MergeSeg& p = segs.back();
+      bool contig = (const char*)p.dst + p.numel * ds == (const char*)s.dst && p.numel + s.numel < (1LL << 40);
+      for (int k = 0; k < n_src && contig; ++k) contig = (const char*)p.src[k] + p.numel * ss == (const char*)s.src[k];
+      if (contig) {
+        p.numel += s.numel;
+        fused = true;
+      }
+    }
+    if (!fused) segs.push_back(s);
+  }
+  std::vector<MergeChunk> chunks;
+  long long total = 0;
+  for (size_t i = 0; i < segs.size(); ++i) {
+    MergeSeg& s = segs[i];
+    uintptr_t bits = (uintptr_t)s.dst;
+    for (int k = 0; k < n_src; ++k) bits |= (uintptr_t)s.src[k];
+    s.aligned = (bits & 31) == 0;
+    const long long n = (s.numel + CHUNK - 1) / CHUNK;
+    MC_REQUIRE(n < (1LL << 31) && (long long)chunks.size() + n < (1LL << 31), "too many chunks");
+    for (long long j = 0; j < n; ++j) chunks.push_back(MergeChunk{(int)i, (int)j});
+    total += s.numel;
+  }
+  mc_ties_plan* p = new (std::nothrow) mc_ties_plan();
+  if (!p) return fail(MC_ERR_NOMEM, "host allocation failed");
+  p->n_src = n_src;
+  p->src_dtype = src_dtype;
+  p->dst_dtype = dst_dtype;
+  p->nsegs = (int)segs.size();
+  p->nchunks = (int)chunks.size();
+  p->total_elems = total;
+  p->d_segs = nullptr;
+  p->d_chunks = nullptr;
+  p->d_state = nullptr;
+  p->d_hist = nullptr;
+  p->d_fix = nullptr;
+  p->sms = sm_count();
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess && p->sms <= 0) e = cudaErrorNoDevice;
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_state, sizeof(TiesState));
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_hist, (size_t)n_src * kHistBinsMax * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_fix, (size_t)kTiesFixCapacity * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(p->d_hist, 0, (size_t)n_src * kHistBinsMax * sizeof(unsigned long long));
+  if (e == cudaSuccess && p->nchunks > 0) {
+    e = cudaMalloc(&p->d_segs, segs.size() * sizeof(MergeSeg));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_chunks, chunks.size() * sizeof(MergeChunk));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_segs, segs.data(), segs.size() * sizeof(MergeSeg), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_chunks, chunks.data(), chunks.size() * sizeof(MergeChunk), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    cudaFree(p->d_segs);
+    cudaFree(p->d_chunks);
+    cudaFree(p->d_state);
+    cudaFree(p->d_hist);
+    cudaFree(p->d_fix);
+    delete p;
+    return fail(MC_ERR_CUDA, "ties plan setup failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return MC_OK;
+}
+
+static int select_passes(int src_dtype) { return src_dtype == MC_F32 ? 3 : 1; }
+
+extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, mc_stream_t stream) {
+  MC_REQUIRE(p != nullptr, "plan is NULL");
+  MC_REQUIRE(func == MC_TIES_SUM || func == MC_TIES_MEAN || func == MC_TIES_MAX, "bad merge function %d", func);
+  MC_REQUIRE(p->dst_dtype == (func == MC_TIES_MEAN ? MC_F32 : p->src_dtype),
+             "dst dtype must be float32 for MEAN and the source dtype for SUM / MAX");
+  MC_REQUIRE(p->total_elems > 0, "nothing to merge");
+  MC_REQUIRE(kth >= 1 && kth <= p->total_elems, "kth %lld outside [1, %lld]", (long long)kth, p->total_elems);
+  const TiesKernels fn = pick_ties(p->src_dtype, p->n_src, func);
+  if (!fn.merge) return fail(MC_ERR_UNSUPPORTED, "ties kernel for dtype %d not built", p->src_dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  // 16-bit dtypes with enough data: sampled bracket + one counting pass; otherwise (and on a bracket miss, decided on
+  // the device) the full-range radix select, most significant digit first.  Unneeded kernels exit at once.
+  const bool sampled = p->src_dtype != MC_F32 && p->nchunks >= 1024;
+  ties_init_kernel<<<1, 32, 0, s>>>(p->d_state, (unsigned long long)kth, p->n_src, sampled ? 0 : 1);
+  if (sampled) {
+    const size_t smem = ((size_t)1 << 15) * sizeof(unsigned int);
+    const size_t bsmem = (((size_t)1 << 15) + 1024) * sizeof(unsigned int);
+    MC_CUDA_OK(cudaFuncSetAttribute(ties_bracket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    dim3 sgrid(std::max(1, std::min((p->nchunks + 31) / 32, p->sms / p->n_src)), p->n_src);
+    dim3 cgrid(std::max(1, std::min((p->nchunks + 3) / 4, p->sms * 2 / p->n_src)), p->n_src);
+    if (p->src_dtype == MC_F16) {
+      MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ties_sample_kernel<__half><<<sgrid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
+      ties_bracket_kernel<<<p->n_src, 1024, bsmem, s>>>(p->d_hist, p->d_state, (unsigned long long)kth, (unsigned long long)p->total_elems);
+      ties_count_kernel<__half><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
+      ties_window_select_kernel<__half><<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, (unsigned long long)kth);
+    } else {
+      MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ties_sample_kernel<__nv_bfloat16><<<sgrid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
+      ties_bracket_kernel<<<p->n_src, 1024, bsmem, s>>>(p->d_hist, p->d_state, (unsigned long long)kth, (unsigned long long)p->total_elems);
+      ties_count_kernel<__nv_bfloat16><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
+      ties_window_select_kernel<__nv_bfloat16><<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, (unsigned long long)kth);
+    }
+  }
+  struct Pass { int shift, bits, hi_shift; };
+  static const Pass k16[] = {{0, 15, 15}};
+  static const Pass k32[] = {{20, 11, 31}, {10, 10, 20}, {0, 10, 10}};
+  const Pass* passes = p->src_dtype == MC_F32 ? k32 : k16;
+  const int n_pass = select_passes(p->src_dtype);
+  const int key_kind = p->src_dtype == MC_F32 ? 0 : (p->src_dtype == MC_F16 ? 1 : 2);
+  const int nsuper = (p->nchunks + 3) / 4;
+  const int gx = std::max(1, std::min(nsuper, p->sms / p->n_src));  // one resident CTA per SM (128 KB of bins), no second wave
+  for (int i = 0; i < n_pass; ++i) {
+    const size_t smem = ((size_t)1 << passes[i].bits) * sizeof(unsigned int);
+    dim3 grid(gx, p->n_src);
+    if (p->src_dtype == MC_F32) {
+      MC_CUDA_OK(cudaFuncSetAttribute(ties_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ties_hist_kernel<float><<<grid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
+                                                                    passes[i].shift, passes[i].bits, passes[i].hi_shift);
+    } else if (p->src_dtype == MC_F16) {
+      MC_CUDA_OK(cudaFuncSetAttribute(ties_hist_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ties_hist_kernel<__half><<<grid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
+                                                                     passes[i].shift, passes[i].bits, passes[i].hi_shift);
+    } else {
+      MC_CUDA_OK(cudaFuncSetAttribute(ties_hist_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ties_hist_kernel<__nv_bfloat16><<<grid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
+                                                                            passes[i].shift, passes[i].bits, passes[i].hi_shift);
+    }
+    ties_select_kernel<<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, passes[i].bits, i == n_pass - 1, key_kind);
+  }
+  fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 0);
+  ties_finalize_kernel<<<1, 1, 0, s>>>(p->d_state, func, (unsigned long long)p->total_elems);
+  fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix);
+  // dense re-merge: a grid-stride launch that is small when it turns out to be a no-op
+  fn.merge<<<std::min(p->nchunks, p->sms * 16), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 1);
+  MC_CUDA_OK(cudaGetLastError());
+  return MC_OK;
+}
+
+extern "C" int mc_ties_plan_stats(const mc_ties_plan_t* p, mc_ties_stats_t* out, mc_stream_t stream) {
+  MC_REQUIRE(p != nullptr && out != nullptr, "NULL argument");
+  TiesState h;
+  MC_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  MC_CUDA_OK(cudaMemcpy(&h, p->d_state, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < MC_MERGE_MAX_SRC; ++i) out->threshold[i] = h.thr[i];
+  out->n_pos = (int64_t)h.n_pos;
+  out->n_neg = (int64_t)h.n_neg;
+  out->n_zero = (int64_t)h.n_zero;
+  out->n_ambiguous = (int64_t)h.n_amb;
+  out->majority = h.majority;
+  out->full_select_ran = h.need_full;
+  out->fix_pass_ran = h.need_fix;  /* 0 none, 1 sparse fix-up of the listed elements, 2 dense re-merge */
+  return MC_OK;
+}
+
+extern "C" int64_t mc_ties_plan_bytes(const mc_ties_plan_t* p) {
+  if (!p) return 0;
+  const int64_t reads = (int64_t)(select_passes(p->src_dtype) + 1) * p->n_src * (int64_t)dtype_size(p->src_dtype);
+  return (int64_t)p->total_elems * (reads + (int64_t)dtype_size(p->dst_dtype));
+}
+
+extern "C" int64_t mc_ties_plan_elements(const mc_ties_plan_t* p) { return p ? (int64_t)p->total_elems : 0; }
+
+extern "C" int mc_ties_plan_destroy(mc_ties_plan_t* p) {
+  if (!p) return MC_OK;
+  cudaFree(p->d_segs);
+  cudaFree(p->d_chunks);
+  cudaFree(p->d_state);
+  cudaFree(p->d_hist);
+  cudaFree(p->d_fix);
+  delete p;
+  return MC_OK;
+}
+
+extern "C" int mc_ties_host(int n_tensors, int n_src, const void* const* h_src, void* const* h_dst, const int64_t* numel,
+                            int64_t kth, int func, int src_dtype, mc_ties_stats_t* stats) {
+  MC_REQUIRE(n_tensors >= 1 && h_src && h_dst && numel, "NULL / empty table");
+  MC_REQUIRE(n_src >= 1 && n_src <= MC_MERGE_MAX_SRC, "n_src %d outside [1, %d]", n_src, MC_MERGE_MAX_SRC);
+  MC_REQUIRE(dtype_valid(src_dtype), "bad dtype");
+  MC_REQUIRE(func == MC_TIES_SUM || func == MC_TIES_MEAN || func == MC_TIES_MAX, "bad merge function %d", func);
+  const int dst_dtype = func == MC_TIES_MEAN ? MC_F32 : src_dtype;
+  const size_t ss = dtype_size(src_dtype), ds = dtype_size(dst_dtype);
+  // one slab per source and one for the output; tensor starts padded to 32 B so every tensor takes the vector path
+  std::vector<long long> off(n_tensors);
+  long long total = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    MC_REQUIRE(numel[t] >= 0, "numel[%d] < 0", t);
+    off[t] = total;
+    total = (total + numel[t] + 15) & ~15LL;
+  }
+  MC_REQUIRE(total > 0, "nothing to merge");
+  std::vector<char*> d_src(n_src, nullptr);
+  char* d_dst = nullptr;
+  mc_ties_plan_t* plan = nullptr;
+  cudaStream_t s = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  for (int k = 0; k < n_src && e == cudaSuccess; ++k) e = cudaMalloc(&d_src[k], (size_t)total * ss);
+  if (e == cudaSuccess) e = cudaMalloc(&d_dst, (size_t)total * ds);
+  int rc = MC_OK;
+  if (e == cudaSuccess) {
+    for (int k = 0; k < n_src && e == cudaSuccess; ++k)
+      for (int t = 0; t < n_tensors && e == cudaSuccess; ++t)
+        if (numel[t])
+          e = cudaMemcpyAsync(d_src[k] + off[t] * ss, h_src[(size_t)k * n_tensors + t], (size_t)numel[t] * ss, cudaMemcpyHostToDevice, s);
+  }
+  if (e == cudaSuccess) {
+    std::vector<const void*> src_tab((size_t)n_src * n_tensors);
+    std::vector<void*> dst_tab(n_tensors);
+    for (int t = 0; t < n_tensors; ++t) {
+      for (int k = 0; k < n_src; ++k) src_tab[(size_t)k * n_tensors + t] = d_src[k] + off[t] * ss;
+      dst_tab[t] = d_dst + off[t] * ds;
+    }
+    rc = mc_ties_plan_create(&plan, n_tensors, n_src, src_tab.data(), dst_tab.data(), numel, src_dtype, dst_dtype);
+    if (rc == MC_OK) rc = mc_ties_plan_run(plan, kth, func, s);
+    if (rc == MC_OK && stats) rc = mc_ties_plan_stats(plan, stats, s);
+    for (int t = 0; t < n_tensors && rc == MC_OK && e == cudaSuccess; ++t)
+      if (numel[t]) e = cudaMemcpyAsync(h_dst[t], d_dst + off[t] * ds, (size_t)numel[t] * ds, cudaMemcpyDeviceToHost, s);
+  }
+  if (s) {
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (plan) mc_ties_plan_destroy(plan);
+  for (int k = 0; k < n_src; ++k) cudaFree(d_src[k]);
+  cudaFree(d_dst);
+  if (s) cudaStreamDestroy(s);
+  if (rc != MC_OK) return rc;
+  if (e != cudaSuccess) return fail(MC_ERR_CUDA, "mc_ties_host failed: %s", cudaGetErrorString(e));
+  return MC_OK;
+}

@@ -47,7 +47,7 @@ class LinearDesc(C.Structure):
                 ("ldr", C.c_int64), ("col_scale", C.c_void_p), ("row_group", C.c_void_p),
                 ("mtile_mask", C.c_void_p), ("group_cols", C.POINTER(C.c_int32)), ("n_groups", C.c_int32),
                 ("epilogue", C.c_int32), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_pos", C.c_void_p),
-                ("rope_seq_len", C.c_int32), ("rope_head_dim", C.c_int32)]
+                ("rope_seq_len", C.c_int32), ("rope_head_dim", C.c_int32), ("c_rowmap", C.c_void_p)]
 
 
 def _mat(t: torch.Tensor, what: str, dtype=None):
@@ -76,6 +76,7 @@ class Problem:
     group_cols: Optional[Sequence[int]] = None
     epilogue: int = EPI_NONE
     rope: Optional[tuple] = None               # EPI_ROPE: (cos table, sin table, int32 position scalar or None, seq_len, head_dim)
+    c_rowmap: Optional[torch.Tensor] = None    # int32 [M]: problem row m is written to row c_rowmap[m] of C
 
 
 class LinearPlan:
@@ -133,6 +134,10 @@ class LinearPlan:
                 d.rope_cos, d.rope_sin = cos.data_ptr(), sin.data_ptr()
                 d.rope_pos = None if pos is None else pos.data_ptr()
                 d.rope_seq_len, d.rope_head_dim = int(seq_len), int(head_dim)
+            if p.c_rowmap is not None:
+                if p.c_rowmap.dtype != torch.int32 or p.c_rowmap.numel() != M or not p.c_rowmap.is_cuda or not p.c_rowmap.is_contiguous():
+                    raise ValueError(f"problem {i}: c_rowmap must be a contiguous CUDA int32 [M]")
+                d.c_rowmap = p.c_rowmap.data_ptr()
             self._keep.append(p)
         self._h = C.c_void_p()
         _cabi.check(_cabi.lib().mc_linear_plan_create(C.byref(self._h), descs, len(problems), _cabi.dtype_code(dtype), tuning),
@@ -164,8 +169,10 @@ class LinearPlan:
             pass
 
 
-def route_tile_masks(row_group: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """int32 [ceil(M/128)]: bit g set iff some row of the 128-row tile belongs to group g."""
+def route_tile_masks(row_group: torch.Tensor, out: Optional[torch.Tensor] = None, coarsen: int = 1) -> torch.Tensor:
+    """int32 [ceil(M/128)]: bit g set iff some row of the 128-row tile belongs to group g.  ``coarsen`` = 2 / 4 gives every
+    tile of an aligned run of 2 / 4 tiles the union of the run: the CTA-pair kernels skip LoRA k-blocks per 256 / 512 rows,
+    so the down-projection must have produced (zeros in) the rank columns of every group present in that many rows."""
     if not row_group.is_cuda or row_group.dtype != torch.uint8 or not row_group.is_contiguous():
         raise ValueError("row_group must be a contiguous CUDA uint8 tensor")
     M = row_group.numel()
@@ -174,6 +181,24 @@ def route_tile_masks(row_group: torch.Tensor, out: Optional[torch.Tensor] = None
         out = torch.empty(n, dtype=torch.int32, device=row_group.device)
     _cabi.check(_cabi.lib().mc_route_tile_masks(row_group.data_ptr(), M, out.data_ptr(), _cabi.current_stream_ptr()),
                 "mc_route_tile_masks")
+    _cabi.count_launch()
+    if coarsen > 1:
+        m = torch.nn.functional.pad(out, (0, (-n) % coarsen)).view(-1, coarsen)
+        union = m[:, 0]
+        for i in range(1, coarsen):
+            union = union | m[:, i]
+        out.copy_(union[:, None].expand(-1, coarsen).reshape(-1)[:n])
+    return out
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """``out[i] = src[index[i]]`` over 2-D row-major views (bit-exact row copy on the GPU)."""
+    s, o = _mat(src, "src"), _mat(out, "out", src.dtype)
+    if index.dtype != torch.int32 or not index.is_cuda or not index.is_contiguous() or index.numel() != o.shape[0] or s.shape[1] != o.shape[1]:
+        raise ValueError("gather_rows: index must be a contiguous CUDA int32 vector with one entry per output row")
+    es = s.element_size()
+    _cabi.check(_cabi.lib().mc_gather_rows(s.data_ptr(), s.stride(0) * es, o.data_ptr(), o.stride(0) * es, index.data_ptr(),
+                                           o.shape[0], s.shape[1] * es, _cabi.current_stream_ptr()), "mc_gather_rows")
     _cabi.count_launch()
     return out
 

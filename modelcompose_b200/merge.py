@@ -8,10 +8,11 @@ there is no torch/CPU arithmetic path in this module.
 from __future__ import annotations
 
 import argparse
+import copy
 import ctypes as C
 import json
 import os
-from collections import defaultdict
+from collections import OrderedDict, defaultdict
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -30,6 +31,7 @@ MODAL_DICT = {
 }
 
 MODES = {"weighted": _cabi.MC_MERGE_WEIGHTED, "sum": _cabi.MC_MERGE_REF_SUM, "mean": _cabi.MC_MERGE_REF_MEAN}
+TIES_FUNCS = {"sum": _cabi.MC_TIES_SUM, "mean": _cabi.MC_TIES_MEAN, "max": _cabi.MC_TIES_MAX}
 
 
 def get_modal_from_config(config: dict) -> str:
@@ -145,6 +147,141 @@ def merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], weights: 
     return outs
 
 
+# ------------------------------------------------------------------------------------------------ TIES merge
+def ties_kth_rank(d: int, K) -> int:
+    """reference ties_merging.py:89-96 — ``K >= 1`` is a percentage; the kept elements are those whose magnitude is at
+    least the ``k = d - int(d * K)``-th smallest (1-based).  The reference's ``kthvalue(k)`` raises for k == 0."""
+    if K >= 1:
+        K = K / 100
+    k = d - int(d * K)
+    if not 1 <= k <= d:
+        raise RuntimeError(f"kthvalue(): selected number k out of range for dimension 1 (k={k}, d={d})")
+    return k
+
+
+def _stats_dict(st: "_cabi.TiesStats", n_src: int) -> dict:
+    return {"thresholds": [float(st.threshold[i]) for i in range(n_src)], "n_pos": int(st.n_pos), "n_neg": int(st.n_neg),
+            "n_zero": int(st.n_zero), "n_ambiguous": int(st.n_ambiguous), "majority": int(st.majority),
+            "full_select_ran": bool(st.full_select_ran), "fix_pass_ran": int(st.fix_pass_ran)}  # 0 none, 1 sparse fix-up, 2 dense re-merge
+
+
+class TiesPlan:
+    """TIES merge (trim / elect sign / disjoint merge, reference ties_merging.py:161-179) of N same-shaped tensor lists
+    resident on ONE device.  ``outputs`` must be float32 for ``func='mean'`` (the reference's result dtype) and the
+    source dtype otherwise.  ``run(K, func)`` enqueues every pass on the current stream; nothing synchronises."""
+
+    def __init__(self, sources: Sequence[Sequence[torch.Tensor]], outputs: Sequence[torch.Tensor]):
+        n_src, n_t = len(sources), len(outputs)
+        if not 1 <= n_src <= _cabi.MC_MERGE_MAX_SRC:
+            raise ValueError(f"need 1..{_cabi.MC_MERGE_MAX_SRC} sources, got {n_src}")
+        if n_t == 0:
+            raise ValueError("nothing to merge")
+        src_dtype, dst_dtype = sources[0][0].dtype, outputs[0].dtype
+        for s in sources:
+            if len(s) != n_t:
+                raise ValueError("every source must hold the same number of tensors")
+        for t in range(n_t):
+            o = outputs[t]
+            _check_device_tensor(o, dst_dtype, o.numel(), f"outputs[{t}]")
+            for k in range(n_src):
+                _check_device_tensor(sources[k][t], src_dtype, o.numel(), f"sources[{k}][{t}]")
+        self._keep = (list(map(list, sources)), list(outputs))
+        self.n_src, self.n_tensors = n_src, n_t
+        self._h = C.c_void_p()
+        _cabi.check(_cabi.lib().mc_ties_plan_create(
+            C.byref(self._h), n_t, n_src, _cabi.ptr_array([sources[k][t].data_ptr() for k in range(n_src) for t in range(n_t)]),
+            _cabi.ptr_array([o.data_ptr() for o in outputs]), _cabi.i64_array([o.numel() for o in outputs]),
+            _cabi.dtype_code(src_dtype), _cabi.dtype_code(dst_dtype)), "mc_ties_plan_create")
+        self.elements = int(_cabi.lib().mc_ties_plan_elements(self._h))
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        return int(_cabi.lib().mc_ties_plan_bytes(self._h))
+
+    def run(self, K=20, func: str = "mean") -> None:
+        _cabi.check(_cabi.lib().mc_ties_plan_run(self._h, ties_kth_rank(self.elements, K), TIES_FUNCS[func],
+                                                 _cabi.current_stream_ptr()), "mc_ties_plan_run")
+        _cabi.count_launch(11)  # init, 4 sampled-select + 2..6 full-select (most exit at once), merge, finalize, fix, re-merge
+
+    def stats(self) -> dict:
+        st = _cabi.TiesStats()
+        _cabi.check(_cabi.lib().mc_ties_plan_stats(self._h, C.byref(st), _cabi.current_stream_ptr()), "mc_ties_plan_stats")
+        return _stats_dict(st, self.n_src)
+
+    def close(self) -> None:
+        if self._h:
+            _cabi.lib().mc_ties_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ties_merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], K=20, func: str = "mean"):
+    """TIES-merge HOST tensors through the GPU (``mc_ties_host``).  ``tensor_lists[s][t]``: CPU tensors, same shapes and
+    dtype across sources.  Returns (new CPU tensors, stats dict); float32 outputs for ``mean``."""
+    if not torch.cuda.is_available():
+        raise _cabi.McError("merging tensors needs a CUDA device (modelcompose_b200 has no CPU fallback)")
+    n_src, n_t = len(tensor_lists), len(tensor_lists[0])
+    srcs = [[t.contiguous() for t in lst] for lst in tensor_lists]
+    src_dtype = srcs[0][0].dtype
+    for lst in srcs:
+        if len(lst) != n_t:
+            raise ValueError("every source must hold the same number of tensors")
+        for a, b in zip(lst, srcs[0]):
+            if a.dtype != src_dtype or a.shape != b.shape or a.is_cuda:
+                raise ValueError("sources must be CPU tensors of identical dtype and shape per key")
+    out_dtype = torch.float32 if func == "mean" else src_dtype
+    outs = [torch.empty(t.shape, dtype=out_dtype) for t in srcs[0]]
+    d = sum(o.numel() for o in outs)
+    st = _cabi.TiesStats()
+    _cabi.check(_cabi.lib().mc_ties_host(
+        n_t, n_src, _cabi.ptr_array([srcs[k][t].data_ptr() for k in range(n_src) for t in range(n_t)]),
+        _cabi.ptr_array([o.data_ptr() for o in outs]), _cabi.i64_array([o.numel() for o in outs]), ties_kth_rank(d, K),
+        TIES_FUNCS[func], _cabi.dtype_code(src_dtype), C.byref(st)), "mc_ties_host")
+    return outs, _stats_dict(st, n_src)
+
+
+def convert_delta_to_ft(delta_weights: Dict[str, List[torch.Tensor]]):
+    """reference ties_merging.py:224-250."""
+    N = -1
+    for key in delta_weights.keys():
+        N = max(N, len(delta_weights[key]))
+    assert N > 0
+    ft_checks = [{} for _ in range(N)]
+    uniques = {}
+    for key in delta_weights.keys():
+        if len(delta_weights[key]) == N:
+            for i in range(N):
+                ft_checks[i][key] = delta_weights[key][i]
+        else:
+            assert len(delta_weights[key]) == 1
+            uniques[key] = delta_weights[key][0]
+    return ft_checks, uniques
+
+
+def do_merging(ft_checks: Sequence[Dict[str, torch.Tensor]], K=20, merge_func: str = "dis-mean", lamda=1):
+    """reference ties_merging.py:182-222 on the GPU: same inputs (a list of state dicts with identical keys), same output
+    (an ordered dict in sorted-key order, tensors shaped like ``ft_checks[0]``; float32 for dis-mean).  The reference
+    flattens each source into one vector; the kernels work on the tensors in place — the trim threshold and the
+    majority sign are statistics over all of them, everything else is elementwise."""
+    if lamda != 1:
+        raise NotImplementedError("the reference only ever calls do_merging with lamda = 1")
+    keys = sorted(ft_checks[0])
+    for check in ft_checks[1:]:
+        if set(check.keys()) != set(keys):
+            raise ValueError("Differing parameter names in models. "
+                             f"The different parameters are {set(keys).symmetric_difference(set(check.keys()))}")
+    func = merge_func.split("-")[-1]
+    if func not in TIES_FUNCS:
+        raise ValueError(f"Merge method {func} is not defined.")
+    outs, _ = ties_merge_host_tensors([[check[k] for k in keys] for check in ft_checks], K=K, func=func)
+    return OrderedDict(zip(keys, outs))
+
+
 # ------------------------------------------------------------------------------------------------ CLI host logic
 def _load_checkpoint_dir(filepath: str):
     """reference :31-36 — adapter_model.bin (fallback mm_projector.bin) + config.json."""
@@ -175,8 +312,9 @@ def merge_checkpoints(filepaths, output_path, strategy="sum", K=20):
     """Drop-in for reference ``merge_checkpoints`` (:28-145): same inputs, same three output files.
 
     Strategies: ``online-merge-[reset-]…`` (key rename + coefficient string into config.json; no arithmetic,
-    exactly as the reference), ``sum`` / ``mean`` (N-source elementwise merge on the GPU).  The ``ties-*`` and
-    ``convert-*`` families are outside this round's scope and raise NotImplementedError."""
+    exactly as the reference), ``sum`` / ``mean`` (N-source elementwise merge on the GPU), ``ties-{sum,mean,max}``
+    (TIES merge on the GPU, ``-K`` = percentage of entries kept), and the ``convert-`` prefix (``same``-strategy
+    checkpoints re-keyed per modality) with its ``convert-drop-*`` variant."""
     configs, weights_to_merge = [], defaultdict(list)
     for filepath in filepaths:
         adapter_weights, modal_config = _load_checkpoint_dir(filepath)
@@ -184,11 +322,39 @@ def merge_checkpoints(filepaths, output_path, strategy="sum", K=20):
         for key in adapter_weights:
             weights_to_merge[key].append(adapter_weights[key])
 
-    if strategy.startswith("convert-") or strategy.startswith("ties-"):
-        raise NotImplementedError(f"strategy family of [{strategy}] is not part of the B200 hot path (SURVEY.md §8(f))")
+    merged_weights = None
+    if strategy.startswith("convert-"):  # :42-71 — 'same'-strategy checkpoints to 'modal+language'
+        strategy = strategy.replace("convert-", "")
+        for config in configs:
+            if "lora_strategy" in config:
+                assert config["lora_strategy"] == "same"
+                config["lora_strategy"] = "modal+language"
+        modal_types = [get_modal_from_config(config) for config in configs]
+        convert_weights_to_merge = defaultdict(list)
+        for key in weights_to_merge:
+            if ".default" in key:
+                for i in range(len(modal_types)):
+                    convert_weights_to_merge[key.replace("default", modal_types[i])].append(copy.deepcopy(weights_to_merge[key][i]))
+        if strategy.startswith("drop-"):
+            ft_checks, uniques = convert_delta_to_ft(weights_to_merge)
+            merged_weights = do_merging(ft_checks, K=K, merge_func=strategy.replace("drop-", "dis-"))
+            merged_weights.update(uniques)
+            for k in convert_weights_to_merge:
+                convert_weights_to_merge[k] = convert_weights_to_merge[k][0]
+            merged_weights.update(convert_weights_to_merge)
+        else:
+            weights_to_merge.update(convert_weights_to_merge)
     print(strategy, strategy.startswith("ties-"))
 
-    if strategy.startswith("online-merge-"):
+    if strategy.startswith("ties-"):  # :75-93
+        assert strategy.replace("ties-", "") in ["sum", "mean", "max"]
+        ft_checks, uniques = convert_delta_to_ft(weights_to_merge)
+        merge_func = strategy.replace("ties-", "dis-")
+        merged_weights = do_merging(ft_checks, K=K, merge_func=merge_func)
+        merged_weights.update(uniques)
+        strategy = f"{merge_func}-{K}"
+        assert sorted(weights_to_merge) == sorted(merged_weights), "the keys should be the same"
+    elif strategy.startswith("online-merge-"):
         merged_weights = {}
         modal_names = [get_modal_from_config(config) for config in configs]
         for key, tensors in weights_to_merge.items():
@@ -202,8 +368,10 @@ def merge_checkpoints(filepaths, output_path, strategy="sum", K=20):
         merged_weights = _elementwise_strategy(weights_to_merge, strategy)
     else:
         print(f"Merge strategy [{strategy}] not implemented, DO NOTHING.")
-        # the reference falls through to torch.save(merged_weights) with the name unbound (:113-115,:139)
-        raise UnboundLocalError("cannot access local variable 'merged_weights' where it is not associated with a value")
+        if merged_weights is None:
+            # the reference falls through to torch.save(merged_weights) with the name unbound (:113-115,:139); after a
+            # `convert-drop-*` it is bound and the run completes
+            raise UnboundLocalError("cannot access local variable 'merged_weights' where it is not associated with a value")
 
     merged_configs = {}
     for config in configs:

@@ -32,6 +32,10 @@ ADAPTER_ORDER = ("audio", "vision", "video", "point")
 # 3 = 256x256 CTA-pair tiles (cta_group::2).  Development switch; both are parity-tested.
 UP_TUNING = int(os.environ.get("MC_LINEAR_UP_TUNING", "0"))
 FUSE_ROPE = os.environ.get("MC_FUSE_ROPE", "1") != "0"  # development switch: 0 = separate mc_rope launch
+# Prefill activations live in MODALITY-MAJOR row order (all text rows of the batch, then all audio rows, ...), so that every
+# 128-row tile of the routed linears holds one adapter group; only attention sees sequence order (the q / k / v epilogues
+# scatter rows back, the attention output is gathered again).  Development switch: 0 = sequence order everywhere.
+MODALITY_MAJOR = os.environ.get("MC_MODALITY_MAJOR", "1") != "0"
 
 
 class MultimodalConfig:
@@ -192,6 +196,10 @@ class _Workspace:
         self.gate = buf(T, I)
         self.logits = buf(T, V)
         self.row_group = torch.zeros(T, dtype=torch.uint8, device=dev)
+        # perm[i] = sequence-order row held at row i of the activation buffers (identity for the decode step / unrouted)
+        self.permute = MODALITY_MAJOR and S > 1
+        self.perm = torch.arange(T, dtype=torch.int32, device=dev) if self.permute else None
+        self.perm_is_identity = True
         # RoPE rides in the q / k projection epilogue when a tile holds whole heads; otherwise mc_rope runs after it
         D = H // cfg.num_attention_heads
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -202,7 +210,59 @@ class _Workspace:
         self.plans: List[Dict[str, LN.LinearPlan]] = []
         for layer in model.layers:
             self.plans.append(self._layer_plans(layer))
-        self.lm_head = LN.LinearPlan([LN.Problem(self.xn, model.lm_head, self.logits)], tuning=1 if T <= LN.TILE_M else 0)
+        self.lm_head = LN.LinearPlan([LN.Problem(self.xn, model.lm_head, self.logits, c_rowmap=self.perm)], tuning=self.up_tuning)
+        # generation only consumes the last position's logits (the reference computes all S' and slices, :720 + HF generate):
+        # a B-row lm_head over the gathered last rows
+        self.last_idx = torch.arange(B, dtype=torch.int32, device=dev) * S + (S - 1)
+        self.xn_last = buf(B, H)
+        self.logits_last = buf(B, V)
+        self.lm_head_last = LN.LinearPlan([LN.Problem(self.xn_last, model.lm_head, self.logits_last)], tuning=1)
+
+    def set_routing(self, modal_id: Optional[torch.Tensor]) -> None:
+        """Routing ids of this batch (sequence order, ``[B, S]`` uint8 or None = all default) -> row permutation, per-row
+        groups in buffer order, per-tile group masks."""
+        if modal_id is None:
+            self.row_group.zero_()
+            if self.permute and not self.perm_is_identity:
+                self.perm.copy_(torch.arange(self.T, dtype=torch.int32, device=self.perm.device))
+                self.perm_is_identity = True
+        elif self.permute:
+            gseq = modal_id.reshape(-1)
+            order = torch.sort(gseq, stable=True).indices  # tiny (T uint8 keys); stable keeps sequence order inside a group
+            self.perm.copy_(order)
+            self.row_group.copy_(gseq[order])
+            self.perm_is_identity = False
+        else:
+            self.row_group.view(self.B, self.S).copy_(modal_id)
+        LN.route_tile_masks(self.row_group, self.mtile, coarsen={3: 4, 4: 2}.get(self.up_tuning & 0xff, 1))
+
+    def last_rows(self) -> torch.Tensor:
+        """int32 [B]: buffer row holding the last position of every sequence."""
+        if self.permute and not self.perm_is_identity:
+            inv = torch.empty_like(self.perm)
+            inv[self.perm.long()] = torch.arange(self.T, dtype=torch.int32, device=self.perm.device)
+            return inv[self.last_idx.long()].contiguous()
+        return self.last_idx
+
+    def load_rows(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+        """dst (buffer order) <- src (sequence order), both [T, width]."""
+        if src.dtype != dst.dtype:
+            src = src.to(dst.dtype)
+        if self.permute and not self.perm_is_identity:
+            LN.gather_rows(src, self.perm, dst)
+        else:
+            dst.copy_(src)
+
+    def sequence_order(self, buf: torch.Tensor) -> torch.Tensor:
+        """A copy of an activation buffer in sequence order ``[B, S, width]`` (hidden-state outputs, tests)."""
+        out = torch.empty_like(buf)
+        if self.permute and not self.perm_is_identity:
+            inv = torch.empty_like(self.perm)
+            inv[self.perm.long()] = torch.arange(self.T, dtype=torch.int32, device=self.perm.device)
+            LN.gather_rows(buf, inv, out)
+        else:
+            out.copy_(buf)
+        return out.view(self.B, self.S, -1)
 
     def _down(self, src, layer: _Layer, names, tbufs):
         return LN.LinearPlan([LN.Problem(src, layer.ad[n].A_all, t, col_scale=layer.ad[n].col_scale, row_group=self.row_group,
@@ -215,9 +275,11 @@ class _Workspace:
         probs = []
         for n, t, o in zip(names, tbufs, outs):
             rope = self.rope if n in ("q_proj", "k_proj") else None
+            # q / k / v leave the modality-major order here: attention needs [B, S, heads, D]
+            rowmap = self.perm if n in ("q_proj", "k_proj", "v_proj") else None
             probs.append(LN.Problem(src, layer.W[n], o, A1=t, B1=layer.ad[n].B_all, mtile_mask=self.mtile,
                                     group_cols=layer.ad[n].group_cols, residual=residual,
-                                    epilogue=LN.EPI_ROPE if rope is not None else epilogue, rope=rope))
+                                    epilogue=LN.EPI_ROPE if rope is not None else epilogue, rope=rope, c_rowmap=rowmap))
         return LN.LinearPlan(probs, tuning=self.up_tuning)
 
     def _layer_plans(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
@@ -454,10 +516,11 @@ class MultimodalLlamaForCausalLM:
             pad = (~attention_mask.bool())[:, None, None, :].to(self.dtype) * neg
             o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
                                                attn_mask=(causal + pad).clamp_min(neg)).transpose(1, 2)
-        ws.attn.view(B, S, nH, D).copy_(o)
+        ws.load_rows(o.reshape(B * S, nH * D), ws.attn)  # back to the buffers' row order for o_proj
 
     def prefill(self, inputs_embeds: torch.Tensor, modal_id: Optional[torch.Tensor], attention_mask=None,
-                use_cache: bool = False, output_hidden_states: bool = False, past_key_values: Optional[KVCache] = None):
+                use_cache: bool = False, output_hidden_states: bool = False, past_key_values: Optional[KVCache] = None,
+                last_logits_only: bool = False):
         """MultimodalLlamaModel.forward + lm_head (:488-619, :720) on (spliced) embeddings; returns (logits, cache, hidden).
         With ``past_key_values`` this is the decode step: ``inputs_embeds`` holds the new token(s) only, every row takes
         the default adapter (``modal_id`` None — the reference drops the modality masks when a cache is present, :436-438)."""
@@ -479,20 +542,16 @@ class MultimodalLlamaForCausalLM:
                     del self._ws[k_]
             self._ws[key] = _Workspace(self, B, S)
         ws = self._ws[key]
-        ws.x.view(B, S, H).copy_(inputs_embeds)
         if ws.pos_value != past:
             ws.pos.fill_(past)
             ws.pos_value = past
-        if modal_id is None:
-            ws.row_group.zero_()
-        else:
-            ws.row_group.view(B, S).copy_(modal_id)
-        LN.route_tile_masks(ws.row_group, ws.mtile)
+        ws.set_routing(modal_id)
+        ws.load_rows(inputs_embeds.reshape(B * S, H), ws.x)
         full = attention_mask is None or bool(attention_mask.all())  # one host sync per call, not per layer
         hidden = []
         for li, (layer, plans) in enumerate(zip(self.layers, ws.plans)):
             if output_hidden_states:
-                hidden.append(ws.x.view(B, S, H).clone())
+                hidden.append(ws.sequence_order(ws.x))
             self._rmsnorm(ws.x, layer.ln1, ws.xn)
             plans["down_qkv"].run()
             plans["up_qkv"].run()
@@ -509,12 +568,17 @@ class MultimodalLlamaForCausalLM:
             cache.length = past + S
         self._rmsnorm(ws.x, self.norm, ws.xn)
         if output_hidden_states:
-            hidden.append(ws.xn.view(B, S, H).clone())
+            hidden.append(ws.sequence_order(ws.xn))
+        if last_logits_only and S > 1:  # generate(): only the last position feeds the sampler
+            LN.gather_rows(ws.xn, ws.last_rows(), ws.xn_last)
+            ws.lm_head_last.run()
+            return ws.logits_last.view(B, 1, -1), cache, (tuple(hidden) if output_hidden_states else None)
         ws.lm_head.run()
         return ws.logits.view(B, S, -1), cache, (tuple(hidden) if output_hidden_states else None)
 
     def forward(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
-                use_cache=None, output_attentions=None, output_hidden_states=None, modal_inputs=None, return_dict=None):
+                use_cache=None, output_attentions=None, output_hidden_states=None, modal_inputs=None, return_dict=None,
+                last_logits_only: bool = False):
         """Reference signature (multimodal_llama.py:676-688).  ``past_key_values`` (a ``KVCache`` returned by an earlier
         call with ``use_cache=True``) selects the decode step: new tokens only, default adapter, no splice (:290-293)."""
         if output_attentions:
@@ -550,7 +614,8 @@ class MultimodalLlamaForCausalLM:
                 modal_id = lut[r.modal_id.long()]
             if self.config.lora_strategy not in ("modal", "modal+language"):  # :703-704
                 modal_id = None
-        logits, kv, hidden = self.prefill(inputs_embeds, modal_id, attention_mask, bool(use_cache), bool(output_hidden_states))
+        logits, kv, hidden = self.prefill(inputs_embeds, modal_id, attention_mask, bool(use_cache), bool(output_hidden_states),
+                                          last_logits_only=last_logits_only and labels is None)
         loss = None
         if labels is not None:  # :723-733
             shift_logits = logits[..., :-1, :].contiguous().view(-1, self.config.vocab_size)
@@ -576,7 +641,7 @@ class MultimodalLlamaForCausalLM:
         B = ids.shape[0]
         if attention_mask is None:
             attention_mask = torch.ones_like(ids)
-        out = self.forward(ids, attention_mask.to(self.device), modal_inputs=modal_inputs, use_cache=True)
+        out = self.forward(ids, attention_mask.to(self.device), modal_inputs=modal_inputs, use_cache=True, last_logits_only=True)
         cache = out.past_key_values
         logits = out.logits[:, -1, :]
         done = torch.zeros(B, dtype=torch.bool, device=self.device)

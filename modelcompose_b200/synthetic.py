@@ -104,6 +104,25 @@ def make_unimodal_checkpoint(modal: str, seed: int, llama: dict = TINY, r: int =
     return sd, cfg
 
 
+def same_strategy_checkpoint(modal: str, seed: int, feat_dim: int, layers: int = 1) -> Tuple[Dict[str, torch.Tensor], dict]:
+    """A ``--lora_strategy same`` checkpoint (reference train_multimodal.py:448-452): one ``default`` adapter on every
+    linear plus the projector — what the ``convert-`` strategies of the merge CLI take (merge_unimodal_modelcompose.py:42-71)."""
+    sd, cfg = make_unimodal_checkpoint(modal, seed=seed, feat_dim=feat_dim, layers=layers, n_prefix=0, n_suffix=0)
+    sd = {k: v for k, v in sd.items() if f".{modal}.weight" not in k}
+    return sd, dict(cfg, lora_strategy="same", num_hidden_layers=layers)
+
+
+def ties_cli_checkpoints():
+    """Inputs of the ties-* / convert-* CLI fixtures (tests/golden/ties.pt): two 1-layer DAMC checkpoints and two
+    1-layer ``same``-strategy checkpoints, (state_dict, config) per modality."""
+    damc = {}
+    for m, s, f in (("vision", 110, 32), ("audio", 111, 24)):
+        sd, cfg = make_unimodal_checkpoint(m, seed=s, feat_dim=f, layers=1)
+        damc[m] = (sd, dict(cfg, num_hidden_layers=1))
+    same = {m: same_strategy_checkpoint(m, s, f) for m, s, f in (("vision", 120, 32), ("audio", 121, 24))}
+    return damc, same
+
+
 def save_checkpoint_dir(path: str, sd: Dict[str, torch.Tensor], cfg: dict) -> None:
     os.makedirs(path, exist_ok=True)
     torch.save(sd, os.path.join(path, "adapter_model.bin"))

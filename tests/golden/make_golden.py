@@ -12,6 +12,8 @@ Fixtures:
   projector.pt   reference build_vision_projector mlp2x_gelu / linear                             A10
   splice.pt      reference prepare_inputs_labels_for_multimodal on 6 cases                        A11-A13
   prefill_c1.pt  reference decoder layers (routed attention + MLP) + thin wrapper → logits        A14-A16
+  ties.pt        reference ties_merging.do_merging on seeded vectors (3 dtypes x 3 functions) and the      §8(f)3
+                 reference CLI with ties-* / convert-* strategies on two 1-layer checkpoints
 """
 from __future__ import annotations
 
@@ -39,6 +41,11 @@ def sd_digest(sd) -> str:
         h.update(k.encode())
         h.update(sd[k].contiguous().view(torch.uint8).numpy().tobytes())
     return h.hexdigest()
+
+
+def tensor_digest(t) -> str:
+    """dtype, shape and sha256 of the raw bytes (bit-exact comparisons without storing the tensor)."""
+    return f"{t.dtype}|{tuple(t.shape)}|" + hashlib.sha256(t.contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()
 
 
 def c1_checkpoints():
@@ -283,14 +290,85 @@ def gen_prefill(merge):
     torch.save(out, os.path.join(HERE, "prefill_c1.pt"))
 
 
+def ties_vectors():
+    """Seeded do_merging inputs: gaussian, tie-heavy integer, negative-majority and exact-cancellation data."""
+    cases = []
+    g = torch.Generator().manual_seed(4242)
+    for i, (dt, n_src, kind, K) in enumerate([
+            (torch.bfloat16, 3, "gauss", 20), (torch.bfloat16, 2, "ints", 50), (torch.bfloat16, 4, "neg", 20),
+            (torch.float16, 3, "gauss", 0.3), (torch.float16, 2, "ints", 20), (torch.float32, 3, "gauss", 20),
+            (torch.float32, 2, "ints", 70), (torch.float32, 3, "neg", 5), (torch.bfloat16, 1, "gauss", 20)]):
+        def gen(shape):
+            if kind == "gauss":
+                return (torch.randn(shape, generator=g) * 0.02).to(dt)
+            if kind == "ints":
+                return torch.randint(-3, 4, shape, generator=g).to(dt)
+            return (torch.randn(shape, generator=g) * 0.02 - 0.03).to(dt)
+        checks = [{"w.b": gen((37, 29)), "w.a": gen((1500,)), "w.c": gen((3,))} for _ in range(n_src)]
+        cases.append({"checks": checks, "K": K, "name": f"{i}-{str(dt)[6:]}-{n_src}src-{kind}"})
+    return cases
+
+
+def gen_ties():
+    import contextlib
+    import io
+    R._install_shells()
+    sys.path.insert(0, os.path.join(R.REFERENCE_ROOT, "scripts", "model_composition"))
+    import ties_merging as T
+    out = {"vectors": [], "cli": {"inputs": {}, "runs": {}}}
+    for case in ties_vectors():
+        res = {}
+        for f in ("dis-sum", "dis-mean", "dis-max"):
+            with contextlib.redirect_stdout(io.StringIO()):
+                res[f] = dict(T.do_merging(case["checks"], K=case["K"], merge_func=f))
+        out["vectors"].append(dict(case, outputs=res))
+    sys.path.pop(0)
+    sys.modules.pop("ties_merging", None)
+    # CLI: ties-* on two 1-layer DAMC checkpoints, convert-* on two 1-layer `same` checkpoints
+    damc, same = syn.ties_cli_checkpoints()
+    # inputs are regenerated from their seeds by the tests; only their digests are stored
+    out["cli"]["inputs"] = {fam: {m: {k: tensor_digest(v) for k, v in ck[m][0].items()} for m in ck}
+                            for fam, ck in (("damc", damc), ("same", same))}
+    runs = [("damc", "ties-mean", 20), ("damc", "ties-sum", 35), ("damc", "ties-max", 20),
+            ("same", "convert-drop-mean", 20), ("same", "convert-ties-sum", 20),
+            ("same", "convert-online-merge-reset-default-vision=0.5,default-audio=0.5", 20), ("same", "convert-sum", 20)]
+    with tempfile.TemporaryDirectory() as tmp:
+        dirs = {}
+        for fam, ck in (("damc", damc), ("same", same)):
+            dirs[fam] = []
+            for m in ("vision", "audio"):
+                d = os.path.join(tmp, f"{fam}_{m}")
+                syn.save_checkpoint_dir(d, ck[m][0], ck[m][1])
+                dirs[fam].append(d)
+        for i, (fam, strategy, K) in enumerate(runs):
+            odir = os.path.join(tmp, f"out-multimodal-{i}")
+            with contextlib.redirect_stdout(io.StringIO()):
+                R.run_merge_cli(dirs[fam] + ["-o", odir, "--strategy", strategy, "-K", str(K)])
+            info = open(os.path.join(odir, "merge_info.txt")).read()
+            info = info.replace(dirs[fam][0], "{IN0}").replace(dirs[fam][1], "{IN1}").replace(odir, "{OUT}")
+            sd = torch.load(os.path.join(odir, "adapter_model.bin"), map_location="cpu")
+            # per-key digests for every run; the full tensors only for two runs (ties outputs are views of one vector: clone)
+            run = {"digest": {k: tensor_digest(v) for k, v in sd.items()},
+                   "config_json_text": open(os.path.join(odir, "config.json")).read(), "merge_info": info}
+            if strategy in ("ties-mean", "convert-drop-mean"):
+                run["state_dict"] = {k: v.clone() for k, v in sd.items()}
+            out["cli"]["runs"][f"{fam}:{strategy}:{K}"] = run
+    torch.save(out, os.path.join(HERE, "ties.pt"))
+    return out
+
+
 def main():
     assert R.reference_available(), "needs /root/reference (authoring container)"
     torch.set_num_threads(1)  # deterministic CPU reductions
+    if "--only-ties" in sys.argv:
+        gen_ties()
+        return
     merge = gen_merge()
     gen_linear(merge)
     gen_projector(merge)
     gen_splice()
     gen_prefill(merge)
+    gen_ties()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

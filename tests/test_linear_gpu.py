@@ -35,7 +35,9 @@ def rnd(shape, dtype, seed, std=1.0):
 @pytest.mark.parametrize("M,N,K,tuning", [(1, 8, 8, 0), (128, 256, 64, 0), (129, 264, 72, 0), (48, 192, 256, 0), (300, 136, 688, 1),
                                           (1000, 1000, 1000, 2), (513, 4096, 384, 0), (960, 688, 256, 0), (77, 32000, 256, 0),
                                           # CTA-pair kernel (cta_group::2)
-                                          (1, 256, 64, 3), (300, 264, 72, 3), (1000, 1000, 1000, 3), (2100, 4096, 512, 3)])
+                                          (1, 256, 64, 3), (300, 264, 72, 3), (1000, 1000, 1000, 3), (2100, 4096, 512, 3),
+                                          # CTA-pair kernel, 256 x 256 pair tiles, overlapped epilogue
+                                          (1, 256, 64, 4), (300, 264, 72, 4), (1000, 1000, 1000, 4), (2100, 4096, 512, 4), (40000, 512, 128, 4)])
 def test_plain_linear(dtype, M, N, K, tuning):
     A, B = rnd((M, K), dtype, 1), rnd((N, K), dtype, 2, std=0.05)
     C = torch.full((M, N), 9.0, dtype=dtype, device="cuda")
@@ -117,7 +119,7 @@ def test_silu_mul_epilogue_matches_separate_ops():
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("D,tuning", [(128, 0), (64, 0), (64, 1), (128, 3)])
+@pytest.mark.parametrize("D,tuning", [(128, 0), (64, 0), (64, 1), (128, 3), (128, 4), (64, 4)])
 def test_rope_epilogue_bit_exact_vs_separate_kernel(dtype, D, tuning):
     """q/k projection with RoPE in the epilogue == projection followed by mc_rope == oracle apply_rope on the rounded projection."""
     Bn, S, nH, K = 3, 50, 4, 192
@@ -141,6 +143,40 @@ def test_rope_epilogue_bit_exact_vs_separate_kernel(dtype, D, tuning):
                             _cabi.dtype_code(dtype), _cabi.current_stream_ptr()), "rope")
     torch.cuda.synchronize()
     assert torch.equal(sep, fused)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("tuning", [0, 1, 3, 4])
+def test_row_map_scatters_output_and_rope_positions(dtype, tuning):
+    """modality-major row order: problem row m lands in row c_rowmap[m] of C, and RoPE takes the position of the mapped row;
+    the result equals the un-permuted launch bit for bit (rows are independent)."""
+    Bn, S, nH, D, K = 3, 50, 2, 128, 192
+    T, H = Bn * S, nH * D
+    g = torch.Generator().manual_seed(31)
+    perm = torch.randperm(T, generator=g).to(torch.int32)
+    x, W = rnd((T, K), dtype, 1).cuda(), rnd((H, K), dtype, 2, 0.1).cuda()
+    cos, sin = (t.cuda() for t in XO.rope_cos_sin(D, 128, dtype))
+    pos = torch.tensor([5], dtype=torch.int32, device="cuda")
+    perm_d = perm.cuda()
+    xp = torch.empty_like(x)
+    LN.gather_rows(x, perm_d, xp)
+    torch.cuda.synchronize()
+    assert torch.equal(xp.cpu(), x.cpu()[perm.long()])
+    for epi, rope in ((LN.EPI_NONE, None), (LN.EPI_ROPE, (cos, sin, pos, S, D))):
+        want = torch.empty((T, H), dtype=dtype, device="cuda")
+        LN.LinearPlan([LN.Problem(x, W, want, epilogue=epi, rope=rope)], tuning=tuning).run()
+        got = torch.full((T, H), 7.0, dtype=dtype, device="cuda")
+        LN.LinearPlan([LN.Problem(xp, W, got, epilogue=epi, rope=rope, c_rowmap=perm_d)], tuning=tuning).run()
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (epi, tuning)
+    # strided gather (a column slice as source and destination)
+    big = rnd((T, 512), dtype, 3).cuda()
+    out = torch.zeros((T, 512), dtype=dtype, device="cuda")
+    LN.gather_rows(big[:, 128:384], perm_d, out[:, 256:512])
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, 256:512].cpu(), big.cpu()[perm.long(), 128:384]) and not out[:, :256].any()
+    with pytest.raises(ValueError):
+        LN.gather_rows(big, perm_d.long(), out)
 
 
 def test_k_extension_unrouted():
@@ -206,6 +242,42 @@ def test_routed_lora_linear_vs_oracle(dtype, T, in_f, out_f, r, runs, down_tunin
     scale = ref.abs().max().item()
     err = (got - ref).abs()
     assert (err <= RTOL[dtype] * ref.abs() + RTOL[dtype] * scale).all(), err.max().item() / scale
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("up_tuning", [3, 4])
+@pytest.mark.parametrize("runs", [True, False])
+def test_routed_up_launch_on_pair_kernels_is_bit_identical(dtype, up_tuning, runs):
+    """The CTA-pair kernels skip LoRA k-blocks on the union of the groups of 256 / 512 rows: the extra blocks only multiply
+    zeros and the k-blocks are accumulated in the same order, so y equals the single-CTA kernel's bit for bit.  Three
+    problems per launch, residual epilogue, ragged M."""
+    T, in_f, out_f, r = 3000, 512, 768, 64
+    modal_names = ["default", "audio", "vision"]
+    dnames = [f"default-{m}" for m in modal_names[1:]]
+    names = modal_names[1:] + dnames
+    A = {n: rnd((r, in_f), dtype, 10 + i, 0.1).cuda() for i, n in enumerate(names)}
+    Bm = {n: rnd((out_f, r), dtype, 30 + i, 0.1).cuda() for i, n in enumerate(names)}
+    scaling = {n: 2.0 for n in names + ["default"]}
+    pk = LN.pack_adapters(A, Bm, scaling, modal_names, dnames, in_f, out_f, dtype, torch.device("cuda"))
+    x, res = rnd((T, in_f), dtype, 7).cuda(), rnd((T, out_f), dtype, 8).cuda()
+    Ws = [rnd((out_f, in_f), dtype, 40 + i, 0.05).cuda() for i in range(3)]
+    rg = make_modal_id(T, 5, len(modal_names), runs).cuda()
+    outs = {}
+    for tuning in (0, up_tuning):
+        # the pair kernels read the rank columns of every group present in 256 / 512 rows: the tile masks are coarsened to
+        # that granularity so the down-projection writes them (T starts as NaN: a column it skipped must never be read)
+        mt = LN.route_tile_masks(rg, coarsen={0: 1, 3: 4, 4: 2}[tuning])
+        Tb = torch.full((T, pk.A_all.shape[0]), float("nan"), dtype=dtype, device="cuda")
+        LN.LinearPlan([LN.Problem(x, pk.A_all, Tb, col_scale=pk.col_scale, row_group=rg, mtile_mask=mt, group_cols=pk.group_cols,
+                                  epilogue=LN.EPI_ROWMASK)], tuning=1).run()
+        ys = [torch.empty((T, out_f), dtype=dtype, device="cuda") for _ in range(3)]
+        LN.LinearPlan([LN.Problem(x, W, y, A1=Tb, B1=pk.B_all, mtile_mask=mt, group_cols=pk.group_cols, residual=res,
+                                  epilogue=LN.EPI_RESIDUAL) for W, y in zip(Ws, ys)], tuning=tuning).run()
+        torch.cuda.synchronize()
+        assert not any(torch.isnan(y).any() for y in ys)
+        outs[tuning] = ys
+    for a, b in zip(outs[0], outs[up_tuning]):
+        assert torch.equal(a, b)
 
 
 def test_route_tile_masks():

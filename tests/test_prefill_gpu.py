@@ -59,10 +59,10 @@ def test_decoder_layers_vs_reference_fixture(golden, key):
     compare(hidden[2], ref["final_norm"], key, "final norm")
     compare(logits, ref["logits"], key, "logits")
     ws = next(iter(model._ws.values()))
-    compare(ws.x.view_as(x), ref["hidden"][1], key, "hidden after layer 1")
+    compare(ws.sequence_order(ws.x), ref["hidden"][1], key, "hidden after layer 1")
     # modal_id=None: every token takes the default adapter (decode-style path, multimodal_llama.py:436-438,:703-704)
     model.prefill(x, None, None)
-    compare(ws.x.view_as(x), ref["hidden_nomask"], key, "hidden (no modality mask)")
+    compare(ws.sequence_order(ws.x), ref["hidden_nomask"], key, "hidden (no modality mask)")
 
 
 def oracle_forward(cfg: dict, base, sd, ids, attn, feats, dtype, n_heads):
@@ -116,6 +116,42 @@ def test_end_to_end_forward_vs_oracle(golden, key):
     assert out.logits.shape == logits.shape
     assert torch.equal(out.modal_id.cpu() == 1, bmasks["audio"]) and torch.equal(out.modal_id.cpu() == 2, bmasks["vision"])
     compare(out.logits, logits, key, "end-to-end logits")
+
+
+def test_modality_major_row_order_is_bit_identical(golden, monkeypatch):
+    """the routed linears run on rows grouped by modality (one adapter group per tile); rows are independent and skipped
+    LoRA blocks only ever multiply zeros, so the logits equal the sequence-order run bit for bit"""
+    g = torch.Generator().manual_seed(19)
+    B = 4
+    ids = syn.make_prompt_ids(B, ["audio", "vision"], 25, 1000, seed=6, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=4)
+    feats = {"audio": torch.randn(B, 30, 48, generator=g).to(torch.bfloat16).cuda(),
+             "vision": torch.randn(B, 41, 64, generator=g).to(torch.bfloat16).cuda()}
+    outs = []
+    for flag in (True, False):
+        monkeypatch.setattr(MD, "MODALITY_MAJOR", flag)
+        model, _, _ = tiny_model(golden, torch.bfloat16)
+        o = model.forward(ids.cuda(), torch.ones_like(ids).cuda(), modal_inputs=feats, output_hidden_states=True)
+        ws = next(iter(model._ws.values()))
+        assert ws.permute == flag and (flag is False or not ws.perm_is_identity)
+        outs.append((o.logits.clone(), [h.clone() for h in o.hidden_states]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
+
+
+@pytest.mark.parametrize("up_tuning", [3, 4])
+def test_pair_kernel_prefill_is_bit_identical(golden, monkeypatch, up_tuning):
+    """the base + LoRA-up launches on the CTA-pair kernels give the same logits as on the single-CTA kernel"""
+    g = torch.Generator().manual_seed(23)
+    B = 5
+    ids = syn.make_prompt_ids(B, ["vision", "audio"], 40, 1000, seed=7, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=4)
+    feats = {"audio": torch.randn(B, 50, 48, generator=g).to(torch.bfloat16).cuda(),
+             "vision": torch.randn(B, 90, 64, generator=g).to(torch.bfloat16).cuda()}
+    outs = []
+    for t in (0, up_tuning):
+        monkeypatch.setattr(MD, "UP_TUNING", t)
+        model, _, _ = tiny_model(golden, torch.bfloat16)
+        outs.append(model.forward(ids.cuda(), torch.ones_like(ids).cuda(), modal_inputs=feats).logits.clone())
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_full_width_layer_vs_oracle():
@@ -194,6 +230,9 @@ def test_decode_step_and_generate(golden, key):
     o2 = model.forward(t1, torch.ones((B, cache.length + 1), dtype=torch.int64, device="cuda"), past_key_values=cache, modal_inputs=feats)
     assert cache.length == o1.logits.shape[1] + 1 and o2.logits.shape == (B, 1, 1000)
     compare(o2.logits[:, 0], full.logits[:, Sp - new, :], key, "decode-step logits vs prefill of the extended sequence")
+    # generate()'s prefill computes the lm_head on the last position only: bit-identical to that row of the full logits
+    o3 = model.forward(ids.cuda(), torch.ones_like(ids).cuda(), modal_inputs=feats, last_logits_only=True)
+    assert o3.logits.shape == (B, 1, 1000) and torch.equal(o3.logits[:, 0], o1.logits[:, -1])
     # sampling path runs and respects eos
     s_ids = model.generate(ids.cuda(), modal_inputs=feats, max_new_tokens=4, do_sample=True, temperature=0.7, top_p=0.9,
                            generator=torch.Generator(device="cuda").manual_seed(0), eos_token_id=int(out_ids[0, ids.shape[1]]))

@@ -1,0 +1,260 @@
+"""GPU parity of the TIES merge (through the C ABI) against oracle/ties_oracle.py, the reference fixtures
+(tests/golden/ties.pt) and — at sizes the oracle cannot reach — size-independent properties.
+
+Bar: bit-exact (raw words, signed zeros and result dtype included)."""
+import copy
+import hashlib
+import json
+import os
+
+import pytest
+import torch
+
+from modelcompose_b200 import merge as M
+from modelcompose_b200 import synthetic as syn
+from oracle import ties_oracle as TO
+
+pytestmark = pytest.mark.gpu
+
+INT_VIEW = {torch.float32: torch.int32, torch.float16: torch.int16, torch.bfloat16: torch.int16}
+SIZES = [1, 7, 16, 17, 4096, 8192, 8193, 40000, (1 << 18) + 5]
+
+
+def tensor_digest(t) -> str:
+    t = t.cpu()
+    return f"{t.dtype}|{tuple(t.shape)}|" + hashlib.sha256(t.contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()
+
+
+def bits_equal(a, b) -> bool:
+    a, b = a.cpu(), b.cpu()
+    return a.dtype == b.dtype and a.shape == b.shape and torch.equal(a.view(INT_VIEW[a.dtype]), b.view(INT_VIEW[b.dtype]))
+
+
+def make_sources(n_src, sizes, dtype, seed, kind):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_src):
+        lst = []
+        for n in sizes:
+            if kind == "gauss":
+                t = torch.randn(n, generator=g) * 0.02
+            elif kind == "ints":      # ties at the threshold, exact cancellations
+                t = torch.randint(-3, 4, (n,), generator=g).float()
+            elif kind == "neg":       # negative majority sign
+                t = torch.randn(n, generator=g) * 0.02 - 0.03
+            else:                     # wide dynamic range incl. subnormals of the 16-bit types
+                t = (torch.randn(n, generator=g) * torch.exp(torch.randn(n, generator=g) * 6.0) * 1e-4).clamp(-6e4, 6e4)  # finite in fp16
+            lst.append(t.to(dtype))
+        out.append(lst)
+    return out
+
+
+def oracle_merge(srcs, K, func):
+    flat = torch.vstack([torch.cat(lst) for lst in srcs])
+    merged, stats = TO.ties_merge_flat(flat, K, func)
+    outs, pos = [], 0
+    for t in srcs[0]:
+        outs.append(merged[pos:pos + t.numel()])
+        pos += t.numel()
+    return outs, stats
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("n_src", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("kind,K", [("gauss", 20), ("ints", 50), ("neg", 20), ("wide", 0.3), ("ints", 5), ("gauss", 99)])
+def test_device_plan_bit_exact(dtype, n_src, kind, K):
+    srcs = make_sources(n_src, SIZES, dtype, seed=17 * n_src + len(kind), kind=kind)
+    dev = [[t.cuda() for t in lst] for lst in srcs]
+    for func in ("sum", "mean", "max"):
+        odt = torch.float32 if func == "mean" else dtype
+        outs = [torch.full((n,), 7.0, dtype=odt, device="cuda") for n in SIZES]
+        plan = M.TiesPlan(dev, outs)
+        plan.run(K, func)
+        st = plan.stats()
+        want, ost = oracle_merge(srcs, K, func)
+        assert st["thresholds"] == [float(x) for x in ost["thresholds"]], (func, st, ost)
+        assert (st["n_pos"], st["n_neg"], st["majority"], st["n_ambiguous"]) == (ost["n_pos"], ost["n_neg"], int(ost["majority"]), ost["ambiguous"])
+        assert st["n_pos"] + st["n_neg"] + st["n_zero"] + st["n_ambiguous"] == sum(SIZES)
+        for t, n in enumerate(SIZES):
+            assert bits_equal(outs[t], want[t]), (func, n, dtype, kind, int((outs[t].cpu().float() != want[t].float()).sum()))
+        passes = 3 if dtype == torch.float32 else 1
+        assert plan.algorithmic_bytes == sum(SIZES) * ((passes + 1) * n_src * srcs[0][0].element_size() + outs[0].element_size())
+        plan.close()
+
+
+def test_fix_pass_only_when_needed():
+    """positive majority: the speculative pass is final; negative majority with cancellations: the listed elements are
+    recomputed (1); MAX with a negative majority or an overflowing list: dense re-merge (2) — all bit-exact vs the oracle"""
+    g = torch.Generator().manual_seed(5)
+    pos = [[(torch.randn(50000, generator=g) * 0.02 + 0.03).to(torch.bfloat16)] for _ in range(3)]
+    out = [torch.empty(50000, dtype=torch.bfloat16, device="cuda")]
+    plan = M.TiesPlan([[t.cuda() for t in lst] for lst in pos], out)
+    plan.run(20, "sum")
+    st = plan.stats()
+    assert st["majority"] == 1 and st["fix_pass_ran"] == 0
+    plan.run(20, "max")
+    assert plan.stats()["fix_pass_ran"] == 0
+    neg = [[torch.randint(-3, 3, (50000,), generator=g).to(torch.bfloat16)] for _ in range(2)]
+    plan2 = M.TiesPlan([[t.cuda() for t in lst] for lst in neg], out)
+    for func, want_fix in (("sum", 1), ("max", 2)):
+        plan2.run(50, func)
+        st = plan2.stats()
+        assert st["majority"] == -1 and st["n_ambiguous"] > 0 and st["fix_pass_ran"] == want_fix
+        assert bits_equal(out[0], oracle_merge(neg, 50, func)[0][0])
+    # more majority-dependent elements than the list holds (2^20): dense fallback
+    n = 9_000_000
+    big = [[torch.randint(-2, 2, (n,), generator=g).to(torch.bfloat16)] for _ in range(2)]
+    out_big = [torch.empty(n, dtype=torch.bfloat16, device="cuda")]
+    plan3 = M.TiesPlan([[t.cuda() for t in lst] for lst in big], out_big)
+    plan3.run(60, "sum")
+    st = plan3.stats()
+    assert st["majority"] == -1 and st["n_ambiguous"] > (1 << 20) and st["fix_pass_ran"] == 2, st
+    assert bits_equal(out_big[0], oracle_merge(big, 60, "sum")[0][0])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_sampled_select_bit_exact(dtype):
+    """>= 1024 chunks: thresholds come from the sampled bracket + one counting pass — same result as the oracle"""
+    g = torch.Generator().manual_seed(21)
+    sizes = [6_000_000, 4096 * 11, 3_300_001]
+    srcs = [[(torch.randn(n, generator=g) * (0.02 + 0.01 * s)).to(dtype) for n in sizes] for s in range(3)]
+    dev = [[t.cuda() for t in lst] for lst in srcs]
+    for func, K in (("sum", 20), ("mean", 3), ("max", 65)):
+        outs = [torch.empty(n, dtype=torch.float32 if func == "mean" else dtype, device="cuda") for n in sizes]
+        plan = M.TiesPlan(dev, outs)
+        plan.run(K, func)
+        st = plan.stats()
+        assert not st["full_select_ran"], st
+        want, ost = oracle_merge(srcs, K, func)
+        assert st["thresholds"] == [float(x) for x in ost["thresholds"]]
+        for o, w in zip(outs, want):
+            assert bits_equal(o, w)
+
+
+def test_bracket_miss_falls_back_to_full_histogram():
+    """data laid out against the sampler (one 512-byte granule per 16 KB chunk is sampled, and exactly those hold zeros):
+    the sample says thr = 0, the rank lies outside the bracket, the full-range passes take over — still exact"""
+    n_chunks, chunk, gran = 1100, 8192, 256
+    g = torch.Generator().manual_seed(22)
+    srcs = []
+    for s in range(2):
+        t = (torch.randn(n_chunks * chunk, generator=g) * 0.02).to(torch.bfloat16)
+        v = t.view(n_chunks, chunk // gran, gran)
+        for c in range(n_chunks):
+            v[c, (c * 7) % 32] = 0
+        srcs.append([t])
+    outs = [torch.empty(n_chunks * chunk, dtype=torch.bfloat16, device="cuda")]
+    plan = M.TiesPlan([[t.cuda() for t in lst] for lst in srcs], outs)
+    plan.run(20, "sum")
+    st = plan.stats()
+    assert st["full_select_ran"], st
+    want, ost = oracle_merge(srcs, 20, "sum")
+    assert st["thresholds"] == [float(x) for x in ost["thresholds"]]
+    assert bits_equal(outs[0], want[0])
+
+
+def test_unaligned_and_fused_tensors():
+    """views at odd offsets take the element path; back-to-back views fuse into one segment — same result either way"""
+    g = torch.Generator().manual_seed(8)
+    n_src, sizes = 3, [5000, 12288, 3, 8192 * 3]
+    slabs = [(torch.randn(sum(sizes) + 1, generator=g) * 0.02).to(torch.bfloat16) for _ in range(n_src)]
+    for shift in (0, 1):
+        srcs, pos = [[] for _ in range(n_src)], shift
+        for n in sizes:
+            for s in range(n_src):
+                srcs[s].append(slabs[s][pos:pos + n])
+            pos += n
+        dslabs = [sl.cuda() for sl in slabs]
+        dev, pos = [[] for _ in range(n_src)], shift
+        for n in sizes:
+            for s in range(n_src):
+                dev[s].append(dslabs[s][pos:pos + n])
+            pos += n
+        outs = [torch.empty(n, dtype=torch.float32, device="cuda") for n in sizes]
+        plan = M.TiesPlan(dev, outs)
+        plan.run(20, "mean")
+        plan.stats()
+        want, _ = oracle_merge([[t.clone() for t in lst] for lst in srcs], 20, "mean")
+        for o, w in zip(outs, want):
+            assert bits_equal(o, w)
+
+
+def test_do_merging_matches_reference_fixture(golden):
+    g = golden("ties.pt")
+    for case in g["vectors"]:
+        for f, want in case["outputs"].items():
+            got = M.do_merging(case["checks"], K=case["K"], merge_func=f)
+            assert list(got) == list(want), case["name"]
+            for k in got:
+                assert tensor_digest(got[k]) == tensor_digest(want[k]), (case["name"], f, k)
+
+
+def test_cli_strategies_match_reference_fixture(golden, tmp_path):
+    g = golden("ties.pt")
+    damc, same = syn.ties_cli_checkpoints()
+    dirs = {}
+    for fam, ck in (("damc", damc), ("same", same)):
+        dirs[fam] = []
+        for m in ("vision", "audio"):
+            d = str(tmp_path / f"{fam}_{m}")
+            syn.save_checkpoint_dir(d, ck[m][0], copy.deepcopy(ck[m][1]))
+            dirs[fam].append(d)
+    for i, (name, run) in enumerate(g["cli"]["runs"].items()):
+        fam, strategy, K = name.split(":")
+        out = str(tmp_path / f"out-multimodal-{i}")
+        M.main(dirs[fam] + ["-o", out, "--strategy", strategy, "-K", K])
+        sd = torch.load(os.path.join(out, "adapter_model.bin"), map_location="cpu")
+        assert list(sd) == list(run["digest"]), name
+        for k in sd:
+            assert tensor_digest(sd[k]) == run["digest"][k], (name, k)
+        assert open(os.path.join(out, "config.json")).read() == run["config_json_text"], name
+        info = open(os.path.join(out, "merge_info.txt")).read()
+        assert info.replace(dirs[fam][0], "{IN0}").replace(dirs[fam][1], "{IN1}").replace(out, "{OUT}") == run["merge_info"], name
+
+
+def test_error_behaviour():
+    x = [[torch.zeros(10, dtype=torch.bfloat16, device="cuda")] for _ in range(2)]
+    with pytest.raises(Exception, match="float32"):
+        M.TiesPlan(x, [torch.zeros(10, dtype=torch.bfloat16, device="cuda")]).run(20, "mean")
+    with pytest.raises(RuntimeError, match="kthvalue"):
+        M.TiesPlan(x, [torch.zeros(10, dtype=torch.bfloat16, device="cuda")]).run(100, "sum")
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        M.TiesPlan([[torch.zeros(10, dtype=torch.bfloat16)]], [torch.zeros(10, dtype=torch.bfloat16, device="cuda")])
+    with pytest.raises(ValueError, match="Differing parameter names"):
+        M.do_merging([{"a": torch.zeros(3)}, {"b": torch.zeros(3)}])
+
+
+@pytest.mark.parametrize("func", ["sum", "mean", "max"])
+def test_full_size_properties(func):
+    """3 sources x 160 M bf16 elements (the shared `default` adapters of three vicuna-7B DAMC checkpoints): exact rank of
+    the thresholds, census consistency, and outputs re-derived with torch ops on the device from the kernel's own thresholds."""
+    n_src, sizes = 3, [4096 * 128, 11008 * 128, 4096 * 128 * 150, 11008 * 128 * 57]   # ~ 160 M elements
+    d = sum(sizes)
+    g = torch.Generator(device="cuda").manual_seed(123)
+    dev = [[(torch.randn(n, generator=g, device="cuda") * 0.02).to(torch.bfloat16) for n in sizes] for _ in range(n_src)]
+    odt = torch.float32 if func == "mean" else torch.bfloat16
+    outs = [torch.empty(n, dtype=odt, device="cuda") for n in sizes]
+    plan = M.TiesPlan(dev, outs)
+    plan.run(20, func)
+    st = plan.stats()
+    k = M.ties_kth_rank(d, 20)
+    for s in range(n_src):
+        thr = st["thresholds"][s]
+        below = sum(int((t.abs().float() < thr).sum()) for t in dev[s])
+        at_or_below = sum(int((t.abs().float() <= thr).sum()) for t in dev[s])
+        assert below < k <= at_or_below, (s, thr, below, at_or_below, k)      # thr IS the k-th smallest magnitude
+    assert st["n_pos"] + st["n_neg"] + st["n_zero"] + st["n_ambiguous"] == d
+    assert st["majority"] == (st["n_pos"] > st["n_neg"]) - (st["n_pos"] < st["n_neg"])
+    # element-wise re-derivation on the largest tensor (torch ops on the device, fp32 arithmetic as the reference's CPU ops)
+    t = 2
+    m = [dev[s][t].float() * (dev[s][t].abs().float() >= st["thresholds"][s]).float() for s in range(n_src)]
+    total = ((m[0] + m[1]) + m[2]).to(torch.bfloat16).float()
+    sg = torch.sign(total)
+    sg = torch.where(sg == 0, torch.full_like(sg, float(st["majority"])), sg)
+    sel = [x * torch.where(sg > 0, x > 0, x < 0).float() for x in m]
+    if func == "max":
+        want = (torch.maximum(torch.maximum(sel[0].abs(), sel[1].abs()), sel[2].abs()).to(torch.bfloat16).float() * sg).to(torch.bfloat16)
+    else:
+        tot = (((torch.zeros_like(sel[0]) + sel[0]) + sel[1]) + sel[2]).to(torch.bfloat16)  # +0 start, as torch's reduction
+        want = tot if func == "sum" else tot.float() / torch.clamp(sum((x != 0).float() for x in sel), min=1)
+    assert bits_equal(outs[t], want)
