@@ -143,7 +143,8 @@ typedef struct mc_ties_stats {
 typedef struct mc_ties_plan mc_ties_plan_t;
 
 /* Pointer / chunk tables as mc_merge_plan_create (src[s * n_tensors + t], dst[t], numel[t]); dst_dtype must be MC_F32
- * when the plan will run MC_TIES_MEAN and src_dtype otherwise (checked at run).  Synchronous. */
+ * when the plan will run MC_TIES_MEAN and src_dtype otherwise (checked at run).  dst may be NULL for a statistics-only
+ * plan (mc_ties_plan_metrics).  Synchronous. */
 MC_API int mc_ties_plan_create(mc_ties_plan_t** plan, int n_tensors, int n_src, const void* const* src, void* const* dst,
                         const int64_t* numel, int src_dtype, int dst_dtype);
 /* Enqueues the whole TIES merge.  kth = 1-based rank (ascending magnitude) of the smallest kept element among the
@@ -155,6 +156,20 @@ MC_API int mc_ties_plan_stats(const mc_ties_plan_t* plan, mc_ties_stats_t* out, 
 MC_API int64_t mc_ties_plan_bytes(const mc_ties_plan_t* plan);
 MC_API int64_t mc_ties_plan_elements(const mc_ties_plan_t* plan);
 MC_API int mc_ties_plan_destroy(mc_ties_plan_t* plan);
+/* Parameter-interference metrics of the reference's scripts/model_composition/calculate_metrics.py:26-37,53-64 over the
+ * sources of a plan (dst may be NULL at plan creation for this use): L2 distance and cosine distance (1 - cos) between
+ * the first two sources, and the soft sign dissimilarity 1 - mean(|sum_s x_s| / sum_s |x_s|) over the elements where the
+ * denominator is non-zero, before (ssd) and after (tssd) the top-k magnitude trim of rank `kth` (as mc_ties_plan_run).
+ * Per-element arithmetic is fp32 as the reference's; the reductions over elements accumulate in fp64.  Synchronises. */
+typedef struct mc_interference_metrics {
+  double l2, cosine, ssd, tssd;
+  int64_t ssd_elements, tssd_elements; /* elements that entered the two means */
+  float threshold[MC_MERGE_MAX_SRC];
+} mc_interference_metrics_t;
+MC_API int mc_ties_plan_metrics(const mc_ties_plan_t* plan, int64_t kth, mc_interference_metrics_t* out, mc_stream_t stream);
+/* Host-buffer form: copies the sources to the device, measures, frees. */
+MC_API int mc_interference_host(int n_tensors, int n_src, const void* const* h_src, const int64_t* numel, int64_t kth,
+                         int src_dtype, mc_interference_metrics_t* out);
 /* Host-buffer form used by the merge CLI: copies every source to the device (all of them must be resident for the two
  * global statistics), runs the plan and copies the result back; returns when h_dst is complete.  stats may be NULL. */
 MC_API int mc_ties_host(int n_tensors, int n_src, const void* const* h_src, void* const* h_dst, const int64_t* numel,

@@ -40,6 +40,8 @@ SIGNATURES = {
     "mc_ties_plan_bytes": (_i64, [_vp]),
     "mc_ties_plan_elements": (_i64, [_vp]),
     "mc_ties_plan_destroy": (_i, [_vp]),
+    "mc_ties_plan_metrics": (_i, [_vp, _i64, _vp, _vp]),
+    "mc_interference_host": (_i, [_i, _i, _pp, C.POINTER(_i64), _i64, _i, _vp]),
     "mc_ties_host": (_i, [_i, _i, _pp, _pp, C.POINTER(_i64), _i64, _i, _i, _vp]),
     # structs are passed as void* (modelcompose_b200.splice defines the ctypes.Structure mirrors)
     "mc_splice_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp, _i]),
@@ -64,6 +66,12 @@ class TiesStats(C.Structure):
     """mirror of mc_ties_stats_t"""
     _fields_ = [("threshold", C.c_float * MC_MERGE_MAX_SRC), ("n_pos", C.c_int64), ("n_neg", C.c_int64), ("n_zero", C.c_int64),
                 ("n_ambiguous", C.c_int64), ("majority", C.c_int32), ("full_select_ran", C.c_int32), ("fix_pass_ran", C.c_int32)]
+
+
+class InterferenceMetrics(C.Structure):
+    """mirror of mc_interference_metrics_t"""
+    _fields_ = [("l2", C.c_double), ("cosine", C.c_double), ("ssd", C.c_double), ("tssd", C.c_double),
+                ("ssd_elements", C.c_int64), ("tssd_elements", C.c_int64), ("threshold", C.c_float * MC_MERGE_MAX_SRC)]
 
 
 class McError(RuntimeError):

@@ -11,6 +11,7 @@
 //            re-merge (list overflow, or MAX with a negative majority); the unused kernels exit at once
 // Algorithmic bytes per element = (passes + 1) * n_src * sizeof(src) + sizeof(dst)  (bf16, 3 sources, sum: 14 B).
 #include <algorithm>
+#include <cmath>
 #include <vector>
 
 #include "mc_ties_kernels.cuh"
@@ -438,6 +439,8 @@ struct mc_ties_plan {
   TiesState* d_state;
   unsigned long long* d_hist;  // n_src x 2^15 bins
   unsigned long long* d_fix;   // kTiesFixCapacity entries
+  TiesMetricSums* d_metrics;
+  bool has_dst;                // false: statistics-only plan (interference metrics), mc_ties_plan_run refuses
 };
 
 static const int kHistBinsMax = 1 << 15;
@@ -450,9 +453,10 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
   MC_REQUIRE(n_src >= 1 && n_src <= MC_MERGE_MAX_SRC, "n_src %d outside [1, %d]", n_src, MC_MERGE_MAX_SRC);
   MC_REQUIRE(dtype_valid(src_dtype) && dtype_valid(dst_dtype), "bad dtype");
   MC_REQUIRE(dst_dtype == src_dtype || dst_dtype == MC_F32, "dst dtype must be the source dtype (sum / max) or float32 (mean)");
-  MC_REQUIRE(n_tensors == 0 || (src && dst && numel), "NULL table");
+  MC_REQUIRE(n_tensors == 0 || (src && numel), "NULL table");
   const size_t ss = dtype_size(src_dtype), ds = dtype_size(dst_dtype);
   const long long CHUNK = kTiesChunkBytes / (long long)ss;
+  const bool has_dst = dst != nullptr;  // dst == NULL: a statistics-only plan for mc_ties_plan_metrics
   std::vector<MergeSeg> segs;
   for (int t = 0; t < n_tensors; ++t) {
     MC_REQUIRE(numel[t] >= 0, "numel[%d] < 0", t);
@@ -462,13 +466,13 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
       s.src[k] = src[(size_t)k * n_tensors + t];
       MC_REQUIRE(s.src[k] != nullptr, "src[%d][%d] is NULL", k, t);
     }
-    s.dst = dst[t];
-    MC_REQUIRE(s.dst != nullptr, "dst[%d] is NULL", t);
+    s.dst = has_dst ? dst[t] : nullptr;
+    MC_REQUIRE(!has_dst || s.dst != nullptr, "dst[%d] is NULL", t);
     s.numel = numel[t];
     bool fused = false;
     if (!segs.empty()) {
       MergeSeg& p = segs.back();
-      bool contig = (const char*)p.dst + p.numel * ds == (const char*)s.dst && p.numel + s.numel < (1LL << 40);
+      bool contig = (!has_dst || (const char*)p.dst + p.numel * ds == (const char*)s.dst) && p.numel + s.numel < (1LL << 40);
       for (int k = 0; k < n_src && contig; ++k) contig = (const char*)p.src[k] + p.numel * ss == (const char*)s.src[k];
       if (contig) {
         p.numel += s.numel;
@@ -502,12 +506,15 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
   p->d_state = nullptr;
   p->d_hist = nullptr;
   p->d_fix = nullptr;
+  p->d_metrics = nullptr;
+  p->has_dst = has_dst;
   p->sms = sm_count();
   cudaError_t e = cudaGetDevice(&p->device);
   if (e == cudaSuccess && p->sms <= 0) e = cudaErrorNoDevice;
   if (e == cudaSuccess) e = cudaMalloc(&p->d_state, sizeof(TiesState));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_hist, (size_t)n_src * kHistBinsMax * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_fix, (size_t)kTiesFixCapacity * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_metrics, sizeof(TiesMetricSums));
   if (e == cudaSuccess) e = cudaMemset(p->d_hist, 0, (size_t)n_src * kHistBinsMax * sizeof(unsigned long long));
   if (e == cudaSuccess && p->nchunks > 0) {
     e = cudaMalloc(&p->d_segs, segs.size() * sizeof(MergeSeg));
@@ -521,6 +528,7 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
     cudaFree(p->d_state);
     cudaFree(p->d_hist);
     cudaFree(p->d_fix);
+    cudaFree(p->d_metrics);
     delete p;
     return fail(MC_ERR_CUDA, "ties plan setup failed: %s", cudaGetErrorString(e));
   }
@@ -530,16 +538,8 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
 
 static int select_passes(int src_dtype) { return src_dtype == MC_F32 ? 3 : 1; }
 
-extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, mc_stream_t stream) {
-  MC_REQUIRE(p != nullptr, "plan is NULL");
-  MC_REQUIRE(func == MC_TIES_SUM || func == MC_TIES_MEAN || func == MC_TIES_MAX, "bad merge function %d", func);
-  MC_REQUIRE(p->dst_dtype == (func == MC_TIES_MEAN ? MC_F32 : p->src_dtype),
-             "dst dtype must be float32 for MEAN and the source dtype for SUM / MAX");
-  MC_REQUIRE(p->total_elems > 0, "nothing to merge");
-  MC_REQUIRE(kth >= 1 && kth <= p->total_elems, "kth %lld outside [1, %lld]", (long long)kth, p->total_elems);
-  const TiesKernels fn = pick_ties(p->src_dtype, p->n_src, func);
-  if (!fn.merge) return fail(MC_ERR_UNSUPPORTED, "ties kernel for dtype %d not built", p->src_dtype);
-  cudaStream_t s = (cudaStream_t)stream;
+// Enqueues the exact k-th-magnitude select of every source (thresholds land in the device state).
+static int enqueue_select(const mc_ties_plan_t* p, int64_t kth, cudaStream_t s) {
   // 16-bit dtypes with enough data: sampled bracket + one counting pass; otherwise (and on a bracket miss, decided on
   // the device) the full-range radix select, most significant digit first.  Unneeded kernels exit at once.
   const bool sampled = p->src_dtype != MC_F32 && p->nchunks >= 1024;
@@ -590,6 +590,23 @@ extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, 
     }
     ties_select_kernel<<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, passes[i].bits, i == n_pass - 1, key_kind);
   }
+  MC_CUDA_OK(cudaGetLastError());
+  return MC_OK;
+}
+
+extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, mc_stream_t stream) {
+  MC_REQUIRE(p != nullptr, "plan is NULL");
+  MC_REQUIRE(p->has_dst, "the plan was created without outputs (statistics only)");
+  MC_REQUIRE(func == MC_TIES_SUM || func == MC_TIES_MEAN || func == MC_TIES_MAX, "bad merge function %d", func);
+  MC_REQUIRE(p->dst_dtype == (func == MC_TIES_MEAN ? MC_F32 : p->src_dtype),
+             "dst dtype must be float32 for MEAN and the source dtype for SUM / MAX");
+  MC_REQUIRE(p->total_elems > 0, "nothing to merge");
+  MC_REQUIRE(kth >= 1 && kth <= p->total_elems, "kth %lld outside [1, %lld]", (long long)kth, p->total_elems);
+  const TiesKernels fn = pick_ties(p->src_dtype, p->n_src, func);
+  if (!fn.merge) return fail(MC_ERR_UNSUPPORTED, "ties kernel for dtype %d not built", p->src_dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rc = enqueue_select(p, kth, s);
+  if (rc != MC_OK) return rc;
   fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 0);
   ties_finalize_kernel<<<1, 1, 0, s>>>(p->d_state, func, (unsigned long long)p->total_elems);
   fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix);
@@ -615,6 +632,80 @@ extern "C" int mc_ties_plan_stats(const mc_ties_plan_t* p, mc_ties_stats_t* out,
   return MC_OK;
 }
 
+extern "C" int mc_ties_plan_metrics(const mc_ties_plan_t* p, int64_t kth, mc_interference_metrics_t* out, mc_stream_t stream) {
+  MC_REQUIRE(p != nullptr && out != nullptr, "NULL argument");
+  MC_REQUIRE(p->n_src >= 2, "interference metrics compare the first two sources: need n_src >= 2");
+  MC_REQUIRE(p->total_elems > 0, "nothing to measure");
+  MC_REQUIRE(kth >= 1 && kth <= p->total_elems, "kth %lld outside [1, %lld]", (long long)kth, p->total_elems);
+  ties_metrics_fn_t fn = p->src_dtype == MC_BF16 ? pick_ties_metrics_bf16(p->n_src)
+                         : p->src_dtype == MC_F16 ? pick_ties_metrics_f16(p->n_src) : pick_ties_metrics_f32(p->n_src);
+  if (!fn) return fail(MC_ERR_UNSUPPORTED, "metrics kernel for dtype %d not built", p->src_dtype);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rc = enqueue_select(p, kth, s);
+  if (rc != MC_OK) return rc;
+  MC_CUDA_OK(cudaMemsetAsync(p->d_metrics, 0, sizeof(TiesMetricSums), s));
+  fn<<<std::min(p->nchunks, p->sms * 8), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_metrics);
+  MC_CUDA_OK(cudaGetLastError());
+  TiesMetricSums h;
+  TiesState hs;
+  MC_CUDA_OK(cudaStreamSynchronize(s));
+  MC_CUDA_OK(cudaMemcpy(&h, p->d_metrics, sizeof(h), cudaMemcpyDeviceToHost));
+  MC_CUDA_OK(cudaMemcpy(&hs, p->d_state, sizeof(hs), cudaMemcpyDeviceToHost));
+  // reference calculate_metrics.py:26-37 — L2 = sqrt(sum (x0 - x1)^2); Cosine = 1 - x0.x1 / max(|x0| |x1|, 1e-8);
+  // SSD = 1 - mean over elements with sum |x| != 0 of |sum x| / sum |x| (NaN when there is none, as torch's empty mean)
+  out->l2 = sqrt(h.d2);
+  out->cosine = 1.0 - h.xy / std::max(sqrt(h.xx) * sqrt(h.yy), 1e-8);
+  out->ssd = h.ssd_n ? 1.0 - h.ssd / (double)h.ssd_n : nan("");
+  out->tssd = h.tssd_n ? 1.0 - h.tssd / (double)h.tssd_n : nan("");
+  out->ssd_elements = (int64_t)h.ssd_n;
+  out->tssd_elements = (int64_t)h.tssd_n;
+  for (int i = 0; i < MC_MERGE_MAX_SRC; ++i) out->threshold[i] = hs.thr[i];
+  return MC_OK;
+}
+
+extern "C" int mc_interference_host(int n_tensors, int n_src, const void* const* h_src, const int64_t* numel, int64_t kth,
+                                    int src_dtype, mc_interference_metrics_t* out) {
+  MC_REQUIRE(n_tensors >= 1 && h_src && numel && out, "NULL / empty table");
+  MC_REQUIRE(n_src >= 2 && n_src <= MC_MERGE_MAX_SRC, "n_src %d outside [2, %d]", n_src, MC_MERGE_MAX_SRC);
+  MC_REQUIRE(dtype_valid(src_dtype), "bad dtype");
+  const size_t ss = dtype_size(src_dtype);
+  std::vector<long long> off(n_tensors);
+  long long total = 0;
+  for (int t = 0; t < n_tensors; ++t) {
+    MC_REQUIRE(numel[t] >= 0, "numel[%d] < 0", t);
+    off[t] = total;
+    total = (total + numel[t] + 15) & ~15LL;
+  }
+  MC_REQUIRE(total > 0, "nothing to measure");
+  std::vector<char*> d_src(n_src, nullptr);
+  mc_ties_plan_t* plan = nullptr;
+  cudaStream_t s = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  for (int k = 0; k < n_src && e == cudaSuccess; ++k) e = cudaMalloc(&d_src[k], (size_t)total * ss);
+  for (int k = 0; k < n_src && e == cudaSuccess; ++k)
+    for (int t = 0; t < n_tensors && e == cudaSuccess; ++t)
+      if (numel[t])
+        e = cudaMemcpyAsync(d_src[k] + off[t] * ss, h_src[(size_t)k * n_tensors + t], (size_t)numel[t] * ss, cudaMemcpyHostToDevice, s);
+  int rc = MC_OK;
+  if (e == cudaSuccess) {
+    std::vector<const void*> src_tab((size_t)n_src * n_tensors);
+    for (int t = 0; t < n_tensors; ++t)
+      for (int k = 0; k < n_src; ++k) src_tab[(size_t)k * n_tensors + t] = d_src[k] + off[t] * ss;
+    rc = mc_ties_plan_create(&plan, n_tensors, n_src, src_tab.data(), nullptr, numel, src_dtype, src_dtype);
+    if (rc == MC_OK) rc = mc_ties_plan_metrics(plan, kth, out, s);
+  }
+  if (s) {
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
+  }
+  if (plan) mc_ties_plan_destroy(plan);
+  for (int k = 0; k < n_src; ++k) cudaFree(d_src[k]);
+  if (s) cudaStreamDestroy(s);
+  if (rc != MC_OK) return rc;
+  if (e != cudaSuccess) return fail(MC_ERR_CUDA, "mc_interference_host failed: %s", cudaGetErrorString(e));
+  return MC_OK;
+}
+
 extern "C" int64_t mc_ties_plan_bytes(const mc_ties_plan_t* p) {
   if (!p) return 0;
   const int64_t reads = (int64_t)(select_passes(p->src_dtype) + 1) * p->n_src * (int64_t)dtype_size(p->src_dtype);
@@ -630,6 +721,7 @@ extern "C" int mc_ties_plan_destroy(mc_ties_plan_t* p) {
   cudaFree(p->d_state);
   cudaFree(p->d_hist);
   cudaFree(p->d_fix);
+  cudaFree(p->d_metrics);
   delete p;
   return MC_OK;
 }

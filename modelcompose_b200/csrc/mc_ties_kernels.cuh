@@ -242,4 +242,142 @@ TiesKernels pick_ties_bf16(int n_src, int func);
 TiesKernels pick_ties_f16(int n_src, int func);
 TiesKernels pick_ties_f32(int n_src, int func);
 
+// ---- interference metrics (reference calculate_metrics.py:26-37,53-64) ---------------------------------------------
+// L2 and cosine distance between the first two sources, soft sign dissimilarity over all sources before and after the
+// top-k trim.  Per-element arithmetic is fp32 exactly as the reference's torch ops (after its .float() on load); the
+// reductions over elements accumulate in fp64 (the reference's fp32 tree sums agree to ~1e-6 relative).
+struct TiesMetricSums {
+  double d2, xy, xx, yy, ssd, tssd;
+  unsigned long long ssd_n, tssd_n;
+};
+
+template <int NSRC, typename S>
+__device__ __forceinline__ void metrics_one(const S (&in)[NSRC], const float (&thr)[NSRC], float (&acc)[6], unsigned int (&cnt)[2]) {
+  float sum = 0.0f, asum = 0.0f, tsum = 0.0f, tasum = 0.0f, x0 = 0.0f, x1 = 0.0f;
+#pragma unroll
+  for (int s = 0; s < NSRC; ++s) {
+    const float x = to_f32<S>(in[s]);
+    const float m = fabsf(x) >= thr[s] ? x : 0.0f;
+    sum = __fadd_rn(sum, x);
+    asum = __fadd_rn(asum, fabsf(x));
+    tsum = __fadd_rn(tsum, m);
+    tasum = __fadd_rn(tasum, fabsf(m));
+    if (s == 0) x0 = x;
+    if (s == 1) x1 = x;
+  }
+  if (NSRC >= 2) {
+    const float d = __fsub_rn(x0, x1);
+    acc[0] += __fmul_rn(d, d);
+    acc[1] += __fmul_rn(x0, x1);
+    acc[2] += __fmul_rn(x0, x0);
+    acc[3] += __fmul_rn(x1, x1);
+  }
+  if (asum != 0.0f) {
+    acc[4] += fabsf(__fdiv_rn(sum, asum));
+    cnt[0] += 1u;
+  }
+  if (tasum != 0.0f) {
+    acc[5] += fabsf(__fdiv_rn(tsum, tasum));
+    cnt[1] += 1u;
+  }
+}
+
+template <int NSRC, typename S>
+__global__ void __launch_bounds__(kTiesMergeThreads)
+ties_metrics_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, const TiesState* __restrict__ st,
+                    TiesMetricSums* __restrict__ out) {
+  constexpr int E = 16 / sizeof(S);
+  constexpr int VPT = 2;
+  constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
+  float thr[NSRC];
+#pragma unroll
+  for (int s = 0; s < NSRC; ++s) thr[s] = st->thr[s];
+  double tot[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  unsigned long long n[2] = {0ull, 0ull};
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const MergeChunk ch = chunks[c];
+    const MergeSeg* sg = segs + ch.seg;
+    const long long base = (long long)ch.idx * CHUNK;
+    const long long rem = sg->numel - base;
+    float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};  // fp32 partials over this thread's <= 16 elements of the chunk
+    unsigned int cnt[2] = {0u, 0u};
+    if (sg->aligned && rem >= CHUNK) {
+      Vec<16> v[NSRC][VPT];
+#pragma unroll
+      for (int s = 0; s < NSRC; ++s) {
+        const Vec<16>* p = reinterpret_cast<const Vec<16>*>(reinterpret_cast<const S*>(sg->src[s]) + base) + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) v[s][j] = ld_stream(p + j * kTiesMergeThreads);
+      }
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          S in[NSRC];
+#pragma unroll
+          for (int s = 0; s < NSRC; ++s) in[s] = reinterpret_cast<const S*>(&v[s][j])[e];
+          metrics_one<NSRC, S>(in, thr, acc, cnt);
+        }
+      }
+    } else {
+      const long long m = rem < CHUNK ? rem : CHUNK;
+      for (long long i = threadIdx.x; i < m; i += kTiesMergeThreads) {
+        S in[NSRC];
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s) in[s] = reinterpret_cast<const S*>(sg->src[s])[base + i];
+        metrics_one<NSRC, S>(in, thr, acc, cnt);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tot[k] += (double)acc[k];
+    n[0] += cnt[0];
+    n[1] += cnt[1];
+  }
+  __shared__ double s_tot[6];
+  __shared__ unsigned long long s_n[2];
+  if (threadIdx.x < 6) s_tot[threadIdx.x] = 0.0;
+  if (threadIdx.x < 2) s_n[threadIdx.x] = 0ull;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double x = tot[k];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_tot[k], x);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    unsigned long long x = n[k];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_n[k], x);
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double* dst = threadIdx.x == 0 ? &out->d2 : threadIdx.x == 1 ? &out->xy : threadIdx.x == 2 ? &out->xx : threadIdx.x == 3 ? &out->yy
+                  : threadIdx.x == 4 ? &out->ssd : &out->tssd;
+    atomicAdd(dst, s_tot[threadIdx.x]);
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 34) atomicAdd(threadIdx.x == 32 ? &out->ssd_n : &out->tssd_n, s_n[threadIdx.x - 32]);
+}
+
+typedef void (*ties_metrics_fn_t)(const MergeSeg*, const MergeChunk*, int, const TiesState*, TiesMetricSums*);
+
+template <typename S>
+static ties_metrics_fn_t ties_pick_metrics(int n_src) {
+  switch (n_src) {
+    case 2: return ties_metrics_kernel<2, S>;
+    case 3: return ties_metrics_kernel<3, S>;
+    case 4: return ties_metrics_kernel<4, S>;
+    case 5: return ties_metrics_kernel<5, S>;
+    case 6: return ties_metrics_kernel<6, S>;
+    case 7: return ties_metrics_kernel<7, S>;
+    case 8: return ties_metrics_kernel<8, S>;
+  }
+  return nullptr;
+}
+ties_metrics_fn_t pick_ties_metrics_bf16(int n_src);
+ties_metrics_fn_t pick_ties_metrics_f16(int n_src);
+ties_metrics_fn_t pick_ties_metrics_f32(int n_src);
+
 }  // namespace mc

@@ -165,32 +165,43 @@ def _stats_dict(st: "_cabi.TiesStats", n_src: int) -> dict:
             "full_select_ran": bool(st.full_select_ran), "fix_pass_ran": int(st.fix_pass_ran)}  # 0 none, 1 sparse fix-up, 2 dense re-merge
 
 
+def _metrics_dict(m: "_cabi.InterferenceMetrics", n_src: int) -> dict:
+    return {"L2": float(m.l2), "Cosine": float(m.cosine), "SSD": float(m.ssd), "TSSD": float(m.tssd),
+            "ssd_elements": int(m.ssd_elements), "tssd_elements": int(m.tssd_elements),
+            "thresholds": [float(m.threshold[i]) for i in range(n_src)]}
+
+
 class TiesPlan:
     """TIES merge (trim / elect sign / disjoint merge, reference ties_merging.py:161-179) of N same-shaped tensor lists
     resident on ONE device.  ``outputs`` must be float32 for ``func='mean'`` (the reference's result dtype) and the
     source dtype otherwise.  ``run(K, func)`` enqueues every pass on the current stream; nothing synchronises."""
 
-    def __init__(self, sources: Sequence[Sequence[torch.Tensor]], outputs: Sequence[torch.Tensor]):
-        n_src, n_t = len(sources), len(outputs)
+    def __init__(self, sources: Sequence[Sequence[torch.Tensor]], outputs: Optional[Sequence[torch.Tensor]] = None):
+        n_src, n_t = len(sources), len(sources[0])
         if not 1 <= n_src <= _cabi.MC_MERGE_MAX_SRC:
             raise ValueError(f"need 1..{_cabi.MC_MERGE_MAX_SRC} sources, got {n_src}")
         if n_t == 0:
             raise ValueError("nothing to merge")
-        src_dtype, dst_dtype = sources[0][0].dtype, outputs[0].dtype
+        src_dtype = sources[0][0].dtype
+        dst_dtype = outputs[0].dtype if outputs is not None else src_dtype
         for s in sources:
             if len(s) != n_t:
                 raise ValueError("every source must hold the same number of tensors")
+        if outputs is not None and len(outputs) != n_t:
+            raise ValueError("one output per tensor")
         for t in range(n_t):
-            o = outputs[t]
-            _check_device_tensor(o, dst_dtype, o.numel(), f"outputs[{t}]")
+            numel = sources[0][t].numel()
+            if outputs is not None:
+                _check_device_tensor(outputs[t], dst_dtype, numel, f"outputs[{t}]")
             for k in range(n_src):
-                _check_device_tensor(sources[k][t], src_dtype, o.numel(), f"sources[{k}][{t}]")
-        self._keep = (list(map(list, sources)), list(outputs))
+                _check_device_tensor(sources[k][t], src_dtype, numel, f"sources[{k}][{t}]")
+        self._keep = (list(map(list, sources)), list(outputs) if outputs is not None else None)
         self.n_src, self.n_tensors = n_src, n_t
         self._h = C.c_void_p()
         _cabi.check(_cabi.lib().mc_ties_plan_create(
             C.byref(self._h), n_t, n_src, _cabi.ptr_array([sources[k][t].data_ptr() for k in range(n_src) for t in range(n_t)]),
-            _cabi.ptr_array([o.data_ptr() for o in outputs]), _cabi.i64_array([o.numel() for o in outputs]),
+            _cabi.ptr_array([o.data_ptr() for o in outputs]) if outputs is not None else None,
+            _cabi.i64_array([t.numel() for t in sources[0]]),
             _cabi.dtype_code(src_dtype), _cabi.dtype_code(dst_dtype)), "mc_ties_plan_create")
         self.elements = int(_cabi.lib().mc_ties_plan_elements(self._h))
 
@@ -202,6 +213,16 @@ class TiesPlan:
         _cabi.check(_cabi.lib().mc_ties_plan_run(self._h, ties_kth_rank(self.elements, K), TIES_FUNCS[func],
                                                  _cabi.current_stream_ptr()), "mc_ties_plan_run")
         _cabi.count_launch(11)  # init, 4 sampled-select + 2..6 full-select (most exit at once), merge, finalize, fix, re-merge
+
+    def metrics(self, reset_thresh=50) -> dict:
+        """Parameter-interference metrics of the plan's sources (reference calculate_metrics.py:26-37,53-64):
+        L2 / cosine distance of the first two sources, soft sign dissimilarity before and after the top-``reset_thresh``
+        trim.  Synchronises the current stream."""
+        m = _cabi.InterferenceMetrics()
+        _cabi.check(_cabi.lib().mc_ties_plan_metrics(self._h, ties_kth_rank(self.elements, reset_thresh), C.byref(m),
+                                                     _cabi.current_stream_ptr()), "mc_ties_plan_metrics")
+        _cabi.count_launch(8)
+        return _metrics_dict(m, self.n_src)
 
     def stats(self) -> dict:
         st = _cabi.TiesStats()
@@ -243,6 +264,29 @@ def ties_merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], K=20
         _cabi.ptr_array([o.data_ptr() for o in outs]), _cabi.i64_array([o.numel() for o in outs]), ties_kth_rank(d, K),
         TIES_FUNCS[func], _cabi.dtype_code(src_dtype), C.byref(st)), "mc_ties_host")
     return outs, _stats_dict(st, n_src)
+
+
+def interference_metrics_host(tensor_lists: Sequence[Sequence[torch.Tensor]], reset_thresh=50) -> dict:
+    """Interference metrics of HOST tensors through the GPU (``mc_interference_host``); ``tensor_lists[s][t]`` as
+    ``ties_merge_host_tensors``.  The reference indexes the second source unconditionally: fewer than two raise IndexError."""
+    if not torch.cuda.is_available():
+        raise _cabi.McError("interference metrics need a CUDA device (modelcompose_b200 has no CPU fallback)")
+    n_src, n_t = len(tensor_lists), len(tensor_lists[0])
+    if n_src < 2:
+        raise IndexError("index 1 is out of bounds for dimension 0 with size 1")
+    srcs = [[t.contiguous() for t in lst] for lst in tensor_lists]
+    src_dtype = srcs[0][0].dtype
+    for lst in srcs:
+        for a, b in zip(lst, srcs[0]):
+            if a.dtype != src_dtype or a.shape != b.shape or a.is_cuda:
+                raise ValueError("sources must be CPU tensors of identical dtype and shape per key")
+    d = sum(t.numel() for t in srcs[0])
+    m = _cabi.InterferenceMetrics()
+    _cabi.check(_cabi.lib().mc_interference_host(
+        n_t, n_src, _cabi.ptr_array([srcs[k][t].data_ptr() for k in range(n_src) for t in range(n_t)]),
+        _cabi.i64_array([t.numel() for t in srcs[0]]), ties_kth_rank(d, reset_thresh), _cabi.dtype_code(src_dtype), C.byref(m)),
+        "mc_interference_host")
+    return _metrics_dict(m, n_src)
 
 
 def convert_delta_to_ft(delta_weights: Dict[str, List[torch.Tensor]]):

@@ -322,6 +322,14 @@ def gen_ties():
             with contextlib.redirect_stdout(io.StringIO()):
                 res[f] = dict(T.do_merging(case["checks"], K=case["K"], merge_func=f))
         out["vectors"].append(dict(case, outputs=res))
+    import calculate_metrics as CM
+    for entry in out["vectors"]:
+        if len(entry["checks"]) < 2:
+            continue
+        flat = torch.vstack([T.state_dict_to_vector({k: v.float() for k, v in c.items()}, []) for c in entry["checks"]])
+        trunc, *_ = T.topk_values_mask(flat.clone(), K=50, return_mask=False)
+        entry["metrics"] = {"L2": float(CM.L2(flat)), "Cosine": float(CM.cos_sim(flat)),
+                            "SSD": float(CM.soft_sign_dissimilarity(flat)), "TSSD": float(CM.soft_sign_dissimilarity(trunc))}
     sys.path.pop(0)
     sys.modules.pop("ties_merging", None)
     # CLI: ties-* on two 1-layer DAMC checkpoints, convert-* on two 1-layer `same` checkpoints
@@ -352,6 +360,15 @@ def gen_ties():
                    "config_json_text": open(os.path.join(odir, "config.json")).read(), "merge_info": info}
             if strategy in ("ties-mean", "convert-drop-mean"):
                 run["state_dict"] = {k: v.clone() for k, v in sd.items()}
+            if strategy == "ties-mean":  # the reference's calculate_metrics.py on this merged directory (paths are still valid)
+                sys.path.insert(0, os.path.join(R.REFERENCE_ROOT, "scripts", "model_composition"))
+                import calculate_metrics as CM2
+                with contextlib.redirect_stdout(io.StringIO()):
+                    CM2.calculate_metrics(odir)
+                sys.path.pop(0)
+                for mname in ("calculate_metrics", "ties_merging"):
+                    sys.modules.pop(mname, None)
+                run["merge_metrics_txt"] = open(os.path.join(odir, "merge_metrics.txt")).read()
             out["cli"]["runs"][f"{fam}:{strategy}:{K}"] = run
     torch.save(out, os.path.join(HERE, "ties.pt"))
     return out

@@ -212,6 +212,50 @@ def test_cli_strategies_match_reference_fixture(golden, tmp_path):
         assert info.replace(dirs[fam][0], "{IN0}").replace(dirs[fam][1], "{IN1}").replace(out, "{OUT}") == run["merge_info"], name
 
 
+METRIC_RTOL = 2e-5  # fp64 reductions here vs the reference's fp32 tree sums
+
+
+def test_interference_metrics_vs_reference_fixture_and_oracle(golden, tmp_path):
+    """calculate_metrics.py: the reference's own numbers on the fixture vectors, the oracle on a sampled-path-sized case,
+    and the CLI end to end (merge_info.txt -> merge_metrics.txt)."""
+    from modelcompose_b200 import metrics as MT
+    g = golden("ties.pt")
+    for case in g["vectors"]:
+        if "metrics" not in case:
+            continue
+        keys = sorted(case["checks"][0])
+        got = M.interference_metrics_host([[c[k] for k in keys] for c in case["checks"]], 50)
+        for k, want in case["metrics"].items():
+            assert abs(got[k] - want) <= METRIC_RTOL * max(1.0, abs(want)), (case["name"], k, got[k], want)
+    gen = torch.Generator().manual_seed(77)
+    srcs = [[(torch.randn(n, generator=gen) * 0.02 + 0.004 * s).to(torch.bfloat16) for n in (5_000_000, 3_700_001)] for s in range(3)]
+    plan = M.TiesPlan([[t.cuda() for t in lst] for lst in srcs])   # statistics-only plan: no outputs
+    got = plan.metrics(50)
+    want = TO.interference_metrics(torch.vstack([torch.cat(lst) for lst in srcs]), 50)
+    for k in ("L2", "Cosine", "SSD", "TSSD"):
+        assert abs(got[k] - want[k]) <= 5e-6 * max(1.0, abs(want[k])), (k, got[k], want[k])   # same fp32 element ops; fp32 partials over 16 elements, then fp64
+    with pytest.raises(Exception, match="without outputs"):
+        plan.run(20, "sum")
+    with pytest.raises(IndexError):
+        M.interference_metrics_host([[torch.zeros(4)]], 50)
+    # CLI: ties-mean merge of the two DAMC fixture checkpoints, then calculate_metrics on the output directory
+    damc, _ = syn.ties_cli_checkpoints()
+    dirs = []
+    for m in ("vision", "audio"):
+        d = str(tmp_path / f"damc_{m}")
+        syn.save_checkpoint_dir(d, damc[m][0], copy.deepcopy(damc[m][1]))
+        dirs.append(d)
+    out = str(tmp_path / "out-multimodal")
+    M.main(dirs + ["-o", out, "--strategy", "ties-mean", "-K", "20"])
+    MT.main([out])
+    ref_txt = g["cli"]["runs"]["damc:ties-mean:20"]["merge_metrics_txt"]
+    got_txt = open(os.path.join(out, "merge_metrics.txt")).read()
+    num = lambda line: float(line.split(": ")[1].replace("tensor(", "").replace(")", ""))
+    for a, b in zip(got_txt.strip().splitlines(), ref_txt.strip().splitlines()):
+        assert a.split(":")[0] == b.split(":")[0] and ("tensor(" in a) == ("tensor(" in b)
+        assert abs(num(a) - num(b)) <= 1e-4 * max(1.0, abs(num(b))), (a, b)     # printed with 4 decimals
+
+
 def test_error_behaviour():
     x = [[torch.zeros(10, dtype=torch.bfloat16, device="cuda")] for _ in range(2)]
     with pytest.raises(Exception, match="float32"):

@@ -137,6 +137,23 @@ def test_live_reference_agrees_on_random_cases():
         sys.modules.pop("ties_merging", None)
 
 
+METRIC_RTOL = 2e-5  # the reference reduces in fp32 (tree sums), the oracle and the kernel in fp64: stated tolerance
+
+
+def test_interference_metrics_match_reference_fixture(golden):
+    g = golden("ties.pt")
+    n = 0
+    for case in g["vectors"]:
+        if "metrics" not in case:
+            continue
+        flat = torch.vstack([TO.state_dict_to_vector(c) for c in case["checks"]])
+        got = TO.interference_metrics(flat, 50)
+        for k, want in case["metrics"].items():
+            assert abs(got[k] - want) <= METRIC_RTOL * max(1.0, abs(want)), (case["name"], k, got[k], want)
+        n += 1
+    assert n >= 8
+
+
 def test_product_host_logic_without_gpu(tmp_path):
     """convert_delta_to_ft and the strategy plumbing are host code; the arithmetic has no CPU path and must say so."""
     a = {"x.default": torch.zeros(3), "u": torch.ones(2)}
