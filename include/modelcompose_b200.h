@@ -325,6 +325,16 @@ MC_API int mc_silu_mul(const void* gate, const void* up, void* out, int64_t rows
  *                pos_offset + t % seq_len (prefill: position_ids = arange(seq_len), :526-533; decode step: seq_len 1,
  *                pos_offset = past length).
  * ---------------------------------------------------------------------------------------------- */
+/* Causal self-attention of the prefill, flash-style on tcgen05 (replaces the eager attention of
+ * modelcompose/model/language_model/multimodal_llama.py:295-312: QK^T / sqrt(d) + causal mask, fp32 softmax, PV — without
+ * materialising the [B, heads, S, S] scores).  q / k / v: device [batch * seq_len, ld_qkv] with head h in columns
+ * [h * head_dim, (h + 1) * head_dim) (the projection outputs as they are, RoPE already applied to q and k); out likewise with
+ * ld_out.  out_rowmap (device int32 [batch * seq_len] or NULL): the output of token t is written to row out_rowmap[t] — the
+ * modality-major buffer order of the routed linears, so no separate gather pass is needed.  head_dim must be 128; every
+ * sequence has seq_len tokens and attends causally to itself (no padding mask, no past keys: those cases stay on the library). */
+MC_API int mc_attention_causal(const void* q, const void* k, const void* v, void* out, int64_t ld_qkv, int64_t ld_out,
+                        const int32_t* out_rowmap, int batch, int seq_len, int n_heads, int head_dim, float softmax_scale,
+                        int dtype, mc_stream_t stream);
 /* dst[i, :] = src[index[i], :] for i < rows (bit-exact row copy, 128-bit accesses; row_bytes % 16 == 0).  Used to put the
  * spliced embeddings / the attention output into the modality-major row order the routed linears run in, and back. */
 MC_API int mc_gather_rows(const void* src, int64_t ld_src_bytes, void* dst, int64_t ld_dst_bytes, const int32_t* index,

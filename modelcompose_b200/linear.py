@@ -191,6 +191,25 @@ def route_tile_masks(row_group: torch.Tensor, out: Optional[torch.Tensor] = None
     return out
 
 
+def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq_len: int,
+                     n_heads: int, softmax_scale: float, out_rowmap: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Causal self-attention over ``[batch * seq_len, n_heads * 128]`` projection outputs (RoPE already applied); the output
+    of token t lands in row ``out_rowmap[t]`` of ``out`` (``None`` = t).  multimodal_llama.py:295-312 without the scores."""
+    qm, km, vm, om = _mat(q, "q"), _mat(k, "k", q.dtype), _mat(v, "v", q.dtype), _mat(out, "out", q.dtype)
+    T = batch * seq_len
+    if any(t.shape[0] != T for t in (qm, km, vm, om)) or qm.shape[1] != n_heads * 128 or not (qm.stride(0) == km.stride(0) == vm.stride(0)):
+        raise ValueError("attention: q / k / v / out must be [batch * seq_len, n_heads * 128] with one common row stride")
+    if out_rowmap is not None and (out_rowmap.dtype != torch.int32 or out_rowmap.numel() != T or not out_rowmap.is_cuda
+                                   or not out_rowmap.is_contiguous()):
+        raise ValueError("attention: out_rowmap must be a contiguous CUDA int32 [batch * seq_len]")
+    _cabi.check(_cabi.lib().mc_attention_causal(qm.data_ptr(), km.data_ptr(), vm.data_ptr(), om.data_ptr(), qm.stride(0), om.stride(0),
+                                                None if out_rowmap is None else out_rowmap.data_ptr(), batch, seq_len, n_heads, 128,
+                                                float(softmax_scale), _cabi.dtype_code(q.dtype), _cabi.current_stream_ptr()),
+                "mc_attention_causal")
+    _cabi.count_launch()
+    return out
+
+
 def gather_rows(src: torch.Tensor, index: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """``out[i] = src[index[i]]`` over 2-D row-major views (bit-exact row copy on the GPU)."""
     s, o = _mat(src, "src"), _mat(out, "out", src.dtype)

@@ -36,6 +36,8 @@ FUSE_ROPE = os.environ.get("MC_FUSE_ROPE", "1") != "0"  # development switch: 0 
 # 128-row tile of the routed linears holds one adapter group; only attention sees sequence order (the q / k / v epilogues
 # scatter rows back, the attention output is gathered again).  Development switch: 0 = sequence order everywhere.
 MODALITY_MAJOR = os.environ.get("MC_MODALITY_MAJOR", "1") != "0"
+# causal prefill attention: 1 = this library's tcgen05 kernel (head_dim 128), 0 = the stock cuDNN / flash-attn call
+ATTENTION_NATIVE = os.environ.get("MC_ATTENTION_NATIVE", "0") != "0"
 
 
 class MultimodalConfig:
@@ -199,6 +201,7 @@ class _Workspace:
         # perm[i] = sequence-order row held at row i of the activation buffers (identity for the decode step / unrouted)
         self.permute = MODALITY_MAJOR and S > 1
         self.perm = torch.arange(T, dtype=torch.int32, device=dev) if self.permute else None
+        self.inv_perm = torch.arange(T, dtype=torch.int32, device=dev) if self.permute else None  # buffer row of sequence row t
         self.perm_is_identity = True
         # RoPE rides in the q / k projection epilogue when a tile holds whole heads; otherwise mc_rope runs after it
         D = H // cfg.num_attention_heads
@@ -225,11 +228,13 @@ class _Workspace:
             self.row_group.zero_()
             if self.permute and not self.perm_is_identity:
                 self.perm.copy_(torch.arange(self.T, dtype=torch.int32, device=self.perm.device))
+                self.inv_perm.copy_(self.perm)
                 self.perm_is_identity = True
         elif self.permute:
             gseq = modal_id.reshape(-1)
             order = torch.sort(gseq, stable=True).indices  # tiny (T uint8 keys); stable keeps sequence order inside a group
             self.perm.copy_(order)
+            self.inv_perm[order] = torch.arange(self.T, dtype=torch.int32, device=self.perm.device)
             self.row_group.copy_(gseq[order])
             self.perm_is_identity = False
         else:
@@ -239,9 +244,7 @@ class _Workspace:
     def last_rows(self) -> torch.Tensor:
         """int32 [B]: buffer row holding the last position of every sequence."""
         if self.permute and not self.perm_is_identity:
-            inv = torch.empty_like(self.perm)
-            inv[self.perm.long()] = torch.arange(self.T, dtype=torch.int32, device=self.perm.device)
-            return inv[self.last_idx.long()].contiguous()
+            return self.inv_perm[self.last_idx.long()].contiguous()
         return self.last_idx
 
     def load_rows(self, src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -257,9 +260,7 @@ class _Workspace:
         """A copy of an activation buffer in sequence order ``[B, S, width]`` (hidden-state outputs, tests)."""
         out = torch.empty_like(buf)
         if self.permute and not self.perm_is_identity:
-            inv = torch.empty_like(self.perm)
-            inv[self.perm.long()] = torch.arange(self.T, dtype=torch.int32, device=self.perm.device)
-            LN.gather_rows(buf, inv, out)
+            LN.gather_rows(buf, self.inv_perm, out)
         else:
             out.copy_(buf)
         return out.view(self.B, self.S, -1)
@@ -507,6 +508,11 @@ class MultimodalLlamaForCausalLM:
                     mask = (mask + (~attention_mask.bool())[:, None, None, :].to(self.dtype) * neg).clamp_min(neg)
             o = F.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), attn_mask=mask,
                                                scale=1.0 / math.sqrt(D)).transpose(1, 2)
+        elif full and D == 128 and ATTENTION_NATIVE:
+            # own tcgen05 kernel: reads the projection outputs in place and writes straight into buffer (modality-major) order
+            LN.attention_causal(ws.q, ws.k, ws.v, ws.attn, B, S, nH, 1.0 / math.sqrt(D),
+                                out_rowmap=ws.inv_perm if ws.permute and not ws.perm_is_identity else None)
+            return
         elif full:
             o = self._causal_attention(q, k, v, 1.0 / math.sqrt(D))
         else:
