@@ -43,8 +43,8 @@ struct AttSmem {
   static constexpr int P = V + 2 * kAttTileBytes;
   static constexpr int BAR = P + kAttTileBytes;    // 192 KB of tiles
   static constexpr int N_BAR = 16;
-  static constexpr int XCH = BAR + N_BAR * 8 + 16;  // per-row partial max / sum of the two column halves: float [2][128]
-  static constexpr int TOTAL = XCH + 2 * kAttTile * 4;
+  static constexpr int XCH = BAR + N_BAR * 8 + 16;  // per-row partials of the two column halves: float [3][2][128]
+  static constexpr int TOTAL = XCH + 3 * 2 * kAttTile * 4;  // (row max, double-buffered by tile parity; row sum)
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
@@ -69,8 +69,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void pair_barrier(int q) {  // the two softmax warps of TMEM lane quadrant q
   asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
 }
-__device__ __forceinline__ uint32_t pack2(float a, float b, bool is_f16) {
-  if (is_f16) {
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (F16) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
   }
@@ -78,6 +79,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, bool is_f16) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_constant__ AttParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -201,7 +203,6 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
     const int q = warp & 3;             // TMEM lane quadrant (hardware: warp id % 4)
     const int half = (warp - 2) >> 2;   // which 64 keys of the score tile / which 64 head-dim columns of the output
     const int r = q * 32 + lane;        // query row inside the tile = TMEM lane
-    const bool is_f16 = P.is_f16 != 0;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t col_off = (uint32_t)(half * 64);
     float* xch = reinterpret_cast<float*>(smem + AttSmem::XCH);
@@ -233,9 +234,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
       }
-      xch[half * kAttTile + r] = mx;
+      float* xm = xch + (j & 1) * 2 * kAttTile;  // double-buffered: the partner may still be reading the previous tile's slot
+      xm[half * kAttTile + r] = mx;
       pair_barrier(q);
-      mx = fmaxf(mx, xch[(half ^ 1) * kAttTile + r]);
+      mx = fmaxf(mx, xm[(half ^ 1) * kAttTile + r]);
       const float m_new = fmaxf(m_run, mx * P.scale_log2);  // key 0 is always visible: finite from the first tile on
       const float alpha = ex2_approx(m_run - m_new);
       m_run = m_new;
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
           if ((int)col_off + i > r) p0 = 0.0f;
           if ((int)col_off + i + 1 > r) p1 = 0.0f;
           l_add += p0 + p1;
-          w[i >> 1] = pack2(p0, p1, is_f16);
+          w[i >> 1] = pack2<F16>(p0, p1);
         }
       } else {
 #pragma unroll
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
           const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), P.scale_log2, -m_new));
           const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), P.scale_log2, -m_new));
           l_add += p0 + p1;
-          w[i >> 1] = pack2(p0, p1, is_f16);
+          w[i >> 1] = pack2<F16>(p0, p1);
         }
       }
       // fold the previous tile's P V into the running half-row, then rescale: O = (O + PV_{j-1}) * alpha
@@ -293,9 +295,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       if (lane == 0) mbar_arrive(p_full);
     }
     // last tile's P V, normalise by the full row sum (both halves), store
-    xch[half * kAttTile + r] = l_run;
+    float* xl = xch + 2 * 2 * kAttTile;
+    xl[half * kAttTile + r] = l_run;
     pair_barrier(q);
-    const float inv = 1.0f / (l_run + xch[(half ^ 1) * kAttTile + r]);
+    const float inv = 1.0f / (l_run + xl[(half ^ 1) * kAttTile + r]);
     mbar_wait(pv_full, (uint32_t)((n_kv - 1) & 1));
     tc_fence_after();
 #pragma unroll
@@ -313,8 +316,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(P.out) + (orow * P.ld_out + col0 + (int)col_off) * 2);
 #pragma unroll
       for (int c = 0; c < 64; c += 8)
-        dst[c >> 3] = make_uint4(pack2(o[c], o[c + 1], is_f16), pack2(o[c + 2], o[c + 3], is_f16), pack2(o[c + 4], o[c + 5], is_f16),
-                                 pack2(o[c + 6], o[c + 7], is_f16));
+        dst[c >> 3] = make_uint4(pack2<F16>(o[c], o[c + 1]), pack2<F16>(o[c + 2], o[c + 3]), pack2<F16>(o[c + 4], o[c + 5]),
+                                 pack2<F16>(o[c + 6], o[c + 7]));
     }
   }
   tc_fence_before();
@@ -361,11 +364,15 @@ extern "C" int mc_attention_causal(const void* q, const void* k, const void* v, 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    MC_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+    MC_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
+    MC_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttSmem::DYN_BYTES));
     configured[dev] = true;
   }
   dim3 grid((seq_len + kAttTile - 1) / kAttTile, n_heads, batch);
-  attention_kernel<<<grid, kAttThreads, AttSmem::DYN_BYTES, (cudaStream_t)stream>>>(P);
+  if (dtype == MC_F16)
+    attention_kernel<true><<<grid, kAttThreads, AttSmem::DYN_BYTES, (cudaStream_t)stream>>>(P);
+  else
+    attention_kernel<false><<<grid, kAttThreads, AttSmem::DYN_BYTES, (cudaStream_t)stream>>>(P);
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
 }
