@@ -8,10 +8,11 @@
 //   warp 1      MMA issuer (one thread): S_j = Q K_j^T (K-major operands) into one of two TMEM score buffers, issued one tile
 //               ahead of the softmax; PV_j = P_j V_j with V consumed MN-major straight from its [keys, d] tile
 //               (warp 1 also owns the TMEM allocation)
-//   warps 2-9   softmax, two warps per TMEM lane quadrant: thread = (query row, 64-key half).  S_j is read from TMEM once and
-//               kept in registers (row max -> exchange with the partner warp through shared memory -> exp2 / sum / 16-bit P_j
-//               into the 128B-swizzled K-major shared-memory tile the PV MMA reads); the running output half-row lives in 64
-//               fp32 registers: O = (O + PV_{j-1}) * alpha_j, so the tensor core never has to rescale an accumulator
+//   warps 2-9   softmax, kAttSplit = 2 warps per TMEM lane quadrant: thread = (query row, 64-key half).  S_j is read from TMEM
+//               once and kept in registers (row max -> exchange with the partner warp through shared memory -> exp2 / sum /
+//               16-bit P_j into the 128B-swizzled K-major shared-memory tile the PV MMA reads); the running output half-row
+//               lives in 64 fp32 registers: O = (O + PV_{j-1}) * alpha_j, so the tensor core never rescales an accumulator.
+//               (kAttSplit = 4, sixteen softmax warps at 96 registers, measured slower: profiles/r01_attention.txt)
 // Roofline: tensor pipe (bf16 / fp16 dense), bounded in practice by the softmax warps (exp2 on the MUFU pipe).
 // head_dim is fixed at 128 (vicuna-7B); other head sizes keep the library call in model.py.
 #include <algorithm>
@@ -22,7 +23,9 @@
 namespace mc {
 
 constexpr int kAttTile = 128;       // query rows per CTA, keys per step, head_dim
-constexpr int kAttThreads = 320;     // warp 0 TMA, warp 1 MMA + TMEM, warps 2-9 softmax
+constexpr int kAttSplit = 2;          // softmax warps per TMEM lane quadrant: each thread owns 128 / kAttSplit keys of its row
+constexpr int kAttCW = kAttTile / kAttSplit;
+constexpr int kAttThreads = 64 + kAttSplit * 128;  // warp 0 TMA, warp 1 MMA + TMEM, then the softmax warps
 constexpr int kAttHalfBytes = kAttTile * 64 * 2;  // one [128 x 64] 16-bit block = 16 KB
 constexpr int kAttTileBytes = 2 * kAttHalfBytes;  // [128 x 128] = 32 KB
 
@@ -43,8 +46,8 @@ struct AttSmem {
   static constexpr int P = V + 2 * kAttTileBytes;
   static constexpr int BAR = P + kAttTileBytes;    // 192 KB of tiles
   static constexpr int N_BAR = 16;
-  static constexpr int XCH = BAR + N_BAR * 8 + 16;  // per-row partials of the two column halves: float [3][2][128]
-  static constexpr int TOTAL = XCH + 3 * 2 * kAttTile * 4;  // (row max, double-buffered by tile parity; row sum)
+  static constexpr int XCH = BAR + N_BAR * 8 + 16;  // per-row partials of the column parts: float [3][kAttSplit][128]
+  static constexpr int TOTAL = XCH + 3 * kAttSplit * kAttTile * 4;  // (row max, double-buffered by tile parity; row sum)
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
@@ -66,8 +69,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void pair_barrier(int q) {  // the two softmax warps of TMEM lane quadrant q
-  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+__device__ __forceinline__ void pair_barrier(int q) {  // the softmax warps of TMEM lane quadrant q
+  asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(kAttSplit * 32) : "memory");
 }
 template <bool F16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -117,11 +120,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 8);
+      mbar_init(&s_empty[s], 4 * kAttSplit);
     }
-    mbar_init(p_full, 8);
+    mbar_init(p_full, 4 * kAttSplit);
     mbar_init(pv_full, 1);
-    mbar_init(pv_empty, 8);
+    mbar_init(pv_empty, 4 * kAttSplit);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -200,76 +203,83 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       }
     }
   } else {
+    constexpr int CW = kAttCW;
     const int q = warp & 3;             // TMEM lane quadrant (hardware: warp id % 4)
-    const int half = (warp - 2) >> 2;   // which 64 keys of the score tile / which 64 head-dim columns of the output
+    const int part = (warp - 2) >> 2;   // which CW keys of the score tile / which CW head-dim columns of the output
     const int r = q * 32 + lane;        // query row inside the tile = TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t col_off = (uint32_t)(half * 64);
+    const uint32_t col_off = (uint32_t)(part * CW);
     float* xch = reinterpret_cast<float*>(smem + AttSmem::XCH);
-    float o[64];
+    float o[CW];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.0f;
+    for (int i = 0; i < CW; ++i) o[i] = 0.0f;
     float m_run = -INFINITY, l_run = 0.0f;
-    uint8_t* p_blk = smem + AttSmem::P + half * kAttHalfBytes + r * 128;  // this thread's 64-key row of the P tile
+    // this thread's CW keys of its row of the P tile: 64-key block, then 16-byte chunks (swizzled per row)
+    uint8_t* p_blk = smem + AttSmem::P + (col_off >> 6) * kAttHalfBytes + r * 128;
+    const int chunk0 = (int)(col_off & 63u) >> 3;
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       const uint32_t ph = (uint32_t)((j >> 1) & 1);
       const bool diag = j == qt;
       mbar_wait(&s_full[st], ph);
       tc_fence_after();
-      // scores of this thread's 64 keys: TMEM -> registers, once; the buffer is free for QK_{j+2} right away
-      uint32_t sv[64];
-      tmem_ld_32x32(tmem_s[st] + lane_off + col_off, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_ld_32x32(tmem_s[st] + lane_off + col_off + 32u, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      // scores of this thread's keys: TMEM -> registers, once; the buffer is free for QK_{j+2} right away
+      uint32_t sv[CW];
+#pragma unroll
+      for (int c = 0; c < CW; c += 32)
+        tmem_ld_32x32(tmem_s[st] + lane_off + col_off + (uint32_t)c, *reinterpret_cast<uint32_t(*)[32]>(&sv[c]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
       if (diag) {  // warp-uniform: only the diagonal tile pays for the causal comparison
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if ((int)col_off + i <= r) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < CW; ++i)
+          if ((int)col_off + i <= r) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        for (int i = 0; i < CW; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(sv[i]));
       }
-      float* xm = xch + (j & 1) * 2 * kAttTile;  // double-buffered: the partner may still be reading the previous tile's slot
-      xm[half * kAttTile + r] = mx;
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float* xm = xch + (j & 1) * kAttSplit * kAttTile;  // double-buffered: a partner may still be reading the previous tile's slots
+      xm[part * kAttTile + r] = mx;
       pair_barrier(q);
-      mx = fmaxf(mx, xm[(half ^ 1) * kAttTile + r]);
+#pragma unroll
+      for (int pp = 0; pp < kAttSplit; ++pp) mx = fmaxf(mx, xm[pp * kAttTile + r]);
       const float m_new = fmaxf(m_run, mx * P.scale_log2);  // key 0 is always visible: finite from the first tile on
       const float alpha = ex2_approx(m_run - m_new);
       m_run = m_new;
       // p = exp2(s * scale - m): fp32 row sum, 16-bit packed pairs kept in registers until the P tile is free
-      float l_add = 0.0f;
-      uint32_t w[32];
+      float l4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      uint32_t w[CW / 2];
       if (diag) {
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
+        for (int i = 0; i < CW; i += 2) {
           float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), P.scale_log2, -m_new));
           float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), P.scale_log2, -m_new));
           if ((int)col_off + i > r) p0 = 0.0f;
           if ((int)col_off + i + 1 > r) p1 = 0.0f;
-          l_add += p0 + p1;
+          l4[(i >> 1) & 3] += p0 + p1;
           w[i >> 1] = pack2<F16>(p0, p1);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 64; i += 2) {
+        for (int i = 0; i < CW; i += 2) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), P.scale_log2, -m_new));
           const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), P.scale_log2, -m_new));
-          l_add += p0 + p1;
+          l4[(i >> 1) & 3] += p0 + p1;
           w[i >> 1] = pack2<F16>(p0, p1);
         }
       }
-      // fold the previous tile's P V into the running half-row, then rescale: O = (O + PV_{j-1}) * alpha
+      const float l_add = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      // fold the previous tile's P V into the running part of the row, then rescale: O = (O + PV_{j-1}) * alpha
       if (j > 0) {
         const bool rescale = __any_sync(0xffffffffu, alpha != 1.0f);
         mbar_wait(pv_full, (uint32_t)((j - 1) & 1));
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 64; c += 32) {
+        for (int c = 0; c < CW; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_pv + lane_off + col_off + (uint32_t)c, v);
           tmem_ld_wait();
@@ -285,24 +295,27 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(pv_empty);
       }
-      // the P tile is free (PV_{j-1} has completed): 16-bit P into the swizzled K-major tile, eight 16-byte chunks per row
+      // the P tile is free (PV_{j-1} has completed): 16-bit P into the swizzled K-major tile, 16-byte chunks of 8 keys
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(p_blk + ((c ^ (r & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      for (int c = 0; c < CW / 8; ++c)
+        *reinterpret_cast<uint4*>(p_blk + (((chunk0 + c) ^ (r & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
       l_run = l_run * alpha + l_add;
       fence_proxy_async_smem();  // the P tile was written through the generic proxy, the MMA reads it through the async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    // last tile's P V, normalise by the full row sum (both halves), store
-    float* xl = xch + 2 * 2 * kAttTile;
-    xl[half * kAttTile + r] = l_run;
+    // last tile's P V, normalise by the full row sum (all parts), store
+    float* xl = xch + 2 * kAttSplit * kAttTile;
+    xl[part * kAttTile + r] = l_run;
     pair_barrier(q);
-    const float inv = 1.0f / (l_run + xl[(half ^ 1) * kAttTile + r]);
+    float l_tot = 0.0f;
+#pragma unroll
+    for (int pp = 0; pp < kAttSplit; ++pp) l_tot += xl[pp * kAttTile + r];
+    const float inv = 1.0f / l_tot;
     mbar_wait(pv_full, (uint32_t)((n_kv - 1) & 1));
     tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 64; c += 32) {
+    for (int c = 0; c < CW; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_pv + lane_off + col_off + (uint32_t)c, v);
       tmem_ld_wait();
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_kernel(const __grid_
       const long long orow = P.out_rowmap ? (long long)P.out_rowmap[t] : t;
       uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(P.out) + (orow * P.ld_out + col0 + (int)col_off) * 2);
 #pragma unroll
-      for (int c = 0; c < 64; c += 8)
+      for (int c = 0; c < CW; c += 8)
         dst[c >> 3] = make_uint4(pack2<F16>(o[c], o[c + 1]), pack2<F16>(o[c + 2], o[c + 3]), pack2<F16>(o[c + 4], o[c + 5]),
                                  pack2<F16>(o[c + 6], o[c + 7]));
     }
