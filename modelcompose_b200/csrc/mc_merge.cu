@@ -250,23 +250,27 @@ extern "C" int mc_merge_host(int n_tensors, int n_src, const void* const* h_src,
     for (int k = 0; k < n_src; ++k) MC_TRY(cudaMalloc(&d_in[b][k], (size_t)slab_elems * ss));
     MC_TRY(cudaMalloc(&d_out[b], (size_t)slab_elems * ds));
   }
-  // plans first (plan creation allocates and synchronises; keep that out of the pipeline)
-  for (size_t i = 0; i < slabs.size() && rc == MC_OK && e == cudaSuccess; ++i) {
-    const int b = (int)(i % NBUF);
-    const auto& pcs = slabs[i];
-    std::vector<const void*> src_tab((size_t)n_src * pcs.size());
-    std::vector<void*> dst_tab(pcs.size());
-    std::vector<int64_t> n_tab(pcs.size());
+  // One plan per staging slot, not per slab: the pieces of a slab sit back to back in the slot (each padded to 16
+  // elements), the merge is elementwise, so the slot is merged as ONE tensor as long as its longest slab; the pad
+  // elements are computed and never copied back (the staging is zeroed once so they are defined).  54 GB through
+  // 64 MB slots used to build 211 plans (allocation + upload + synchronise each) before the first byte moved.
+  long long slot_len[NBUF] = {};
+  for (size_t i = 0; i < slabs.size(); ++i) {
     long long pos = 0;
-    for (size_t j = 0; j < pcs.size(); ++j) {
-      for (int k = 0; k < n_src; ++k) src_tab[(size_t)k * pcs.size() + j] = d_in[b][k] + pos * ss;
-      dst_tab[j] = d_out[b] + pos * ds;
-      n_tab[j] = pcs[j].n;
-      pos = (pos + pcs[j].n + 15) & ~15LL;
+    for (const Piece& pc : slabs[i]) pos = (pos + pc.n + 15) & ~15LL;
+    slot_len[i % NBUF] = std::max(slot_len[i % NBUF], std::min(pos, slab_elems));
+  }
+  for (int b = 0; b < NBUF && rc == MC_OK && e == cudaSuccess; ++b) {
+    if (slot_len[b] == 0) break;
+    const void* src_tab[MC_MERGE_MAX_SRC];
+    for (int k = 0; k < n_src; ++k) {
+      src_tab[k] = d_in[b][k];
+      MC_TRY(cudaMemsetAsync(d_in[b][k], 0, (size_t)slab_elems * ss, s_in));
     }
+    void* dst_tab[1] = {d_out[b]};
+    const int64_t n_tab[1] = {slot_len[b]};
     mc_merge_plan_t* plan = nullptr;
-    rc = mc_merge_plan_create(&plan, (int)pcs.size(), n_src, src_tab.data(), dst_tab.data(), n_tab.data(), src_dtype,
-                              dst_dtype, 0);
+    rc = mc_merge_plan_create(&plan, 1, n_src, src_tab, dst_tab, n_tab, src_dtype, dst_dtype, 0);
     if (rc == MC_OK) plans.push_back(plan);
   }
   for (size_t i = 0; i < slabs.size() && e == cudaSuccess && rc == MC_OK; ++i) {
@@ -287,7 +291,7 @@ extern "C" int mc_merge_host(int n_tensors, int n_src, const void* const* h_src,
     MC_TRY(cudaStreamWaitEvent(s_k, in_done[b], 0));
     if (i >= NBUF) MC_TRY(cudaStreamWaitEvent(s_k, out_done[b], 0));  // slot b's output staging drained
     if (e != cudaSuccess) break;
-    rc = mc_merge_plan_run(plans[i], weights, mode, s_k);
+    rc = mc_merge_plan_run(plans[b], weights, mode, s_k);
     if (rc != MC_OK) break;
     MC_TRY(cudaEventRecord(k_done[b], s_k));
     MC_TRY(cudaStreamWaitEvent(s_out, k_done[b], 0));

@@ -294,25 +294,34 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   const unsigned int lo2 = lo | (lo << 16), hi2 = (lo + span) | ((lo + span) << 16) | 0x80008000u;
   unsigned int below = 0u, ge_acc = 0u, n_fast = 0u;  // ge_acc = 128 x (#keys >= lo) over the n_fast vector-path elements
   unsigned long long below_total = 0ull;
+  // The chunk -> segment -> data pointer chain (two dependent loads per chunk) is resolved one iteration ahead, while
+  // the data of the current iteration is in flight: the streaming loads never wait for metadata.
+  const Vec<16>* ptr[PAIR];  // vector path: this thread's first vector of chunk c0 + j; NULL = tail / unaligned / none
+#define MC_TIES_RESOLVE(FIRST)                                                                                        \
+  _Pragma("unroll") for (int j = 0; j < PAIR; ++j) {                                                                  \
+    const long long c_ = (FIRST) + j;                                                                                 \
+    ptr[j] = nullptr;                                                                                                 \
+    if (c_ < nchunks) {                                                                                               \
+      const MergeChunk ch_ = chunks[c_];                                                                              \
+      const MergeSeg* sg_ = segs + ch_.seg;                                                                           \
+      const long long base_ = (long long)ch_.idx * CHUNK;                                                             \
+      if (sg_->aligned && sg_->numel - base_ >= CHUNK)                                                                \
+        ptr[j] = reinterpret_cast<const Vec<16>*>(reinterpret_cast<const S*>(sg_->src[src]) + base_) + threadIdx.x;   \
+    }                                                                                                                 \
+  }
+  MC_TIES_RESOLVE((long long)blockIdx.x * PAIR)
   for (int c0 = blockIdx.x * PAIR; c0 < nchunks; c0 += gridDim.x * PAIR) {
     Vec<16> v[PAIR][VPT];
     bool fast[PAIR];
 #pragma unroll
     for (int j = 0; j < PAIR; ++j) {
-      const int c = c0 + j;
-      fast[j] = false;
-      if (c < nchunks) {
-        const MergeChunk ch = chunks[c];
-        const MergeSeg* sg = segs + ch.seg;
-        const long long base = (long long)ch.idx * CHUNK;
-        if (sg->aligned && sg->numel - base >= CHUNK) {
-          fast[j] = true;
-          const Vec<16>* p = reinterpret_cast<const Vec<16>*>(reinterpret_cast<const S*>(sg->src[src]) + base) + threadIdx.x;
+      fast[j] = ptr[j] != nullptr;
+      if (fast[j]) {
 #pragma unroll
-          for (int u = 0; u < VPT; ++u) v[j][u] = ld_stream(p + u * kTiesCountThreads);
-        }
+        for (int u = 0; u < VPT; ++u) v[j][u] = ld_stream(ptr[j] + u * kTiesCountThreads);
       }
     }
+    MC_TIES_RESOLVE((long long)c0 + (long long)gridDim.x * PAIR)
 #pragma unroll
     for (int j = 0; j < PAIR; ++j) {
       const int c = c0 + j;
@@ -352,6 +361,7 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
       below = ge_acc = n_fast = 0u;
     }
   }
+#undef MC_TIES_RESOLVE
   below_total += below + (n_fast - (ge_acc >> 7));
   // block reduction of the below-counts (64-bit), then one global atomic per CTA
   unsigned long long x = below_total;
@@ -644,7 +654,7 @@ extern "C" int mc_ties_plan_metrics(const mc_ties_plan_t* p, int64_t kth, mc_int
   const int rc = enqueue_select(p, kth, s);
   if (rc != MC_OK) return rc;
   MC_CUDA_OK(cudaMemsetAsync(p->d_metrics, 0, sizeof(TiesMetricSums), s));
-  fn<<<std::min(p->nchunks, p->sms * 8), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_metrics);
+  fn<<<std::min(p->nchunks, p->sms * 8), kTiesMetricsThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_metrics);
   MC_CUDA_OK(cudaGetLastError());
   TiesMetricSums h;
   TiesState hs;

@@ -22,7 +22,8 @@ struct TiesState {
 };
 
 constexpr int kTiesChunkBytes = 16384;  // one chunk = 1024 16-byte vectors of every source
-constexpr int kTiesMergeThreads = 512;
+constexpr int kTiesMergeThreads = 256;    // x 4 vectors per source per thread = one chunk; every load issued up front
+constexpr int kTiesMetricsThreads = 512;
 constexpr int kTiesHistThreads = 1024;
 constexpr int kTiesCountThreads = 512;
 constexpr int kTiesWindowBins = 2048;   // widest bracket the counting pass histograms (8 KB of shared memory)
@@ -43,13 +44,23 @@ constexpr unsigned int kTiesFixCapacity = 1u << 20;
 // The kept entries all share one sign, so "sum kept" is the left-to-right fp32 sum of the positive (or of the negative)
 // survivors with +0 in the other slots — both candidates are accumulated in the same sweep as the sign election and the
 // elected one is picked afterwards.  Zero results are +0 (torch's reductions start from +0) except MAX, whose `* s` keeps -0.
+// element e of a 16-byte vector of S as float32 (bf16: one shift / mask on the packed word, no byte permute)
+template <typename S>
+__device__ __forceinline__ float vec_elem_f32(const Vec<16>& v, int e) {
+  if constexpr (std::is_same<S, __nv_bfloat16>::value) {
+    const uint32_t w = v.w[e >> 1];
+    return __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
+  } else {
+    return to_f32<S>(reinterpret_cast<const S*>(&v)[e]);
+  }
+}
 template <int NSRC, typename S, typename D, int FUNC>
-__device__ __forceinline__ D ties_one(const S (&in)[NSRC], const float (&thr)[NSRC], float majority, int& cls) {
+__device__ __forceinline__ D ties_one_ref(const float (&in)[NSRC], const float (&thr)[NSRC], float majority, int& cls) {
   float acc = 0.0f, pos = 0.0f, neg = 0.0f;  // pos / neg double as the running max / min for MAX
   int n_pos = 0, n_neg = 0;
 #pragma unroll
   for (int s = 0; s < NSRC; ++s) {
-    const float x = to_f32<S>(in[s]);
+    const float x = in[s];
     const float m = fabsf(x) >= thr[s] ? x : 0.0f;
     acc = __fadd_rn(acc, m);
     if (FUNC == MC_TIES_MAX) {
@@ -78,6 +89,89 @@ __device__ __forceinline__ D ties_one(const S (&in)[NSRC], const float (&thr)[NS
   return from_f32<D>(__fmul_rn(to_f32<S>(from_f32<S>(up ? pos : fabsf(neg))), sg));  // |.| first: (+0) * -1 = -0 as torch
 }
 
+// a * b rounded to nearest, then clamped to [0, 1] with NaN -> +0 (PTX .sat): mul_sat(k, +inf) is the indicator of k > 0
+// for k >= +0 on the FMA pipe (0 * inf = NaN -> 0; any positive k, subnormals included, -> inf -> 1).
+__device__ __forceinline__ float mul_sat(float a, float b) {
+  float r;
+  asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+
+// SUM / MEAN over 16-bit sources: the same results bit for bit as ties_one_ref with the arithmetic moved off the
+// half-rate ALU pipe that bounded the first version of this pass (profiles/r01_ties.txt: 57 instructions per element,
+// ALU 65 %, DRAM 39 %) — no predicate, select or min/max per source, everything but the trim compare is FMUL/FADD/FFMA:
+//   * trim by multiplication, m = x * [|x| >= thr] (the reference's own form, ties_merging.py:98-101);
+//   * the sign is elected from the fp32 sum itself: rounding it to the 16-bit dtype first (:121) never changes the sign
+//     and never turns a non-zero sum into zero (the sum is a multiple of the dtype's smallest subnormal, overflow keeps
+//     the sign).  p = [acc > 0] and n = [acc < 0] are mul_sat(+-acc, inf), and half the elected sign is
+//     hs = mh + p (0.5 - mh) - n (0.5 + mh) with mh = +-0.5 the majority default: exact, values in {-0.5, +0.5};
+//   * only the elected candidate is summed, in a second sweep over the registers: k = max(sigma m, 0) computed as
+//     0.5 |m| + hs m, exact for 16-bit values (halving never drops a bit in fp32), so sum k is the reference's
+//     left-to-right sum of the kept entries with +0 in the other slots, negated for sigma = -1 (round-to-nearest is
+//     symmetric); fma(sum k, sigma, +0) restores the reference's +0 when nothing is kept;
+//   * MEAN: #kept != 0 is sum of mul_sat(k, inf); the float32 division by that small integer c is
+//     q0 = x r, q1 = fma(fma(-q0, c, x), r, q0) with r ~ 1 / c (MUFU), the correctly rounded quotient for every 16-bit x,
+//     c <= 8 and any r within 2 ulp of 1 / c (checked exhaustively: tests/test_ties_oracle.py); min(q1, x) returns
+//     x = inf when the 16-bit rounding of the sum overflowed (q1 = NaN there);
+//   * survivors that cancel exactly (class 3) are acc == 0 with a non-empty candidate, for either default sign:
+//     amb = [sum k > 0] (1 - p - n).
+// p, n, amb come back as 0.0 / 1.0 so that the census is three float adds per element.
+template <int NSRC, typename S, typename D, int FUNC>
+__device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float (&thr)[NSRC], float mh, float& p, float& n, float& amb) {
+  static_assert(sizeof(S) == 2 && FUNC != MC_TIES_MAX, "16-bit sources, SUM / MEAN");
+  const float inf = __int_as_float(0x7f800000);
+  float m[NSRC];
+#pragma unroll
+  for (int s = 0; s < NSRC; ++s) m[s] = __fmul_rn(in[s], fabsf(in[s]) >= thr[s] ? 1.0f : 0.0f);
+  float acc = m[0];
+#pragma unroll
+  for (int s = 1; s < NSRC; ++s) acc = __fadd_rn(acc, m[s]);
+  p = mul_sat(acc, inf);
+  n = mul_sat(acc, -inf);
+  const float hs = __fmaf_rn(-n, __fadd_rn(0.5f, mh), __fmaf_rn(p, __fsub_rn(0.5f, mh), mh));
+  const float sg = __fadd_rn(hs, hs);
+  float ksum = 0.0f, cnt = 0.0f;
+#pragma unroll
+  for (int s = 0; s < NSRC; ++s) {
+    const float k = __fmaf_rn(0.5f, fabsf(m[s]), __fmul_rn(m[s], hs));
+    ksum = s == 0 ? k : __fadd_rn(ksum, k);
+    if (FUNC == MC_TIES_MEAN) {
+      const float one = mul_sat(k, inf);
+      cnt = s == 0 ? one : __fadd_rn(cnt, one);
+    }
+  }
+  const float some = FUNC == MC_TIES_MEAN ? mul_sat(cnt, 1.0f) : mul_sat(ksum, inf);  // [a kept entry != 0]
+  amb = __fmaf_rn(-some, __fadd_rn(p, n), some);
+  if (FUNC == MC_TIES_SUM) return from_f32<D>(__fmaf_rn(ksum, sg, 0.0f));
+  const float x = to_f32<S>(from_f32<S>(ksum));  // >= +0: the sign goes on last
+  const float c = fmaxf(cnt, 1.0f), r = rcp_approx(c);
+  const float q0 = __fmul_rn(x, r);
+  const float q1 = __fmaf_rn(__fmaf_rn(-q0, c, x), r, q0);
+  return from_f32<D>(__fmaf_rn(fminf(q1, x), sg, 0.0f));
+}
+
+template <typename S, int FUNC>
+struct TiesFast {
+  static constexpr bool value = sizeof(S) == 2 && FUNC != MC_TIES_MAX;
+};
+
+template <int NSRC, typename S, typename D, int FUNC>
+__device__ __forceinline__ D ties_one(const float (&in)[NSRC], const float (&thr)[NSRC], float majority, int& cls) {
+  if constexpr (TiesFast<S, FUNC>::value) {
+    float p, n, amb;
+    const D out = ties_one_fast<NSRC, S, D, FUNC>(in, thr, majority > 0.0f ? 0.5f : -0.5f, p, n, amb);
+    cls = p != 0.0f ? 0 : (n != 0.0f ? 1 : (amb != 0.0f ? 3 : 2));
+    return out;
+  } else {
+    return ties_one_ref<NSRC, S, D, FUNC>(in, thr, majority, cls);
+  }
+}
+
 // mode 0: speculative merge with majority = +1, census of the elected signs, list of majority-dependent elements.
 // mode 1: dense re-merge with the real majority; exits at once unless ties_finalize_kernel asked for it (need_fix == 2).
 template <int NSRC, typename S, typename D, int FUNC>
@@ -85,7 +179,7 @@ __global__ void __launch_bounds__(kTiesMergeThreads)
 ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, TiesState* st,
                   unsigned long long* __restrict__ fix_list, int mode) {
   constexpr int E = 16 / sizeof(S);
-  constexpr int VPT = 2;  // vectors per source per thread
+  constexpr int VPT = 4;  // vectors per source per thread
   constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
   static_assert(CHUNK == kTiesMergeThreads * VPT * E, "chunk geometry");
   using VS = Vec<16>;
@@ -98,7 +192,10 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   float thr[NSRC];
 #pragma unroll
   for (int s = 0; s < NSRC; ++s) thr[s] = st->thr[s];
+  constexpr bool kFast = TiesFast<S, FUNC>::value;
+  const float mh = majority > 0.0f ? 0.5f : -0.5f;
   unsigned int c_pos = 0u, c_neg = 0u, c_amb = 0u;  // elements without survivors are derived: total - pos - neg - amb
+  float f_pos = 0.0f, f_neg = 0.0f;                 // fast path: per-chunk census in float (<= 16 per chunk: exact)
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     const MergeChunk ch = chunks[c];
     const MergeSeg* sg = segs + ch.seg;
@@ -114,19 +211,46 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
       }
       VD* q = reinterpret_cast<VD*>(reinterpret_cast<D*>(sg->dst) + base) + threadIdx.x;
 #pragma unroll
+      // Class-3 elements (rare) are collected as one bit per element in float accumulators (mask_j += amb * 2^e, an FFMA)
+      // and appended to the fix-up list after the sweep: the hot path is ONE basic block, so every load above issues
+      // before the first element is touched (ptxas sinks loads whose first use sits in a later block).
+      float amb_mask[VPT];
+#pragma unroll
       for (int j = 0; j < VPT; ++j) {
         VD o;
         D* oe = reinterpret_cast<D*>(&o);
+        amb_mask[j] = 0.0f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-          S in[NSRC];
+          float in[NSRC];
 #pragma unroll
-          for (int s = 0; s < NSRC; ++s) in[s] = reinterpret_cast<const S*>(&v[s][j])[e];
-          int cls;
-          oe[e] = ties_one<NSRC, S, D, FUNC>(in, thr, majority, cls);
-          c_pos += cls == 0;
-          c_neg += cls == 1;
-          if (cls == 3) {
+          for (int s = 0; s < NSRC; ++s) in[s] = vec_elem_f32<S>(v[s][j], e);
+          if constexpr (kFast) {
+            float p, n, amb;
+            oe[e] = ties_one_fast<NSRC, S, D, FUNC>(in, thr, mh, p, n, amb);
+            f_pos += p;
+            f_neg += n;
+            amb_mask[j] = __fmaf_rn(amb, (float)(1 << e), amb_mask[j]);
+          } else {
+            int cls;
+            oe[e] = ties_one<NSRC, S, D, FUNC>(in, thr, majority, cls);
+            c_pos += cls == 0;
+            c_neg += cls == 1;
+            amb_mask[j] += cls == 3 ? (float)(1 << e) : 0.0f;
+          }
+        }
+        st_stream(q + j * kTiesMergeThreads, o);
+      }
+      float amb_any = 0.0f;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) amb_any += amb_mask[j];
+      if (amb_any != 0.0f) {
+#pragma unroll 1
+        for (int j = 0; j < VPT; ++j) {
+          unsigned int bits = (unsigned int)amb_mask[j];
+          while (bits) {
+            const int e = __ffs((int)bits) - 1;
+            bits &= bits - 1u;
             c_amb += 1u;
             if (mode == 0) {
               const unsigned int slot = atomicAdd(&st->fix_count, 1u);
@@ -135,14 +259,13 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
             }
           }
         }
-        st_stream(q + j * kTiesMergeThreads, o);
       }
     } else {
       const long long n = rem < CHUNK ? rem : CHUNK;
       for (long long i = threadIdx.x; i < n; i += kTiesMergeThreads) {
-        S in[NSRC];
+        float in[NSRC];
 #pragma unroll
-        for (int s = 0; s < NSRC; ++s) in[s] = reinterpret_cast<const S*>(sg->src[s])[base + i];
+        for (int s = 0; s < NSRC; ++s) in[s] = to_f32<S>(reinterpret_cast<const S*>(sg->src[s])[base + i]);
         int cls;
         reinterpret_cast<D*>(sg->dst)[base + i] = ties_one<NSRC, S, D, FUNC>(in, thr, majority, cls);
         c_pos += cls == 0;
@@ -155,6 +278,11 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
           }
         }
       }
+    }
+    if constexpr (kFast) {
+      c_pos += (unsigned int)f_pos;
+      c_neg += (unsigned int)f_neg;
+      f_pos = f_neg = 0.0f;
     }
   }
   if (mode == 1) return;
@@ -193,9 +321,9 @@ ties_fix_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict_
     const MergeChunk ch = chunks[(int)(packed >> 32)];
     const MergeSeg* sg = segs + ch.seg;
     const long long idx = (long long)ch.idx * CHUNK + (long long)(unsigned int)packed;
-    S in[NSRC];
+    float in[NSRC];
 #pragma unroll
-    for (int s = 0; s < NSRC; ++s) in[s] = reinterpret_cast<const S*>(sg->src[s])[idx];
+    for (int s = 0; s < NSRC; ++s) in[s] = to_f32<S>(reinterpret_cast<const S*>(sg->src[s])[idx]);
     int cls;
     reinterpret_cast<D*>(sg->dst)[idx] = ties_one<NSRC, S, D, FUNC>(in, thr, majority, cls);
   }
@@ -283,7 +411,7 @@ __device__ __forceinline__ void metrics_one(const S (&in)[NSRC], const float (&t
 }
 
 template <int NSRC, typename S>
-__global__ void __launch_bounds__(kTiesMergeThreads)
+__global__ void __launch_bounds__(kTiesMetricsThreads)
 ties_metrics_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, const TiesState* __restrict__ st,
                     TiesMetricSums* __restrict__ out) {
   constexpr int E = 16 / sizeof(S);
@@ -307,7 +435,7 @@ ties_metrics_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restr
       for (int s = 0; s < NSRC; ++s) {
         const Vec<16>* p = reinterpret_cast<const Vec<16>*>(reinterpret_cast<const S*>(sg->src[s]) + base) + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < VPT; ++j) v[s][j] = ld_stream(p + j * kTiesMergeThreads);
+        for (int j = 0; j < VPT; ++j) v[s][j] = ld_stream(p + j * kTiesMetricsThreads);
       }
 #pragma unroll
       for (int j = 0; j < VPT; ++j) {
@@ -321,7 +449,7 @@ ties_metrics_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restr
       }
     } else {
       const long long m = rem < CHUNK ? rem : CHUNK;
-      for (long long i = threadIdx.x; i < m; i += kTiesMergeThreads) {
+      for (long long i = threadIdx.x; i < m; i += kTiesMetricsThreads) {
         S in[NSRC];
 #pragma unroll
         for (int s = 0; s < NSRC; ++s) in[s] = reinterpret_cast<const S*>(sg->src[s])[base + i];

@@ -1,0 +1,150 @@
+"""CPU checks of the arithmetic identities behind ``ties_one_fast`` (modelcompose_b200/csrc/mc_ties_kernels.cuh).
+
+The GPU kernel replaces the compare / select / min-max formulation of the TIES element (oracle/ties_oracle.py,
+reference ties_merging.py:98-155) by FMUL / FADD / FFMA forms.  Two things are proven here without a GPU:
+
+* a numpy float32 emulation of the kernel's exact instruction sequence (every op one IEEE round-to-nearest step, FMA
+  emulated where the product is exact) reproduces the oracle bit for bit on random, cancelling, subnormal and
+  overflowing 16-bit inputs, for both default signs;
+* the division-free MEAN quotient ``q1 = fma(fma(-q0, c, x), r, q0)``, ``q0 = x * r`` is the correctly rounded
+  ``x / c`` for EVERY non-negative finite bf16 / fp16 value x, every count c <= 8 and every reciprocal r within 2 ulp
+  of 1 / c (the hardware's rcp.approx is within 1 ulp) — exhaustive.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ties_oracle as TO
+
+F32 = np.float32
+INF = F32(np.inf)
+
+
+def mul_sat(a, b):
+    """PTX mul.rn.sat.f32: clamp to [0, 1], NaN -> +0."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        r = (a.astype(F32) * F32(b)).astype(F32)
+    r = np.where(np.isnan(r), F32(0), r)
+    return np.clip(r, F32(0), F32(1)).astype(F32)
+
+
+def round_dt(x, dt):
+    return torch.from_numpy(x.astype(F32)).to(dt).to(torch.float32).numpy()
+
+
+def rn32_sum(hi_terms):
+    """RN32(a + b) for float64 a, b whose exact sum may need more than 53 bits: TwoSum + midpoint tie-break."""
+    a, b = hi_terms
+    s = a + b
+    bb = s - a
+    err = (a - (s - bb)) + (b - bb)          # exact error of the float64 addition
+    c32 = s.astype(F32)
+    d = s - c32.astype(np.float64)
+    with np.errstate(over="ignore", invalid="ignore"):
+        other = np.nextafter(c32, np.where(d > 0, INF, -INF).astype(F32)).astype(np.float64)
+    mid = (c32.astype(np.float64) + other) / 2
+    is_mid = (d != 0) & (s == mid)
+    toward_other = is_mid & (np.sign(err) == np.sign(d)) & (err != 0)
+    # at an exact float32 midpoint the float64 rounding error decides; numpy's own tie-to-even is right when err == 0
+    away_c32 = is_mid & (np.sign(err) == -np.sign(d)) & (err != 0)
+    out = np.where(toward_other, other.astype(F32), c32)
+    out = np.where(away_c32, c32, out)
+    return out.astype(F32)
+
+
+def fast_divide(x, c, r):
+    """The kernel's MEAN quotient (x >= 0 float32 holding a 16-bit value, c float32 count, r float32 ~ 1 / c)."""
+    x64, c64, r64 = x.astype(np.float64), c.astype(np.float64), r.astype(np.float64)
+    q0 = (x64 * r64).astype(F32)                           # exact product (<= 11 + 24 bits), one rounding
+    res = (x64 - q0.astype(np.float64) * c64).astype(F32)  # fma(-q0, c, x): product exact, difference exact in float64
+    q1 = rn32_sum((q0.astype(np.float64), res.astype(np.float64) * r64))  # fma(res, r, q0): product exact (<= 48 bits)
+    return np.fmin(q1, x)                                  # fminf: returns x when q1 is NaN (x = inf)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_mean_quotient_is_correctly_rounded_exhaustive(dt):
+    bits = torch.arange(0, 1 << 15, dtype=torch.int32).to(torch.int16)
+    x = bits.view(dt).to(torch.float32).numpy()
+    x = x[np.isfinite(x)]
+    assert x.size > 30000 and x.min() == 0.0
+    for c in range(1, 9):
+        cf = np.full_like(x, c, dtype=F32)
+        want = (x / cf).astype(F32)                        # IEEE float32 division
+        r_exact = F32(1.0) / F32(c)
+        for ulps in (-2, -1, 0, 1, 2):
+            r = r_exact
+            for _ in range(abs(ulps)):
+                r = np.nextafter(r, INF if ulps > 0 else -INF, dtype=F32)
+            got = fast_divide(x, cf, np.full_like(x, r))
+            bad = got.view(np.uint32) != want.view(np.uint32)
+            assert not bad.any(), (dt, c, ulps, x[bad][:4], got[bad][:4], want[bad][:4])
+    # overflowed 16-bit sum: x = inf stays inf
+    got = fast_divide(np.array([np.inf], F32), np.array([2], F32), np.array([0.5], F32))
+    assert np.isinf(got[0]) and got[0] > 0
+
+
+def emulate_fast(flat: torch.Tensor, thr, majority: float, func: str):
+    """ties_one_fast, op for op, on [n_src, d] 16-bit inputs; returns (out, p, n, amb)."""
+    dt = flat.dtype
+    x = flat.to(torch.float32).numpy()
+    n_src = x.shape[0]
+    mh = F32(0.5 if majority > 0 else -0.5)
+    with np.errstate(invalid="ignore", over="ignore"):
+        m = [(x[s] * (np.abs(x[s]) >= F32(thr[s])).astype(F32)).astype(F32) for s in range(n_src)]
+        acc = m[0]
+        for s in range(1, n_src):
+            acc = (acc + m[s]).astype(F32)
+        p, n = mul_sat(acc, INF), mul_sat(acc, -INF)
+        hs = (-n * (F32(0.5) + mh) + (p * (F32(0.5) - mh) + mh)).astype(F32)   # every step exact
+        sg = (hs + hs).astype(F32)
+        ksum = cnt = None
+        for s in range(n_src):
+            k = (F32(0.5) * np.abs(m[s]) + (m[s] * hs).astype(F32)).astype(F32)  # both products exact: one rounding
+            ksum = k if s == 0 else (ksum + k).astype(F32)
+            one = mul_sat(k, INF)
+            cnt = one if s == 0 else (cnt + one).astype(F32)
+        some = mul_sat(cnt, 1.0) if func == "mean" else mul_sat(ksum, INF)
+        amb = (-some * (p + n) + some).astype(F32)
+        if func == "sum":
+            out = torch.from_numpy((ksum * sg + F32(0)).astype(F32)).to(dt)
+        else:
+            xr = round_dt(ksum, dt)
+            c = np.maximum(cnt, F32(1))
+            q = np.fmin((xr / c).astype(F32), xr)           # the quotient itself is covered by the exhaustive test
+            out = torch.from_numpy((q * sg + F32(0)).astype(F32))
+    return out, p, n, amb
+
+
+def make_flat(kind, n_src, d, dt, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "gauss":
+        t = torch.randn(n_src, d, generator=g) * 0.02
+    elif kind == "ints":
+        t = torch.randint(-3, 4, (n_src, d), generator=g).float()
+    elif kind == "neg":
+        t = torch.randn(n_src, d, generator=g) * 0.02 - 0.03
+    elif kind == "subnormal":
+        tiny = 2.0 ** -130 if dt == torch.bfloat16 else 2.0 ** -22
+        t = torch.randint(-6, 7, (n_src, d), generator=g).float() * tiny
+    else:  # overflowing sums in fp16, wide dynamic range in bf16
+        t = (torch.randn(n_src, d, generator=g) * torch.exp(torch.randn(n_src, d, generator=g) * 6.0)).clamp(-6e4, 6e4)
+    return t.to(dt)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("kind,K", [("gauss", 20), ("ints", 50), ("ints", 99), ("neg", 20), ("subnormal", 60), ("wide", 30)])
+@pytest.mark.parametrize("n_src", [1, 2, 3, 5, 8])
+def test_fast_formulation_matches_oracle(dt, kind, K, n_src):
+    flat = make_flat(kind, n_src, 20011, dt, seed=31 * n_src + len(kind))
+    for func in ("sum", "mean"):
+        want, st = TO.ties_merge_flat(flat, K, func)
+        thr = st["thresholds"].numpy()
+        for majority in (st["majority"], -st["majority"] if st["majority"] else 1.0):
+            ref = TO.merge_given_statistics(flat, thr, majority, func)
+            got, p, n, amb = emulate_fast(flat, thr, majority, func)
+            iv = torch.int16 if got.dtype != torch.float32 else torch.int32
+            assert got.dtype == ref.dtype
+            assert torch.equal(got.view(iv), ref.view(iv)), (func, majority, int((got.float() != ref.float()).sum()))
+        got, p, n, amb = emulate_fast(flat, thr, st["majority"], func)
+        assert (int(p.sum()), int(n.sum()), int(amb.sum())) == (st["n_pos"], st["n_neg"], st["ambiguous"])
+        assert set(np.unique(np.concatenate([p, n, amb]))) <= {0.0, 1.0}
