@@ -344,6 +344,24 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
     def step():
         _cabi.check(lib.mc_merge_host(len(pick), n_src, sp, dp, ne, w, _cabi.MC_MERGE_WEIGHTED, _cabi.MC_BF16,
                                       _cabi.MC_BF16, 0), "mc_merge_host")
+
+    def pcie_probe():
+        """Plain pinned-memory copy rates of this box (what bounds the e2e number): 1 GiB each way, CUDA events."""
+        big = max(range(len(pick)), key=lambda k: h_src[0][k].numel())
+        hbuf, dbuf = h_src[0][big].view(-1), srcs[0][pick[big]].view(-1).clone()
+        reps = max(1, (1 << 30) // (hbuf.numel() * 2))
+        out = {}
+        for name, (dst, src) in (("h2d_GBps", (dbuf, hbuf)), ("d2h_GBps", (h_out[big].view(-1), dbuf))):
+            dst.copy_(src, non_blocking=True)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                dst.copy_(src, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            out[name] = round(reps * hbuf.numel() * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+        return out
+    probe = pcie_probe()
     steps = max(1, min(args.steps, 3))
     step()  # warm-up
     barrier()
@@ -365,7 +383,9 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
             "api": "mc_merge_host (pinned host buffers, H2D/kernel/D2H pipelined, returns after last D2H)",
             "sample": "whole shard" if stride == 1 else f"every {stride}th tensor of the shard (host RAM bound)",
-            "timer": "host wall clock around the synchronous call, max over ranks"}
+            "timer": "host wall clock around the synchronous call, max over ranks",
+            "pcie_probe": probe,
+            "pcie_bound_GBps": round(float(elems * 2 * (n_src + 1)) / (h2d / (probe["h2d_GBps"] * 1e9)) / 1e9 * world, 1)}
 
 
 # ------------------------------------------------------------------------------------------------ TIES workload

@@ -12,6 +12,7 @@
 // Algorithmic bytes per element = (passes + 1) * n_src * sizeof(src) + sizeof(dst)  (bf16, 3 sources, sum: 14 B).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "mc_ties_kernels.cuh"
@@ -294,6 +295,13 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   const unsigned int lo2 = lo | (lo << 16), hi2 = (lo + span) | ((lo + span) << 16) | 0x80008000u;
   unsigned int below = 0u, ge_acc = 0u, n_fast = 0u;  // ge_acc = 128 x (#keys >= lo) over the n_fast vector-path elements
   unsigned long long below_total = 0ull;
+  // narrow bracket: thresholds lo + 1 and lo + 2 (clamped to 0x8000, above every key, so that no borrow crosses the halves)
+  const bool narrow = span <= 1u;
+  const unsigned int t1 = min(lo + 1u, 0x8000u), t2 = min(lo + 2u, 0x8000u);
+  unsigned int t1_2 = t1 | (t1 << 16), t2_2 = t2 | (t2 << 16);
+  asm volatile("" : "+r"(t1_2), "+r"(t2_2));  // keep the packed forms in registers (else each use re-derives t * 0x10001)
+  unsigned int ge1_acc = 0u, ge2_acc = 0u;
+  unsigned long long bin0_total = 0ull, bin1_total = 0ull;
   // The chunk -> segment -> data pointer chain (two dependent loads per chunk) is resolved one iteration ahead, while
   // the data of the current iteration is in flight: the streaming loads never wait for metadata.
   const Vec<16>* ptr[PAIR];  // vector path: this thread's first vector of chunk c0 + j; NULL = tail / unaligned / none
@@ -327,19 +335,36 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
       const int c = c0 + j;
       if (c >= nchunks) break;
       if (fast[j]) {
-        // two 15-bit keys per 32-bit word: (0x8000 | key) - lo keeps bit 15 iff key >= lo, (0x8000 | hi) - key keeps it iff
-        // key <= hi (no borrow crosses the halves); the flag bytes (0x80) are summed with one dp4a per word
+        // two 15-bit keys per 32-bit word: (0x8000 | key) - t keeps bit 15 iff key >= t (no borrow crosses the halves); the
+        // flag bytes (0x80) are summed with one dp4a per word
+        if (narrow) {
+          // bracket of one or two bins (the usual outcome of the sampling): three ">= t" counters, t = lo, lo + 1, lo + 2,
+          // give the count below the bracket and both bin counts with no branch and no atomic — the divergent
+          // shared-memory atomic path below, taken by ~1 % of the elements, doubled the instruction count of this pass
 #pragma unroll
-        for (int u = 0; u < VPT; ++u) {
+          for (int u = 0; u < VPT; ++u) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const unsigned int keys = v[j][u].w[w] & 0x7fff7fffu;
-            const unsigned int ge = ((keys | 0x80008000u) - lo2) & 0x80008000u;
-            ge_acc = __dp4a(ge, 0x01010101u, ge_acc);
-            const unsigned int in = ge & (hi2 - keys);
-            if (in) {
-              if (in & 0x00008000u) atomicAdd(&s_win[(keys & 0xffffu) - lo], 1u);
-              if (in & 0x80000000u) atomicAdd(&s_win[(keys >> 16) - lo], 1u);
+            for (int w = 0; w < 4; ++w) {
+              const unsigned int k = v[j][u].w[w] | 0x80008000u;
+              ge_acc = __dp4a((k - lo2) & 0x80008000u, 0x01010101u, ge_acc);
+              ge1_acc = __dp4a((k - t1_2) & 0x80008000u, 0x01010101u, ge1_acc);
+              ge2_acc = __dp4a((k - t2_2) & 0x80008000u, 0x01010101u, ge2_acc);
+            }
+          }
+        } else {
+          // wide bracket: (0x8000 | hi) - key keeps bit 15 iff key <= hi; keys inside go to the shared-memory bins
+#pragma unroll
+          for (int u = 0; u < VPT; ++u) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const unsigned int keys = v[j][u].w[w] & 0x7fff7fffu;
+              const unsigned int ge = ((keys | 0x80008000u) - lo2) & 0x80008000u;
+              ge_acc = __dp4a(ge, 0x01010101u, ge_acc);
+              const unsigned int in = ge & (hi2 - keys);
+              if (in) {
+                if (in & 0x00008000u) atomicAdd(&s_win[(keys & 0xffffu) - lo], 1u);
+                if (in & 0x80000000u) atomicAdd(&s_win[(keys >> 16) - lo], 1u);
+              }
             }
           }
         }
@@ -358,11 +383,25 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
     }
     if (n_fast > (1u << 24)) {  // keep the 32-bit per-thread counters (ge_acc counts in units of 128) from wrapping
       below_total += below + (n_fast - (ge_acc >> 7));
-      below = ge_acc = n_fast = 0u;
+      bin0_total += (ge_acc >> 7) - (ge1_acc >> 7);
+      bin1_total += (ge1_acc >> 7) - (ge2_acc >> 7);
+      below = ge_acc = ge1_acc = ge2_acc = n_fast = 0u;
     }
   }
 #undef MC_TIES_RESOLVE
   below_total += below + (n_fast - (ge_acc >> 7));
+  if (narrow) {  // warp-reduced bin counts of the vector path join the scalar path's shared-memory bins
+    unsigned long long b0 = bin0_total + ((ge_acc >> 7) - (ge1_acc >> 7)), b1 = bin1_total + ((ge1_acc >> 7) - (ge2_acc >> 7));
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      b0 += __shfl_xor_sync(0xffffffffu, b0, d);
+      b1 += __shfl_xor_sync(0xffffffffu, b1, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (b0) atomicAdd(&s_win[0], (unsigned int)b0);
+      if (b1 && span == 1u) atomicAdd(&s_win[1], (unsigned int)b1);
+    }
+  }
   // block reduction of the below-counts (64-bit), then one global atomic per CTA
   unsigned long long x = below_total;
 #pragma unroll
@@ -617,11 +656,15 @@ extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, 
   cudaStream_t s = (cudaStream_t)stream;
   const int rc = enqueue_select(p, kth, s);
   if (rc != MC_OK) return rc;
-  fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 0);
+  // L2 prefetch distance of the merge pass: one generation of resident CTAs (MC_TIES_PREFETCH=0 turns it off, a
+  // development switch for the ncu comparison)
+  static const int pf_env = [] { const char* e = getenv("MC_TIES_PREFETCH"); return e ? atoi(e) : -1; }();
+  const int pf_dist = pf_env >= 0 ? pf_env : p->sms * 6;
+  fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 0, pf_dist);
   ties_finalize_kernel<<<1, 1, 0, s>>>(p->d_state, func, (unsigned long long)p->total_elems);
   fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix);
   // dense re-merge: a grid-stride launch that is small when it turns out to be a no-op
-  fn.merge<<<std::min(p->nchunks, p->sms * 16), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 1);
+  fn.merge<<<std::min(p->nchunks, p->sms * 16), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 1, 0);
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
 }

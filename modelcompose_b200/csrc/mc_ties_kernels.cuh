@@ -172,12 +172,17 @@ __device__ __forceinline__ D ties_one(const float (&in)[NSRC], const float (&thr
   }
 }
 
+// Ask L2 for `bytes` (multiple of 16) starting at the 16-byte aligned global address p: one instruction, no destination.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned int bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // mode 0: speculative merge with majority = +1, census of the elected signs, list of majority-dependent elements.
 // mode 1: dense re-merge with the real majority; exits at once unless ties_finalize_kernel asked for it (need_fix == 2).
 template <int NSRC, typename S, typename D, int FUNC>
 __global__ void __launch_bounds__(kTiesMergeThreads)
 ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, TiesState* st,
-                  unsigned long long* __restrict__ fix_list, int mode) {
+                  unsigned long long* __restrict__ fix_list, int mode, int pf_dist) {
   constexpr int E = 16 / sizeof(S);
   constexpr int VPT = 4;  // vectors per source per thread
   constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
@@ -197,6 +202,25 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   unsigned int c_pos = 0u, c_neg = 0u, c_amb = 0u;  // elements without survivors are derived: total - pos - neg - amb
   float f_pos = 0.0f, f_neg = 0.0f;                 // fast path: per-chunk census in float (<= 16 per chunk: exact)
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    // ptxas sinks this long block's loads next to their first use (three 16-byte loads in flight per thread), so the
+    // memory-level parallelism comes from L2 prefetches instead: one thread asks L2 for the whole chunk that the CTA
+    // scheduled pf_dist blocks later will stream (one generation of resident CTAs ahead; the first generation asks
+    // for its own), and the demand loads below mostly hit L2.
+    if (pf_dist > 0 && threadIdx.x == 0) {
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) {
+        const long long cq = rep == 0 ? (long long)c + pf_dist : (long long)c;
+        if (cq >= nchunks || (rep == 1 && c >= pf_dist)) continue;
+        const MergeChunk pch = chunks[cq];
+        const MergeSeg* psg = segs + pch.seg;
+        const long long pbase = (long long)pch.idx * CHUNK;
+        if (psg->aligned && psg->numel - pbase >= CHUNK) {
+#pragma unroll
+          for (int s = 0; s < NSRC; ++s)
+            l2_prefetch_bulk(reinterpret_cast<const S*>(psg->src[s]) + pbase, (unsigned int)(CHUNK * sizeof(S)));
+        }
+      }
+    }
     const MergeChunk ch = chunks[c];
     const MergeSeg* sg = segs + ch.seg;
     const long long base = (long long)ch.idx * CHUNK;
@@ -329,7 +353,7 @@ ties_fix_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict_
   }
 }
 
-typedef void (*ties_fn_t)(const MergeSeg*, const MergeChunk*, int, TiesState*, unsigned long long*, int);
+typedef void (*ties_fn_t)(const MergeSeg*, const MergeChunk*, int, TiesState*, unsigned long long*, int, int);
 typedef void (*ties_fix_fn_t)(const MergeSeg*, const MergeChunk*, const TiesState*, const unsigned long long*);
 struct TiesKernels {
   ties_fn_t merge;
