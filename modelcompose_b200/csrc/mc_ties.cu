@@ -295,13 +295,20 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   const unsigned int lo2 = lo | (lo << 16), hi2 = (lo + span) | ((lo + span) << 16) | 0x80008000u;
   unsigned int below = 0u, ge_acc = 0u, n_fast = 0u;  // ge_acc = 128 x (#keys >= lo) over the n_fast vector-path elements
   unsigned long long below_total = 0ull;
-  // narrow bracket: thresholds lo + 1 and lo + 2 (clamped to 0x8000, above every key, so that no borrow crosses the halves)
-  const bool narrow = span <= 1u;
-  const unsigned int t1 = min(lo + 1u, 0x8000u), t2 = min(lo + 2u, 0x8000u);
-  unsigned int t1_2 = t1 | (t1 << 16), t2_2 = t2 | (t2 << 16);
-  asm volatile("" : "+r"(t1_2), "+r"(t2_2));  // keep the packed forms in registers (else each use re-derives t * 0x10001)
-  unsigned int ge1_acc = 0u, ge2_acc = 0u;
-  unsigned long long bin0_total = 0ull, bin1_total = 0ull;
+  // narrow bracket (<= 4 bins, the usual outcome of the sampling): ">= t" counters for t = lo + 1 .. lo + 4 (clamped to
+  // 0x8000, above every key, so that no borrow crosses the halves) replace the shared-memory bins of the vector path
+  constexpr int NT = 4;
+  const bool narrow = span < (unsigned int)NT;
+  unsigned int tn2[NT], gen_acc[NT];
+  unsigned long long bin_total[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const unsigned int t = min(lo + 1u + (unsigned int)i, 0x8000u);
+    tn2[i] = t | (t << 16);
+    asm volatile("" : "+r"(tn2[i]));  // keep the packed form in a register (else each use re-derives t * 0x10001)
+    gen_acc[i] = 0u;
+    bin_total[i] = 0ull;
+  }
   // The chunk -> segment -> data pointer chain (two dependent loads per chunk) is resolved one iteration ahead, while
   // the data of the current iteration is in flight: the streaming loads never wait for metadata.
   const Vec<16>* ptr[PAIR];  // vector path: this thread's first vector of chunk c0 + j; NULL = tail / unaligned / none
@@ -338,19 +345,28 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
         // two 15-bit keys per 32-bit word: (0x8000 | key) - t keeps bit 15 iff key >= t (no borrow crosses the halves); the
         // flag bytes (0x80) are summed with one dp4a per word
         if (narrow) {
-          // bracket of one or two bins (the usual outcome of the sampling): three ">= t" counters, t = lo, lo + 1, lo + 2,
-          // give the count below the bracket and both bin counts with no branch and no atomic — the divergent
-          // shared-memory atomic path below, taken by ~1 % of the elements, doubled the instruction count of this pass
-#pragma unroll
-          for (int u = 0; u < VPT; ++u) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const unsigned int k = v[j][u].w[w] | 0x80008000u;
-              ge_acc = __dp4a((k - lo2) & 0x80008000u, 0x01010101u, ge_acc);
-              ge1_acc = __dp4a((k - t1_2) & 0x80008000u, 0x01010101u, ge1_acc);
-              ge2_acc = __dp4a((k - t2_2) & 0x80008000u, 0x01010101u, ge2_acc);
-            }
+          // three instructions per threshold and word (subtract, mask, dp4a), no branch, no atomic: the divergent
+          // shared-memory atomic path below, taken by ~1 % of the elements, doubled the instruction count of this pass.
+          // Thresholds above the bracket are skipped (span is CTA-uniform).
+#define MC_TIES_COUNT_WORDS(N_T)                                                                     \
+  _Pragma("unroll") for (int u = 0; u < VPT; ++u) {                                                  \
+    _Pragma("unroll") for (int w = 0; w < 4; ++w) {                                                  \
+      const unsigned int k = v[j][u].w[w] | 0x80008000u;                                             \
+      ge_acc = __dp4a((k - lo2) & 0x80008000u, 0x01010101u, ge_acc);                                 \
+      _Pragma("unroll") for (int i = 0; i < (N_T); ++i)                                              \
+        gen_acc[i] = __dp4a((k - tn2[i]) & 0x80008000u, 0x01010101u, gen_acc[i]);                    \
+    }                                                                                                \
+  }
+          if (span == 0u) {
+            MC_TIES_COUNT_WORDS(1)
+          } else if (span == 1u) {
+            MC_TIES_COUNT_WORDS(2)
+          } else if (span == 2u) {
+            MC_TIES_COUNT_WORDS(3)
+          } else {
+            MC_TIES_COUNT_WORDS(NT)
           }
+#undef MC_TIES_COUNT_WORDS
         } else {
           // wide bracket: (0x8000 | hi) - key keeps bit 15 iff key <= hi; keys inside go to the shared-memory bins
 #pragma unroll
@@ -383,23 +399,25 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
     }
     if (n_fast > (1u << 24)) {  // keep the 32-bit per-thread counters (ge_acc counts in units of 128) from wrapping
       below_total += below + (n_fast - (ge_acc >> 7));
-      bin0_total += (ge_acc >> 7) - (ge1_acc >> 7);
-      bin1_total += (ge1_acc >> 7) - (ge2_acc >> 7);
-      below = ge_acc = ge1_acc = ge2_acc = n_fast = 0u;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        bin_total[i] += ((i == 0 ? ge_acc : gen_acc[i - 1]) >> 7) - (gen_acc[i] >> 7);
+        if (i) gen_acc[i - 1] = 0u;
+      }
+      gen_acc[NT - 1] = 0u;
+      below = ge_acc = n_fast = 0u;
     }
   }
 #undef MC_TIES_RESOLVE
   below_total += below + (n_fast - (ge_acc >> 7));
   if (narrow) {  // warp-reduced bin counts of the vector path join the scalar path's shared-memory bins
-    unsigned long long b0 = bin0_total + ((ge_acc >> 7) - (ge1_acc >> 7)), b1 = bin1_total + ((ge1_acc >> 7) - (ge2_acc >> 7));
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      b0 += __shfl_xor_sync(0xffffffffu, b0, d);
-      b1 += __shfl_xor_sync(0xffffffffu, b1, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      if (b0) atomicAdd(&s_win[0], (unsigned int)b0);
-      if (b1 && span == 1u) atomicAdd(&s_win[1], (unsigned int)b1);
+    for (int i = 0; i < NT; ++i) {
+      // counters of thresholds above the bracket were never advanced: bins beyond the span are not flushed
+      unsigned long long b = bin_total[i] + (((i == 0 ? ge_acc : gen_acc[i - 1]) >> 7) - (gen_acc[i] >> 7));
+#pragma unroll
+      for (int d = 16; d; d >>= 1) b += __shfl_xor_sync(0xffffffffu, b, d);
+      if ((threadIdx.x & 31) == 0 && b && (unsigned int)i <= span) atomicAdd(&s_win[i], (unsigned int)b);
     }
   }
   // block reduction of the below-counts (64-bit), then one global atomic per CTA
@@ -659,7 +677,7 @@ extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, 
   // L2 prefetch distance of the merge pass: one generation of resident CTAs (MC_TIES_PREFETCH=0 turns it off, a
   // development switch for the ncu comparison)
   static const int pf_env = [] { const char* e = getenv("MC_TIES_PREFETCH"); return e ? atoi(e) : -1; }();
-  const int pf_dist = pf_env >= 0 ? pf_env : p->sms * 6;
+  const int pf_dist = pf_env >= 0 ? pf_env : p->sms * 4;
   fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 0, pf_dist);
   ties_finalize_kernel<<<1, 1, 0, s>>>(p->d_state, func, (unsigned long long)p->total_elems);
   fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix);

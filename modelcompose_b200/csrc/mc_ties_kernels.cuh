@@ -102,6 +102,31 @@ __device__ __forceinline__ float rcp_approx(float a) {
   return r;
 }
 
+// Packed trim of one 32-bit word (two 16-bit values): entries with |x| < thr become +0, the others keep their bits.
+// thr2 holds the threshold (a value of the dtype: it is the k-th |x| of the data) in both halves.
+template <typename S>
+__device__ __forceinline__ uint32_t trim_word(uint32_t w, uint32_t thr2) {
+  const uint32_t a = w & 0x7fff7fffu;
+  if constexpr (std::is_same<S, __nv_bfloat16>::value) {
+    __nv_bfloat162_raw ra, rt;
+    ra.x = (unsigned short)a; ra.y = (unsigned short)(a >> 16);
+    rt.x = (unsigned short)thr2; rt.y = (unsigned short)(thr2 >> 16);
+    return w & __hge2_mask(__nv_bfloat162(ra), __nv_bfloat162(rt));
+  } else {
+    __half2_raw ra, rt;
+    ra.x = (unsigned short)a; ra.y = (unsigned short)(a >> 16);
+    rt.x = (unsigned short)thr2; rt.y = (unsigned short)(thr2 >> 16);
+    return w & __hge2_mask(__half2(ra), __half2(rt));
+  }
+}
+template <typename S>
+__device__ __forceinline__ uint32_t pack_thr(float thr) {
+  uint32_t h;  // the conversion is exact
+  if constexpr (std::is_same<S, __nv_bfloat16>::value) h = __bfloat16_as_ushort(__float2bfloat16_rn(thr));
+  else h = __half_as_ushort(__float2half_rn(thr));
+  return h | (h << 16);
+}
+
 // SUM / MEAN over 16-bit sources: the same results bit for bit as ties_one_ref with the arithmetic moved off the
 // half-rate ALU pipe that bounded the first version of this pass (profiles/r01_ties.txt: 57 instructions per element,
 // ALU 65 %, DRAM 39 %) — no predicate, select or min/max per source, everything but the trim compare is FMUL/FADD/FFMA:
@@ -121,13 +146,13 @@ __device__ __forceinline__ float rcp_approx(float a) {
 //   * survivors that cancel exactly (class 3) are acc == 0 with a non-empty candidate, for either default sign:
 //     amb = [sum k > 0] (1 - p - n).
 // p, n, amb come back as 0.0 / 1.0 so that the census is three float adds per element.
-template <int NSRC, typename S, typename D, int FUNC>
+template <int NSRC, typename S, typename D, int FUNC, bool TRIMMED = false>
 __device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float (&thr)[NSRC], float mh, float& p, float& n, float& amb) {
   static_assert(sizeof(S) == 2 && FUNC != MC_TIES_MAX, "16-bit sources, SUM / MEAN");
   const float inf = __int_as_float(0x7f800000);
   float m[NSRC];
 #pragma unroll
-  for (int s = 0; s < NSRC; ++s) m[s] = __fmul_rn(in[s], fabsf(in[s]) >= thr[s] ? 1.0f : 0.0f);
+  for (int s = 0; s < NSRC; ++s) m[s] = TRIMMED ? in[s] : __fmul_rn(in[s], fabsf(in[s]) >= thr[s] ? 1.0f : 0.0f);
   float acc = m[0];
 #pragma unroll
   for (int s = 1; s < NSRC; ++s) acc = __fadd_rn(acc, m[s]);
@@ -199,6 +224,11 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   for (int s = 0; s < NSRC; ++s) thr[s] = st->thr[s];
   constexpr bool kFast = TiesFast<S, FUNC>::value;
   const float mh = majority > 0.0f ? 0.5f : -0.5f;
+  uint32_t thr2[NSRC];
+  if constexpr (kFast) {
+#pragma unroll
+    for (int s = 0; s < NSRC; ++s) thr2[s] = pack_thr<S>(thr[s]);
+  }
   unsigned int c_pos = 0u, c_neg = 0u, c_amb = 0u;  // elements without survivors are derived: total - pos - neg - amb
   float f_pos = 0.0f, f_neg = 0.0f;                 // fast path: per-chunk census in float (<= 16 per chunk: exact)
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -244,6 +274,13 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
         VD o;
         D* oe = reinterpret_cast<D*>(&o);
         amb_mask[j] = 0.0f;
+        if constexpr (kFast) {  // trim two values per instruction on the packed words, before they are widened
+#pragma unroll
+          for (int s = 0; s < NSRC; ++s) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) v[s][j].w[w] = trim_word<S>(v[s][j].w[w], thr2[s]);
+          }
+        }
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           float in[NSRC];
@@ -251,7 +288,7 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
           for (int s = 0; s < NSRC; ++s) in[s] = vec_elem_f32<S>(v[s][j], e);
           if constexpr (kFast) {
             float p, n, amb;
-            oe[e] = ties_one_fast<NSRC, S, D, FUNC>(in, thr, mh, p, n, amb);
+            oe[e] = ties_one_fast<NSRC, S, D, FUNC, true>(in, thr, mh, p, n, amb);
             f_pos += p;
             f_neg += n;
             amb_mask[j] = __fmaf_rn(amb, (float)(1 << e), amb_mask[j]);
