@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(1024) ties_bracket_kernel(unsigned long long* 
 // The streaming pass: keys below the bracket are counted, keys inside it histogrammed (a few bins, rarely hit).
 template <typename S>
 __global__ void __launch_bounds__(kTiesCountThreads, 2)
-ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, TiesState* st,
-                  unsigned long long* __restrict__ ghist) {
+ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, const void* const* __restrict__ vec,
+                  int nchunks, TiesState* st, unsigned long long* __restrict__ ghist) {
   __shared__ unsigned int s_win[kTiesWindowBins];
   __shared__ unsigned int s_below;
   if (st->need_full) return;
@@ -309,20 +309,15 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
     gen_acc[i] = 0u;
     bin_total[i] = 0ull;
   }
-  // The chunk -> segment -> data pointer chain (two dependent loads per chunk) is resolved one iteration ahead, while
-  // the data of the current iteration is in flight: the streaming loads never wait for metadata.
+  // The address of every whole chunk comes from the plan's flat table (one 8-byte load; walking chunk -> segment cost
+  // three instructions per element), resolved one iteration ahead so the streaming loads never wait for it.
   const Vec<16>* ptr[PAIR];  // vector path: this thread's first vector of chunk c0 + j; NULL = tail / unaligned / none
-#define MC_TIES_RESOLVE(FIRST)                                                                                        \
-  _Pragma("unroll") for (int j = 0; j < PAIR; ++j) {                                                                  \
-    const long long c_ = (FIRST) + j;                                                                                 \
-    ptr[j] = nullptr;                                                                                                 \
-    if (c_ < nchunks) {                                                                                               \
-      const MergeChunk ch_ = chunks[c_];                                                                              \
-      const MergeSeg* sg_ = segs + ch_.seg;                                                                           \
-      const long long base_ = (long long)ch_.idx * CHUNK;                                                             \
-      if (sg_->aligned && sg_->numel - base_ >= CHUNK)                                                                \
-        ptr[j] = reinterpret_cast<const Vec<16>*>(reinterpret_cast<const S*>(sg_->src[src]) + base_) + threadIdx.x;   \
-    }                                                                                                                 \
+  const int row = (int)gridDim.y + 1;
+#define MC_TIES_RESOLVE(FIRST)                                                                          \
+  _Pragma("unroll") for (int j = 0; j < PAIR; ++j) {                                                    \
+    const long long c_ = (FIRST) + j;                                                                   \
+    const void* a_ = c_ < nchunks ? vec[c_ * row + src] : nullptr;                                      \
+    ptr[j] = a_ ? reinterpret_cast<const Vec<16>*>(a_) + threadIdx.x : nullptr;                         \
   }
   MC_TIES_RESOLVE((long long)blockIdx.x * PAIR)
   for (int c0 = blockIdx.x * PAIR; c0 < nchunks; c0 += gridDim.x * PAIR) {
@@ -503,6 +498,7 @@ struct mc_ties_plan {
   long long total_elems;
   MergeSeg* d_segs;
   MergeChunk* d_chunks;
+  const void** d_vec;          // [nchunks][n_src + 1]: source / destination address of every whole, aligned chunk (NULL row = tail / unaligned)
   TiesState* d_state;
   unsigned long long* d_hist;  // n_src x 2^15 bins
   unsigned long long* d_fix;   // kTiesFixCapacity entries
@@ -570,6 +566,7 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
   p->total_elems = total;
   p->d_segs = nullptr;
   p->d_chunks = nullptr;
+  p->d_vec = nullptr;
   p->d_state = nullptr;
   p->d_hist = nullptr;
   p->d_fix = nullptr;
@@ -588,10 +585,22 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
     if (e == cudaSuccess) e = cudaMalloc(&p->d_chunks, chunks.size() * sizeof(MergeChunk));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_segs, segs.data(), segs.size() * sizeof(MergeSeg), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_chunks, chunks.data(), chunks.size() * sizeof(MergeChunk), cudaMemcpyHostToDevice);
+    // flat address table of the vector path: the streaming kernels read one row instead of walking chunk -> segment
+    std::vector<const void*> vec(chunks.size() * (size_t)(n_src + 1), nullptr);
+    for (size_t c = 0; c < chunks.size(); ++c) {
+      const MergeSeg& sg = segs[chunks[c].seg];
+      const long long base = (long long)chunks[c].idx * CHUNK;
+      if (!sg.aligned || sg.numel - base < CHUNK) continue;
+      for (int k = 0; k < n_src; ++k) vec[c * (n_src + 1) + k] = (const char*)sg.src[k] + base * (long long)ss;
+      vec[c * (n_src + 1) + n_src] = has_dst ? (const char*)sg.dst + base * (long long)ds : nullptr;
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_vec, vec.size() * sizeof(void*));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_vec, vec.data(), vec.size() * sizeof(void*), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) {
     cudaFree(p->d_segs);
     cudaFree(p->d_chunks);
+    cudaFree(p->d_vec);
     cudaFree(p->d_state);
     cudaFree(p->d_hist);
     cudaFree(p->d_fix);
@@ -621,13 +630,13 @@ static int enqueue_select(const mc_ties_plan_t* p, int64_t kth, cudaStream_t s) 
       MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ties_sample_kernel<__half><<<sgrid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
       ties_bracket_kernel<<<p->n_src, 1024, bsmem, s>>>(p->d_hist, p->d_state, (unsigned long long)kth, (unsigned long long)p->total_elems);
-      ties_count_kernel<__half><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
+      ties_count_kernel<__half><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_hist);
       ties_window_select_kernel<__half><<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, (unsigned long long)kth);
     } else {
       MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ties_sample_kernel<__nv_bfloat16><<<sgrid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
       ties_bracket_kernel<<<p->n_src, 1024, bsmem, s>>>(p->d_hist, p->d_state, (unsigned long long)kth, (unsigned long long)p->total_elems);
-      ties_count_kernel<__nv_bfloat16><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
+      ties_count_kernel<__nv_bfloat16><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_hist);
       ties_window_select_kernel<__nv_bfloat16><<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, (unsigned long long)kth);
     }
   }
@@ -678,11 +687,11 @@ extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, 
   // development switch for the ncu comparison)
   static const int pf_env = [] { const char* e = getenv("MC_TIES_PREFETCH"); return e ? atoi(e) : -1; }();
   const int pf_dist = pf_env >= 0 ? pf_env : p->sms * 4;
-  fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 0, pf_dist);
+  fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 0, pf_dist);
   ties_finalize_kernel<<<1, 1, 0, s>>>(p->d_state, func, (unsigned long long)p->total_elems);
   fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix);
   // dense re-merge: a grid-stride launch that is small when it turns out to be a no-op
-  fn.merge<<<std::min(p->nchunks, p->sms * 16), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_fix, 1, 0);
+  fn.merge<<<std::min(p->nchunks, p->sms * 16), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 1, 0);
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
 }
@@ -789,6 +798,7 @@ extern "C" int mc_ties_plan_destroy(mc_ties_plan_t* p) {
   if (!p) return MC_OK;
   cudaFree(p->d_segs);
   cudaFree(p->d_chunks);
+  cudaFree(p->d_vec);
   cudaFree(p->d_state);
   cudaFree(p->d_hist);
   cudaFree(p->d_fix);

@@ -206,8 +206,8 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned int byt
 // mode 1: dense re-merge with the real majority; exits at once unless ties_finalize_kernel asked for it (need_fix == 2).
 template <int NSRC, typename S, typename D, int FUNC>
 __global__ void __launch_bounds__(kTiesMergeThreads)
-ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, TiesState* st,
-                  unsigned long long* __restrict__ fix_list, int mode, int pf_dist) {
+ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, const void* const* __restrict__ vec,
+                  int nchunks, TiesState* st, unsigned long long* __restrict__ fix_list, int mode, int pf_dist) {
   constexpr int E = 16 / sizeof(S);
   constexpr int VPT = 4;  // vectors per source per thread
   constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
@@ -236,34 +236,29 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
     // memory-level parallelism comes from L2 prefetches instead: one thread asks L2 for the whole chunk that the CTA
     // scheduled pf_dist blocks later will stream (one generation of resident CTAs ahead; the first generation asks
     // for its own), and the demand loads below mostly hit L2.
+    // addresses of a whole, aligned chunk come from the plan's flat table (row = sources..., destination; NULL = tail)
+    const void* const* row = vec + (long long)c * (NSRC + 1);
     if (pf_dist > 0 && threadIdx.x == 0) {
 #pragma unroll 1
       for (int rep = 0; rep < 2; ++rep) {
         const long long cq = rep == 0 ? (long long)c + pf_dist : (long long)c;
         if (cq >= nchunks || (rep == 1 && c >= pf_dist)) continue;
-        const MergeChunk pch = chunks[cq];
-        const MergeSeg* psg = segs + pch.seg;
-        const long long pbase = (long long)pch.idx * CHUNK;
-        if (psg->aligned && psg->numel - pbase >= CHUNK) {
+        const void* const* prow = vec + cq * (NSRC + 1);
+        if (prow[0] != nullptr) {
 #pragma unroll
-          for (int s = 0; s < NSRC; ++s)
-            l2_prefetch_bulk(reinterpret_cast<const S*>(psg->src[s]) + pbase, (unsigned int)(CHUNK * sizeof(S)));
+          for (int s = 0; s < NSRC; ++s) l2_prefetch_bulk(prow[s], (unsigned int)(CHUNK * sizeof(S)));
         }
       }
     }
-    const MergeChunk ch = chunks[c];
-    const MergeSeg* sg = segs + ch.seg;
-    const long long base = (long long)ch.idx * CHUNK;
-    const long long rem = sg->numel - base;
-    if (sg->aligned && rem >= CHUNK) {
+    if (row[0] != nullptr) {
       VS v[NSRC][VPT];
 #pragma unroll
       for (int s = 0; s < NSRC; ++s) {
-        const VS* p = reinterpret_cast<const VS*>(reinterpret_cast<const S*>(sg->src[s]) + base) + threadIdx.x;
+        const VS* p = reinterpret_cast<const VS*>(row[s]) + threadIdx.x;
 #pragma unroll
         for (int j = 0; j < VPT; ++j) v[s][j] = ld_stream(p + j * kTiesMergeThreads);
       }
-      VD* q = reinterpret_cast<VD*>(reinterpret_cast<D*>(sg->dst) + base) + threadIdx.x;
+      VD* q = reinterpret_cast<VD*>(const_cast<void*>(row[NSRC])) + threadIdx.x;
 #pragma unroll
       // Class-3 elements (rare) are collected as one bit per element in float accumulators (mask_j += amb * 2^e, an FFMA)
       // and appended to the fix-up list after the sweep: the hot path is ONE basic block, so every load above issues
@@ -322,6 +317,10 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
         }
       }
     } else {
+      const MergeChunk ch = chunks[c];
+      const MergeSeg* sg = segs + ch.seg;
+      const long long base = (long long)ch.idx * CHUNK;
+      const long long rem = sg->numel - base;
       const long long n = rem < CHUNK ? rem : CHUNK;
       for (long long i = threadIdx.x; i < n; i += kTiesMergeThreads) {
         float in[NSRC];
@@ -390,7 +389,7 @@ ties_fix_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict_
   }
 }
 
-typedef void (*ties_fn_t)(const MergeSeg*, const MergeChunk*, int, TiesState*, unsigned long long*, int, int);
+typedef void (*ties_fn_t)(const MergeSeg*, const MergeChunk*, const void* const*, int, TiesState*, unsigned long long*, int, int);
 typedef void (*ties_fix_fn_t)(const MergeSeg*, const MergeChunk*, const TiesState*, const unsigned long long*);
 struct TiesKernels {
   ties_fn_t merge;
