@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(1024) ties_bracket_kernel(unsigned long long* 
 
 // The streaming pass: keys below the bracket are counted, keys inside it histogrammed (a few bins, rarely hit).
 template <typename S>
-__global__ void __launch_bounds__(kTiesCountThreads, 2)
+__global__ void __launch_bounds__(kTiesCountThreads, 4)
 ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, const void* const* __restrict__ vec,
                   int nchunks, TiesState* st, unsigned long long* __restrict__ ghist) {
   __shared__ unsigned int s_win[kTiesWindowBins];
@@ -284,7 +284,7 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   if (st->need_full) return;
   constexpr int E = 16 / sizeof(S);
   constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
-  constexpr int VPT = 2, PAIR = 4;  // one chunk = 512 threads x 2 vectors; four chunks (eight 128-bit loads per thread) per iteration
+  constexpr int VPT = 4, PAIR = 2;  // one chunk = 256 threads x 4 vectors; two chunks (eight 128-bit loads per thread) per iteration
   static_assert(CHUNK == kTiesCountThreads * VPT * E, "chunk geometry");
   const int src = blockIdx.y;
   const unsigned int lo = st->win_lo[src], span = st->win_hi[src] - lo;
@@ -309,79 +309,85 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
     gen_acc[i] = 0u;
     bin_total[i] = 0ull;
   }
-  // The address of every whole chunk comes from the plan's flat table (one 8-byte load; walking chunk -> segment cost
-  // three instructions per element), resolved one iteration ahead so the streaming loads never wait for it.
-  const Vec<16>* ptr[PAIR];  // vector path: this thread's first vector of chunk c0 + j; NULL = tail / unaligned / none
+  // The address of every whole chunk comes from the plan's flat table (one 8-byte load per chunk, walked with a running
+  // pointer; the chunk -> segment walk and its 64-bit index arithmetic cost three instructions per element), read one
+  // iteration ahead so the streaming loads never wait for it.
   const int row = (int)gridDim.y + 1;
-#define MC_TIES_RESOLVE(FIRST)                                                                          \
-  _Pragma("unroll") for (int j = 0; j < PAIR; ++j) {                                                    \
-    const long long c_ = (FIRST) + j;                                                                   \
-    const void* a_ = c_ < nchunks ? vec[c_ * row + src] : nullptr;                                      \
-    ptr[j] = a_ ? reinterpret_cast<const Vec<16>*>(a_) + threadIdx.x : nullptr;                         \
+  const long long stride = (long long)gridDim.x * PAIR;
+  long long c0 = (long long)blockIdx.x * PAIR;
+  const void* const* vp = vec + c0 * row + src;
+  const long long vstep = stride * row;
+  const void* nxt[PAIR];  // whole, aligned chunk c0 + j of this source, or NULL (tail / unaligned / past the end)
+#pragma unroll
+  for (int j = 0; j < PAIR; ++j) nxt[j] = c0 + j < nchunks ? vp[j * row] : nullptr;
+  // three instructions per threshold and word (subtract, mask, dp4a), no branch, no atomic
+#define MC_TIES_COUNT_WORDS(N_T)                                                                       \
+  _Pragma("unroll") for (int j = 0; j < PAIR; ++j) {                                                   \
+    if (cur[j] == nullptr) continue;                                                                   \
+    _Pragma("unroll") for (int u = 0; u < VPT; ++u) {                                                  \
+      _Pragma("unroll") for (int w = 0; w < 4; ++w) {                                                  \
+        const unsigned int k = v[j][u].w[w] | 0x80008000u;                                             \
+        ge_acc = __dp4a((k - lo2) & 0x80008000u, 0x01010101u, ge_acc);                                 \
+        _Pragma("unroll") for (int i = 0; i < (N_T); ++i)                                              \
+          gen_acc[i] = __dp4a((k - tn2[i]) & 0x80008000u, 0x01010101u, gen_acc[i]);                    \
+      }                                                                                                \
+    }                                                                                                  \
   }
-  MC_TIES_RESOLVE((long long)blockIdx.x * PAIR)
-  for (int c0 = blockIdx.x * PAIR; c0 < nchunks; c0 += gridDim.x * PAIR) {
+  for (; c0 < nchunks; c0 += stride) {
+    const void* cur[PAIR];
     Vec<16> v[PAIR][VPT];
-    bool fast[PAIR];
 #pragma unroll
     for (int j = 0; j < PAIR; ++j) {
-      fast[j] = ptr[j] != nullptr;
-      if (fast[j]) {
+      cur[j] = nxt[j];
+      if (cur[j] != nullptr) {
 #pragma unroll
-        for (int u = 0; u < VPT; ++u) v[j][u] = ld_stream(ptr[j] + u * kTiesCountThreads);
+        for (int u = 0; u < VPT; ++u) v[j][u] = ld_stream(reinterpret_cast<const Vec<16>*>(cur[j]) + threadIdx.x + u * kTiesCountThreads);
       }
     }
-    MC_TIES_RESOLVE((long long)c0 + (long long)gridDim.x * PAIR)
+    vp += vstep;
 #pragma unroll
-    for (int j = 0; j < PAIR; ++j) {
-      const int c = c0 + j;
-      if (c >= nchunks) break;
-      if (fast[j]) {
-        // two 15-bit keys per 32-bit word: (0x8000 | key) - t keeps bit 15 iff key >= t (no borrow crosses the halves); the
-        // flag bytes (0x80) are summed with one dp4a per word
-        if (narrow) {
-          // three instructions per threshold and word (subtract, mask, dp4a), no branch, no atomic: the divergent
-          // shared-memory atomic path below, taken by ~1 % of the elements, doubled the instruction count of this pass.
-          // Thresholds above the bracket are skipped (span is CTA-uniform).
-#define MC_TIES_COUNT_WORDS(N_T)                                                                     \
-  _Pragma("unroll") for (int u = 0; u < VPT; ++u) {                                                  \
-    _Pragma("unroll") for (int w = 0; w < 4; ++w) {                                                  \
-      const unsigned int k = v[j][u].w[w] | 0x80008000u;                                             \
-      ge_acc = __dp4a((k - lo2) & 0x80008000u, 0x01010101u, ge_acc);                                 \
-      _Pragma("unroll") for (int i = 0; i < (N_T); ++i)                                              \
-        gen_acc[i] = __dp4a((k - tn2[i]) & 0x80008000u, 0x01010101u, gen_acc[i]);                    \
-    }                                                                                                \
-  }
-          if (span == 0u) {
-            MC_TIES_COUNT_WORDS(1)
-          } else if (span == 1u) {
-            MC_TIES_COUNT_WORDS(2)
-          } else if (span == 2u) {
-            MC_TIES_COUNT_WORDS(3)
-          } else {
-            MC_TIES_COUNT_WORDS(NT)
-          }
-#undef MC_TIES_COUNT_WORDS
-        } else {
-          // wide bracket: (0x8000 | hi) - key keeps bit 15 iff key <= hi; keys inside go to the shared-memory bins
+    for (int j = 0; j < PAIR; ++j) nxt[j] = c0 + stride + j < nchunks ? vp[j * row] : nullptr;
+    // two 15-bit keys per 32-bit word: (0x8000 | key) - t keeps bit 15 iff key >= t (no borrow crosses the halves); the
+    // flag bytes (0x80) are summed with one dp4a per word
+    if (narrow) {
+      // bracket of at most four bins: the divergent shared-memory atomic path below, taken by ~1 % of the elements,
+      // doubled the instruction count of this pass.  Thresholds above the bracket are skipped (span is CTA-uniform).
+      if (span == 0u) {
+        MC_TIES_COUNT_WORDS(1)
+      } else if (span == 1u) {
+        MC_TIES_COUNT_WORDS(2)
+      } else if (span == 2u) {
+        MC_TIES_COUNT_WORDS(3)
+      } else {
+        MC_TIES_COUNT_WORDS(NT)
+      }
+    } else {
+      // wide bracket: (0x8000 | hi) - key keeps bit 15 iff key <= hi; keys inside go to the shared-memory bins
 #pragma unroll
-          for (int u = 0; u < VPT; ++u) {
+      for (int j = 0; j < PAIR; ++j) {
+        if (cur[j] == nullptr) continue;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              const unsigned int keys = v[j][u].w[w] & 0x7fff7fffu;
-              const unsigned int ge = ((keys | 0x80008000u) - lo2) & 0x80008000u;
-              ge_acc = __dp4a(ge, 0x01010101u, ge_acc);
-              const unsigned int in = ge & (hi2 - keys);
-              if (in) {
-                if (in & 0x00008000u) atomicAdd(&s_win[(keys & 0xffffu) - lo], 1u);
-                if (in & 0x80000000u) atomicAdd(&s_win[(keys >> 16) - lo], 1u);
-              }
+        for (int u = 0; u < VPT; ++u) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const unsigned int keys = v[j][u].w[w] & 0x7fff7fffu;
+            const unsigned int ge = ((keys | 0x80008000u) - lo2) & 0x80008000u;
+            ge_acc = __dp4a(ge, 0x01010101u, ge_acc);
+            const unsigned int in = ge & (hi2 - keys);
+            if (in) {
+              if (in & 0x00008000u) atomicAdd(&s_win[(keys & 0xffffu) - lo], 1u);
+              if (in & 0x80000000u) atomicAdd(&s_win[(keys >> 16) - lo], 1u);
             }
           }
         }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PAIR; ++j) {
+      if (cur[j] != nullptr) {
         n_fast += (unsigned int)(VPT * E);
-      } else {
-        const MergeChunk ch = chunks[c];
+      } else if (c0 + j < nchunks) {
+        const MergeChunk ch = chunks[c0 + j];
         const MergeSeg* sg = segs + ch.seg;
         const long long base = (long long)ch.idx * CHUNK;
         const long long n = min((long long)CHUNK, sg->numel - base);
@@ -403,7 +409,7 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
       below = ge_acc = n_fast = 0u;
     }
   }
-#undef MC_TIES_RESOLVE
+#undef MC_TIES_COUNT_WORDS
   below_total += below + (n_fast - (ge_acc >> 7));
   if (narrow) {  // warp-reduced bin counts of the vector path join the scalar path's shared-memory bins
 #pragma unroll
@@ -625,7 +631,7 @@ static int enqueue_select(const mc_ties_plan_t* p, int64_t kth, cudaStream_t s) 
     const size_t bsmem = (((size_t)1 << 15) + 1024) * sizeof(unsigned int);
     MC_CUDA_OK(cudaFuncSetAttribute(ties_bracket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
     dim3 sgrid(std::max(1, std::min((p->nchunks + 31) / 32, p->sms / p->n_src)), p->n_src);
-    dim3 cgrid(std::max(1, std::min((p->nchunks + 3) / 4, p->sms * 2 / p->n_src)), p->n_src);
+    dim3 cgrid(std::max(1, std::min((p->nchunks + 1) / 2, p->sms * 4 / p->n_src)), p->n_src);
     if (p->src_dtype == MC_F16) {
       MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ties_sample_kernel<__half><<<sgrid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);

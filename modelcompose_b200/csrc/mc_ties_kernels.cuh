@@ -25,7 +25,7 @@ constexpr int kTiesChunkBytes = 16384;  // one chunk = 1024 16-byte vectors of e
 constexpr int kTiesMergeThreads = 256;    // x 4 vectors per source per thread = one chunk; every load issued up front
 constexpr int kTiesMetricsThreads = 512;
 constexpr int kTiesHistThreads = 1024;
-constexpr int kTiesCountThreads = 512;
+constexpr int kTiesCountThreads = 256;
 constexpr int kTiesWindowBins = 2048;   // widest bracket the counting pass histograms (8 KB of shared memory)
 constexpr int kTiesSampleEvery = 32;    // the sampling pass reads one 512-byte granule (1/32) of every chunk
 
