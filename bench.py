@@ -450,7 +450,7 @@ def run_ties(device, steps: int = 10, K: int = 20, func: str = "mean"):
            "ms_per_step": round(ms, 4), "dtype": "bf16", "data": "synthetic",
            "config": {"workload": "ties-%s of the `default` LoRA adapters of 3 vicuna-7B DAMC checkpoints" % func, "tensors": len(shapes),
                       "elements_per_source": d, "algorithmic_bytes": plan.algorithmic_bytes,
-                      "passes": "1 counting pass + 1 merge pass over 3 sources, fp32 output"},
+                      "passes": "1 sampling pass over 1/32 of the data + 1 counting pass + 1 merge pass over 3 sources, fp32 output"},
            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
                         "traffic": None, "peak_source": peak_src, "kernel": "whole mc_ties_plan_run (sample, bracket, count, select, merge, fix-up)"},
            "stats": st, "gpu_launches": 11 * steps}
