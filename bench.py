@@ -683,11 +683,21 @@ def main():
         run_reference_arm(args)
         return
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON: anything native libraries print there (NCCL's version banner under
+    # NCCL_DEBUG) goes to stderr instead — fd 1 is pointed at fd 2 while the job runs and the line is written to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     dist, rank, world, device, barrier = setup_dist(args)
     line = None
     if args.workload == "ties":
         if rank == 0:
-            print(json.dumps(run_ties(device)), flush=True)
+            emit(run_ties(device))
         if world > 1:
             barrier()
             dist.destroy_process_group()
@@ -706,7 +716,7 @@ def main():
             elif line is not None:
                 line["prefill"] = pre
     if rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         barrier()
         dist.destroy_process_group()

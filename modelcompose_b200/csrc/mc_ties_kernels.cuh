@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t pack_thr(float thr) {
   return h | (h << 16);
 }
 
-// SUM / MEAN over 16-bit sources: the same results bit for bit as ties_one_ref with the arithmetic moved off the
+// 16-bit sources: the same results bit for bit as ties_one_ref with the arithmetic moved off the
 // half-rate ALU pipe that bounded the first version of this pass (profiles/r01_ties.txt: 57 instructions per element,
 // ALU 65 %, DRAM 39 %) — no predicate, select or min/max per source, everything but the trim compare is FMUL/FADD/FFMA:
 //   * trim by multiplication, m = x * [|x| >= thr] (the reference's own form, ties_merging.py:98-101);
@@ -144,11 +144,12 @@ __device__ __forceinline__ uint32_t pack_thr(float thr) {
 //     c <= 8 and any r within 2 ulp of 1 / c (checked exhaustively: tests/test_ties_oracle.py); min(q1, x) returns
 //     x = inf when the 16-bit rounding of the sum overflowed (q1 = NaN there);
 //   * survivors that cancel exactly (class 3) are acc == 0 with a non-empty candidate, for either default sign:
-//     amb = [sum k > 0] (1 - p - n).
+//     amb = [sum k > 0] (1 - p - n);
+//   * MAX keeps the running maximum of k instead of the sum; (max k) * sigma is exact and keeps torch's -0.
 // p, n, amb come back as 0.0 / 1.0 so that the census is three float adds per element.
 template <int NSRC, typename S, typename D, int FUNC, bool TRIMMED = false>
 __device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float (&thr)[NSRC], float mh, float& p, float& n, float& amb) {
-  static_assert(sizeof(S) == 2 && FUNC != MC_TIES_MAX, "16-bit sources, SUM / MEAN");
+  static_assert(sizeof(S) == 2, "16-bit sources");
   const float inf = __int_as_float(0x7f800000);
   float m[NSRC];
 #pragma unroll
@@ -164,7 +165,7 @@ __device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float 
 #pragma unroll
   for (int s = 0; s < NSRC; ++s) {
     const float k = __fmaf_rn(0.5f, fabsf(m[s]), __fmul_rn(m[s], hs));
-    ksum = s == 0 ? k : __fadd_rn(ksum, k);
+    ksum = s == 0 ? k : (FUNC == MC_TIES_MAX ? fmaxf(ksum, k) : __fadd_rn(ksum, k));  // MAX: running max |kept|
     if (FUNC == MC_TIES_MEAN) {
       const float one = mul_sat(k, inf);
       cnt = s == 0 ? one : __fadd_rn(cnt, one);
@@ -173,6 +174,7 @@ __device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float 
   const float some = FUNC == MC_TIES_MEAN ? mul_sat(cnt, 1.0f) : mul_sat(ksum, inf);  // [a kept entry != 0]
   amb = __fmaf_rn(-some, __fadd_rn(p, n), some);
   if (FUNC == MC_TIES_SUM) return from_f32<D>(__fmaf_rn(ksum, sg, 0.0f));
+  if (FUNC == MC_TIES_MAX) return from_f32<D>(__fmul_rn(ksum, sg));  // a 16-bit value already; (+0) * -1 = -0 as torch
   const float x = to_f32<S>(from_f32<S>(ksum));  // >= +0: the sign goes on last
   const float c = fmaxf(cnt, 1.0f), r = rcp_approx(c);
   const float q0 = __fmul_rn(x, r);
@@ -182,7 +184,7 @@ __device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float 
 
 template <typename S, int FUNC>
 struct TiesFast {
-  static constexpr bool value = sizeof(S) == 2 && FUNC != MC_TIES_MAX;
+  static constexpr bool value = sizeof(S) == 2;
 };
 
 template <int NSRC, typename S, typename D, int FUNC>

@@ -100,13 +100,15 @@ def emulate_fast(flat: torch.Tensor, thr, majority: float, func: str):
         ksum = cnt = None
         for s in range(n_src):
             k = (F32(0.5) * np.abs(m[s]) + (m[s] * hs).astype(F32)).astype(F32)  # both products exact: one rounding
-            ksum = k if s == 0 else (ksum + k).astype(F32)
+            ksum = k if s == 0 else (np.maximum(ksum, k) if func == "max" else (ksum + k).astype(F32))
             one = mul_sat(k, INF)
             cnt = one if s == 0 else (cnt + one).astype(F32)
         some = mul_sat(cnt, 1.0) if func == "mean" else mul_sat(ksum, INF)
         amb = (-some * (p + n) + some).astype(F32)
         if func == "sum":
             out = torch.from_numpy((ksum * sg + F32(0)).astype(F32)).to(dt)
+        elif func == "max":
+            out = torch.from_numpy((ksum * sg).astype(F32)).to(dt)
         else:
             xr = round_dt(ksum, dt)
             c = np.maximum(cnt, F32(1))
@@ -136,7 +138,7 @@ def make_flat(kind, n_src, d, dt, seed):
 @pytest.mark.parametrize("n_src", [1, 2, 3, 5, 8])
 def test_fast_formulation_matches_oracle(dt, kind, K, n_src):
     flat = make_flat(kind, n_src, 20011, dt, seed=31 * n_src + len(kind))
-    for func in ("sum", "mean"):
+    for func in ("sum", "mean", "max"):
         want, st = TO.ties_merge_flat(flat, K, func)
         thr = st["thresholds"].numpy()
         for majority in (st["majority"], -st["majority"] if st["majority"] else 1.0):

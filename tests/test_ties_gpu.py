@@ -131,6 +131,59 @@ def test_sampled_select_bit_exact(dtype):
             assert bits_equal(o, w)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n_values,K", [(8, 45), (8, 50), (8, 75), (256, 20), (256, 50.2), (700, 33), (3000, 20)])
+def test_counting_pass_every_bracket_width(dtype, n_values, K):
+    """The counting pass keeps one SIMD counter per bin boundary for brackets of 1-4 bins and falls back to shared-memory
+    bins for wider ones.  Magnitudes drawn uniformly from `n_values` ADJACENT values of the dtype put a chosen share of
+    the data in every bin: 8 values -> the bracket is one bin (K = 45) or the two bins around a boundary (K = 50, 75);
+    256 / 700 values -> 2-4 bins; 3000 values -> wider than four.  Thresholds and outputs must equal the oracle's."""
+    g = torch.Generator().manual_seed(1000 + n_values)
+    n = 8192 * 1030 + 77                                   # >= 1024 chunks: the sampled select runs
+    base = torch.tensor([1.0], dtype=dtype).view(torch.int16).item()
+    srcs = []
+    for s in range(2):
+        keys = (base + torch.randint(0, n_values, (n,), generator=g)).to(torch.int16)
+        sign = torch.randint(0, 2, (n,), generator=g).to(torch.int16) << 15
+        srcs.append([(keys | sign).view(dtype)])
+    outs = [torch.empty(n, dtype=dtype, device="cuda")]
+    plan = M.TiesPlan([[t.cuda() for t in lst] for lst in srcs], outs)
+    plan.run(K, "sum")
+    st = plan.stats()
+    assert not st["full_select_ran"], st
+    want, ost = oracle_merge(srcs, K, "sum")
+    assert st["thresholds"] == [float(x) for x in ost["thresholds"]], (st["thresholds"], ost["thresholds"])
+    assert (st["n_pos"], st["n_neg"], st["n_ambiguous"]) == (ost["n_pos"], ost["n_neg"], ost["ambiguous"])
+    assert bits_equal(outs[0], want[0])
+    plan.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_mean_quotient_every_value_on_device(dtype):
+    """`mean` divides by the number of kept entries without a division instruction (q1 = fma(fma(-q0, c, x), r, q0) with the
+    hardware's approximate reciprocal r): every finite positive value of the dtype as the kept sum, every count 1..8.
+    Source 0 carries the values, c - 1 further sources the smallest subnormal with the same sign (kept: it is their
+    threshold; too small to move the 16-bit sum of all but the smallest values), the rest zeros."""
+    bits = torch.arange(1, 1 << 15, dtype=torch.int32).to(torch.int16)
+    vals = bits.view(dtype)
+    vals = vals[torch.isfinite(vals.float())]
+    vals = torch.cat([vals, -vals])                        # both elected signs
+    tiny = torch.tensor([1], dtype=torch.int16).view(dtype)
+    n = vals.numel()
+    for c in range(1, 9):
+        srcs = [[vals.clone()]]
+        for s in range(1, 8):
+            t = (tiny.expand(n).clone() * torch.sign(vals.float()).to(dtype)) if s < c else torch.zeros(n, dtype=dtype)
+            srcs.append([t])
+        outs = [torch.empty(n, dtype=torch.float32, device="cuda")]
+        plan = M.TiesPlan([[t.cuda() for t in lst] for lst in srcs], outs)
+        plan.run(99.99, "mean")                             # trims the 6 smallest magnitudes only
+        want, _ = oracle_merge(srcs, 99.99, "mean")
+        assert bits_equal(outs[0], want[0]), (dtype, c, int((outs[0].cpu() != want[0]).sum()))
+        assert len(torch.unique(want[0])) > (n * 2) // (3 * c)  # the quotients really cover the value range
+        plan.close()
+
+
 def test_bracket_miss_falls_back_to_full_histogram():
     """data laid out against the sampler (one 512-byte granule per 16 KB chunk is sampled, and exactly those hold zeros):
     the sample says thr = 0, the rank lies outside the bracket, the full-range passes take over — still exact"""
