@@ -217,6 +217,10 @@ def setup_dist(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # one process per GPU: stage host buffers on the GPU's own NUMA node (at N = 1 the rank keeps every core: it also
+        # runs the CPU baseline)
+        from modelcompose_b200 import _cabi
+        _cabi.bind_host_thread_to_gpu(local_rank)
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():

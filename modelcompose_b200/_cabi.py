@@ -143,3 +143,27 @@ def f32_array(vals):
 def current_stream_ptr() -> int:
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+def bind_host_thread_to_gpu(device_index: int) -> bool:
+    """Pin the calling thread to the CPUs next to GPU ``device_index`` (NVML's ideal affinity), so that the pinned host
+    buffers it allocates afterwards live on that GPU's NUMA node.  One process per GPU: without this, eight ranks staging
+    checkpoints from whatever node they woke up on share the socket interconnect (the host-buffer merge at N = 4 / 8 is
+    bound by exactly that).  Returns False (and changes nothing) when NVML is not available."""
+    try:
+        import os
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = getattr(torch.cuda.get_device_properties(device_index), "uuid", None)
+        if uuid is not None:
+            name = str(uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID((name if name.startswith("GPU-") else "GPU-" + name).encode())
+        else:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].isdigit() else device_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
