@@ -4,8 +4,10 @@
 // scripts/model_composition/merge_unimodal_modelcompose.py:59-64,75-85 (`ties-*`, `convert-drop-*`).
 //
 // Roofline: HBM.  Every pass streams the sources once with 128-bit L1::no_allocate loads:
-//   select   1 pass (bf16 / fp16: 2^15 shared-memory bins cover the whole magnitude) or 3 passes (fp32: 11+10+10 bits)
-//            ties_hist_kernel -> ties_select_kernel (one CTA per source walks the histogram to the k-th bin)
+//   select   bf16 / fp16: ties_sample_kernel (1/32 of the data, 2^15 shared-memory bins) -> ties_bracket_kernel (key bracket of
+//            the k-th magnitude) -> ties_count_kernel (one pass: SIMD ">= t" counters per bin boundary of the bracket) ->
+//            ties_window_select_kernel; a bracket miss, small inputs and fp32 take the full-range radix passes
+//            (ties_hist_kernel -> ties_select_kernel, 1 pass of 15 bits or 3 passes of 11+10+10 bits)
 //   merge    ties_merge_kernel, speculative majority +1, census of elected signs (mc_ties_kernels.cuh)
 //   fix      ties_finalize_kernel decides: nothing / ties_fix_kernel over the listed majority-dependent elements / a dense
 //            re-merge (list overflow, or MAX with a negative majority); the unused kernels exit at once
