@@ -1148,6 +1148,9 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     double b_bytes = 0;
     for (int i = 0; i < n_problems; ++i) b_bytes = std::max(b_bytes, (double)desc[i].N * (desc[i].K0 + desc[i].K1) * 2.0);
     p->params.group_m = b_bytes > 48e6 ? 32 : 8;
+    // the group is meant in ROWS (1024 / 4096): the pair kernels' tiles are 512 / 256 rows tall, and 32 of those per group
+    // put 360 MB of down_proj activations between two visits of a weight tile
+    p->params.group_m = std::max(1, p->params.group_m * kBM / bm);
     if ((tuning >> 8) & 0xff) p->params.group_m = (tuning >> 8) & 0xff;
   }
   // compact schedule for routed-N launches whose problems share M, N tiling and routing

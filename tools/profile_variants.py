@@ -21,4 +21,14 @@ for M, N, K in shapes:
         for _ in range(iters):
             plan.run()
         torch.cuda.synchronize()
+        if os.environ.get("MC_TIME"):  # CUDA-event timing instead of an ncu target
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = int(os.environ["MC_TIME"])
+            a.record()
+            for _ in range(n):
+                plan.run()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / n
+            print(f"M={M} N={N} K={K} tuning={tuning} group_m={gm or 'default'}: {ms:.4f} ms  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
 print("done")
