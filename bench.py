@@ -682,6 +682,7 @@ def main():
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="profiling aid: run rank 0's shard of a K-way job on one GPU (ncu captures)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: skip the host-buffer e2e and CPU legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="tuning aid: skip the CPU baseline of the prefill line (never a bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -714,7 +715,7 @@ def main():
         pre = run_prefill(args, device, rank, world, dist, barrier, args.prefill_config)
         if rank == 0:
             # CPU baseline on rank 0 at N=1 only (under torchrun the other ranks would wait on it)
-            pre["cpu_baseline"] = cpu_prefill_layer_rate(args.prefill_config) if world == 1 else None
+            pre["cpu_baseline"] = cpu_prefill_layer_rate(args.prefill_config) if world == 1 and not args.no_cpu_baseline else None
             if args.workload == "prefill":
                 line = pre
             elif line is not None:
