@@ -156,11 +156,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], bool is_f16) {
 // One 128-row x BN-column accumulator tile: TMEM -> registers -> epilogue -> global.  Executed by the 4 epilogue warps;
 // `row` is this thread's output row, `taddr` the TMEM address of its lane quadrant and accumulator stage.
 // The RESIDUAL / SILU_MUL operand is fetched one 32-column chunk ahead so its latency hides behind the TMEM load.
-// [c_begin, c_end) restricts the call to a column range of the tile (multiples of 32; whole heads for ROPE): the pair kernel
-// splits a tile's columns between two warps of the same TMEM lane quadrant.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16, uint32_t taddr, int row, int n0,
-                                              int c_begin = 0, int c_end = BN) {
+__device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16, uint32_t taddr, int row, int n0) {
   const bool row_ok = row < pr.M;
   const int epi = pr.epilogue;
   const bool has_aux = (epi == MC_LINEAR_EPI_RESIDUAL || epi == MC_LINEAR_EPI_SILU_MUL) && row_ok;
@@ -177,17 +174,17 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
     const char* cosr = reinterpret_cast<const char*>(pr.rope_cos) + (long long)pos * D * 2;
     const char* sinr = reinterpret_cast<const char*>(pr.rope_sin) + (long long)pos * D * 2;
 #pragma unroll 1
-    for (int h0 = c_begin; h0 < c_end; h0 += D) {
+    for (int h0 = 0; h0 < BN; h0 += D) {
       if (n0 + h0 >= pr.N) break;  // warp-uniform (N is a multiple of head_dim)
 #pragma unroll 1
-      for (int c = 0; c < half; c += 16) {  // 16 column pairs at a time: the pair kernel's epilogue warps have 96 registers
-        uint32_t lo[16], hi[16];
-        tmem_ld_32x16(taddr + (uint32_t)(h0 + c), lo);
-        tmem_ld_32x16(taddr + (uint32_t)(h0 + half + c), hi);
-        uint4 cv[2], sv[2];
+      for (int c = 0; c < half; c += 32) {
+        uint32_t lo[32], hi[32];
+        tmem_ld_32x32(taddr + (uint32_t)(h0 + c), lo);
+        tmem_ld_32x32(taddr + (uint32_t)(h0 + half + c), hi);
+        uint4 cv[4], sv[4];
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < 4; ++j) {
             cv[j] = *reinterpret_cast<const uint4*>(cosr + (c + 8 * j) * 2);
             sv[j] = *reinterpret_cast<const uint4*>(sinr + (c + 8 * j) * 2);
           }
@@ -195,7 +192,7 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < 4; ++j) {
             float x1[8], x2[8], cs[8], sn[8], o1[8], o2[8], p1[8], p2[8], p3[8], p4[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -236,11 +233,11 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
   for (int j = 0; j < 4; ++j) {
     aux[j] = make_uint4(0u, 0u, 0u, 0u);
     aux_next[j] = make_uint4(0u, 0u, 0u, 0u);
-    const int col = n0 + c_begin + 8 * j;
+    const int col = n0 + 8 * j;
     if (has_aux && col < pr.N) aux[j] = *reinterpret_cast<const uint4*>(rrow + (long long)col * 2);
   }
 #pragma unroll 1
-  for (int c = c_begin; c < c_end; c += 32) {
+  for (int c = 0; c < BN; c += 32) {
     if (n0 + c >= pr.N) break;  // warp-uniform
     uint32_t v[32];
     tmem_ld_32x32(taddr + (uint32_t)c, v);
@@ -248,7 +245,7 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int col = n0 + c + 32 + 8 * j;
-        if (c + 32 < c_end && col < pr.N) aux_next[j] = *reinterpret_cast<const uint4*>(rrow + (long long)col * 2);
+        if (c + 32 < BN && col < pr.N) aux_next[j] = *reinterpret_cast<const uint4*>(rrow + (long long)col * 2);
       }
     }
     tmem_ld_wait();
@@ -545,10 +542,7 @@ __device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {
                : "memory");
 }
 
-// 3 control warps + 16 epilogue warps (warps 3..18): four per TMEM lane quadrant = (accumulator half) x (column half).  The
-// accumulator is single-buffered, so every cycle of the epilogue is a cycle without MMAs: twice the warps halve it.
-constexpr int kThreads2 = 608;
-constexpr int kEpiWarp0_2 = 3;
+constexpr int kThreads2 = 384;  // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant, one per accumulator half)
 
 template <int STAGES>
 struct SmemLayout2 {
@@ -609,7 +603,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
       mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit from the leader
     }
     mbar_init(tfull_bar, 1);     // multicast tcgen05.commit from the leader
-    mbar_init(tempty_bar, 32);   // 16 epilogue warps x 2 CTAs arrive on the leader's copy
+    mbar_init(tempty_bar, 16);   // 8 epilogue warps x 2 CTAs arrive on the leader's copy
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
@@ -686,8 +680,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
         t_phase ^= 1u;
       }
     }
-  } else if (warp >= kEpiWarp0_2) {
-    const int q = warp & 3, h = ((warp - kEpiWarp0_2) >> 2) & 1, part = (warp - kEpiWarp0_2) >> 3;
+  } else if (warp >= 4) {
+    const int q = warp & 3, h = (warp - 4) >> 2;
     const bool is_f16 = P.is_f16 != 0;
     uint32_t t_phase = 0;
     for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
@@ -697,10 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
       mbar_wait(tfull_bar, t_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN);
-      // column halves; a RoPE head wider than half a tile stays with one warp (rotate_half pairs columns D / 2 apart)
-      const bool whole = pr.epilogue == MC_LINEAR_EPI_ROPE && pr.rope_head_dim > BN / 2;
-      const int c_begin = whole ? 0 : part * (BN / 2), c_end = whole ? (part == 0 ? BN : 0) : c_begin + BN / 2;
-      epilogue_tile<BN>(pr, is_f16, taddr, row, t.nt * BN, c_begin, c_end);
+      epilogue_tile<BN>(pr, is_f16, taddr, row, t.nt * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
