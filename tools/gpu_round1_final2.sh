@@ -1,0 +1,10 @@
+#!/bin/bash
+# end-of-round validation of HEAD: whole GPU suite, smoke(), default bench line, C4 / C5 prefill lines, reference arm
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 2>&1 | tail -8 > gpurun_out/pytest_final2.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_final2.log 2>&1
+timeout 900 python bench.py > gpurun_out/bench_final2.json 2> gpurun_out/bench_final2.err
+timeout 600 python bench.py --workload prefill --prefill-config c4 --prefill-steps 5 > gpurun_out/bench_final2_c4.json 2> gpurun_out/bench_final2_c4.err
+timeout 600 python bench.py --workload prefill --prefill-config c5 --prefill-steps 3 > gpurun_out/bench_final2_c5.json 2> gpurun_out/bench_final2_c5.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final2_ref.json 2> gpurun_out/bench_final2_ref.err
