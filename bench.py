@@ -590,6 +590,10 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
         dist.all_gather(gathered, probe)
         verified = all(torch.equal(g, gathered[0]) for g in gathered)
     peak_sus, peak_burst, peak_src = bf16_peaks()
+    up_tuning = next(iter(model._ws.values())).up_tuning & 0xff
+    up_kernel = {3: "mc::linear2_kernel<4> (512x256 CTA-pair tiles, cta_group::2) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down",
+                 4: "mc::linear3_kernel<6> (256x256 CTA-pair tiles) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down"
+                 }.get(up_tuning, "mc::linear_kernel<256,4>")
     res = {
         "metric": "composed-prefill tokens/s", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
@@ -600,7 +604,7 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
                    "algorithmic_tflop_per_step_per_gpu": round(flops["total"] * batch / 1e12, 2)},
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s",
                      "frac": round(achieved / peak_sus, 4), "traffic": None, "peak_source": peak_src,
-                     "kernel": "mc::linear_kernel<256,4> (routed LoRA linears, projector, lm_head)",
+                     "kernel": up_kernel + " (routed LoRA linears, projector, lm_head)",
                      "launches_per_step": lin_n // 2, "kernel_ms_per_step": round(lin_ms, 3),
                      "kernel_share_of_step": round(lin_ms / ms_per_step, 4),
                      "algorithmic_tflop_per_step": round(lin_flops / 1e12, 2), "frac_of_burst_peak": round(achieved / peak_burst, 4),

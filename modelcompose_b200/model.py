@@ -28,9 +28,14 @@ from . import linear as LN
 from . import splice as SP
 
 ADAPTER_ORDER = ("audio", "vision", "video", "point")
-# kernel variant of the base + LoRA-up launches (mc_linear_plan_create `tuning`): 0 = 128x256 single-CTA tiles (default),
-# 3 = 256x256 CTA-pair tiles (cta_group::2).  Development switch; both are parity-tested.
-UP_TUNING = int(os.environ.get("MC_LINEAR_UP_TUNING", "0"))
+# kernel variant of the base + LoRA-up launches (mc_linear_plan_create `tuning`): 0 = 128x256 single-CTA tiles, 3 = 512x256
+# CTA-pair tiles (cta_group::2), 4 = 256x256 CTA-pair tiles; all bit-identical (tests/test_prefill_gpu.py).  Unset = auto: the
+# 512x256 pair kernel once the batch has enough rows to fill 74 CTA pairs several times over — it takes the same time for the
+# linears at lower power, and the power-capped step as a whole runs 2 % faster (profiles/r01_linear_pair_instep.txt) — and the
+# single-CTA kernel below that.
+_UP_TUNING_ENV = os.environ.get("MC_LINEAR_UP_TUNING")
+UP_TUNING = int(_UP_TUNING_ENV) if _UP_TUNING_ENV not in (None, "", "auto") else None
+UP_TUNING_PAIR_MIN_ROWS = 8192
 FUSE_ROPE = os.environ.get("MC_FUSE_ROPE", "1") != "0"  # development switch: 0 = separate mc_rope launch
 # Prefill activations live in MODALITY-MAJOR row order (all text rows of the batch, then all audio rows, ...), so that every
 # 128-row tile of the routed linears holds one adapter group; only attention sees sequence order (the q / k / v epilogues
@@ -187,7 +192,7 @@ class _Workspace:
         R = model.rank_total
         self.B, self.S, self.T = B, S, T
         # a decode step has at most 128 rows: 128x128 tiles double the number of CTAs streaming the weights
-        self.up_tuning = 1 if T <= LN.TILE_M else UP_TUNING
+        self.up_tuning = 1 if T <= LN.TILE_M else (UP_TUNING if UP_TUNING is not None else (3 if T >= UP_TUNING_PAIR_MIN_ROWS else 0))
 
         def buf(*shape, dtype=dt):
             return torch.empty(shape, dtype=dtype, device=dev)

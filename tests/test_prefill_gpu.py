@@ -154,6 +154,28 @@ def test_pair_kernel_prefill_is_bit_identical(golden, monkeypatch, up_tuning):
     assert torch.equal(outs[0], outs[1])
 
 
+def test_auto_variant_takes_the_pair_kernel_for_large_batches(golden, monkeypatch):
+    """unset MC_LINEAR_UP_TUNING: batches of >= 8192 rows run their base + LoRA-up launches on the 512x256 CTA-pair kernel
+    (smaller ones on the single-CTA kernel) — same logits bit for bit as the single-CTA kernel forced"""
+    g = torch.Generator().manual_seed(29)
+    B = 24
+    ids = syn.make_prompt_ids(B, ["vision", "audio"], 40, 1000, seed=9, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=4)
+    feats = {"audio": torch.randn(B, 60, 48, generator=g).to(torch.bfloat16).cuda(),
+             "vision": torch.randn(B, 260, 64, generator=g).to(torch.bfloat16).cuda()}
+    outs = []
+    for t, want in ((None, 3), (0, 0)):
+        monkeypatch.setattr(MD, "UP_TUNING", t)
+        model, _, _ = tiny_model(golden, torch.bfloat16)
+        outs.append(model.forward(ids.cuda(), torch.ones_like(ids).cuda(), modal_inputs=feats).logits.clone())
+        ws = next(iter(model._ws.values()))
+        assert ws.T >= MD.UP_TUNING_PAIR_MIN_ROWS and ws.up_tuning == want, (ws.T, ws.up_tuning)
+    assert torch.equal(outs[0], outs[1])
+    monkeypatch.setattr(MD, "UP_TUNING", None)
+    model, _, _ = tiny_model(golden, torch.bfloat16)
+    model.forward(ids[:2].cuda(), torch.ones_like(ids[:2]).cuda(), modal_inputs={k: v[:2] for k, v in feats.items()})
+    assert next(iter(model._ws.values())).up_tuning == 0
+
+
 def test_full_width_layer_vs_oracle():
     """vicuna-7B WIDTH (H 4096, I 11008, r 128, vocab 32000, 3 merged adapters at 0.333, 5+5 prefix/suffix), one decoder
     layer, 2 requests with video + image + audio blocks of reduced length (the CPU oracle runs the reference's
