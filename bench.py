@@ -331,6 +331,11 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
     while need / stride > 0.45 * psutil.virtual_memory().available / world and stride < 64:
         stride *= 2
     pick = list(range(0, len(mine), stride))
+    # the staging buffers belong on the GPU's own NUMA node (the rank is bound for this leg only: at N = 1 it also runs the
+    # CPU baseline on every core afterwards)
+    from modelcompose_b200 import _cabi
+    saved_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_bound = _cabi.bind_host_thread_to_gpu(device.index)
     h_src = [[torch.empty(srcs[s][j].shape, dtype=torch.bfloat16).pin_memory() for j in pick] for s in range(n_src)]
     for s in range(n_src):
         for hj, j in zip(h_src[s], pick):
@@ -338,7 +343,6 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
     elems = sum(srcs[0][j].numel() for j in pick)
     h2d, d2h = elems * 2 * n_src, elems * 2
     h_out = [torch.empty(srcs[0][j].shape, dtype=torch.bfloat16).pin_memory() for j in pick]
-    from modelcompose_b200 import _cabi
     lib = _cabi.lib()
     sp = _cabi.ptr_array([h_src[s][k].data_ptr() for s in range(n_src) for k in range(len(pick))])
     dp = _cabi.ptr_array([o.data_ptr() for o in h_out])
@@ -381,6 +385,8 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
     ok = all(torch.equal(h_out[k].view(torch.int16), outs[j].cpu().view(torch.int16)) for k, j in
              list(zip(range(len(pick)), pick))[:3])
+    if saved_affinity is not None and world == 1:
+        os.sched_setaffinity(0, saved_affinity)
     if not ok:
         raise SystemExit("PARITY FAILURE: host-streamed merge differs from the device-resident merge")
     return {"value": round(float(b.item()) / (float(t.item()) / steps) / 1e9, 2), "unit": "GB/s",
@@ -388,7 +394,7 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             "api": "mc_merge_host (pinned host buffers, H2D/kernel/D2H pipelined, returns after last D2H)",
             "sample": "whole shard" if stride == 1 else f"every {stride}th tensor of the shard (host RAM bound)",
             "timer": "host wall clock around the synchronous call, max over ranks",
-            "pcie_probe": probe,
+            "pcie_probe": probe, "host_numa_bound": bool(numa_bound),
             "pcie_bound_GBps": round(float(elems * 2 * (n_src + 1)) / (h2d / (probe["h2d_GBps"] * 1e9)) / 1e9 * world, 1)}
 
 
