@@ -36,6 +36,11 @@ ADAPTER_ORDER = ("audio", "vision", "video", "point")
 _UP_TUNING_ENV = os.environ.get("MC_LINEAR_UP_TUNING")
 UP_TUNING = int(_UP_TUNING_ENV) if _UP_TUNING_ENV not in (None, "", "auto") else None
 UP_TUNING_PAIR_MIN_ROWS = 8192
+# ... except for the launches whose epilogue is heavy or whose K is short: the pair kernel's accumulator is single-buffered (its
+# epilogue is not overlapped with the next tile), and ncu shows its tensor pipe at 63 % on the up_proj launch that carries
+# SiLU(gate)·up and 67 % on o_proj, against 78 - 81 % on gate_proj / down_proj (profiles/r01_linear_pair_ncu_instep.txt).
+# Those two stay on the single-CTA kernel, whose epilogue overlaps the next tile's MMAs.
+UP_AUTO_SINGLE_CTA = ("up_u", "up_o")
 FUSE_ROPE = os.environ.get("MC_FUSE_ROPE", "1") != "0"  # development switch: 0 = separate mc_rope launch
 # Prefill activations live in MODALITY-MAJOR row order (all text rows of the batch, then all audio rows, ...), so that every
 # 128-row tile of the routed linears holds one adapter group; only attention sees sequence order (the q / k / v epilogues
@@ -193,6 +198,7 @@ class _Workspace:
         self.B, self.S, self.T = B, S, T
         # a decode step has at most 128 rows: 128x128 tiles double the number of CTAs streaming the weights
         self.up_tuning = 1 if T <= LN.TILE_M else (UP_TUNING if UP_TUNING is not None else (3 if T >= UP_TUNING_PAIR_MIN_ROWS else 0))
+        self.up_mixed = UP_TUNING is None and self.up_tuning == 3  # auto: per-launch choice (UP_AUTO_SINGLE_CTA)
 
         def buf(*shape, dtype=dt):
             return torch.empty(shape, dtype=dtype, device=dev)
@@ -275,7 +281,8 @@ class _Workspace:
                                          mtile_mask=self.mtile, group_cols=layer.ad[n].group_cols, epilogue=LN.EPI_ROWMASK)
                               for n, t in zip(names, tbufs)], tuning=1)  # 128x128 tiles: one routing group per N tile
 
-    def _up(self, src, layer: _Layer, names, tbufs, outs, residual=None, epilogue=None):
+    def _up(self, src, layer: _Layer, names, tbufs, outs, residual=None, epilogue=None, launch=None):
+        tuning = 0 if (self.up_mixed and launch in UP_AUTO_SINGLE_CTA) else self.up_tuning
         if epilogue is None:
             epilogue = LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE
         probs = []
@@ -286,7 +293,7 @@ class _Workspace:
             probs.append(LN.Problem(src, layer.W[n], o, A1=t, B1=layer.ad[n].B_all, mtile_mask=self.mtile,
                                     group_cols=layer.ad[n].group_cols, residual=residual,
                                     epilogue=LN.EPI_ROPE if rope is not None else epilogue, rope=rope, c_rowmap=rowmap))
-        return LN.LinearPlan(probs, tuning=self.up_tuning)
+        return LN.LinearPlan(probs, tuning=tuning)
 
     def _layer_plans(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
         qkv, gu = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
@@ -294,11 +301,12 @@ class _Workspace:
             "down_qkv": self._down(self.xn, layer, qkv, self.t),
             "up_qkv": self._up(self.xn, layer, qkv, self.t, (self.q, self.k, self.v)),
             "down_o": self._down(self.attn, layer, ("o_proj",), self.t[:1]),
-            "up_o": self._up(self.attn, layer, ("o_proj",), self.t[:1], (self.x,), residual=self.x),
+            "up_o": self._up(self.attn, layer, ("o_proj",), self.t[:1], (self.x,), residual=self.x, launch="up_o"),
             "down_gu": self._down(self.xn, layer, gu, self.t[:2]),
             # gate first, then up with the SiLU·mul folded into its epilogue (act overwrites the gate buffer)
             "up_g": self._up(self.xn, layer, gu[:1], self.t[:1], (self.gate,)),
-            "up_u": self._up(self.xn, layer, gu[1:], self.t[1:2], (self.gate,), residual=self.gate, epilogue=LN.EPI_SILU_MUL),
+            "up_u": self._up(self.xn, layer, gu[1:], self.t[1:2], (self.gate,), residual=self.gate, epilogue=LN.EPI_SILU_MUL,
+                             launch="up_u"),
             "down_d": self._down(self.gate, layer, ("down_proj",), self.t[:1]),
             "up_d": self._up(self.gate, layer, ("down_proj",), self.t[:1], (self.x,), residual=self.x),
         }
