@@ -368,6 +368,29 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             b.record()
             torch.cuda.synchronize()
             out[name] = round(reps * hbuf.numel() * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+        try:
+            # both directions at once, as the pipelined merge drives the link (3 bytes in per byte out): what the e2e number
+            # can reach on THIS box — boxes of this pool differ by 20 % here while the one-way rates agree
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            dbuf2 = dbuf.clone()
+            torch.cuda.synchronize()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            s_in.wait_event(a)
+            s_out.wait_event(a)
+            with torch.cuda.stream(s_in):
+                for _ in range(3 * reps):
+                    dbuf.copy_(hbuf, non_blocking=True)
+                b.record(s_in)
+            with torch.cuda.stream(s_out):
+                for _ in range(reps):
+                    h_out[big].view(-1).copy_(dbuf2, non_blocking=True)
+                c.record(s_out)
+            torch.cuda.synchronize()
+            out["h2d_GBps_while_d2h"] = round(3 * reps * hbuf.numel() * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+            out["d2h_GBps_while_h2d"] = round(reps * hbuf.numel() * 2 / (a.elapsed_time(c) * 1e-3) / 1e9, 1)
+        except Exception as exc:  # a probe must never cost the bench line
+            out["bidirectional_probe_error"] = str(exc)[:80]
         return out
     probe = pcie_probe()
     steps = max(1, min(args.steps, 3))
@@ -395,7 +418,8 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             "sample": "whole shard" if stride == 1 else f"every {stride}th tensor of the shard (host RAM bound)",
             "timer": "host wall clock around the synchronous call, max over ranks",
             "pcie_probe": probe, "host_numa_bound": bool(numa_bound),
-            "pcie_bound_GBps": round(float(elems * 2 * (n_src + 1)) / (h2d / (probe["h2d_GBps"] * 1e9)) / 1e9 * world, 1)}
+            "pcie_bound_GBps": round(float(elems * 2 * (n_src + 1)) / (h2d / (probe.get("h2d_GBps_while_d2h", probe["h2d_GBps"]) * 1e9))
+                                     / 1e9 * world, 1)}
 
 
 # ------------------------------------------------------------------------------------------------ TIES workload
@@ -596,10 +620,13 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
         dist.all_gather(gathered, probe)
         verified = all(torch.equal(g, gathered[0]) for g in gathered)
     peak_sus, peak_burst, peak_src = bf16_peaks()
-    up_tuning = next(iter(model._ws.values())).up_tuning & 0xff
+    ws0 = next(iter(model._ws.values()))
+    up_tuning = ws0.up_tuning & 0xff
     up_kernel = {3: "mc::linear2_kernel<4> (512x256 CTA-pair tiles, cta_group::2) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down",
                  4: "mc::linear3_kernel<6> (256x256 CTA-pair tiles) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down"
                  }.get(up_tuning, "mc::linear_kernel<256,4>")
+    if getattr(ws0, "up_mixed", False):
+        up_kernel += "; up_proj(+SiLU*mul) and o_proj on mc::linear_kernel<256,4> (single-CTA, overlapped epilogue)"
     res = {
         "metric": "composed-prefill tokens/s", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
