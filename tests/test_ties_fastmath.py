@@ -150,3 +150,25 @@ def test_fast_formulation_matches_oracle(dt, kind, K, n_src):
         got, p, n, amb = emulate_fast(flat, thr, st["majority"], func)
         assert (int(p.sum()), int(n.sum()), int(amb.sum())) == (st["n_pos"], st["n_neg"], st["ambiguous"])
         assert set(np.unique(np.concatenate([p, n, amb]))) <= {0.0, 1.0}
+
+
+def test_packed_threshold_counter_has_no_cross_half_borrow():
+    """ties_count_kernel counts ">= t" for two 15-bit keys per 32-bit word: k = word | 0x80008000, flags = (k - (t | t << 16))
+    & 0x80008000, summed with dp4a (0x80 per flag).  Every low key x a spread of thresholds (incl. 0, 1, 0x7fff and the clamp
+    0x8000) x high keys at the extremes: the flag of each half equals key >= t, i.e. no borrow ever crosses the halves."""
+    lo_keys = np.arange(1 << 15, dtype=np.uint32)
+    rng = np.random.default_rng(3)
+    thresholds = np.unique(np.concatenate([[0, 1, 2, 0x3f80, 0x7ffe, 0x7fff, 0x8000], rng.integers(0, 0x8001, 200)])).astype(np.uint32)
+    hi_keys = np.array([0, 1, 0x3f80, 0x7ffe, 0x7fff], dtype=np.uint32)
+    for sign_bits in (0x00000000, 0x80008000, 0x80000000):       # the sign bits of the data are overwritten by the OR
+        for hk in hi_keys:
+            words = (lo_keys | (hk << 16) | np.uint32(sign_bits)).astype(np.uint32)
+            k = words | np.uint32(0x80008000)
+            for t in thresholds:
+                t2 = np.uint32(t | (t << 16))
+                flags = (k - t2) & np.uint32(0x80008000)          # uint32 wrap-around arithmetic, as the GPU
+                assert np.array_equal((flags & 0x8000) != 0, lo_keys >= t), (hk, t)
+                assert np.all(((flags >> 31) & 1) == (1 if hk >= t else 0)), (hk, t)
+                # dp4a with 0x01010101 adds the four bytes: 0x80 per set flag
+                dp = (flags & 0xff) + ((flags >> 8) & 0xff) + ((flags >> 16) & 0xff) + ((flags >> 24) & 0xff)
+                assert np.array_equal(dp >> 7, (lo_keys >= t).astype(np.uint32) + (1 if hk >= t else 0))
