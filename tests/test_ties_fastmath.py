@@ -83,14 +83,18 @@ def test_mean_quotient_is_correctly_rounded_exhaustive(dt):
     assert np.isinf(got[0]) and got[0] > 0
 
 
-def emulate_fast(flat: torch.Tensor, thr, majority: float, func: str):
-    """ties_one_fast, op for op, on [n_src, d] 16-bit inputs; returns (out, p, n, amb)."""
+def emulate_fast(flat: torch.Tensor, thr, majority: float, func: str, packed_trim: bool = False):
+    """ties_one_fast, op for op, on [n_src, d] 16-bit inputs; returns (out, p, n, amb).  ``packed_trim``: the vector path's
+    trim on the packed words (``w & mask(|x| >= thr)``: trimmed entries become +0 instead of x * 0 = +-0)."""
     dt = flat.dtype
     x = flat.to(torch.float32).numpy()
     n_src = x.shape[0]
     mh = F32(0.5 if majority > 0 else -0.5)
     with np.errstate(invalid="ignore", over="ignore"):
-        m = [(x[s] * (np.abs(x[s]) >= F32(thr[s])).astype(F32)).astype(F32) for s in range(n_src)]
+        if packed_trim:
+            m = [np.where(np.abs(x[s]) >= F32(thr[s]), x[s], F32(0)).astype(F32) for s in range(n_src)]
+        else:
+            m = [(x[s] * (np.abs(x[s]) >= F32(thr[s])).astype(F32)).astype(F32) for s in range(n_src)]
         acc = m[0]
         for s in range(1, n_src):
             acc = (acc + m[s]).astype(F32)
@@ -143,10 +147,11 @@ def test_fast_formulation_matches_oracle(dt, kind, K, n_src):
         thr = st["thresholds"].numpy()
         for majority in (st["majority"], -st["majority"] if st["majority"] else 1.0):
             ref = TO.merge_given_statistics(flat, thr, majority, func)
-            got, p, n, amb = emulate_fast(flat, thr, majority, func)
-            iv = torch.int16 if got.dtype != torch.float32 else torch.int32
-            assert got.dtype == ref.dtype
-            assert torch.equal(got.view(iv), ref.view(iv)), (func, majority, int((got.float() != ref.float()).sum()))
+            for packed in (False, True):   # scalar tail path (multiply) and vector path (packed mask) of the kernel
+                got, p, n, amb = emulate_fast(flat, thr, majority, func, packed_trim=packed)
+                iv = torch.int16 if got.dtype != torch.float32 else torch.int32
+                assert got.dtype == ref.dtype
+                assert torch.equal(got.view(iv), ref.view(iv)), (func, majority, packed, int((got.float() != ref.float()).sum()))
         got, p, n, amb = emulate_fast(flat, thr, st["majority"], func)
         assert (int(p.sum()), int(n.sum()), int(amb.sum())) == (st["n_pos"], st["n_neg"], st["ambiguous"])
         assert set(np.unique(np.concatenate([p, n, amb]))) <= {0.0, 1.0}
