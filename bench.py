@@ -389,6 +389,15 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             torch.cuda.synchronize()
             out["h2d_GBps_while_d2h"] = round(3 * reps * hbuf.numel() * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
             out["d2h_GBps_while_h2d"] = round(reps * hbuf.numel() * 2 / (a.elapsed_time(c) * 1e-3) / 1e9, 1)
+            # one pass over every pinned tensor of source 0, each touched once (the same bytes land where they came from):
+            # the rate of a cold stream, which is what the merge does, as opposed to the warm 1 GiB loop above
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for hk, j in zip(h_src[0], pick):
+                srcs[0][j].copy_(hk, non_blocking=True)
+            b.record()
+            torch.cuda.synchronize()
+            out["h2d_GBps_cold_stream"] = round(sum(hk.numel() for hk in h_src[0]) * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
         except Exception as exc:  # a probe must never cost the bench line
             out["bidirectional_probe_error"] = str(exc)[:80]
         return out
