@@ -390,8 +390,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
   const int n_own = P.compact ? s_n_own : 0;
 
   if (warp == 0) {
-    // ===== TMA producer (one thread) =====
-    if (lane == 0) {
+    // ===== TMA producer: the whole warp walks the schedule (converged), one elected lane issues the copies =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       TileIter tiles(P, s_own, n_own, s_mm);
@@ -404,10 +404,13 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
           const int k = ext ? kb - pr.nkb0 : kb;
           if (ext && pr.kb1_mask && (pr.kb1_mask[k] & t.gmask) == 0u) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          tma_load_2d(ext ? &pr.tmA1 : &pr.tmA0, &full_bar[stage], sa, k * kBK, m0);
-          tma_load_2d(ext ? &pr.tmB1 : &pr.tmB0, &full_bar[stage], sa + L::A_BYTES, k * kBK, n0);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            tma_load_2d(ext ? &pr.tmA1 : &pr.tmA0, &full_bar[stage], sa, k * kBK, m0);
+            tma_load_2d(ext ? &pr.tmB1 : &pr.tmB0, &full_bar[stage], sa + L::A_BYTES, k * kBK, n0);
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -416,8 +419,9 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: whole warp converged, one elected lane issues (under a plain `lane == 0` branch ptxas wraps every
+    // tcgen05.mma in an election loop of ~10 instructions, which at BN = 128 costs as much as the 64-cycle MMA itself) =====
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       TileIter tiles(P, s_own, n_own, s_mm);
@@ -435,19 +439,23 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t a_desc = umma_smem_desc(sa), b_desc = umma_smem_desc(sa + L::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes (16 elements) along K inside the 128-byte swizzle row: start-address field += 2
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate);
-            accumulate = 1;
+            for (int k = 0; k < kBK / 16; ++k) {
+              // +32 bytes (16 elements) along K inside the 128-byte swizzle row: start-address field += 2
+              umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          __syncwarp();
+          accumulate = 1;
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -615,7 +623,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
 
   // the pair walks tiles pair, pair + n_pairs, ...; both CTAs decode identically
   if (warp == 0) {
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues (see linear_kernel)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
@@ -629,11 +638,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
           if (ext && pr.kb1_mask && (pr.kb1_mask[k] & gmask) == 0u) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // both CTAs' bytes land on this barrier
-          else mbar_arrive_cluster(full_leader);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          tma_load_2d_cg2(ext ? &pr.tmA1 : &pr.tmA0, full_leader, sa, k * kBK, m0);
-          tma_load_2d_cg2(ext ? &pr.tmB1 : &pr.tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // both CTAs' bytes land on this barrier
+            else mbar_arrive_cluster(full_leader);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            tma_load_2d_cg2(ext ? &pr.tmA1 : &pr.tmA0, full_leader, sa, k * kBK, m0);
+            tma_load_2d_cg2(ext ? &pr.tmB1 : &pr.tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -642,7 +654,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0, t_phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
@@ -660,23 +672,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t b_desc = umma_smem_desc(sa + L::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if ((kbm & hmask[h]) == 0u) continue;  // this half's rows carry none of the k-block's adapter group
-            const uint64_t a_desc = umma_smem_desc(sa + h * L::A_HALF);
+            for (int h = 0; h < 2; ++h) {
+              if ((kbm & hmask[h]) == 0u) continue;  // this half's rows carry none of the k-block's adapter group
+              const uint64_t a_desc = umma_smem_desc(sa + h * L::A_HALF);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              umma_f16_cg2(tmem_base + (uint32_t)(h * BN), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate[h]);
-              accumulate[h] = 1;
+              for (int k = 0; k < kBK / 16; ++k)
+                umma_f16_cg2(tmem_base + (uint32_t)(h * BN), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc,
+                             (accumulate[h] | (uint32_t)k) ? 1u : 0u);
             }
+            umma_commit_cg2(&empty_bar[stage]);
           }
-          umma_commit_cg2(&empty_bar[stage]);
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if ((kbm & hmask[h]) != 0u) accumulate[h] = 1;
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit_cg2(tfull_bar);
+        if (elect_one()) umma_commit_cg2(tfull_bar);
+        __syncwarp();
         t_phase ^= 1u;
       }
     }
@@ -779,8 +797,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (one thread per CTA): own A rows + own half of B, bytes complete on the leader's barrier =====
-    if (lane == 0) {
+    // ===== TMA producer (one elected lane per CTA): own A rows + own half of B, bytes complete on the leader's barrier =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
@@ -794,11 +812,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
           if (ext && pr.kb1_mask && (pr.kb1_mask[k] & gmask) == 0u) continue;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-          else mbar_arrive_cluster(full_leader);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          tma_load_2d_cg2(ext ? &pr.tmA1 : &pr.tmA0, full_leader, sa, k * kBK, m0);
-          tma_load_2d_cg2(ext ? &pr.tmB1 : &pr.tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+            else mbar_arrive_cluster(full_leader);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            tma_load_2d_cg2(ext ? &pr.tmA1 : &pr.tmA0, full_leader, sa, k * kBK, m0);
+            tma_load_2d_cg2(ext ? &pr.tmB1 : &pr.tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -807,8 +828,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread of the leader CTA) =====
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer (one elected lane of the leader CTA) =====
+    if (rank == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
@@ -826,18 +847,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t a_desc = umma_smem_desc(sa), b_desc = umma_smem_desc(sa + L::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            umma_f16_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, accumulate);
-            accumulate = 1;
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_f16_cg2(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), P.idesc, (accumulate | (uint32_t)k) ? 1u : 0u);
+            umma_commit_cg2(&empty_bar[stage]);  // frees the stage in both CTAs once these MMAs have read it
           }
-          umma_commit_cg2(&empty_bar[stage]);  // frees the stage in both CTAs once these MMAs have read it
+          __syncwarp();
+          accumulate = 1;
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit_cg2(&tfull_bar[acc]);  // accumulator complete -> both CTAs' epilogues
+        if (elect_one()) umma_commit_cg2(&tfull_bar[acc]);  // accumulator complete -> both CTAs' epilogues
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

@@ -193,6 +193,9 @@ __device__ __forceinline__ D ties_one(const float (&in)[NSRC], const float (&thr
     float p, n, amb;
     const D out = ties_one_fast<NSRC, S, D, FUNC>(in, thr, majority > 0.0f ? 0.5f : -0.5f, p, n, amb);
     cls = p != 0.0f ? 0 : (n != 0.0f ? 1 : (amb != 0.0f ? 3 : 2));
+    // majority sign exactly 0 (n_pos == n_neg): the reference multiplies max |kept| by sign 0 (ties_merging.py:152-153), so
+    // every element without an elected sign is +0 for MAX; SUM / MEAN never multiply by the sign and keep the negative side
+    if (FUNC == MC_TIES_MAX && majority == 0.0f && cls >= 2) return from_f32<D>(0.0f);
     return out;
   } else {
     return ties_one_ref<NSRC, S, D, FUNC>(in, thr, majority, cls);
@@ -261,7 +264,6 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
         for (int j = 0; j < VPT; ++j) v[s][j] = ld_stream(p + j * kTiesMergeThreads);
       }
       VD* q = reinterpret_cast<VD*>(const_cast<void*>(row[NSRC])) + threadIdx.x;
-#pragma unroll
       // Class-3 elements (rare) are collected as one bit per element in float accumulators (mask_j += amb * 2^e, an FFMA)
       // and appended to the fix-up list after the sweep: the hot path is ONE basic block, so every load above issues
       // before the first element is touched (ptxas sinks loads whose first use sits in a later block).
@@ -286,6 +288,7 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
           if constexpr (kFast) {
             float p, n, amb;
             oe[e] = ties_one_fast<NSRC, S, D, FUNC, true>(in, thr, mh, p, n, amb);
+            if (FUNC == MC_TIES_MAX && majority == 0.0f && p == 0.0f && n == 0.0f) oe[e] = from_f32<D>(0.0f);  // sign 0 (see ties_one)
             f_pos += p;
             f_neg += n;
             amb_mask[j] = __fmaf_rn(amb, (float)(1 << e), amb_mask[j]);

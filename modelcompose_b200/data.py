@@ -25,41 +25,42 @@ MODAL_TOKEN_MAPPING = {MODAL_TOKENS[k]: MODAL_TOKEN_INDEXES[k] for k in MODAL_TO
 
 
 def split_string_by_list(input_string: str, split_list: Sequence[str]):
-    """mm_utils.py:60-78 — [(text, separator or None), ...]; the first separator of ``split_list`` found in the running
-    chunk wins (list order, not position), exactly as the reference scans character by character."""
-    splits, current = [], ""
-    for char in input_string:
-        current += char
-        if any(sep in current for sep in split_list):
-            split_char = next(sep for sep in split_list if sep in current)
-            text_part, _ = current.split(split_char, 1)
-            splits.append((text_part, split_char))
-            current = ""
-    if current:
-        splits.append((current, None))
-    return splits
+    """``[(text, separator or None), ...]`` with the semantics of mm_utils.py:64-78.  The reference grows a chunk one
+    character at a time and cuts as soon as any separator is contained in it, i.e. at the separator whose match ENDS first
+    (ties: list order).  Here that is computed directly: per separator one ``str.find`` from the current position, the
+    smallest end offset wins."""
+    pieces, pos, n = [], 0, len(input_string)
+    while pos < n:
+        cut = None  # (end, start, separator)
+        for sep in split_list:
+            at = input_string.find(sep, pos) if sep else -1
+            if at >= 0 and (cut is None or at + len(sep) < cut[0]):
+                cut = (at + len(sep), at, sep)
+        if cut is None:
+            pieces.append((input_string[pos:], None))
+            break
+        pieces.append((input_string[pos:cut[1]], cut[2]))
+        pos = cut[0]
+    return pieces
 
 
 def tokenizer_modal_token(prompt: str, tokenizer, return_tensors: Optional[str] = None):
-    """mm_utils.py:81-101 — tokenise the text between modality placeholders and put the sentinel id of each placeholder
-    in between; a leading BOS is kept once."""
-    chunks = split_string_by_list(prompt, list(MODAL_TOKEN_MAPPING.keys()))
-    chunks_input_ids = [tokenizer(chunk).input_ids for chunk, _ in chunks]
-    input_ids: List[int] = []
-    offset = 0
-    if len(chunks_input_ids) > 0 and len(chunks_input_ids[0]) > 0 and chunks_input_ids[0][0] == tokenizer.bos_token_id:
-        offset = 1
-        input_ids.append(chunks_input_ids[0][0])
-    for i in range(len(chunks_input_ids)):
-        input_ids.extend(chunks_input_ids[i][offset:])
-        sep = chunks[i][1]
+    """mm_utils.py:81-101: the text between modality placeholders is tokenised piece by piece and each placeholder becomes
+    its negative sentinel id; the BOS the tokenizer puts in front of every piece survives once, at the very start."""
+    pieces = split_string_by_list(prompt, list(MODAL_TOKEN_MAPPING))
+    tokenised = [tokenizer(text).input_ids for text, _ in pieces]
+    has_bos = bool(tokenised) and bool(tokenised[0]) and tokenised[0][0] == tokenizer.bos_token_id
+    skip = 1 if has_bos else 0
+    input_ids: List[int] = [tokenised[0][0]] if has_bos else []
+    for toks, (_, sep) in zip(tokenised, pieces):
+        input_ids += toks[skip:]
         if sep is not None:
             input_ids.append(MODAL_TOKEN_MAPPING[sep])
-    if return_tensors is not None:
-        if return_tensors == "pt":
-            return torch.tensor(input_ids, dtype=torch.long)
+    if return_tensors is None:
+        return input_ids
+    if return_tensors != "pt":
         raise ValueError(f"Unsupported tensor type: {return_tensors}")
-    return input_ids
+    return torch.tensor(input_ids, dtype=torch.long)
 
 
 class FeatureCollator:

@@ -192,7 +192,7 @@ def route_tile_masks(row_group: torch.Tensor, out: Optional[torch.Tensor] = None
 
 
 def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq_len: int,
-                     n_heads: int, softmax_scale: float, out_rowmap: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     n_heads: int, softmax_scale: float, out_rowmap: Optional[torch.Tensor] = None, tuning: int = 0) -> torch.Tensor:
     """Causal self-attention over ``[batch * seq_len, n_heads * 128]`` projection outputs (RoPE already applied); the output
     of token t lands in row ``out_rowmap[t]`` of ``out`` (``None`` = t).  multimodal_llama.py:295-312 without the scores."""
     qm, km, vm, om = _mat(q, "q"), _mat(k, "k", q.dtype), _mat(v, "v", q.dtype), _mat(out, "out", q.dtype)
@@ -202,10 +202,10 @@ def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: tor
     if out_rowmap is not None and (out_rowmap.dtype != torch.int32 or out_rowmap.numel() != T or not out_rowmap.is_cuda
                                    or not out_rowmap.is_contiguous()):
         raise ValueError("attention: out_rowmap must be a contiguous CUDA int32 [batch * seq_len]")
-    _cabi.check(_cabi.lib().mc_attention_causal(qm.data_ptr(), km.data_ptr(), vm.data_ptr(), om.data_ptr(), qm.stride(0), om.stride(0),
-                                                None if out_rowmap is None else out_rowmap.data_ptr(), batch, seq_len, n_heads, 128,
-                                                float(softmax_scale), _cabi.dtype_code(q.dtype), _cabi.current_stream_ptr()),
-                "mc_attention_causal")
+    _cabi.check(_cabi.lib().mc_attention_causal_tuned(qm.data_ptr(), km.data_ptr(), vm.data_ptr(), om.data_ptr(), qm.stride(0),
+                                                      om.stride(0), None if out_rowmap is None else out_rowmap.data_ptr(), batch,
+                                                      seq_len, n_heads, 128, float(softmax_scale), _cabi.dtype_code(q.dtype),
+                                                      int(tuning), _cabi.current_stream_ptr()), "mc_attention_causal")
     _cabi.count_launch()
     return out
 

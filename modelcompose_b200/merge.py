@@ -133,10 +133,11 @@ def merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], weights: 
         raise _cabi.McError("merging tensors needs a CUDA device (modelcompose_b200 has no CPU fallback)")
     srcs = [[t.contiguous() for t in lst] for lst in tensor_lists]
     src_dtype = srcs[0][0].dtype if n_t else torch.bfloat16
-    for lst in srcs:
-        for a, b in zip(lst, srcs[0]):
+    for si, lst in enumerate(srcs):
+        for ti, (a, b) in enumerate(zip(lst, srcs[0])):
             if a.dtype != src_dtype or a.shape != b.shape or a.is_cuda:
-                raise ValueError("sources must be CPU tensors of identical dtype and shape per key")
+                raise ValueError(f"source {si}, tensor {ti}: sources must be CPU tensors of one dtype and shape per launch "
+                                 f"(got {a.dtype} {tuple(a.shape)} vs {src_dtype} {tuple(b.shape)})")
     out_dtype = out_dtype or src_dtype
     outs = [torch.empty(t.shape, dtype=out_dtype) for t in srcs[0]]
     w = _cabi.f32_array(weights if weights is not None else [1.0] * n_src)
@@ -241,20 +242,37 @@ class TiesPlan:
             pass
 
 
-def ties_merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], K=20, func: str = "mean"):
-    """TIES-merge HOST tensors through the GPU (``mc_ties_host``).  ``tensor_lists[s][t]``: CPU tensors, same shapes and
-    dtype across sources.  Returns (new CPU tensors, stats dict); float32 outputs for ``mean``."""
+def _promoted_sources(tensor_lists: Sequence[Sequence[torch.Tensor]], names: Optional[Sequence[str]] = None):
+    """Contiguous CPU copies of ``tensor_lists[s][t]`` in ONE dtype: the reference flattens every checkpoint with
+    ``torch.cat`` and stacks the vectors with ``vstack`` (ties_merging.py:12-19,:188-190; calculate_metrics casts with
+    ``.float()``), both of which type-promote, so a float32 projector beside bf16 adapters makes the whole problem float32."""
+    n_t = len(tensor_lists[0])
+    common = None
+    for si, lst in enumerate(tensor_lists):
+        if len(lst) != n_t:
+            raise ValueError("every source must hold the same number of tensors")
+        for ti, (a, b) in enumerate(zip(lst, tensor_lists[0])):
+            what = names[ti] if names is not None else f"tensor {ti}"
+            if a.is_cuda or a.shape != b.shape:
+                raise ValueError(f"source {si}, {what}: sources must be CPU tensors of identical shape per key "
+                                 f"(got {tuple(a.shape)} vs {tuple(b.shape)})")
+            if not a.dtype.is_floating_point:
+                raise ValueError(f"source {si}, {what}: {a.dtype} is not a floating-point dtype")
+            common = a.dtype if common is None else torch.promote_types(common, a.dtype)
+    if common not in (torch.float32, torch.float16, torch.bfloat16):
+        raise ValueError(f"sources promote to {common}; the kernels take float32, float16 or bfloat16")
+    return [[t.to(common).contiguous() for t in lst] for lst in tensor_lists], common
+
+
+def ties_merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], K=20, func: str = "mean",
+                            names: Optional[Sequence[str]] = None):
+    """TIES-merge HOST tensors through the GPU (``mc_ties_host``).  ``tensor_lists[s][t]``: CPU tensors, same shapes across
+    sources; mixed dtypes are promoted to one (as the reference's flatten does).  Returns (new CPU tensors, stats dict);
+    float32 outputs for ``mean``."""
     if not torch.cuda.is_available():
         raise _cabi.McError("merging tensors needs a CUDA device (modelcompose_b200 has no CPU fallback)")
     n_src, n_t = len(tensor_lists), len(tensor_lists[0])
-    srcs = [[t.contiguous() for t in lst] for lst in tensor_lists]
-    src_dtype = srcs[0][0].dtype
-    for lst in srcs:
-        if len(lst) != n_t:
-            raise ValueError("every source must hold the same number of tensors")
-        for a, b in zip(lst, srcs[0]):
-            if a.dtype != src_dtype or a.shape != b.shape or a.is_cuda:
-                raise ValueError("sources must be CPU tensors of identical dtype and shape per key")
+    srcs, src_dtype = _promoted_sources(tensor_lists, names)
     out_dtype = torch.float32 if func == "mean" else src_dtype
     outs = [torch.empty(t.shape, dtype=out_dtype) for t in srcs[0]]
     d = sum(o.numel() for o in outs)
@@ -274,12 +292,7 @@ def interference_metrics_host(tensor_lists: Sequence[Sequence[torch.Tensor]], re
     n_src, n_t = len(tensor_lists), len(tensor_lists[0])
     if n_src < 2:
         raise IndexError("index 1 is out of bounds for dimension 0 with size 1")
-    srcs = [[t.contiguous() for t in lst] for lst in tensor_lists]
-    src_dtype = srcs[0][0].dtype
-    for lst in srcs:
-        for a, b in zip(lst, srcs[0]):
-            if a.dtype != src_dtype or a.shape != b.shape or a.is_cuda:
-                raise ValueError("sources must be CPU tensors of identical dtype and shape per key")
+    srcs, src_dtype = _promoted_sources(tensor_lists)
     d = sum(t.numel() for t in srcs[0])
     m = _cabi.InterferenceMetrics()
     _cabi.check(_cabi.lib().mc_interference_host(
@@ -290,21 +303,21 @@ def interference_metrics_host(tensor_lists: Sequence[Sequence[torch.Tensor]], re
 
 
 def convert_delta_to_ft(delta_weights: Dict[str, List[torch.Tensor]]):
-    """reference ties_merging.py:224-250."""
-    N = -1
-    for key in delta_weights.keys():
-        N = max(N, len(delta_weights[key]))
-    assert N > 0
-    ft_checks = [{} for _ in range(N)]
-    uniques = {}
-    for key in delta_weights.keys():
-        if len(delta_weights[key]) == N:
-            for i in range(N):
-                ft_checks[i][key] = delta_weights[key][i]
+    """``{key: [tensor of every checkpoint that has the key]}`` -> (one state dict per checkpoint holding the keys ALL of them
+    share, dict of the keys a single checkpoint contributes), the split the reference makes before flattening
+    (ties_merging.py:224-250).  Any other multiplicity is a caller error, as there."""
+    n_ckpt = max((len(tensors) for tensors in delta_weights.values()), default=0)
+    assert n_ckpt > 0
+    shared = [dict() for _ in range(n_ckpt)]
+    single = {}
+    for key, tensors in delta_weights.items():
+        if len(tensors) == n_ckpt:
+            for state, t in zip(shared, tensors):
+                state[key] = t
         else:
-            assert len(delta_weights[key]) == 1
-            uniques[key] = delta_weights[key][0]
-    return ft_checks, uniques
+            assert len(tensors) == 1
+            single[key] = tensors[0]
+    return shared, single
 
 
 def do_merging(ft_checks: Sequence[Dict[str, torch.Tensor]], K=20, merge_func: str = "dis-mean", lamda=1):
@@ -322,7 +335,7 @@ def do_merging(ft_checks: Sequence[Dict[str, torch.Tensor]], K=20, merge_func: s
     func = merge_func.split("-")[-1]
     if func not in TIES_FUNCS:
         raise ValueError(f"Merge method {func} is not defined.")
-    outs, _ = ties_merge_host_tensors([[check[k] for k in keys] for check in ft_checks], K=K, func=func)
+    outs, _ = ties_merge_host_tensors([[check[k] for k in keys] for check in ft_checks], K=K, func=func, names=keys)
     return OrderedDict(zip(keys, outs))
 
 
@@ -343,10 +356,22 @@ def _elementwise_strategy(weights_to_merge: Dict[str, List[torch.Tensor]], strat
     multi-tensor launch; results are bit-identical to the reference's per-add storage-dtype rounding."""
     merged: Dict[str, torch.Tensor] = {}
     by_count: Dict[tuple, List[str]] = defaultdict(list)
+    promoted: Dict[str, List[torch.Tensor]] = {}
     for key, tensors in weights_to_merge.items():
+        dtypes = {t.dtype for t in tensors}
+        if len(dtypes) > 1:
+            # Python's sum() adds left to right and torch promotes each add.  With two sources the only add of two non-zero
+            # operands runs in the promoted dtype, so casting both up first gives the same bits; with more, earlier partial
+            # sums would round in the narrower dtype — not reproduced here, so say so instead of returning other bits.
+            if len(tensors) > 2:
+                raise ValueError(f"{key}: {len(tensors)} sources in mixed dtypes {sorted(map(str, dtypes))} — cast the "
+                                 "checkpoints to one dtype before merging")
+            common = torch.promote_types(tensors[0].dtype, tensors[1].dtype)
+            tensors = [t.to(common) for t in tensors]
+        promoted[key] = tensors
         by_count[(len(tensors), tensors[0].dtype)].append(key)
     for (n_src, _), keys in by_count.items():
-        lists = [[weights_to_merge[k][s] for k in keys] for s in range(n_src)]
+        lists = [[promoted[k][s] for k in keys] for s in range(n_src)]
         outs = merge_host_tensors(lists, mode=strategy)
         merged.update(zip(keys, outs))
     return {k: merged[k] for k in weights_to_merge}  # first-seen key order, as the reference dict has

@@ -321,6 +321,12 @@ class MultimodalLlamaForCausalLM:
         if dtype not in (torch.float16, torch.bfloat16):
             raise ValueError("inference dtype must be float16 (reference builder.py:185) or bfloat16")
         self.config, self.device, self.dtype = config, torch.device(device), dtype
+        if getattr(config, "rope_scaling", None) is not None:
+            raise NotImplementedError("rope_scaling (linear / dynamic NTK rotary embeddings, multimodal_llama.py:222-238) is not "
+                                      "implemented on this path: the composed vicuna checkpoints use plain RoPE")
+        if config.num_key_value_heads != config.num_attention_heads:
+            raise NotImplementedError(f"grouped-query attention (num_key_value_heads {config.num_key_value_heads} != "
+                                      f"num_attention_heads {config.num_attention_heads}) is not implemented on this path")
         self.modal_names = infer_modals(config)
         sd = adapter_state_dict or {}
         r, alpha = config.lora_r, config.lora_alpha
@@ -663,6 +669,7 @@ class MultimodalLlamaForCausalLM:
         out = self.forward(ids, attention_mask.to(self.device), modal_inputs=modal_inputs, use_cache=True, last_logits_only=True)
         cache = out.past_key_values
         logits = out.logits[:, -1, :]
+        text_mask = attention_mask.to(self.device)
         done = torch.zeros(B, dtype=torch.bool, device=self.device)
         pad = pad_token_id if pad_token_id is not None else (eos_token_id if eos_token_id is not None else 0)
         new_tokens = []
@@ -686,7 +693,13 @@ class MultimodalLlamaForCausalLM:
                     break
             if step + 1 == max_new_tokens:
                 break
-            step_mask = torch.ones((B, cache.length + 1), dtype=attention_mask.dtype, device=self.device)
+            if modal_inputs:
+                # multimodal_arch.py:291-292: with modal inputs the mask is rebuilt as all ones over past + 1
+                step_mask = torch.ones((B, cache.length + 1), dtype=attention_mask.dtype, device=self.device)
+            else:
+                # text-only: HF generate appends a ones column to the caller's mask, so padded positions stay masked
+                text_mask = torch.cat([text_mask, torch.ones((B, 1), dtype=text_mask.dtype, device=self.device)], dim=1)
+                step_mask = text_mask
             o = self.forward(nxt[:, None], step_mask, past_key_values=cache, use_cache=True)
             logits = o.logits[:, -1, :]
         return torch.cat([ids, torch.stack(new_tokens, dim=1)], dim=1)

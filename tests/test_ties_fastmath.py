@@ -112,7 +112,10 @@ def emulate_fast(flat: torch.Tensor, thr, majority: float, func: str, packed_tri
         if func == "sum":
             out = torch.from_numpy((ksum * sg + F32(0)).astype(F32)).to(dt)
         elif func == "max":
-            out = torch.from_numpy((ksum * sg).astype(F32)).to(dt)
+            o = (ksum * sg).astype(F32)
+            if majority == 0:   # ties_one: the reference multiplies by sign 0 where no sign was elected
+                o = np.where((p == 0) & (n == 0), F32(0), o).astype(F32)
+            out = torch.from_numpy(o).to(dt)
         else:
             xr = round_dt(ksum, dt)
             c = np.maximum(cnt, F32(1))
@@ -145,7 +148,7 @@ def test_fast_formulation_matches_oracle(dt, kind, K, n_src):
     for func in ("sum", "mean", "max"):
         want, st = TO.ties_merge_flat(flat, K, func)
         thr = st["thresholds"].numpy()
-        for majority in (st["majority"], -st["majority"] if st["majority"] else 1.0):
+        for majority in (st["majority"], -st["majority"] if st["majority"] else 1.0, 0.0):
             ref = TO.merge_given_statistics(flat, thr, majority, func)
             for packed in (False, True):   # scalar tail path (multiply) and vector path (packed mask) of the kernel
                 got, p, n, amb = emulate_fast(flat, thr, majority, func, packed_trim=packed)

@@ -112,6 +112,33 @@ def test_fix_pass_only_when_needed():
     assert bits_equal(out_big[0], oracle_merge(big, 60, "sum")[0][0])
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_majority_sign_exactly_zero(dtype):
+    """n_pos == n_neg: the reference's majority sign is 0 (ties_merging.py:111-118), so `max` multiplies the elements whose
+    survivors cancel by 0 (+0) while `sum` / `mean` keep the negative side.  Vector path (whole chunks) and scalar tail."""
+    g = torch.Generator().manual_seed(11)
+    n = 3 * 8192 + 77
+    a = (torch.randint(1, 6, (n,), generator=g).float() * 0.25)
+    third = n // 3
+    s0, s1 = a.clone(), a.clone()
+    s0[third:2 * third] *= -1           # both negative
+    s1[third:2 * third] *= -1
+    s1[2 * third:] *= -1                # survivors cancel exactly
+    s0[2 * third + 100:2 * third + 200] = 0   # ... and some elements with no survivors at all
+    s1[2 * third + 100:2 * third + 200] = 0
+    srcs = [[s0.to(dtype)], [s1.to(dtype)]]
+    dev = [[t.cuda() for t in lst] for lst in srcs]
+    for func in ("sum", "mean", "max"):
+        out = [torch.full((n,), 7.0, dtype=torch.float32 if func == "mean" else dtype, device="cuda")]
+        plan = M.TiesPlan(dev, out)
+        plan.run(99, func)
+        st = plan.stats()
+        want, ost = oracle_merge(srcs, 99, func)
+        assert st["majority"] == 0 == int(ost["majority"]) and st["n_ambiguous"] > 0 and st["n_zero"] == 100, st
+        assert bits_equal(out[0], want[0]), (func, dtype, int((out[0].cpu().float() != want[0].float()).sum()))
+        plan.close()
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 def test_sampled_select_bit_exact(dtype):
     """>= 1024 chunks: thresholds come from the sampled bracket + one counting pass — same result as the oracle"""
