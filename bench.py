@@ -26,8 +26,6 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WEIGHTS = (0.333, 0.333, 0.333)
-SOURCE_SEEDS = (1000, 1001, 1002)  # video, audio, vision (README.md:86-91 order)
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -95,18 +93,25 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def measured_traffic(key_prefix: str, world: int):
-    """DRAM bytes per launch from the committed ncu --set full capture of this kernel (profiles/traffic.json), or None."""
+def measured_traffic(kernel: str, world: int, launch_bytes: int):
+    """DRAM bytes per launch from the committed ncu --set full captures of this kernel (profiles/traffic.json).  A capture of
+    exactly this launch (same algorithmic bytes) is returned as measured; otherwise the capture's traffic / algorithmic ratio
+    (1.000 - 1.012 for every capture so far) is applied to this launch's algorithmic bytes.  None when the kernel has no capture."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as f:
         d = json.load(f)
-    want = "N=1" if world == 1 else ("1/8 shard" if world == 8 else None)
+    best = None
     for k, v in d.items():
-        if want and k.startswith(key_prefix) and want in k:
+        if not k.startswith(kernel) or "dram_bytes" not in v or "algorithmic_bytes" not in v:
+            continue
+        if v["algorithmic_bytes"] == launch_bytes:
             return v["dram_bytes"]
-    return None
+        gap = abs(v["algorithmic_bytes"] - launch_bytes)
+        if best is None or gap < best[0]:
+            best = (gap, v["dram_bytes"] / v["algorithmic_bytes"])
+    return None if best is None else int(round(best[1] * launch_bytes))
 
 
 def dist_env():
@@ -114,53 +119,62 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------ merge workload
+MERGE_CONFIGS = {
+    # name: (description, source seeds, weights, kernel label)
+    "c2": ("3-way vicuna-7B-shaped merge video=0.333,audio=0.333,vision=0.333 (C2)", (1000, 1001, 1002), (0.333, 0.333, 0.333)),
+    "n4": ("4-way vicuna-7B-shaped merge video,audio,vision,point at 0.25 each (MCUB-4 checkpoints of C5)", (1000, 1001, 1002, 1003),
+           (0.25, 0.25, 0.25, 0.25)),
+    "c2b": ("base + 3 materialised blend W_eff = (1 - 0.999) W_base + 0.333 (video + audio + vision) (C2b, "
+            "convert_to_multimodal.py:111-113 form)", (1003, 1000, 1001, 1002), (1.0 - 0.999, 0.333, 0.333, 0.333)),
+}
+SPLIT_ROWS_ABOVE = 1 << 26   # elements: embed_tokens / lm_head (131 M each) are cut into row slices when sharding
+
+
+def merge_items(world: int):
+    """The job's work items: (name, shape) of every tensor; for world > 1 the two 131 M-element matrices are cut into `world`
+    row slices first (the merge is elementwise, so any row range is an independent item) — by whole tensors the heaviest
+    rank carried 6.80 GB against 6.74 ideal at 8 ranks."""
+    from modelcompose_b200 import synthetic as syn
+    items = []
+    for name, shape in syn.dense_7b_tensor_shapes():
+        n = int(torch.Size(shape).numel())
+        if world > 1 and n > SPLIT_ROWS_ABOVE and len(shape) == 2:
+            rows = shape[0]
+            for k in range(world):
+                r0, r1 = rows * k // world, rows * (k + 1) // world
+                items.append((f"{name}[{r0}:{r1}]", (r1 - r0, shape[1])))
+        else:
+            items.append((name, tuple(shape)))
+    return items
+
+
 def merge_shard(world: int, rank: int):
     from modelcompose_b200 import synthetic as syn
-    shapes = syn.dense_7b_tensor_shapes()
+    shapes = merge_items(world)
     sizes = [int(torch.Size(s).numel()) for _, s in shapes]
     mine = syn.shard_tensors_greedy(sizes, world)[rank]
     return shapes, sizes, mine
 
 
-def make_device_sources(shapes, mine, device):
-    """3 sources x this rank's tensors, bf16 N(0, 0.02), one allocation per tensor (as a loaded checkpoint has)."""
-    srcs = []
-    for m, seed in enumerate(SOURCE_SEEDS):
-        g = torch.Generator(device=device).manual_seed(seed)
-        lst = []
-        for i in mine:
-            t = torch.empty(shapes[i][1], dtype=torch.bfloat16, device=device)
-            t.normal_(0.0, 0.02, generator=g)
-            lst.append(t)
-        srcs.append(lst)
-    return srcs
+def make_device_source(shapes, mine, device, seed):
+    """This rank's tensors of one checkpoint: bf16 N(0, 0.02), one allocation per tensor (as a loaded checkpoint has)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    lst = []
+    for i in mine:
+        t = torch.empty(shapes[i][1], dtype=torch.bfloat16, device=device)
+        t.normal_(0.0, 0.02, generator=g)
+        lst.append(t)
+    return lst
 
 
-def cpu_merge_rate(sample_tensors, min_seconds: float, max_passes: int = 50):
-    """Times the oracle port of the reference CPU merge arithmetic on host cores; returns (GB/s, seconds, passes)."""
-    from oracle import merge_oracle as MO
-    nbytes = sum(t[0].numel() for t in sample_tensors) * 2 * (len(WEIGHTS) + 1)
-    MO.weighted_merge(sample_tensors[0], WEIGHTS)  # warm the allocator / thread pool
-    t0 = time.perf_counter()
-    passes = 0
-    while True:
-        for ts in sample_tensors:
-            MO.weighted_merge(ts, WEIGHTS)
-        passes += 1
-        dt = time.perf_counter() - t0
-        if dt >= min_seconds or passes >= max_passes:
-            break
-    return nbytes * passes / dt / 1e9, dt, passes
-
-
-def cpu_sample_tensors():
+def cpu_sample_tensors(n_src: int = 3):
     """One decoder layer of each source (202,383,360 elements: q,k,v,o,gate,up,down + 2 norms), seeded on CPU."""
     from modelcompose_b200 import synthetic as syn
     shapes = [s for n, s in syn.dense_7b_tensor_shapes() if n.startswith("model.layers.0.")]
     out = []
     for shp in shapes:
         ts = []
-        for seed in SOURCE_SEEDS:
+        for seed in range(1000, 1000 + n_src):
             g = torch.Generator().manual_seed(seed + 7)
             # cheap deterministic fill (randn over 200M elements x3 would dominate the bench's wall time)
             base = torch.randn(4096, generator=g) * 0.02
@@ -170,6 +184,31 @@ def cpu_sample_tensors():
     return out, "one vicuna-7B decoder layer x 3 sources (202,383,360 elements per source, 1.62 GB algorithmic)"
 
 
+def cpu_merge_rates(sample_tensors, min_seconds: float, max_passes: int = 50):
+    """The reference's CPU merge on the host's cores, both forms, as GB/s of (3 reads + 1 write) x 2 B:
+    `sum`      — the arithmetic the reference CLI literally runs (merge_unimodal_modelcompose.py:105-108: Python sum() of the
+                 bf16 tensors, every add rounded to bf16), restated in oracle/merge_oracle.reference_sum;
+    `weighted` — the materialised online-merge-reset blend (multimodal_llama.py:130-149 coefficients applied to full
+                 weights, fp32 temporaries), oracle/merge_oracle.weighted_merge: the arithmetic the GPU arm's headline runs."""
+    from oracle import merge_oracle as MO
+    w = MERGE_CONFIGS["c2"][2]
+    nbytes = sum(t[0].numel() for t in sample_tensors) * 2 * (len(w) + 1)
+    out = {}
+    for name, fn in (("sum", lambda ts: MO.ref_sum(ts)), ("weighted", lambda ts: MO.weighted_merge(ts, w))):
+        fn(sample_tensors[0])  # warm the allocator / thread pool
+        t0 = time.perf_counter()
+        passes = 0
+        while True:
+            for ts in sample_tensors:
+                fn(ts)
+            passes += 1
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds or passes >= max_passes:
+                break
+        out[name] = (nbytes * passes / dt / 1e9, dt, passes)
+    return out
+
+
 def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -177,25 +216,34 @@ def run_reference_arm(args):
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; rank 0 alone works here, on every host core
     sample, desc = cpu_sample_tensors()
     from oracle import merge_oracle as MO
-    nbytes = sum(t[0].numel() for t in sample) * 2 * (len(WEIGHTS) + 1)
-    for _ in range(max(args.warmup, 1)):
-        for ts in sample:
-            MO.weighted_merge(ts, WEIGHTS)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for ts in sample:
-            MO.weighted_merge(ts, WEIGHTS)
-    dt = time.perf_counter() - t0
-    gbs = nbytes * args.steps / dt / 1e9
+    w = MERGE_CONFIGS["c2"][2]
+    nbytes = sum(t[0].numel() for t in sample) * 2 * (len(w) + 1)
+    rates = {}
+    for name, fn in (("sum", lambda ts: MO.ref_sum(ts)), ("weighted", lambda ts: MO.weighted_merge(ts, w))):
+        for _ in range(max(args.warmup, 1)):
+            for ts in sample:
+                fn(ts)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for ts in sample:
+                fn(ts)
+        rates[name] = (time.perf_counter() - t0) / args.steps
+    # headline of this arm = the faster of the two CPU forms (the reference's own `sum` arithmetic needs no fp32 temporaries)
+    best = min(rates, key=rates.get)
+    dt = rates[best]
+    gbs = nbytes / dt / 1e9
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": "3x7B merge GB/s", "value": round(gbs, 3), "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "3-way vicuna-7B-shaped merge video=0.333,audio=0.333,vision=0.333 (C2)",
-                   "step": "bounded sample: " + desc, "l2": "sample larger than L2/LLC"},
+        "config": {"workload": MERGE_CONFIGS["c2"][0], "step": "bounded sample: " + desc, "l2": "sample larger than L2/LLC",
+                   "cpu_form": best},
         "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": cores, "kind": "port", "sample": desc,
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(), "form": best,
+                         "forms_GBps": {k: round(nbytes / v / 1e9, 3) for k, v in rates.items()},
+                         "note": "the reference is pure Python and /root/reference does not travel to the GPU box: "
+                                 "oracle/merge_oracle.py restates merge_unimodal_modelcompose.py:105-108 (`sum`) and the materialised blend"},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -231,23 +279,78 @@ def setup_dist(args):
     return dist, rank, world, device, barrier
 
 
-def run_merge(args, dist, rank, world, device, barrier):
+class MergeJob:
+    """Device-resident sources of this rank's shard (generated once, shared by the C2 / 4-way / base+N lines), the output
+    tensors, and — for the e2e legs — one pinned host ARENA per checkpoint holding the same tensors back to back."""
+
+    def __init__(self, args, world, rank, device):
+        if args.emulate_world > 1:  # profiling aid: rank 0's shard of a K-way job in one process (never a bench value)
+            self.shapes, self.sizes, self.mine = merge_shard(args.emulate_world, 0)
+        else:
+            self.shapes, self.sizes, self.mine = merge_shard(world, rank)
+        self.device, self.world, self.rank = device, world, rank
+        self.src = {}
+        self.outs = [torch.empty(self.shapes[i][1], dtype=torch.bfloat16, device=device) for i in self.mine]
+        self.h_src, self.h_out, self.pick = {}, None, None
+        self.total_elems = sum(self.sizes)
+        self.emulated = args.emulate_world > 1
+
+    def source(self, seed):
+        if seed not in self.src:
+            self.src[seed] = make_device_source(self.shapes, self.mine, self.device, seed)
+        return self.src[seed]
+
+    # ---- pinned host copies for the e2e leg
+    def host_pick(self, n_src):
+        """Every k-th tensor of the shard when host RAM is short (keeps pinned memory below 45 % of what the host has)."""
+        if self.pick is None:
+            import psutil
+            need = sum(self.sizes[i] for i in self.mine) * 2 * (n_src + 1)
+            stride = 1
+            while need / stride > 0.45 * psutil.virtual_memory().available / self.world and stride < 64:
+                stride *= 2
+            self.pick, self.stride = list(range(0, len(self.mine), stride)), stride
+        return self.pick
+
+    def _arena(self, numels):
+        """One pinned allocation, carved into per-tensor views at 256-byte aligned offsets."""
+        offs, total = [], 0
+        for n in numels:
+            offs.append(total)
+            total += (n * 2 + 255) // 256 * 256
+        arena = torch.empty(max(total, 256), dtype=torch.uint8).pin_memory()
+        return arena, [arena[o:o + n * 2].view(torch.bfloat16) for o, n in zip(offs, numels)]
+
+    def host_source(self, seed):
+        if seed not in self.h_src:
+            dev = self.source(seed)
+            arena, views = self._arena([dev[j].numel() for j in self.pick])
+            for v, j in zip(views, self.pick):
+                v.copy_(dev[j].view(-1))
+            self.h_src[seed] = (arena, views)
+        return self.h_src[seed][1]
+
+    def host_out(self):
+        if self.h_out is None:
+            self.h_out = self._arena([self.outs[j].numel() for j in self.pick])
+        return self.h_out[1]
+
+
+def run_merge(args, dist, rank, world, device, barrier, job: MergeJob, cfg_name: str, with_cpu: bool):
     from modelcompose_b200 import merge as M
+    desc, seeds, weights = MERGE_CONFIGS[cfg_name]
+    n_src = len(seeds)
     local_rank = device.index
-    if args.emulate_world > 1:  # profiling aid: rank 0's shard of a K-way job in one process (never a bench value)
-        shapes, sizes, mine = merge_shard(args.emulate_world, 0)
-    else:
-        shapes, sizes, mine = merge_shard(world, rank)
-    srcs = make_device_sources(shapes, mine, device)
-    outs = [torch.empty(shapes[i][1], dtype=torch.bfloat16, device=device) for i in mine]
+    srcs = [job.source(sd) for sd in seeds]
+    outs, shapes, sizes, mine = job.outs, job.shapes, job.sizes, job.mine
     plan = M.MergePlan(srcs, outs, tuning=args.tuning)
     my_bytes = plan.algorithmic_bytes
-    total_bytes = sum(sizes) * 2 * (len(WEIGHTS) + 1)
-    if args.emulate_world > 1:
+    total_bytes = job.total_elems * 2 * (n_src + 1)
+    if job.emulated:
         total_bytes = my_bytes
 
     for _ in range(args.warmup):
-        plan.run(WEIGHTS)
+        plan.run(weights)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -255,7 +358,7 @@ def run_merge(args, dist, rank, world, device, barrier):
         t_start.record()
         for a, b in ev:
             a.record()
-            plan.run(WEIGHTS)
+            plan.run(weights)
             b.record()
         t_end.record()
         barrier()
@@ -272,93 +375,92 @@ def run_merge(args, dist, rank, world, device, barrier):
     from oracle import merge_oracle as MO
     order = sorted(range(len(mine)), key=lambda j: sizes[mine[j]])
     for j in (order[0], order[len(order) // 2]):
-        want = MO.weighted_merge([srcs[s][j].cpu() for s in range(3)], WEIGHTS)
+        want = MO.weighted_merge([srcs[s][j].cpu() for s in range(n_src)], weights)
         if not torch.equal(outs[j].cpu().view(torch.int16), want.view(torch.int16)):
-            raise SystemExit(f"PARITY FAILURE on tensor {shapes[mine[j]][0]}")
+            raise SystemExit(f"PARITY FAILURE ({cfg_name}) on tensor {shapes[mine[j]][0]}")
 
-    # ---- e2e: same merge through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timing)
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps({"profiling_only": True, "ms_per_step": round(ms_per_step, 4), "GBps": round(value, 1),
+            print(json.dumps({"profiling_only": True, "config": cfg_name, "ms_per_step": round(ms_per_step, 4), "GBps": round(value, 1),
                               "launch_ms": round(launch_ms, 4), "emulate_world": args.emulate_world}), flush=True)
+        plan.close()
         return None
-    e2e = run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barrier, dist)
+    # ---- e2e: same merge through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timing)
+    e2e = run_merge_e2e(args, job, seeds, weights, device, world, barrier, dist, probe=(cfg_name == "c2"))
 
+    line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         achieved = my_bytes / (launch_ms * 1e-3) / 1e9
-        if world == 1:
-            cpu_sample, desc = cpu_sample_tensors()
-            cpu_gbs, cpu_s, passes = cpu_merge_rate(cpu_sample, min_seconds=10.0)
-            cpu_baseline = {"value": round(cpu_gbs, 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": f"{desc}, {passes} passes in {cpu_s:.1f} s", "host_cpus": os.cpu_count()}
-        else:
-            cpu_baseline = None  # reported at N=1 only
+        cpu_baseline = None  # reported at N=1 only, on the primary line
+        if with_cpu and world == 1:
+            cpu_sample, sdesc = cpu_sample_tensors()
+            rates = cpu_merge_rates(cpu_sample, min_seconds=6.0)
+            best = max(rates, key=lambda k: rates[k][0])
+            cpu_baseline = {"value": round(rates[best][0], 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "form": best, "forms_GBps": {k: round(v[0], 3) for k, v in rates.items()},
+                            "sample": f"{sdesc}; `sum` = the reference CLI's own arithmetic (merge_unimodal_modelcompose.py:105-108), "
+                                      f"`weighted` = the materialised blend; {rates[best][2]} passes in {rates[best][1]:.1f} s",
+                            "host_cpus": os.cpu_count()}
+        kern = f"mc::merge_kernel<{n_src},bf16,bf16>"
         line = {
-            "metric": "3x7B merge GB/s", "value": round(value, 2), "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "metric": "3x7B merge GB/s" if cfg_name == "c2" else f"{n_src}x7B merge GB/s", "value": round(value, 2), "unit": "GB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "3-way vicuna-7B-shaped merge video=0.333,audio=0.333,vision=0.333 (C2)",
-                       "tensors": len(sizes), "elements_per_source": sum(sizes), "sharding": f"by-tensor greedy x{world}",
+            "config": {"workload": desc, "tensors": len(sizes), "elements_per_source": job.total_elems, "weights": list(weights),
+                       "sharding": f"greedy by work item x{world} (tensors; embed_tokens / lm_head cut into {world} row slices)" if world > 1
+                       else "one GPU holds every tensor",
                        "algorithmic_bytes": total_bytes, "l2": "inputs larger than L2 (%.2f GB per GPU vs 0.13 GB)" % (my_bytes / 1e9),
                        "tuning": args.tuning},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": measured_traffic("merge_kernel<3,bf16,bf16>", world),
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/traffic.json)", "peak_source": peak_src,
-                         "kernel": "mc::merge_kernel<3,bf16,bf16>", "launch_ms": round(launch_ms, 4),
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic(kern, world, my_bytes),
+                         "traffic_unit": "bytes per launch: DRAM read+write bytes of the committed ncu --set full capture of this kernel "
+                                         "(profiles/traffic.json), scaled by this launch's algorithmic bytes when the capture ran another shard",
+                         "peak_source": peak_src, "kernel": kern, "launch_ms": round(launch_ms, 4),
                          "frac_of_8TBps_nominal": round(achieved / 8000.0, 4)},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": args.steps * world,
             "clocks": clocks.summary(),
         }
-    else:
-        line = None
-    del plan, srcs, outs
-    torch.cuda.empty_cache()
+    plan.close()
     return line
 
 
-def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barrier, dist):
-    """Whole-shard merge through ``mc_merge_host`` from pinned host buffers; value = all ranks' bytes / max time."""
-    import psutil
-    n_src = len(srcs)
-    my_elems = sum(sizes[i] for i in mine)
-    need = my_elems * 2 * (n_src + 1)
-    avail = psutil.virtual_memory().available / max(world, 1) * (1 if world == 1 else 1)
-    # keep pinned memory well below what the host has: use every k-th tensor when RAM is short
-    stride = 1
-    while need / stride > 0.45 * psutil.virtual_memory().available / world and stride < 64:
-        stride *= 2
-    pick = list(range(0, len(mine), stride))
+def run_merge_e2e(args, job: MergeJob, seeds, weights, device, world, barrier, dist, probe: bool):
+    """Whole-shard merge through ``mc_merge_host`` from pinned host arenas; value = all ranks' bytes / max time."""
+    from modelcompose_b200 import _cabi
+    n_src = len(seeds)
     # the staging buffers belong on the GPU's own NUMA node (the rank is bound for this leg only: at N = 1 it also runs the
     # CPU baseline on every core afterwards)
-    from modelcompose_b200 import _cabi
     saved_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
     numa_bound = _cabi.bind_host_thread_to_gpu(device.index)
-    h_src = [[torch.empty(srcs[s][j].shape, dtype=torch.bfloat16).pin_memory() for j in pick] for s in range(n_src)]
-    for s in range(n_src):
-        for hj, j in zip(h_src[s], pick):
-            hj.copy_(srcs[s][j])
-    elems = sum(srcs[0][j].numel() for j in pick)
+    pick = job.host_pick(max(n_src, 4))
+    h_src = [job.host_source(sd) for sd in seeds]
+    h_out = job.host_out()
+    srcs = [job.source(sd) for sd in seeds]
+    outs = job.outs
+    elems = sum(o.numel() for o in h_out)
     h2d, d2h = elems * 2 * n_src, elems * 2
-    h_out = [torch.empty(srcs[0][j].shape, dtype=torch.bfloat16).pin_memory() for j in pick]
     lib = _cabi.lib()
     sp = _cabi.ptr_array([h_src[s][k].data_ptr() for s in range(n_src) for k in range(len(pick))])
     dp = _cabi.ptr_array([o.data_ptr() for o in h_out])
     ne = _cabi.i64_array([o.numel() for o in h_out])
-    w = _cabi.f32_array(WEIGHTS)
+    w = _cabi.f32_array(weights)
 
     def step():
         _cabi.check(lib.mc_merge_host(len(pick), n_src, sp, dp, ne, w, _cabi.MC_MERGE_WEIGHTED, _cabi.MC_BF16,
                                       _cabi.MC_BF16, 0), "mc_merge_host")
 
     def pcie_probe():
-        """Plain pinned-memory copy rates of this box (what bounds the e2e number): 1 GiB each way, CUDA events."""
+        """Plain pinned-memory copy rates of this box (what bounds the e2e number): 1 GiB each way, CUDA events; then both
+        directions at once in the merge's 3 : 1 byte ratio, and one cold pass over a whole pinned arena.  With N ranks the
+        probes of all ranks run at the same time (barrier first), so the numbers are what N concurrent links give."""
         big = max(range(len(pick)), key=lambda k: h_src[0][k].numel())
         hbuf, dbuf = h_src[0][big].view(-1), srcs[0][pick[big]].view(-1).clone()
         reps = max(1, (1 << 30) // (hbuf.numel() * 2))
         out = {}
+        barrier()
         for name, (dst, src) in (("h2d_GBps", (dbuf, hbuf)), ("d2h_GBps", (h_out[big].view(-1), dbuf))):
             dst.copy_(src, non_blocking=True)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -369,11 +471,9 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             torch.cuda.synchronize()
             out[name] = round(reps * hbuf.numel() * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
         try:
-            # both directions at once, as the pipelined merge drives the link (3 bytes in per byte out): what the e2e number
-            # can reach on THIS box — boxes of this pool differ by 20 % here while the one-way rates agree
             s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
             dbuf2 = dbuf.clone()
-            torch.cuda.synchronize()
+            barrier()
             a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a.record()
             s_in.wait_event(a)
@@ -389,20 +489,24 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
             torch.cuda.synchronize()
             out["h2d_GBps_while_d2h"] = round(3 * reps * hbuf.numel() * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
             out["d2h_GBps_while_h2d"] = round(reps * hbuf.numel() * 2 / (a.elapsed_time(c) * 1e-3) / 1e9, 1)
-            # one pass over every pinned tensor of source 0, each touched once (the same bytes land where they came from):
-            # the rate of a cold stream, which is what the merge does, as opposed to the warm 1 GiB loop above
+            # the whole arena of source 0 once, as one copy: a cold stream (what the merge does) rather than a warm 1 GiB loop
+            arena = job.h_src[seeds[0]][0]
+            scratch = torch.empty(arena.numel(), dtype=torch.uint8, device=device)
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            for hk, j in zip(h_src[0], pick):
-                srcs[0][j].copy_(hk, non_blocking=True)
+            scratch.copy_(arena, non_blocking=True)
             b.record()
             torch.cuda.synchronize()
-            out["h2d_GBps_cold_stream"] = round(sum(hk.numel() for hk in h_src[0]) * 2 / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+            out["h2d_GBps_cold_stream"] = round(arena.numel() / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+            del scratch
         except Exception as exc:  # a probe must never cost the bench line
             out["bidirectional_probe_error"] = str(exc)[:80]
         return out
-    probe = pcie_probe()
-    steps = max(1, min(args.steps, 3))
+    probe_res = pcie_probe() if probe else None
+    if probe:
+        job.probe = probe_res
+    steps = max(1, min(args.steps, 3 if probe else 2))
     step()  # warm-up
     barrier()
     t0 = time.perf_counter()
@@ -415,20 +519,26 @@ def run_merge_e2e(args, M, srcs, outs, shapes, sizes, mine, device, world, barri
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
-    ok = all(torch.equal(h_out[k].view(torch.int16), outs[j].cpu().view(torch.int16)) for k, j in
+    ok = all(torch.equal(h_out[k].view(torch.int16), outs[j].cpu().view(-1).view(torch.int16)) for k, j in
              list(zip(range(len(pick)), pick))[:3])
     if saved_affinity is not None and world == 1:
         os.sched_setaffinity(0, saved_affinity)
     if not ok:
         raise SystemExit("PARITY FAILURE: host-streamed merge differs from the device-resident merge")
-    return {"value": round(float(b.item()) / (float(t.item()) / steps) / 1e9, 2), "unit": "GB/s",
-            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
-            "api": "mc_merge_host (pinned host buffers, H2D/kernel/D2H pipelined, returns after last D2H)",
-            "sample": "whole shard" if stride == 1 else f"every {stride}th tensor of the shard (host RAM bound)",
-            "timer": "host wall clock around the synchronous call, max over ranks",
-            "pcie_probe": probe, "host_numa_bound": bool(numa_bound),
-            "pcie_bound_GBps": round(float(elems * 2 * (n_src + 1)) / (h2d / (probe.get("h2d_GBps_while_d2h", probe["h2d_GBps"]) * 1e9))
-                                     / 1e9 * world, 1)}
+    pr = getattr(job, "probe", None) or {}
+    res = {"value": round(float(b.item()) / (float(t.item()) / steps) / 1e9, 2), "unit": "GB/s",
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
+           "api": "mc_merge_host (one pinned host arena per checkpoint, H2D/kernel/D2H pipelined, returns after last D2H)",
+           "sample": "whole shard" if job.stride == 1 else f"every {job.stride}th tensor of the shard (host RAM bound)",
+           "timer": "host wall clock around the synchronous call, max over ranks",
+           "host_numa_bound": bool(numa_bound)}
+    if pr:
+        res["pcie_probe"] = pr
+        res["pcie_probe_note"] = f"{world} rank(s) probing at the same time: rates per GPU"
+        h2d_rate = pr.get("h2d_GBps_while_d2h", pr["h2d_GBps"])
+        res["pcie_bound_GBps"] = round(float(elems * 2 * (n_src + 1)) / (h2d / (h2d_rate * 1e9)) / 1e9 * world, 1)
+        res["frac_of_pcie_bound"] = round(res["value"] / res["pcie_bound_GBps"], 3)
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ TIES workload
@@ -532,6 +642,9 @@ def build_prefill(cfg_name: str, device, rank: int, layers=None):
     coeff = 0.25 if len(merged) == 4 else 0.333
     cfg, base, adapters = syn.make_composed_on_device(merged, device, torch.bfloat16, coeff=coeff, seed=1, layers=layers)
     model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, adapters, device=device, dtype=torch.bfloat16)
+    # layer 0 as the checkpoint has it (unpacked adapters): the untimed oracle spot-check evaluates the reference schedule on it
+    model._bench_layer0 = ({k: v for k, v in base.items() if k.startswith("model.layers.0.")},
+                           {k: v for k, v in adapters.items() if k.startswith("model.layers.0.")}, cfg)
     del base, adapters
     n_head = 36
     n_text = n_text_total - n_head - 2 * len(present)
@@ -551,6 +664,58 @@ def build_prefill(cfg_name: str, device, rank: int, layers=None):
     mask_h = torch.ones_like(ids).pin_memory()
     flops = syn.prefill_flops(cfg, {m: syn.MODAL_TOKENS[m] for m in present}, n_text_total, len(merged), cfg["lora_r"])
     return model, desc, batch, ids_h, mask_h, feats, flops
+
+
+def prefill_spot_check(model, cfg_name: str, device):
+    """Untimed parity check of the bench's own full-width model, failing the run on mismatch: one short probe request with
+    every modality of the config (reduced block lengths, so the CPU oracle's dense-then-mask schedule finishes in seconds)
+    goes through the public forward; the hidden state after decoder layer 0 (RMSNorm, routed q/k/v + RoPE, causal attention,
+    routed o / gate / up / down, residuals — every routing group of the config) is compared with oracle/model_oracle.py
+    evaluated on the same spliced embeddings and modality masks.  Bar as tests/test_prefill_gpu.py: max-abs <= 2^-5 of the
+    tensor's scale, cosine >= 0.9995 (bf16)."""
+    from modelcompose_b200 import splice as SP
+    from modelcompose_b200 import synthetic as syn
+    from oracle import merge_oracle as MO
+    from oracle import model_oracle as XO
+    _, _, merged, present, _ = PREFILL_CONFIGS[cfg_name]
+    base0, ad0, cfg = model._bench_layer0
+    g = torch.Generator().manual_seed(77)
+    ids = syn.make_prompt_ids(1, present, 24, cfg["vocab_size"], 78, SP.MODAL_TOKEN_INDEXES, 8)
+    feats = {}
+    for i, m in enumerate(present):
+        n = 20 + 7 * i
+        shape = (1, 2, n // 2, syn.MODAL_FEATURE_DIM[m]) if m == "video" else (1, n, syn.MODAL_FEATURE_DIM[m])
+        feats[m] = torch.randn(shape, generator=g).to(torch.bfloat16).to(device)
+    out = model.forward(ids.to(device), torch.ones_like(ids).to(device), modal_inputs=feats, output_hidden_states=True)
+    torch.cuda.synchronize()
+    x0, x1 = out.hidden_states[0].cpu(), out.hidden_states[1].float().cpu()
+    names = model.modal_names
+    mid = out.modal_id.cpu()
+    masks = {m: (mid == i) for i, m in enumerate(names)}
+    _, scaling, dnames = MO.effective_scaling(names, cfg["lora_r"], cfg["lora_alpha"], cfg["reset_scaling_weights"])
+    cpu = lambda t: t.detach().to("cpu", torch.bfloat16)
+    layer = {"input_layernorm": cpu(base0["model.layers.0.input_layernorm.weight"]),
+             "post_attention_layernorm": cpu(base0["model.layers.0.post_attention_layernorm.weight"])}
+    for ln in syn.LINEAR_NAMES:
+        pfx = f"model.layers.0.{ln}."
+        A = {k[len(pfx) + 7:-7]: cpu(v) for k, v in ad0.items() if k.startswith(pfx + "lora_A.")}
+        Bm = {k[len(pfx) + 7:-7]: cpu(v) for k, v in ad0.items() if k.startswith(pfx + "lora_B.")}
+        layer[ln.split(".")[1]] = XO.LinearParams(cpu(base0[pfx + "weight"]), A, Bm, scaling, dnames)
+    S = x0.shape[1]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref = XO.decoder_layer_forward(x0, layer, masks, names, cfg["num_attention_heads"], torch.arange(S)[None],
+                                       XO.causal_additive_mask(1, S, torch.bfloat16), cfg["rms_norm_eps"]).float()
+    err, scale = (x1 - ref).abs().max().item(), ref.abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(x1.flatten(), ref.flatten(), dim=0).item()
+    groups = {m: int(masks[m].sum()) for m in names}
+    ok = err <= 2.0 ** -5 * scale and cos >= 0.9995 and all(groups[m] > 0 for m in ["default"] + list(present))
+    res = {"what": "hidden state after decoder layer 0 of a short probe request vs oracle/model_oracle.decoder_layer_forward",
+           "tokens": S, "rows_per_routing_group": groups, "max_abs": round(err, 5), "scale": round(scale, 4), "cosine": round(cos, 7),
+           "bar": "max_abs <= 2^-5 * scale and cosine >= 0.9995", "ok": bool(ok), "oracle_seconds": round(time.perf_counter() - t0, 1)}
+    if not ok:
+        raise SystemExit(f"PARITY FAILURE (prefill {cfg_name}): {json.dumps(res)}")
+    return res
 
 
 def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
@@ -629,13 +794,14 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
         dist.all_gather(gathered, probe)
         verified = all(torch.equal(g, gathered[0]) for g in gathered)
     peak_sus, peak_burst, peak_src = bf16_peaks()
-    ws0 = next(iter(model._ws.values()))
+    ws0 = next(ws for key, ws in model._ws.items() if key[0] == batch)
     up_tuning = ws0.up_tuning & 0xff
     up_kernel = {3: "mc::linear2_kernel<4> (512x256 CTA-pair tiles, cta_group::2) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down",
                  4: "mc::linear3_kernel<6> (256x256 CTA-pair tiles) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down"
                  }.get(up_tuning, "mc::linear_kernel<256,4>")
     if getattr(ws0, "up_mixed", False):
         up_kernel += "; up_proj(+SiLU*mul) and o_proj on mc::linear_kernel<256,4> (single-CTA, overlapped epilogue)"
+    spot = prefill_spot_check(model, cfg_name, device) if rank == 0 else None  # replaces the batch's workspace: keep it last
     res = {
         "metric": "composed-prefill tokens/s", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
@@ -655,7 +821,9 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
                 "steps": e_steps, "api": "MultimodalLlamaForCausalLM.forward(input_ids, attention_mask, modal_inputs=...) from pinned host "
                 "buffers; last-position logits copied back", "timer": "host wall clock incl. synchronize, max over ranks"},
         "gpu_launches": int(launches) * world,
-        "verification": {"finite_logits": finite, "probe_request_identical_across_ranks": verified,
+        "attention": "mc::attention3_kernel (tcgen05, P / O in TMEM)" if __import__("modelcompose_b200.model", fromlist=["x"]).ATTENTION_NATIVE
+                     else "library call (cuDNN via torch SDPA)",
+        "verification": {"finite_logits": finite, "oracle_spot_check": spot, "probe_request_identical_across_ranks": verified,
                          "collective": "ncclAllGather of request 0 last-position logits, outside the timed region" if world > 1 else None},
         "clocks": clocks.summary(),
     }
@@ -724,6 +892,9 @@ def main():
     ap.add_argument("--prefill-config", default="c3", choices=sorted(PREFILL_CONFIGS))
     ap.add_argument("--prefill-steps", type=int, default=5)
     ap.add_argument("--prefill-layers", type=int, default=None, help="development aid: fewer decoder layers (never a bench value)")
+    ap.add_argument("--merge-config", default="c2", choices=sorted(MERGE_CONFIGS))
+    ap.add_argument("--merge-all", action="store_true", help="with --workload merge: also nest the other merge configs")
+    ap.add_argument("--quick", action="store_true", help="development aid: primary merge line + one prefill config only (no nested lines)")
     ap.add_argument("--tuning", type=int, default=0)
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="profiling aid: run rank 0's shard of a K-way job on one GPU (ncu captures)")
@@ -753,19 +924,34 @@ def main():
             barrier()
             dist.destroy_process_group()
         return
+    nested = args.workload == "all" and not args.no_e2e and not args.quick
     if args.workload in ("all", "merge"):
-        line = run_merge(args, dist, rank, world, device, barrier)
+        job = MergeJob(args, world, rank, device)
+        line = run_merge(args, dist, rank, world, device, barrier, job, args.merge_config, with_cpu=True)
+        if nested or args.workload == "merge" and args.merge_all:
+            # the other merge shapes BASELINE names: 4 checkpoints (config 5) and base + N (the materialised blend)
+            for name in ("n4", "c2b"):
+                if name == args.merge_config:
+                    continue
+                sub = run_merge(args, dist, rank, world, device, barrier, job, name, with_cpu=False)
+                if line is not None and sub is not None:
+                    line["merge_" + name] = sub
+        del job
+        torch.cuda.empty_cache()
         if line is not None and world == 1 and not args.no_e2e:
             line["ties"] = run_ties(device)  # the other merge strategy family of the CLI, one GPU
     if args.workload in ("all", "prefill") and not args.no_e2e:
-        pre = run_prefill(args, device, rank, world, dist, barrier, args.prefill_config)
-        if rank == 0:
-            # CPU baseline on rank 0 at N=1 only (under torchrun the other ranks would wait on it)
-            pre["cpu_baseline"] = cpu_prefill_layer_rate(args.prefill_config) if world == 1 and not args.no_cpu_baseline else None
-            if args.workload == "prefill":
-                line = pre
-            elif line is not None:
-                line["prefill"] = pre
+        configs = [args.prefill_config] + ([c for c in ("c4", "c5") if c != args.prefill_config] if nested else [])
+        for i, cfg_name in enumerate(configs):
+            pre = run_prefill(args, device, rank, world, dist, barrier, cfg_name)
+            if rank == 0:
+                # CPU baseline on rank 0 at N=1 only (under torchrun the other ranks would wait on it), first config only
+                pre["cpu_baseline"] = (cpu_prefill_layer_rate(cfg_name, max_seconds=15.0)
+                                       if world == 1 and not args.no_cpu_baseline and i == 0 else None)
+                if args.workload == "prefill" and i == 0:
+                    line = pre
+                elif line is not None:
+                    line["prefill" if i == 0 and args.workload == "all" else "prefill_" + cfg_name] = pre
     if rank == 0 and line is not None:
         emit(line)
     if world > 1:

@@ -8,8 +8,8 @@ Mirrors (all paths relative to the reference root
   modelcompose/model/multimodal_arch.py:197-268              encode_modal_inputs (projector + prefix/suffix)
   modelcompose/model/multimodal_projector/builder.py:202-219 projector types
 
-Every matrix product, the splice, RMSNorm, RoPE and SiLU·mul run in ``libmodelcompose_b200.so`` (no torch fallback; a
-missing library raises).  Causal attention is the one stock-library call (flash-attn).  The modality
+Every matrix product, the causal attention of the prefill, the splice, RMSNorm, RoPE and SiLU·mul run in
+``libmodelcompose_b200.so`` (no torch fallback; a missing library raises).  The modality
 encoders are frozen third-party feature extractors outside the hot path: ``modal_inputs`` here
 carries their OUTPUT features (``[b, n, d]``, video ``[b, t, n, d]``), i.e. what ``encoder(inputs)`` returns at
 multimodal_arch.py:231-243.
@@ -46,8 +46,9 @@ FUSE_ROPE = os.environ.get("MC_FUSE_ROPE", "1") != "0"  # development switch: 0 
 # 128-row tile of the routed linears holds one adapter group; only attention sees sequence order (the q / k / v epilogues
 # scatter rows back, the attention output is gathered again).  Development switch: 0 = sequence order everywhere.
 MODALITY_MAJOR = os.environ.get("MC_MODALITY_MAJOR", "1") != "0"
-# causal prefill attention: 1 = this library's tcgen05 kernel (head_dim 128), 0 = the stock cuDNN / flash-attn call
-ATTENTION_NATIVE = os.environ.get("MC_ATTENTION_NATIVE", "0") != "0"
+# causal prefill attention: 1 (default) = this library's tcgen05 kernel (head_dim 128); 0 = the stock cuDNN / flash-attn call,
+# kept as a development switch for A/B timing only
+ATTENTION_NATIVE = os.environ.get("MC_ATTENTION_NATIVE", "1") != "0"
 
 
 class MultimodalConfig:

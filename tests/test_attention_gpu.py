@@ -48,6 +48,23 @@ def test_causal_attention_vs_fp32_reference(dtype, B, S, nH):
     assert torch.equal(out2[perm.long()], out)
 
 
+@pytest.mark.parametrize("tuning", [0x10, 0x20, 0x30, 0x40, 0x120])
+def test_kernel_variants_agree_with_reference(tuning):
+    """exp2 split between the MUFU pipe and the FMA-pipe polynomial (0 .. 3 pairs of 4), lazy vs eager rescaling: every
+    variant meets the same bar; peaky logits (amplitude 6) exercise the rescale path"""
+    B, S, nH = 2, 700, 2
+    g = torch.Generator(device="cuda").manual_seed(tuning)
+    H, T = nH * 128, B * S
+    q, k, v = (torch.randn((T, H), generator=g, device="cuda").mul_(6.0 if i < 2 else 1.0).to(torch.bfloat16) for i in range(3))
+    out = torch.empty((T, H), dtype=torch.bfloat16, device="cuda")
+    scale = 1.0 / math.sqrt(128)
+    LN.attention_causal(q, k, v, out, B, S, nH, scale, tuning=tuning)
+    torch.cuda.synchronize()
+    ref = reference(q, k, v, B, S, nH, scale)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= TOL[torch.bfloat16] * ref.abs().max().item(), (hex(tuning), err, ref.abs().max().item())
+
+
 def test_argument_errors():
     x = torch.zeros((4, 64), dtype=torch.bfloat16, device="cuda")
     with pytest.raises(ValueError):

@@ -176,20 +176,25 @@ def test_auto_variant_takes_the_pair_kernel_for_large_batches(golden, monkeypatc
     assert next(iter(model._ws.values())).up_tuning == 0
 
 
-def test_full_width_layer_vs_oracle():
-    """vicuna-7B WIDTH (H 4096, I 11008, r 128, vocab 32000, 3 merged adapters at 0.333, 5+5 prefix/suffix), one decoder
-    layer, 2 requests with video + image + audio blocks of reduced length (the CPU oracle runs the reference's
-    dense-then-mask schedule, so the token count is kept where it finishes in seconds)."""
+@pytest.mark.parametrize("merged,coeff", [(["audio", "vision", "video"], 0.333), (["audio", "vision", "video", "point"], 0.25)])
+def test_full_width_layer_vs_oracle(merged, coeff):
+    """vicuna-7B WIDTH (H 4096, I 11008, r 128, vocab 32000, 5+5 prefix/suffix), one decoder layer, 2 requests with one block of
+    every merged modality at reduced length (the CPU oracle runs the reference's dense-then-mask schedule, so the token count
+    is kept where it finishes in seconds).  3 merged adapters at 0.333 (BASELINE configs 3 / 4: 4 routing groups, text rank 384)
+    and 4 at 0.25 (config 5, MCUB-4: 5 routing groups, text rank 512, point-cloud projector with 384-wide features)."""
     dev = torch.device("cuda")
-    cfg, base, sd = syn.make_composed_on_device(["audio", "vision", "video"], dev, torch.bfloat16, seed=1, layers=1)
+    cfg, base, sd = syn.make_composed_on_device(merged, dev, torch.bfloat16, coeff=coeff, seed=1, layers=1)
     model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, sd, device=dev, dtype=torch.bfloat16)
+    assert model.modal_names == ["default"] + merged and model.rank_total == 128 * 2 * len(merged)
     g = torch.Generator().manual_seed(4)
     B = 2
-    ids = syn.make_prompt_ids(B, ["video", "vision", "audio"], 30, cfg["vocab_size"], seed=5,
-                              modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=10)
+    present = ["video", "vision", "audio"] + (["point"] if "point" in merged else [])
+    ids = syn.make_prompt_ids(B, present, 30, cfg["vocab_size"], seed=5, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=10)
     feats = {"audio": torch.randn(B, 40, 768, generator=g).to(torch.bfloat16),
              "vision": torch.randn(B, 70, 1024, generator=g).to(torch.bfloat16),
              "video": torch.randn(B, 2, 45, 1024, generator=g).to(torch.bfloat16)}
+    if "point" in merged:
+        feats["point"] = torch.randn(B, 33, syn.MODAL_FEATURE_DIM["point"], generator=g).to(torch.bfloat16)
     attn = torch.ones_like(ids)
     out = model.forward(ids.cuda(), attn.cuda(), modal_inputs={k: v.cuda() for k, v in feats.items()})
     torch.cuda.synchronize()
@@ -197,7 +202,8 @@ def test_full_width_layer_vs_oracle():
     assert out.logits.shape == logits.shape
     for i, m in enumerate(names):
         assert torch.equal(out.modal_id.cpu() == i, bmasks[m]), m
-    compare(out.logits, logits, "torch.bfloat16", "full-width one-layer logits")
+        assert int(bmasks[m].sum()) > 0, m   # every routing group is exercised
+    compare(out.logits, logits, "torch.bfloat16", f"full-width one-layer logits, {len(names)} routing groups")
 
 
 def test_loader_from_disk_and_text_only(tmp_path, golden):

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+{
+for t in 0x13 0x23 0x33; do
+  timeout 200 python tools/att_dev.py --tuning $t || echo "variant $t exit code $?"
+done
+} > gpurun_out/r2_att6.log 2>&1
+grep -v "ok$" gpurun_out/r2_att6.log | tail -60
