@@ -184,17 +184,28 @@ def cpu_sample_tensors(n_src: int = 3):
     return out, "one vicuna-7B decoder layer x 3 sources (202,383,360 elements per source, 1.62 GB algorithmic)"
 
 
+CPU_FORM = "mean"   # the reference arm's headline form
+
+
+def CPU_FORMS(MO, w):
+    """The reference's CPU merge arithmetic, as callables over the list of one tensor per source:
+    `mean`     — the reference CLI's own equal-weight merge (merge_unimodal_modelcompose.py:109-112: Python sum() of the bf16
+                 tensors, every add rounded to bf16, then `/ len`): for three sources the closest thing the reference has to
+                 the 0.333 / 0.333 / 0.333 blend, and the form the CPU arm is quoted on;
+    `sum`      — :105-108, the same without the division;
+    `weighted` — the materialised online-merge-reset blend itself (multimodal_llama.py:130-149 coefficients applied to full
+                 weights, fp32 temporaries), oracle/merge_oracle.weighted_merge: bit for bit what the GPU arm's headline computes."""
+    return (("mean", lambda ts: MO.ref_sum(ts) / len(ts)), ("sum", lambda ts: MO.ref_sum(ts)),
+            ("weighted", lambda ts: MO.weighted_merge(ts, w)))
+
+
 def cpu_merge_rates(sample_tensors, min_seconds: float, max_passes: int = 50):
-    """The reference's CPU merge on the host's cores, both forms, as GB/s of (3 reads + 1 write) x 2 B:
-    `sum`      — the arithmetic the reference CLI literally runs (merge_unimodal_modelcompose.py:105-108: Python sum() of the
-                 bf16 tensors, every add rounded to bf16), restated in oracle/merge_oracle.reference_sum;
-    `weighted` — the materialised online-merge-reset blend (multimodal_llama.py:130-149 coefficients applied to full
-                 weights, fp32 temporaries), oracle/merge_oracle.weighted_merge: the arithmetic the GPU arm's headline runs."""
+    """Every form of CPU_FORMS on the host's cores, as GB/s of (3 reads + 1 write) x 2 B."""
     from oracle import merge_oracle as MO
     w = MERGE_CONFIGS["c2"][2]
     nbytes = sum(t[0].numel() for t in sample_tensors) * 2 * (len(w) + 1)
     out = {}
-    for name, fn in (("sum", lambda ts: MO.ref_sum(ts)), ("weighted", lambda ts: MO.weighted_merge(ts, w))):
+    for name, fn in CPU_FORMS(MO, w):
         fn(sample_tensors[0])  # warm the allocator / thread pool
         t0 = time.perf_counter()
         passes = 0
@@ -219,7 +230,7 @@ def run_reference_arm(args):
     w = MERGE_CONFIGS["c2"][2]
     nbytes = sum(t[0].numel() for t in sample) * 2 * (len(w) + 1)
     rates = {}
-    for name, fn in (("sum", lambda ts: MO.ref_sum(ts)), ("weighted", lambda ts: MO.weighted_merge(ts, w))):
+    for name, fn in CPU_FORMS(MO, w):
         for _ in range(max(args.warmup, 1)):
             for ts in sample:
                 fn(ts)
@@ -228,8 +239,7 @@ def run_reference_arm(args):
             for ts in sample:
                 fn(ts)
         rates[name] = (time.perf_counter() - t0) / args.steps
-    # headline of this arm = the faster of the two CPU forms (the reference's own `sum` arithmetic needs no fp32 temporaries)
-    best = min(rates, key=rates.get)
+    best = CPU_FORM
     dt = rates[best]
     gbs = nbytes / dt / 1e9
     cores = torch.get_num_threads()
@@ -243,7 +253,7 @@ def run_reference_arm(args):
                          "host_cpus": os.cpu_count(), "form": best,
                          "forms_GBps": {k: round(nbytes / v / 1e9, 3) for k, v in rates.items()},
                          "note": "the reference is pure Python and /root/reference does not travel to the GPU box: "
-                                 "oracle/merge_oracle.py restates merge_unimodal_modelcompose.py:105-108 (`sum`) and the materialised blend"},
+                                 "oracle/merge_oracle.py restates merge_unimodal_modelcompose.py:105-112 (`sum`, `mean`) and the materialised blend"},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -395,12 +405,12 @@ def run_merge(args, dist, rank, world, device, barrier, job: MergeJob, cfg_name:
         cpu_baseline = None  # reported at N=1 only, on the primary line
         if with_cpu and world == 1:
             cpu_sample, sdesc = cpu_sample_tensors()
-            rates = cpu_merge_rates(cpu_sample, min_seconds=6.0)
-            best = max(rates, key=lambda k: rates[k][0])
+            rates = cpu_merge_rates(cpu_sample, min_seconds=4.0)
+            best = CPU_FORM
             cpu_baseline = {"value": round(rates[best][0], 3), "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
                             "form": best, "forms_GBps": {k: round(v[0], 3) for k, v in rates.items()},
-                            "sample": f"{sdesc}; `sum` = the reference CLI's own arithmetic (merge_unimodal_modelcompose.py:105-108), "
-                                      f"`weighted` = the materialised blend; {rates[best][2]} passes in {rates[best][1]:.1f} s",
+                            "sample": f"{sdesc}; `mean` = the reference CLI's own equal-weight merge (merge_unimodal_modelcompose.py:109-112), "
+                                      f"`weighted` = the materialised blend the GPU arm computes; {rates[best][2]} passes in {rates[best][1]:.1f} s",
                             "host_cpus": os.cpu_count()}
         kern = f"mc::merge_kernel<{n_src},bf16,bf16>"
         line = {
@@ -507,11 +517,18 @@ def run_merge_e2e(args, job: MergeJob, seeds, weights, device, world, barrier, d
     if probe:
         job.probe = probe_res
     steps = max(1, min(args.steps, 3 if probe else 2))
-    step()  # warm-up
+    for _ in range(2):  # warm-up: the first pass over freshly pinned arenas runs 20 - 30 % below the steady rate
+        tw = time.perf_counter()
+        step()
+        if args.e2e_trace:
+            print(f"e2e warm-up pass: {time.perf_counter() - tw:.3f} s", file=sys.stderr, flush=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
+        tw = time.perf_counter()
         step()  # returns after the last D2H byte landed (synchronous contract)
+        if args.e2e_trace:
+            print(f"e2e timed pass: {time.perf_counter() - tw:.3f} s", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device=device)
@@ -633,7 +650,7 @@ def bf16_peaks():
     return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def build_prefill(cfg_name: str, device, rank: int, layers=None):
+def build_prefill(cfg_name: str, device, rank: int, layers=None, materialize=None):
     """Random-init composed model + one batch of requests (ids on host and device, encoder features on host and device)."""
     from modelcompose_b200 import model as MD
     from modelcompose_b200 import splice as SP
@@ -641,7 +658,8 @@ def build_prefill(cfg_name: str, device, rank: int, layers=None):
     desc, batch, merged, present, n_text_total = PREFILL_CONFIGS[cfg_name]
     coeff = 0.25 if len(merged) == 4 else 0.333
     cfg, base, adapters = syn.make_composed_on_device(merged, device, torch.bfloat16, coeff=coeff, seed=1, layers=layers)
-    model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, adapters, device=device, dtype=torch.bfloat16)
+    model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, adapters, device=device, dtype=torch.bfloat16,
+                                          materialize=materialize)
     # layer 0 as the checkpoint has it (unpacked adapters): the untimed oracle spot-check evaluates the reference schedule on it
     model._bench_layer0 = ({k: v for k, v in base.items() if k.startswith("model.layers.0.")},
                            {k: v for k, v in adapters.items() if k.startswith("model.layers.0.")}, cfg)
@@ -718,12 +736,13 @@ def prefill_spot_check(model, cfg_name: str, device):
     return res
 
 
-def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
+def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materialize=None):
     """Composed prefill, batch-sharded (every rank holds a full replica and its own requests; no collective on the timed
     path).  Returns the result dict (rank 0) with tokens/s, roofline of the routed-linear kernel, e2e and verification."""
     from modelcompose_b200 import _cabi
     from modelcompose_b200 import linear as LN
-    model, desc, batch, ids_h, mask_h, feats_h, flops = build_prefill(cfg_name, device, rank, layers=args.prefill_layers)
+    model, desc, batch, ids_h, mask_h, feats_h, flops = build_prefill(cfg_name, device, rank, layers=args.prefill_layers,
+                                                                      materialize=materialize)
     ids_d, mask_d = ids_h.to(device), mask_h.to(device)
     feats_d = {m: v.to(device) for m, v in feats_h.items()}
     S_out = int(flops["seq_len"])
@@ -758,7 +777,9 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
         step_resident()
     lin_ms, lin_n = LN.stop_profile()
     lin_ms /= 2
-    lin_flops = flops["linears"] * batch
+    # FLOPs of the linears as EXECUTED: the materialised form has no low-rank branches (their work went into W_eff at load)
+    lin_flops = (flops["linears"] - (flops["lora"] if model.materialize else 0.0)) * batch
+    step_flops = (flops["total"] - (flops["lora"] if model.materialize else 0.0)) * batch
     achieved = lin_flops / (lin_ms * 1e-3) / 1e12
 
     # ---- e2e through the public forward API: pinned host ids/features -> device, last-position logits -> host, per step
@@ -796,7 +817,8 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
     peak_sus, peak_burst, peak_src = bf16_peaks()
     ws0 = next(ws for key, ws in model._ws.items() if key[0] == batch)
     up_tuning = ws0.up_tuning & 0xff
-    up_kernel = {3: "mc::linear2_kernel<4> (512x256 CTA-pair tiles, cta_group::2) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down",
+    up_kernel = {3: "mc::linear2_kernel<4> (512x256 CTA-pair tiles, cta_group::2), segmented by routing group" if model.materialize else
+                 "mc::linear2_kernel<4> (512x256 CTA-pair tiles, cta_group::2) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down",
                  4: "mc::linear3_kernel<6> (256x256 CTA-pair tiles) for the base + LoRA-up launches, mc::linear_kernel<128,6> for LoRA-down"
                  }.get(up_tuning, "mc::linear_kernel<256,4>")
     if getattr(ws0, "up_mixed", False):
@@ -809,14 +831,16 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str):
         "config": {"workload": desc, "requests_per_gpu": batch, "seq_len_after_splice": S_out, "prefix_suffix": "5+5",
                    "layers": model.config.num_hidden_layers, "sharding": f"by request batch x{world}, full replica per GPU",
                    "l2": "weights 13.5 GB + activations per step, far larger than L2",
-                   "algorithmic_tflop_per_step_per_gpu": round(flops["total"] * batch / 1e12, 2)},
+                   "linear_form": "materialised W_eff per routing group (grouped GEMM, weights blended at load by the merge kernel)"
+                   if model.materialize else "base weight + low-rank branch of the token's group (the reference's form)",
+                   "algorithmic_tflop_per_step_per_gpu": round(step_flops / 1e12, 2)},
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s",
                      "frac": round(achieved / peak_sus, 4), "traffic": None, "peak_source": peak_src,
                      "kernel": up_kernel + " (routed LoRA linears, projector, lm_head)",
                      "launches_per_step": lin_n // 2, "kernel_ms_per_step": round(lin_ms, 3),
                      "kernel_share_of_step": round(lin_ms / ms_per_step, 4),
                      "algorithmic_tflop_per_step": round(lin_flops / 1e12, 2), "frac_of_burst_peak": round(achieved / peak_burst, 4),
-                     "whole_step_tflops": round(flops["total"] * batch / (ms_per_step * 1e-3) / 1e12, 1)},
+                     "whole_step_tflops": round(step_flops / (ms_per_step * 1e-3) / 1e12, 1)},
         "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e_steps, "api": "MultimodalLlamaForCausalLM.forward(input_ids, attention_mask, modal_inputs=...) from pinned host "
                 "buffers; last-position logits copied back", "timer": "host wall clock incl. synchronize, max over ranks"},
@@ -891,10 +915,13 @@ def main():
                          "merge / prefill: that workload alone as the primary line")
     ap.add_argument("--prefill-config", default="c3", choices=sorted(PREFILL_CONFIGS))
     ap.add_argument("--prefill-steps", type=int, default=5)
+    ap.add_argument("--materialize", action="store_true", default=os.environ.get("MC_MATERIALIZE", "0") != "0",
+                    help="evaluate the routed linears in the materialised form (dense W_eff per routing group) on the primary prefill lines")
     ap.add_argument("--prefill-layers", type=int, default=None, help="development aid: fewer decoder layers (never a bench value)")
     ap.add_argument("--merge-config", default="c2", choices=sorted(MERGE_CONFIGS))
     ap.add_argument("--merge-all", action="store_true", help="with --workload merge: also nest the other merge configs")
     ap.add_argument("--quick", action="store_true", help="development aid: primary merge line + one prefill config only (no nested lines)")
+    ap.add_argument("--e2e-trace", action="store_true", help="development aid: per-pass times of the host-buffer merge on stderr")
     ap.add_argument("--tuning", type=int, default=0)
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="profiling aid: run rank 0's shard of a K-way job on one GPU (ncu captures)")
@@ -941,9 +968,12 @@ def main():
         if line is not None and world == 1 and not args.no_e2e:
             line["ties"] = run_ties(device)  # the other merge strategy family of the CLI, one GPU
     if args.workload in ("all", "prefill") and not args.no_e2e:
-        configs = [args.prefill_config] + ([c for c in ("c4", "c5") if c != args.prefill_config] if nested else [])
-        for i, cfg_name in enumerate(configs):
-            pre = run_prefill(args, device, rank, world, dist, barrier, cfg_name)
+        configs = [(args.prefill_config, args.materialize)]
+        if nested:
+            configs += [(c, args.materialize) for c in ("c4", "c5") if c != args.prefill_config]
+            configs += [(args.prefill_config, not args.materialize)]   # the other evaluation form of the linears, same config
+        for i, (cfg_name, mat) in enumerate(configs):
+            pre = run_prefill(args, device, rank, world, dist, barrier, cfg_name, materialize=mat)
             if rank == 0:
                 # CPU baseline on rank 0 at N=1 only (under torchrun the other ranks would wait on it), first config only
                 pre["cpu_baseline"] = (cpu_prefill_layer_rate(cfg_name, max_seconds=15.0)
@@ -951,7 +981,10 @@ def main():
                 if args.workload == "prefill" and i == 0:
                     line = pre
                 elif line is not None:
-                    line["prefill" if i == 0 and args.workload == "all" else "prefill_" + cfg_name] = pre
+                    key = "prefill" if i == 0 and args.workload == "all" else "prefill_" + cfg_name
+                    if mat != args.materialize:
+                        key += "_materialized" if mat else "_branch"
+                    line[key] = pre
     if rank == 0 and line is not None:
         emit(line)
     if world > 1:

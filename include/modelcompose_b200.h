@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MC_ABI_VERSION 1
+#define MC_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MC_API __attribute__((visibility("default")))
@@ -258,6 +258,7 @@ MC_API int mc_splice_plan_destroy(mc_splice_plan_t* plan);
  *     multiples of 64); 64-wide K1 blocks of groups absent from the M tile are skipped.
  * ---------------------------------------------------------------------------------------------- */
 #define MC_LINEAR_MAX_PROBLEMS 4
+#define MC_LINEAR_MAX_SEGMENTS 8
 
 typedef enum mc_linear_epilogue {
   MC_LINEAR_EPI_NONE = 0,
@@ -294,6 +295,15 @@ typedef struct mc_linear_desc {
   const int32_t* c_rowmap;      /* device [M] or NULL: row m of the problem is written to row c_rowmap[m] of C (a permutation:
                                    activations kept in modality-major row order scatter back to sequence order for
                                    attention / the logits); ROPE takes the token position from the mapped row */
+  /* Segmented problem (grouped GEMM over per-group weights — the materialised form W_eff,g = W + sum_a s_a B_a A_a of the
+   * reference's per-forward blend, multimodal_llama.py:130-149; full-weight formula scripts/convert_to_multimodal.py:111-113):
+   * rows [seg_start[g], seg_start[g+1]) of A0 / C multiply with B0_seg[g] instead of B0.  seg_start is a DEVICE array of
+   * n_seg + 1 ascending row offsets (seg_start[0] >= 0, seg_start[n_seg] <= M), read by the kernel at run time: the caller
+   * rewrites it per batch (rows sorted by routing group) without touching the plan.  n_seg = 0: ordinary problem.
+   * Every problem of a launch must use the same seg_start / n_seg; K1 must be 0; not for ROWMASK launches or tuning 4. */
+  const int32_t* seg_start;
+  int32_t n_seg;                /* 0 .. MC_LINEAR_MAX_SEGMENTS */
+  const void* const* B0_seg;    /* HOST array of n_seg device pointers, each [N, K0] with leading dimension ldb0 */
 } mc_linear_desc_t;
 
 typedef struct mc_linear_plan mc_linear_plan_t;

@@ -101,7 +101,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.mc_abi_version() != 1:
+        if handle.mc_abi_version() != 2:
             raise McError("libmodelcompose_b200.so ABI version mismatch; rebuild")
         _LIB = handle
     return _LIB

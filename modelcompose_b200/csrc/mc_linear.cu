@@ -38,8 +38,11 @@ constexpr int kThreads = 256;
 constexpr int kMaxOwnTiles = 256;    // compact schedule: tiles one CTA may own (plan falls back to the static schedule beyond)
 constexpr int kMaxMaskTiles = 2048;  // compact schedule: M tiles whose group masks are staged in shared memory
 
+constexpr int kMaxSeg = MC_LINEAR_MAX_SEGMENTS;  // row segments (routing groups) of a segmented launch
+
 struct alignas(64) LinProblem {
   CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  const CUtensorMap* tmB_seg;  // segmented launch: device array of one B0 map per row segment (the group's own weights)
   void* C;
   const void* bias;
   const float* col_scale;
@@ -64,30 +67,79 @@ struct alignas(64) LinParams {
   unsigned int idesc;
   int group_m;  // tile rasterisation: group_m M-tiles share a sweep over N (keeps the operand working set in L2)
   int compact;  // 1: every CTA first compacts the (M tile, N tile) pairs that survive routing and owns every grid-th of them
+  // Segmented launch (grouped GEMM over materialised per-group weights): the rows of every problem are cut into n_seg
+  // consecutive segments whose boundaries live in DEVICE memory (seg_start[0 .. n_seg], written per batch by the host code
+  // that sorts the rows by routing group — no host synchronisation, no re-planning); segment g multiplies with tmB_seg[g].
+  // M tiles never straddle a segment: tile counts are derived in the kernel prologue.
+  const int* seg_start;
+  int n_seg;                        // 0 = ordinary launch
+  int bm;                           // rows of an M tile (128; 512 / 256 for the CTA-pair kernels)
+  int cum_tiles_n[kMaxProb + 1];    // prefix sums of tiles_n over the problems (segmented launches share the M tiling)
 };
+
+struct SegTable {  // shared memory, filled in the kernel prologue of a segmented launch
+  int row[kMaxSeg + 1];   // first row of segment g
+  int tile[kMaxSeg + 1];  // first M tile of segment g; tile[n_seg] = number of M tiles
+};
+
+__device__ __forceinline__ void seg_table_fill(const LinParams& P, SegTable* seg) {  // one thread
+  int acc = 0;
+  for (int g = 0; g <= P.n_seg; ++g) {
+    const int r = P.seg_start[g];
+    seg->row[g] = r;
+    seg->tile[g] = acc;
+    if (g < P.n_seg) acc += (P.seg_start[g + 1] - r + P.bm - 1) / P.bm;
+  }
+}
 
 // ---- tile scheduling (identical in all three roles) -----------------------------------------------------
 struct Tile {
   int p, mt, nt;
+  int m0, m_end;       // first row of the tile, and the row bound of its problem / segment (rows >= m_end are not stored)
+  int seg;             // row segment (segmented launches), else -1
   unsigned int gmask;  // groups present in the M tile (all ones when unrouted)
   bool skip;
 };
 
-__device__ __forceinline__ Tile decode_tile(const LinParams& P, int tile) {
+__device__ __forceinline__ int total_tiles(const LinParams& P, const SegTable* seg) {
+  return P.n_seg ? seg->tile[P.n_seg] * P.cum_tiles_n[P.n_prob] : P.total_tiles;
+}
+
+__device__ __forceinline__ Tile decode_tile(const LinParams& P, int tile, const SegTable* seg) {
   Tile t;
-  int p = 0, begin = 0;
-  while (p < P.n_prob - 1 && tile >= P.prob[p].tile_end) {
-    begin = P.prob[p].tile_end;
-    ++p;
+  int p = 0, begin = 0, tiles_m;
+  if (P.n_seg) {
+    tiles_m = seg->tile[P.n_seg];
+    while (p < P.n_prob - 1 && tile >= tiles_m * P.cum_tiles_n[p + 1]) ++p;
+    begin = tiles_m * P.cum_tiles_n[p];
+  } else {
+    while (p < P.n_prob - 1 && tile >= P.prob[p].tile_end) {
+      begin = P.prob[p].tile_end;
+      ++p;
+    }
+    tiles_m = P.prob[p].tiles_m;
   }
   const LinProblem& pr = P.prob[p];
   const int local = tile - begin;
   const int per_group = P.group_m * pr.tiles_n;
   const int g = local / per_group, within = local % per_group;
-  const int gsize = min(P.group_m, pr.tiles_m - g * P.group_m);
+  const int gsize = min(P.group_m, tiles_m - g * P.group_m);
   t.p = p;
   t.mt = g * P.group_m + within % gsize;
   t.nt = within / gsize;
+  if (P.n_seg) {
+    int sg = 0;
+    while (sg < P.n_seg - 1 && t.mt >= seg->tile[sg + 1]) ++sg;
+    t.seg = sg;
+    t.m0 = seg->row[sg] + (t.mt - seg->tile[sg]) * P.bm;
+    t.m_end = seg->row[sg + 1];
+    t.gmask = 0xffffffffu;
+    t.skip = false;
+    return t;
+  }
+  t.seg = -1;
+  t.m0 = t.mt * P.bm;
+  t.m_end = pr.M;
   t.gmask = pr.mtile_mask ? pr.mtile_mask[t.mt] : 0xffffffffu;
   t.skip = pr.ntile_mask != nullptr && (pr.ntile_mask[t.nt] & t.gmask) == 0u;
   return t;
@@ -98,9 +150,10 @@ struct TileIter {
   const LinParams& P;
   const int* own;
   const unsigned int* mm;
-  int n_own, it;
-  __device__ __forceinline__ TileIter(const LinParams& P_, const int* own_, int n_own_, const unsigned int* mm_)
-      : P(P_), own(own_), mm(mm_), n_own(n_own_), it(0) {}
+  const SegTable* seg;
+  int n_own, it, total;
+  __device__ __forceinline__ TileIter(const LinParams& P_, const int* own_, int n_own_, const unsigned int* mm_, const SegTable* seg_)
+      : P(P_), own(own_), mm(mm_), seg(seg_), n_own(n_own_), it(0), total(total_tiles(P_, seg_)) {}
   __device__ __forceinline__ bool next(Tile& t) {
     if (P.compact) {
       if (it >= n_own) return false;
@@ -108,14 +161,17 @@ struct TileIter {
       t.p = packed >> 28;
       t.mt = (packed >> 10) & 0x3ffff;
       t.nt = packed & 0x3ff;
+      t.m0 = t.mt * kBM;
+      t.m_end = P.prob[t.p].M;
+      t.seg = -1;
       t.gmask = mm[t.mt];
       t.skip = false;
       return true;
     }
     for (;;) {
       const int tile = blockIdx.x + (it++) * gridDim.x;
-      if (tile >= P.total_tiles) return false;
-      t = decode_tile(P, tile);
+      if (tile >= total) return false;
+      t = decode_tile(P, tile, seg);
       if (!t.skip) return true;
     }
   }
@@ -157,8 +213,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], bool is_f16) {
 // `row` is this thread's output row, `taddr` the TMEM address of its lane quadrant and accumulator stage.
 // The RESIDUAL / SILU_MUL operand is fetched one 32-column chunk ahead so its latency hides behind the TMEM load.
 template <int BN>
-__device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16, uint32_t taddr, int row, int n0) {
-  const bool row_ok = row < pr.M;
+__device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16, uint32_t taddr, int row, int m_end, int n0) {
+  const bool row_ok = row < m_end;
   const int epi = pr.epilogue;
   const bool has_aux = (epi == MC_LINEAR_EPI_RESIDUAL || epi == MC_LINEAR_EPI_SILU_MUL) && row_ok;
   const int rg = (epi == MC_LINEAR_EPI_ROWMASK && row_ok) ? (int)pr.row_group[row] : -1;
@@ -352,6 +408,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
   __shared__ int s_own[kMaxOwnTiles];
   __shared__ unsigned int s_mm[kMaxMaskTiles];
   __shared__ int s_n_own;
+  __shared__ SegTable s_seg;
+  if (P.n_seg && threadIdx.x == 96) seg_table_fill(P, &s_seg);
   if (P.compact) {
     // Routed-N launch (LoRA down-projection): most (M tile, N tile) pairs are skipped, and a static round-robin over
     // the full grid of pairs leaves the survivors unevenly spread.  Every CTA compacts the surviving pairs (identical
@@ -394,11 +452,12 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
     {
       int stage = 0;
       uint32_t phase = 0;
-      TileIter tiles(P, s_own, n_own, s_mm);
+      TileIter tiles(P, s_own, n_own, s_mm, &s_seg);
       Tile t;
       while (tiles.next(t)) {
         const LinProblem& pr = P.prob[t.p];
-        const int m0 = t.mt * kBM, n0 = t.nt * BN;
+        const int m0 = t.m0, n0 = t.nt * BN;
+        const CUtensorMap* tmB0 = t.seg >= 0 ? &pr.tmB_seg[t.seg] : &pr.tmB0;
         for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
           const bool ext = kb >= pr.nkb0;
           const int k = ext ? kb - pr.nkb0 : kb;
@@ -408,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
             mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             tma_load_2d(ext ? &pr.tmA1 : &pr.tmA0, &full_bar[stage], sa, k * kBK, m0);
-            tma_load_2d(ext ? &pr.tmB1 : &pr.tmB0, &full_bar[stage], sa + L::A_BYTES, k * kBK, n0);
+            tma_load_2d(ext ? &pr.tmB1 : tmB0, &full_bar[stage], sa + L::A_BYTES, k * kBK, n0);
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -424,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
     {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      TileIter tiles(P, s_own, n_own, s_mm);
+      TileIter tiles(P, s_own, n_own, s_mm, &s_seg);
       Tile t;
       while (tiles.next(t)) {
         const LinProblem& pr = P.prob[t.p];
@@ -466,16 +525,16 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
     const bool is_f16 = P.is_f16 != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    TileIter tiles(P, s_own, n_own, s_mm);
+    TileIter tiles(P, s_own, n_own, s_mm, &s_seg);
     Tile t;
     while (tiles.next(t)) {
       const LinProblem& pr = P.prob[t.p];
-      const int row = t.mt * kBM + q * 32 + lane;
+      const int row = t.m0 + q * 32 + lane;
       const int n0 = t.nt * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN>(pr, is_f16, taddr, row, n0);
+      epilogue_tile<BN>(pr, is_f16, taddr, row, t.m_end, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -615,11 +674,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_cg2<TMEM_COLS>(tmem_slot);
+  __shared__ SegTable s_seg;
+  if (P.n_seg && threadIdx.x == 96) seg_table_fill(P, &s_seg);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int n_tiles = total_tiles(P, &s_seg);
 
   // the pair walks tiles pair, pair + n_pairs, ...; both CTAs decode identically
   if (warp == 0) {
@@ -627,11 +689,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-        const Tile t = decode_tile(P, tile);
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        const Tile t = decode_tile(P, tile, &s_seg);
         const LinProblem& pr = P.prob[t.p];
         const unsigned int gmask = pair_half_mask(pr, t.mt, 0) | pair_half_mask(pr, t.mt, 1);
-        const int m0 = t.mt * 512 + (int)rank * 256, n0 = t.nt * BN + (int)rank * 128;
+        const int m0 = t.m0 + (int)rank * 256, n0 = t.nt * BN + (int)rank * 128;
+        const CUtensorMap* tmB0 = t.seg >= 0 ? &pr.tmB_seg[t.seg] : &pr.tmB0;
         for (int kb = 0; kb < pr.nkb0 + pr.nkb1; ++kb) {
           const bool ext = kb >= pr.nkb0;
           const int k = ext ? kb - pr.nkb0 : kb;
@@ -643,7 +706,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
             else mbar_arrive_cluster(full_leader);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             tma_load_2d_cg2(ext ? &pr.tmA1 : &pr.tmA0, full_leader, sa, k * kBK, m0);
-            tma_load_2d_cg2(ext ? &pr.tmB1 : &pr.tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
+            tma_load_2d_cg2(ext ? &pr.tmB1 : tmB0, full_leader, sa + L::A_BYTES, k * kBK, n0);
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -657,8 +720,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
     if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0, t_phase = 0;
-      for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-        const Tile t = decode_tile(P, tile);
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        const Tile t = decode_tile(P, tile, &s_seg);
         const LinProblem& pr = P.prob[t.p];
         const unsigned int hmask[2] = {pair_half_mask(pr, t.mt, 0), pair_half_mask(pr, t.mt, 1)};
         mbar_wait(tempty_bar, t_phase ^ 1u);  // both CTAs' epilogues have drained the previous tile
@@ -702,14 +765,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
     const int q = warp & 3, h = (warp - 4) >> 2;
     const bool is_f16 = P.is_f16 != 0;
     uint32_t t_phase = 0;
-    for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-      const Tile t = decode_tile(P, tile);
+    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      const Tile t = decode_tile(P, tile, &s_seg);
       const LinProblem& pr = P.prob[t.p];
-      const int row = t.mt * 512 + (int)rank * 256 + h * 128 + q * 32 + lane;
+      const int row = t.m0 + (int)rank * 256 + h * 128 + q * 32 + lane;
       mbar_wait(tfull_bar, t_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN);
-      epilogue_tile<BN>(pr, is_f16, taddr, row, t.nt * BN);
+      epilogue_tile<BN>(pr, is_f16, taddr, row, t.m_end, t.nt * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -802,7 +865,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-        const Tile t = decode_tile(P, tile);
+        const Tile t = decode_tile(P, tile, nullptr);
         const LinProblem& pr = P.prob[t.p];
         const unsigned int gmask = pair256_mask(pr, t.mt);
         const int m0 = t.mt * 256 + (int)rank * 128, n0 = t.nt * BN + (int)rank * 128;
@@ -833,7 +896,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-        const Tile t = decode_tile(P, tile);
+        const Tile t = decode_tile(P, tile, nullptr);
         const LinProblem& pr = P.prob[t.p];
         const unsigned int gmask = pair256_mask(pr, t.mt);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
@@ -873,13 +936,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < P.total_tiles; tile += n_pairs) {
-      const Tile t = decode_tile(P, tile);
+      const Tile t = decode_tile(P, tile, nullptr);
       const LinProblem& pr = P.prob[t.p];
       const int row = t.mt * 256 + (int)rank * 128 + q * 32 + lane;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN>(pr, is_f16, taddr, row, t.nt * BN);
+      epilogue_tile<BN>(pr, is_f16, taddr, row, pr.M, t.nt * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1103,6 +1166,10 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     const bool routed_n = d.epilogue == MC_LINEAR_EPI_ROWMASK;
     PLAN_REQUIRE(!(two && routed_n), "problem %d: the CTA-pair kernel does not take ROWMASK launches", i);
     const bool routed_k = d.K1 > 0 && d.n_groups > 0;
+    PLAN_REQUIRE(d.n_seg >= 0 && d.n_seg <= kMaxSeg, "problem %d: n_seg %d outside [0, %d]", i, d.n_seg, kMaxSeg);
+    PLAN_REQUIRE(d.n_seg == desc[0].n_seg && d.seg_start == desc[0].seg_start, "problem %d: every problem of a launch shares one segment table", i);
+    PLAN_REQUIRE(d.n_seg == 0 || (d.seg_start && d.B0_seg && d.K1 == 0 && !routed_n && pair_mode != 2),
+                 "problem %d: a segmented problem needs seg_start and B0_seg, K1 = 0, no ROWMASK epilogue and not tuning 4", i);
     PLAN_REQUIRE(!routed_n || (d.n_groups >= 1 && d.n_groups <= 32 && d.group_cols && d.row_group && d.col_scale),
                  "problem %d: ROWMASK epilogue needs n_groups in [1,32], group_cols, row_group and col_scale", i);
     PLAN_REQUIRE(!routed_k || (d.n_groups <= 32 && d.group_cols && d.mtile_mask), "problem %d: routed K1 needs group_cols and mtile_mask", i);
@@ -1110,8 +1177,9 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     pr.N = d.N;
     pr.nkb0 = (d.K0 + kBK - 1) / kBK;
     pr.nkb1 = (d.K1 + kBK - 1) / kBK;
-    pr.tiles_m = (d.M + bm - 1) / bm;
+    pr.tiles_m = (d.M + bm - 1) / bm + d.n_seg;  // segmented: upper bound (every segment may end in a partial tile)
     pr.tiles_n = (d.N + bn - 1) / bn;
+    p->params.cum_tiles_n[i + 1] = p->params.cum_tiles_n[i] + pr.tiles_n;
     tile_end += pr.tiles_m * pr.tiles_n;
     pr.tile_end = tile_end;
     pr.epilogue = d.epilogue;
@@ -1154,6 +1222,22 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     }
     rc = encode_operand(&pr.tmA0, d.A0, d.M, d.K0, d.lda0, a_box, dtype);
     if (rc == MC_OK) rc = encode_operand(&pr.tmB0, d.B0, d.N, d.K0, d.ldb0, two ? 128 : bn, dtype);
+    if (rc == MC_OK && d.n_seg > 0) {
+      std::vector<CUtensorMap> maps(d.n_seg);
+      for (int g = 0; g < d.n_seg && rc == MC_OK; ++g) {
+        if (!d.B0_seg[g] || ((uintptr_t)d.B0_seg[g] & 15)) rc = fail(MC_ERR_INVALID, "problem %d: B0_seg[%d] is NULL or misaligned", i, g);
+        else rc = encode_operand(&maps[g], d.B0_seg[g], d.N, d.K0, d.ldb0, two ? 128 : bn, dtype);
+      }
+      if (rc == MC_OK) {
+        CUtensorMap* dm = nullptr;  // cudaMalloc returns 256-byte aligned memory: fine for 64-byte aligned tensor maps
+        e = cudaMalloc(&dm, sizeof(CUtensorMap) * d.n_seg);
+        if (e == cudaSuccess) {
+          p->owned.push_back(dm);
+          e = cudaMemcpy(dm, maps.data(), sizeof(CUtensorMap) * d.n_seg, cudaMemcpyHostToDevice);
+          pr.tmB_seg = dm;
+        }
+      }
+    }
     if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmA1, d.A1, d.M, d.K1, d.lda1, a_box, dtype);
     if (rc == MC_OK && d.K1 > 0) rc = encode_operand(&pr.tmB1, d.B1, d.N, d.K1, d.ldb1, two ? 128 : bn, dtype);
     p->flops += 2.0 * d.M * (double)d.N * (double)(d.K0 + d.K1);
@@ -1166,6 +1250,9 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
   }
   p->params.n_prob = n_problems;
   p->params.total_tiles = tile_end;
+  p->params.seg_start = desc[0].seg_start;
+  p->params.n_seg = desc[0].n_seg;
+  p->params.bm = bm;
   // rasterisation: when B (weights) alone overflows a good part of L2, sweep N over 32 M-tiles at a time so B streams
   // from HBM once per 4096 rows instead of once per 1024; tuning bits 8-15 override
   {

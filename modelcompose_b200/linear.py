@@ -18,6 +18,7 @@ from . import _cabi
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_ROWMASK, EPI_RESIDUAL, EPI_SILU_MUL, EPI_ROPE = 0, 1, 2, 3, 4, 5, 6
 MAX_PROBLEMS = 4
+MAX_SEGMENTS = 8
 TILE_M = 128
 K_BLOCK = 64
 
@@ -47,7 +48,8 @@ class LinearDesc(C.Structure):
                 ("ldr", C.c_int64), ("col_scale", C.c_void_p), ("row_group", C.c_void_p),
                 ("mtile_mask", C.c_void_p), ("group_cols", C.POINTER(C.c_int32)), ("n_groups", C.c_int32),
                 ("epilogue", C.c_int32), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_pos", C.c_void_p),
-                ("rope_seq_len", C.c_int32), ("rope_head_dim", C.c_int32), ("c_rowmap", C.c_void_p)]
+                ("rope_seq_len", C.c_int32), ("rope_head_dim", C.c_int32), ("c_rowmap", C.c_void_p),
+                ("seg_start", C.c_void_p), ("n_seg", C.c_int32), ("B0_seg", C.POINTER(C.c_void_p))]
 
 
 def _mat(t: torch.Tensor, what: str, dtype=None):
@@ -77,6 +79,9 @@ class Problem:
     epilogue: int = EPI_NONE
     rope: Optional[tuple] = None               # EPI_ROPE: (cos table, sin table, int32 position scalar or None, seq_len, head_dim)
     c_rowmap: Optional[torch.Tensor] = None    # int32 [M]: problem row m is written to row c_rowmap[m] of C
+    # segmented problem (grouped GEMM over materialised per-group weights): rows [seg_start[g], seg_start[g+1]) use B0_groups[g]
+    seg_start: Optional[torch.Tensor] = None   # CUDA int32 [len(B0_groups) + 1], rewritten by the caller per batch
+    B0_groups: Optional[Sequence[torch.Tensor]] = None
 
 
 class LinearPlan:
@@ -134,6 +139,19 @@ class LinearPlan:
                 d.rope_cos, d.rope_sin = cos.data_ptr(), sin.data_ptr()
                 d.rope_pos = None if pos is None else pos.data_ptr()
                 d.rope_seq_len, d.rope_head_dim = int(seq_len), int(head_dim)
+            if p.B0_groups is not None:
+                G = len(p.B0_groups)
+                if not 1 <= G <= MAX_SEGMENTS or p.seg_start is None or p.seg_start.dtype != torch.int32 or not p.seg_start.is_cuda \
+                        or p.seg_start.numel() != G + 1 or not p.seg_start.is_contiguous() or p.A1 is not None:
+                    raise ValueError(f"problem {i}: a segmented problem takes 1..{MAX_SEGMENTS} B0_groups, a contiguous CUDA int32 "
+                                     "seg_start of len(B0_groups) + 1 entries, and no A1 / B1")
+                for g, Bg in enumerate(p.B0_groups):
+                    Bg = _mat(Bg, f"B0_groups[{g}]", dtype)
+                    if tuple(Bg.shape) != tuple(B0.shape) or Bg.stride(0) != B0.stride(0):
+                        raise ValueError(f"problem {i}: B0_groups[{g}] must match B0 in shape and row stride")
+                arr = (C.c_void_p * G)(*[Bg.data_ptr() for Bg in p.B0_groups])
+                self._keep.append(arr)
+                d.seg_start, d.n_seg, d.B0_seg = p.seg_start.data_ptr(), G, arr
             if p.c_rowmap is not None:
                 if p.c_rowmap.dtype != torch.int32 or p.c_rowmap.numel() != M or not p.c_rowmap.is_cuda or not p.c_rowmap.is_contiguous():
                     raise ValueError(f"problem {i}: c_rowmap must be a contiguous CUDA int32 [M]")

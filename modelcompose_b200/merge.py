@@ -468,15 +468,64 @@ def merge_checkpoints(filepaths, output_path, strategy="sum", K=20):
     return merged_weights, merged_configs
 
 
+def write_dense_text_weights(merged_weights: Dict[str, torch.Tensor], merged_configs: dict, model_base: str, output_path: str,
+                             device="cuda", dtype=None) -> Dict[str, torch.Tensor]:
+    """The online-merge-reset composition as DENSE weights of the language model's text path, written next to the adapter
+    checkpoint as ``effective_weights.bin``: for every decoder linear
+        W_eff = (1 − Σ_m w_m) · W_base + Σ_m w_m · (W_base + s · B_{default-m} A_{default-m}),
+    the weighted combination of the N modality checkpoints with the reset coefficients w_m of the strategy string — the
+    materialisation the reference's tooling performs on the CPU (scripts/convert_to_multimodal.py:111-113,
+    scripts/model_composition/delta_weights_compare.py:24-31,61) and the blend its model evaluates per forward
+    (multimodal_llama.py:130-149).  Runs on the GPU: rank-r GEMMs for the dense unimodal checkpoints, the N-source merge kernel
+    for the blend (``materialize.effective_weights``).  Keys follow the base checkpoint (``model.layers.{l}.….weight``)."""
+    from . import builder as BD
+    from . import materialize as MZ
+    from . import model as MD
+    if not torch.cuda.is_available():
+        raise _cabi.McError("materialising the merged weights needs a CUDA device (modelcompose_b200 has no CPU fallback)")
+    cfg = MD.MultimodalConfig.from_dict(merged_configs)
+    modal_names = MD.infer_modals(cfg)
+    names, scaling, default_names = MD.adapter_scaling(modal_names, cfg.lora_r, cfg.lora_alpha, cfg.reset_scaling_weights)
+    if default_names is None:
+        raise ValueError("nothing to materialise: the strategy carries no default-<modal> coefficients "
+                         "(use --strategy online-merge-reset-default-<modal>=w,...)")
+    base = BD._load_base_state_dict(model_base)
+    out: Dict[str, torch.Tensor] = {}
+    for key, W in base.items():
+        if not key.endswith(".weight") or W.dim() != 2 or ".layers." not in key:
+            continue
+        stem = key[:-len(".weight")]
+        A = {a: merged_weights[f"{stem}.lora_A.{a}.weight"] for a in default_names if f"{stem}.lora_A.{a}.weight" in merged_weights}
+        if not A:
+            continue
+        dt = dtype or W.dtype
+        if dt not in (torch.float16, torch.bfloat16):
+            dt = torch.float16   # the reference loads the language model in fp16 (builder.py:185)
+        Wd = W.to(device=device, dtype=dt).contiguous()
+        Ad = {a: t.to(device=device, dtype=dt).contiguous() for a, t in A.items()}
+        Bd = {a: merged_weights[f"{stem}.lora_B.{a}.weight"].to(device=device, dtype=dt).contiguous() for a in A}
+        (Weff,) = MZ.effective_weights(Wd, Ad, Bd, scaling, ["default"], default_names, cfg.lora_alpha / cfg.lora_r)
+        out[key] = Weff.cpu()
+    torch.cuda.synchronize()
+    torch.save(out, os.path.join(output_path, "effective_weights.bin"))
+    print(f"Dense text-path weights of {len(out)} linears saved to {os.path.join(output_path, 'effective_weights.bin')}")
+    return out
+
+
 def main(argv=None):
-    """reference :151-159 — identical flags."""
+    """reference :151-159 — identical flags, plus ``--materialize-base DIR``: after an ``online-merge-reset-…`` merge also
+    write the composed text-path weights as a dense checkpoint (``write_dense_text_weights``)."""
     parser = argparse.ArgumentParser(description="Merge multiple torch checkpoints")
     parser.add_argument("filepaths", nargs="+", help="List of checkpoint file paths to merge")
     parser.add_argument("-o", "--output", default="merged_checkpoint.pth", help="Output file path")
     parser.add_argument("--strategy", default="sum", help="Merge strategy")
     parser.add_argument("-K", default=20, type=int, help="K for ties-merging")
+    parser.add_argument("--materialize-base", default=None, metavar="DIR",
+                        help="base language model directory: also write the merged (reset-blended) dense weights of the text path")
     args = parser.parse_args(argv)
-    merge_checkpoints(args.filepaths, args.output, args.strategy, args.K)
+    merged_weights, merged_configs = merge_checkpoints(args.filepaths, args.output, args.strategy, args.K)
+    if args.materialize_base:
+        write_dense_text_weights(merged_weights, merged_configs, args.materialize_base, args.output)
 
 
 if __name__ == "__main__":

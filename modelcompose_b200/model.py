@@ -25,6 +25,7 @@ import torch
 
 from . import _cabi
 from . import linear as LN
+from . import materialize as MZ
 from . import splice as SP
 
 ADAPTER_ORDER = ("audio", "vision", "video", "point")
@@ -49,6 +50,14 @@ MODALITY_MAJOR = os.environ.get("MC_MODALITY_MAJOR", "1") != "0"
 # causal prefill attention: 1 (default) = this library's tcgen05 kernel (head_dim 128); 0 = the stock cuDNN / flash-attn call,
 # kept as a development switch for A/B timing only
 ATTENTION_NATIVE = os.environ.get("MC_ATTENTION_NATIVE", "1") != "0"
+# Evaluation form of the routed linears.  0 (default): the reference's own form — base weight plus the low-rank branch of the
+# token's group, evaluated per forward (LocalLoraLinear.forward, multimodal_llama.py:130-149).  1: MATERIALISED — at load one
+# dense W_eff,g per routing group is built on the device (materialize.py: rank-r GEMMs + the N-source merge kernel for the
+# online-merge-reset blend of the text group) and every linear becomes one grouped GEMM over the modality-major rows; costs
+# one extra copy of the decoder weights per group in HBM, removes the four LoRA-down launches per layer and the rank-space
+# traffic.  W_eff is rounded once to the storage dtype, so logits differ from form 0 within the bar stated in
+# tests/test_prefill_gpu.py (reference tooling for the dense form: delta_weights_compare.py:24-31,61).
+MATERIALIZE = os.environ.get("MC_MATERIALIZE", "0") != "0"
 
 
 class MultimodalConfig:
@@ -156,6 +165,7 @@ def _linear_key(layer: int, name: str) -> str:
 class _Layer:
     W: Dict[str, torch.Tensor] = field(default_factory=dict)
     ad: Dict[str, LN.PackedAdapters] = field(default_factory=dict)
+    Weff: Dict[str, List[torch.Tensor]] = field(default_factory=dict)  # materialised form: one dense weight per routing group
     ln1: torch.Tensor = None
     ln2: torch.Tensor = None
 
@@ -206,7 +216,11 @@ class _Workspace:
         self.x = buf(T, H)
         self.xn = buf(T, H)
         self.q, self.k, self.v, self.attn = buf(T, H), buf(T, H), buf(T, H), buf(T, H)
-        self.t = [buf(T, R) for _ in range(3)]
+        self.dense = model.materialize
+        self.t = [] if self.dense else [buf(T, R) for _ in range(3)]
+        # materialised form: first buffer row of every routing group (rows are modality-major), rewritten per batch
+        self.seg_start = torch.zeros(len(model.modal_names) + 1, dtype=torch.int32, device=dev)
+        self.seg_start[1:] = T
         self.gate = buf(T, I)
         self.logits = buf(T, V)
         self.row_group = torch.zeros(T, dtype=torch.uint8, device=dev)
@@ -223,8 +237,10 @@ class _Workspace:
         self.rope = (model._rope[0], model._rope[1], self.pos, S, D) if self.rope_fused else None
         self.mtile = torch.zeros((T + LN.TILE_M - 1) // LN.TILE_M, dtype=torch.int32, device=dev)
         self.plans: List[Dict[str, LN.LinearPlan]] = []
+        if self.dense and MODALITY_MAJOR is False and S > 1:
+            raise ValueError("the materialised form needs the modality-major row order (MC_MODALITY_MAJOR=1)")
         for layer in model.layers:
-            self.plans.append(self._layer_plans(layer))
+            self.plans.append(self._layer_plans_dense(layer) if self.dense else self._layer_plans(layer))
         self.lm_head = LN.LinearPlan([LN.Problem(self.xn, model.lm_head, self.logits, c_rowmap=self.perm)], tuning=self.up_tuning)
         # generation only consumes the last position's logits (the reference computes all S' and slices, :720 + HF generate):
         # a B-row lm_head over the gathered last rows
@@ -242,6 +258,7 @@ class _Workspace:
                 self.perm.copy_(torch.arange(self.T, dtype=torch.int32, device=self.perm.device))
                 self.inv_perm.copy_(self.perm)
                 self.perm_is_identity = True
+            self.seg_start[1:] = self.T
         elif self.permute:
             gseq = modal_id.reshape(-1)
             order = torch.sort(gseq, stable=True).indices  # tiny (T uint8 keys); stable keeps sequence order inside a group
@@ -249,9 +266,15 @@ class _Workspace:
             self.inv_perm[order] = torch.arange(self.T, dtype=torch.int32, device=self.perm.device)
             self.row_group.copy_(gseq[order])
             self.perm_is_identity = False
+            if self.dense:  # rows of group g: [seg_start[g], seg_start[g + 1]) — stays on the device, the kernels read it
+                counts = torch.bincount(gseq.int(), minlength=self.seg_start.numel() - 1)
+                self.seg_start[1:] = torch.cumsum(counts, 0).to(torch.int32)
         else:
+            if self.dense:
+                raise ValueError("the materialised form needs rows grouped by modality: route in modality-major order")
             self.row_group.view(self.B, self.S).copy_(modal_id)
-        LN.route_tile_masks(self.row_group, self.mtile, coarsen={3: 4, 4: 2}.get(self.up_tuning & 0xff, 1))
+        if not self.dense:
+            LN.route_tile_masks(self.row_group, self.mtile, coarsen={3: 4, 4: 2}.get(self.up_tuning & 0xff, 1))
 
     def last_rows(self) -> torch.Tensor:
         """int32 [B]: buffer row holding the last position of every sequence."""
@@ -296,6 +319,32 @@ class _Workspace:
                                     epilogue=LN.EPI_ROPE if rope is not None else epilogue, rope=rope, c_rowmap=rowmap))
         return LN.LinearPlan(probs, tuning=tuning)
 
+    def _dense(self, src, layer: _Layer, names, outs, residual=None, epilogue=None, launch=None):
+        """Grouped GEMM over the materialised weights: rows of routing group g (a contiguous segment of the modality-major
+        buffers) multiply with W_eff,g."""
+        tuning = 0 if (self.up_mixed and launch in UP_AUTO_SINGLE_CTA) else self.up_tuning
+        if tuning == 4:
+            tuning = 3
+        if epilogue is None:
+            epilogue = LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE
+        probs = []
+        for n, o in zip(names, outs):
+            rope = self.rope if n in ("q_proj", "k_proj") else None
+            rowmap = self.perm if n in ("q_proj", "k_proj", "v_proj") else None
+            probs.append(LN.Problem(src, layer.W[n], o, residual=residual, epilogue=LN.EPI_ROPE if rope is not None else epilogue,
+                                    rope=rope, c_rowmap=rowmap, seg_start=self.seg_start, B0_groups=layer.Weff[n]))
+        return LN.LinearPlan(probs, tuning=tuning)
+
+    def _layer_plans_dense(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
+        qkv = ("q_proj", "k_proj", "v_proj")
+        return {
+            "up_qkv": self._dense(self.xn, layer, qkv, (self.q, self.k, self.v)),
+            "up_o": self._dense(self.attn, layer, ("o_proj",), (self.x,), residual=self.x, launch="up_o"),
+            "up_g": self._dense(self.xn, layer, ("gate_proj",), (self.gate,)),
+            "up_u": self._dense(self.xn, layer, ("up_proj",), (self.gate,), residual=self.gate, epilogue=LN.EPI_SILU_MUL, launch="up_u"),
+            "up_d": self._dense(self.gate, layer, ("down_proj",), (self.x,), residual=self.x),
+        }
+
     def _layer_plans(self, layer: _Layer) -> Dict[str, LN.LinearPlan]:
         qkv, gu = ("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj")
         return {
@@ -317,8 +366,10 @@ class MultimodalLlamaForCausalLM:
     """Inference-only drop-in for the reference class of the same name (multimodal_llama.py:622-767)."""
 
     def __init__(self, config: MultimodalConfig, base_state_dict: Dict[str, torch.Tensor],
-                 adapter_state_dict: Optional[Dict[str, torch.Tensor]] = None, device="cuda", dtype=torch.float16):
+                 adapter_state_dict: Optional[Dict[str, torch.Tensor]] = None, device="cuda", dtype=torch.float16,
+                 materialize: Optional[bool] = None):
         _cabi.lib()  # fail loudly if the CUDA library is missing
+        self.materialize = MATERIALIZE if materialize is None else bool(materialize)
         if dtype not in (torch.float16, torch.bfloat16):
             raise ValueError("inference dtype must be float16 (reference builder.py:185) or bfloat16")
         self.config, self.device, self.dtype = config, torch.device(device), dtype
@@ -353,13 +404,17 @@ class MultimodalLlamaForCausalLM:
                 # and contribute exactly nothing, so they are simply left out of the packed layout
                 A = {a: dev(sd[f"{key}.lora_A.{a}.weight"]) for a in self.adapter_names if f"{key}.lora_A.{a}.weight" in sd}
                 Bm = {a: dev(sd[f"{key}.lora_B.{a}.weight"]) for a in A}
-                layer.ad[name] = LN.pack_adapters(A, Bm, self.scaling, self.modal_names, self.default_adapter_names,
-                                                  W.shape[1], W.shape[0], dtype, self.device)
+                if self.materialize:
+                    layer.Weff[name] = MZ.effective_weights(W, A, Bm, self.scaling, self.modal_names, self.default_adapter_names,
+                                                            alpha / r)
+                else:
+                    layer.ad[name] = LN.pack_adapters(A, Bm, self.scaling, self.modal_names, self.default_adapter_names,
+                                                      W.shape[1], W.shape[0], dtype, self.device)
             self.layers.append(layer)
-        self.rank_total = self.layers[0].ad["q_proj"].A_all.shape[0] if self.layers else LN.K_BLOCK
+        self.rank_total = self.layers[0].ad["q_proj"].A_all.shape[0] if self.layers and not self.materialize else LN.K_BLOCK
         for layer in self.layers:
             for name in LINEARS:
-                if layer.ad[name].A_all.shape[0] != self.rank_total:
+                if not self.materialize and layer.ad[name].A_all.shape[0] != self.rank_total:
                     raise ValueError("every linear must carry the same adapter ranks")
 
         # projectors (multimodal_projector/builder.py:202-219): 'linear' or 'mlp{N}x_gelu'
@@ -578,17 +633,22 @@ class MultimodalLlamaForCausalLM:
         for li, (layer, plans) in enumerate(zip(self.layers, ws.plans)):
             if output_hidden_states:
                 hidden.append(ws.sequence_order(ws.x))
+            dense = ws.dense  # materialised form: no rank-space (LoRA-down) launches
             self._rmsnorm(ws.x, layer.ln1, ws.xn)
-            plans["down_qkv"].run()
+            if not dense:
+                plans["down_qkv"].run()
             plans["up_qkv"].run()
             self._attention(ws, attention_mask, full, cache, li, past)
-            plans["down_o"].run()
+            if not dense:
+                plans["down_o"].run()
             plans["up_o"].run()
             self._rmsnorm(ws.x, layer.ln2, ws.xn)
-            plans["down_gu"].run()
+            if not dense:
+                plans["down_gu"].run()
             plans["up_g"].run()
             plans["up_u"].run()
-            plans["down_d"].run()
+            if not dense:
+                plans["down_d"].run()
             plans["up_d"].run()
         if cache is not None:
             cache.length = past + S

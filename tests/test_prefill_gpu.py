@@ -206,6 +206,97 @@ def test_full_width_layer_vs_oracle(merged, coeff):
     compare(out.logits, logits, "torch.bfloat16", f"full-width one-layer logits, {len(names)} routing groups")
 
 
+def test_materialised_weights_vs_oracle(golden):
+    """W_eff,g built on the device (rank-r GEMM + merge-kernel blend) against the fp32 formula of the reference's own tooling
+    (delta_weights_compare.py:24-31,61, restated in oracle/merge_oracle.materialise_effective_weight): within 1.5 ulp of the
+    16-bit dtype relative to the weight's magnitude (the text group is a blend of ROUNDED dense checkpoints: two roundings)."""
+    from modelcompose_b200 import materialize as MZ
+    run = golden("merge_c1.pt")["runs"][STRATEGY_C1]
+    cfg = MD.MultimodalConfig.from_dict(run["config"])
+    base, sd = syn.make_base_llm(seed=1), run["state_dict"]
+    names = MD.infer_modals(cfg)
+    _, scaling, dnames = MD.adapter_scaling(names, cfg.lora_r, cfg.lora_alpha, cfg.reset_scaling_weights)
+    for dtype, ulp in ((torch.bfloat16, 2.0 ** -8), (torch.float16, 2.0 ** -11)):
+        for key in ("model.layers.0.self_attn.q_proj", "model.layers.1.mlp.down_proj"):
+            W = base[key + ".weight"].to(dtype)
+            A = {a: sd[f"{key}.lora_A.{a}.weight"].to(dtype) for a in names[1:] + dnames}
+            Bm = {a: sd[f"{key}.lora_B.{a}.weight"].to(dtype) for a in A}
+            got = MZ.effective_weights(W.cuda(), {a: t.cuda() for a, t in A.items()}, {a: t.cuda() for a, t in Bm.items()},
+                                       scaling, names, dnames, cfg.lora_alpha / cfg.lora_r)
+            torch.cuda.synchronize()
+            assert len(got) == len(names)
+            for gi, name in enumerate(names):
+                members = dnames if gi == 0 else [name]
+                want = MO.materialise_effective_weight(W, [A[a] for a in members], [Bm[a] for a in members],
+                                                       [scaling[a] for a in members], out_dtype=torch.float32)
+                err = (got[gi].float().cpu() - want).abs().max().item()
+                assert err <= 1.5 * ulp * want.abs().max().item(), (dtype, key, name, err, want.abs().max().item())
+
+
+@pytest.mark.parametrize("key", list(DTYPES))
+def test_materialised_form_vs_reference_fixture_and_branch_form(golden, key):
+    """The grouped-GEMM evaluation over materialised per-group weights against (a) the unmodified reference's decoder-layer
+    outputs (same bar as the branch form: the dense form rounds W_eff once, the reference rounds every branch) and (b) this
+    library's branch form on an end-to-end forward with every routing group present."""
+    dtype = DTYPES[key]
+    run = golden("merge_c1.pt")["runs"][STRATEGY_C1]
+    cfg = MD.MultimodalConfig.from_dict(run["config"])
+    base = syn.make_base_llm(seed=1)
+    dense = MD.MultimodalLlamaForCausalLM(cfg, base, run["state_dict"], device="cuda", dtype=dtype, materialize=True)
+    branch = MD.MultimodalLlamaForCausalLM(cfg, base, run["state_dict"], device="cuda", dtype=dtype, materialize=False)
+    g = golden("prefill_c1.pt")
+    ref = g["out"][key]
+    x = g["x"].to(dtype).cuda()
+    mid = torch.zeros(x.shape[:2], dtype=torch.uint8)
+    for i, m in enumerate(dense.modal_names):
+        mid[g["masks"][m]] = i
+    logits, _, hidden = dense.prefill(x, mid.cuda(), None, output_hidden_states=True)
+    torch.cuda.synchronize()
+    compare(hidden[1], ref["hidden"][0], key, "materialised: hidden after layer 0")
+    compare(logits, ref["logits"], key, "materialised: logits")
+    dense.prefill(x, None, None)   # every row on the text group's weights
+    ws = next(iter(dense._ws.values()))
+    compare(ws.sequence_order(ws.x), ref["hidden_nomask"], key, "materialised: hidden (no modality mask)")
+    gen = torch.Generator().manual_seed(31)
+    B = 3
+    ids = syn.make_prompt_ids(B, ["vision", "audio"], 20, 1000, seed=4, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=6)
+    feats = {"audio": torch.randn(B, 9, 48, generator=gen).to(dtype).cuda(), "vision": torch.randn(B, 14, 64, generator=gen).to(dtype).cuda()}
+    a = dense.forward(ids.cuda(), torch.ones_like(ids).cuda(), modal_inputs=feats).logits
+    b = branch.forward(ids.cuda(), torch.ones_like(ids).cuda(), modal_inputs=feats).logits
+    compare(a, b, key, "materialised vs branch form, end-to-end logits")
+
+
+def test_materialised_full_width_layer_vs_oracle():
+    """vicuna-7B width, one layer, 5 routing groups (MCUB-4), materialised form: every group's segment, the partial tiles at
+    the segment boundaries and the CTA-pair kernel's 512-row tiles, against the CPU oracle (branch form)."""
+    dev = torch.device("cuda")
+    merged = ["audio", "vision", "video", "point"]
+    cfg, base, sd = syn.make_composed_on_device(merged, dev, torch.bfloat16, coeff=0.25, seed=1, layers=1)
+    model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, sd, device=dev, dtype=torch.bfloat16, materialize=True)
+    g = torch.Generator().manual_seed(4)
+    B = 2
+    present = ["video", "vision", "audio", "point"]
+    ids = syn.make_prompt_ids(B, present, 30, cfg["vocab_size"], seed=5, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=10)
+    feats = {"audio": torch.randn(B, 40, 768, generator=g).to(torch.bfloat16), "vision": torch.randn(B, 70, 1024, generator=g).to(torch.bfloat16),
+             "video": torch.randn(B, 2, 45, 1024, generator=g).to(torch.bfloat16),
+             "point": torch.randn(B, 33, syn.MODAL_FEATURE_DIM["point"], generator=g).to(torch.bfloat16)}
+    attn = torch.ones_like(ids)
+    out = model.forward(ids.cuda(), attn.cuda(), modal_inputs={k: v.cuda() for k, v in feats.items()})
+    torch.cuda.synchronize()
+    logits, bmasks, names = oracle_forward(cfg, base, sd, ids, attn, feats, torch.bfloat16, 32)
+    compare(out.logits, logits, "torch.bfloat16", "materialised full-width one-layer logits, 5 routing groups")
+    # the pair kernel (512-row tiles) on the same rows gives the single-CTA kernel's bits
+    import modelcompose_b200.model as MDm
+    old = MDm.UP_TUNING
+    try:
+        MDm.UP_TUNING = 3
+        model._ws.clear()
+        out3 = model.forward(ids.cuda(), attn.cuda(), modal_inputs={k: v.cuda() for k, v in feats.items()})
+        assert torch.equal(out3.logits, out.logits)
+    finally:
+        MDm.UP_TUNING = old
+
+
 def test_loader_from_disk_and_text_only(tmp_path, golden):
     """merge CLI output dir + base dir -> load_pretrained_model (fp16 like the reference) -> forward."""
     from modelcompose_b200 import merge as MG
@@ -226,6 +317,38 @@ def test_loader_from_disk_and_text_only(tmp_path, golden):
         BD.load_pretrained_model(odir, bdir, "llava-thing")
     with pytest.raises(TypeError):
         model.forward(ids[:, :1], torch.ones_like(ids), past_key_values=[()])
+
+
+def test_cli_writes_dense_merged_weights(tmp_path, golden):
+    """merge CLI with --materialize-base: besides the reference's three output files, the reset-blended dense weights of the
+    text path; checked against the fp32 formula, and the loader with materialize=True runs on the same directory."""
+    from modelcompose_b200 import merge as MG
+    (v_sd, v_cfg), (a_sd, a_cfg) = golden("merge_c1.pt")["inputs"]["vision"], golden("merge_c1.pt")["inputs"]["audio"]
+    vdir, adir, odir, bdir = (str(tmp_path / n) for n in ("vision", "audio", "out-multimodal", "base"))
+    syn.save_checkpoint_dir(vdir, v_sd, v_cfg)
+    syn.save_checkpoint_dir(adir, a_sd, a_cfg)
+    os.makedirs(bdir)
+    base = syn.make_base_llm(seed=1)
+    torch.save(base, os.path.join(bdir, "pytorch_model.bin"))
+    MG.main([vdir, adir, "-o", odir, "--strategy", STRATEGY_C1, "--materialize-base", bdir])
+    dense = torch.load(os.path.join(odir, "effective_weights.bin"))
+    merged = torch.load(os.path.join(odir, "adapter_model.bin"))
+    assert len(dense) == 2 * 7   # every decoder linear of the 2-layer model
+    key = "model.layers.1.mlp.up_proj"
+    got = dense[key + ".weight"]
+    dt = base[key + ".weight"].dtype if base[key + ".weight"].dtype in (torch.float16, torch.bfloat16) else torch.float16
+    assert got.dtype == dt   # the base checkpoint's 16-bit dtype (fp16 for an fp32 base, as the reference loads it)
+    W = base[key + ".weight"].to(dt)
+    members = ["default-vision", "default-audio"]
+    want = MO.materialise_effective_weight(W, [merged[f"{key}.lora_A.{a}.weight"].to(dt) for a in members],
+                                           [merged[f"{key}.lora_B.{a}.weight"].to(dt) for a in members],
+                                           [16 / 8 * 0.5, 16 / 8 * 0.5], out_dtype=torch.float32)
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    assert (got.float() - want).abs().max().item() <= 1.5 * ulp * want.abs().max().item()
+    tok, model, procs, ctx = BD.load_pretrained_model(odir, bdir, "out-multimodal", materialize=True)
+    assert model.materialize and len(model.layers[0].Weff["q_proj"]) == 3
+    ids = torch.randint(3, 1000, (2, 17), generator=torch.Generator().manual_seed(0)).cuda()
+    assert torch.isfinite(model.forward(ids, torch.ones_like(ids)).logits).all()
 
 
 @pytest.mark.parametrize("key", list(DTYPES))
