@@ -347,14 +347,10 @@ MC_API int mc_attention_causal(const void* q, const void* k, const void* v, void
                         int dtype, mc_stream_t stream);
 /* Same, with a tuning word (development / profiling aid; 0 = the library default, what mc_attention_causal runs):
  * bits 4-7: 1 + number of element pairs out of every 4 whose exp2 runs as a polynomial on the FMA pipe instead of the MUFU pipe
- * (0 = default: 1 pair of 4); bit 8: rescale on every new row maximum instead of lazily; bit 9: record a clock64 timeline of one
- * CTA (mc_attention_debug_read); bit 10: skip the softmax arithmetic (timing experiment: results are wrong). */
+ * (0 = default: none — with persistent CTAs the all-MUFU form measured fastest); bit 8: rescale on every new row maximum instead of lazily. */
 MC_API int mc_attention_causal_tuned(const void* q, const void* k, const void* v, void* out, int64_t ld_qkv, int64_t ld_out,
                               const int32_t* out_rowmap, int batch, int seq_len, int n_heads, int head_dim, float softmax_scale,
                               int dtype, int tuning, mc_stream_t stream);
-/* Development aid: with tuning bit 9 set the attention kernel records a clock64() timeline of CTA (0,0,0) — [softmax A, softmax B,
- * MMA A, MMA B][step < 64][event < 8] int64 — which this call copies to host_out (16,384 bytes).  Synchronises the device. */
-MC_API int mc_attention_debug_read(long long* host_out, size_t bytes);
 /* dst[i, :] = src[index[i], :] for i < rows (bit-exact row copy, 128-bit accesses; row_bytes % 16 == 0).  Used to put the
  * spliced embeddings / the attention output into the modality-major row order the routed linears run in, and back. */
 MC_API int mc_gather_rows(const void* src, int64_t ld_src_bytes, void* dst, int64_t ld_dst_bytes, const int32_t* index,

@@ -58,7 +58,6 @@ SIGNATURES = {
     "mc_silu_mul": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _i64, _i, _vp]),
     "mc_attention_causal": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i, C.c_float, _i, _vp]),
     "mc_attention_causal_tuned": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i, C.c_float, _i, _i, _vp]),
-    "mc_attention_debug_read": (_i, [_vp, C.c_size_t]),
     "mc_gather_rows": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp]),
     "mc_rmsnorm": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, C.c_float, _i, _vp]),
     "mc_rope": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i64, _i64, _i, _vp]),

@@ -15,6 +15,7 @@
 // Roofline: tensor pipe (bf16 / fp16 dense); what bounds it in practice, and every variant measured on the way, is in
 // profiles/r02_attention.txt and DESIGN.md §4.6.  head_dim is fixed at 128 (vicuna-7B).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include "mc_tc.cuh"
@@ -33,7 +34,8 @@ struct AttParams {
   int seq_len, n_heads, is_f16;
   float scale_log2;           // softmax scale * log2(e)
   unsigned int idesc_qk, idesc_pv;
-  int dbg;                    // development: record a clock64 timeline of CTA (0,0,0) (mc_attention_debug_read)
+  int n_items;                // (sequence, head, 256-row query block) work items
+  unsigned int* counter;      // device: next item to hand out (zeroed before the launch)
 };
 
 // MN-major B operand (V tile: rows = keys = K dimension, 64 head-dim columns per 128-byte row, two column halves 16 KB apart):
@@ -150,65 +152,91 @@ __device__ __forceinline__ void exp2_poly2(uint64_t x, float& p0, float& p1) {
 }
 
 // =====================================================================================================================
-// The kernel: 64-key steps; scores, probabilities and output each have their own TMEM columns.
+// The kernel: persistent CTAs, 64-key steps; scores, probabilities and output each have their own TMEM columns.
 //
 // An earlier version kept P in the first half of the score tile it came from (128-key steps, one score tile per query
-// tile); ncu showed tensor pipe 47 %, MUFU pipe 48 %, and a clock64 timeline of one CTA why — per query tile the chain  S = Q K^T -> softmax -> O += P V -> next S  is strictly serial because P
-// overwrites the score buffer: the next score MMA can only be issued after the softmax has finished AND the P V MMA has
-// consumed P.  Double-buffering the scores alone does not break the chain (tried: same time).  Here a step is 64 keys and a
-// tile owns  S (64 columns) | P[0] | P[1] (32 columns each: 64 keys as 16-bit pairs) | O (128 columns) — 256 columns per tile,
-// 512 for the CTA's two tiles.  The softmax warp copies S(j) into registers and releases the score columns AT ONCE
-// (s_empty), so Q K_{j+1}^T runs underneath the softmax of step j and S(j + 1) is waiting when that softmax ends; P(j) goes to
-// buffer j & 1, which only needs P V(j - 2) to have completed.  The softmax warps never wait for the tensor pipe in steady
-// state; one MMA warp issues  Q_t K_{j+1}^T  (on s_empty_t(j))  for both tiles, another  O_t += P_t(j) V_j  (on p_full_t(j)).
-// Barriers that a waiter may lag by two phases are split per buffer (a parity wait cannot tell phase k from k + 2).
+// tile); ncu showed tensor pipe 47 %, MUFU pipe 48 %, and a clock64 timeline of one CTA why — per query tile the chain
+// S = Q K^T -> softmax -> O += P V -> next S  is strictly serial because P overwrites the score buffer: the next score MMA
+// can only be issued after the softmax has finished AND the P V MMA has consumed P.  Double-buffering the scores alone does
+// not break the chain (tried: same time).  Here a step is 64 keys and a tile owns
+//     S (64 columns) | P[0] | P[1] (32 columns each: 64 keys as 16-bit pairs) | O (128 columns)
+// — 256 columns per tile, 512 for the CTA's two tiles.  The softmax warp copies S(j) into registers and releases the score
+// columns AT ONCE (s_empty), so Q K_{j+1}^T runs underneath the softmax of step j and S(j + 1) is waiting when that softmax ends;
+// P(j) goes to buffer j & 1, which only needs P V(j - 2) to have completed.  One MMA warp issues Q_t K_{j+1}^T (on
+// s_empty_t(j)) for both tiles, another O_t += P_t(j) V_j (on p_full_t(j)): a warp that issues both kinds serialises two
+// barrier waits per step and was the bottleneck.  Barriers that a waiter may lag by two phases are split per buffer (a
+// parity wait cannot tell phase k from k + 2).
+//
+// Persistent: one CTA per SM takes (sequence, head, 256-row query block) work items from a global counter, a head's blocks
+// consecutively and heaviest first (the CTAs that run next to each other share that head's K / V in L2).  A one-item-per-CTA
+// launch spent ~11,000 cycles per CTA outside the steps (850 set-up, 6,400 until the first score tile — Q is 64 KB at one
+// SM's share of the bandwidth —, 5,000 drain), 20 % of the kernel at S = 3046 and 40 % at S = 980.  Here every role walks the
+// item sequence at its own pace (the scheduler warp broadcasts item ids through a 2-slot ring): the producer loads the next
+// item's Q as soon as the last score MMA of the current one has read it, the first scores of the next item are computed while
+// the softmax warps store the current output, and every ring / barrier phase simply keeps counting across items.
 // =====================================================================================================================
-__device__ long long g_att_dbg[4][64][8];
-__device__ long long g_att_dbg2[2][8];     // CTA life cycle of the heaviest and the lightest query block of (head 0, sequence 0)   // development timeline: [softmax A, softmax B, MMA A, MMA B][step][event]
-
 constexpr int kA3Keys = 64;                          // keys per step
 constexpr int kA3KvBytes = kA3Keys * kAttTile * 2;   // one K or V step tile: 16 KB (two [64 x 64] halves)
 constexpr int kA3KStages = 5, kA3VStages = 5;
 constexpr uint32_t kA3TileCols = 256, kA3ColP = 64, kA3ColO = 128;   // TMEM columns of a tile: S at 0, P[b] at 64 + 32 b, O at 128
+constexpr int kA3Consumers = 11;                     // warps that read the item ring: TMA, Q K, P V, 8 softmax
 
 struct Att3Smem {
   static constexpr int Q = 0;                                   // Q_A, Q_B
   static constexpr int K = Q + 2 * kAttTileBytes;
   static constexpr int V = K + kA3KStages * kA3KvBytes;
   static constexpr int BAR = V + kA3VStages * kA3KvBytes;       // 224 KB of tiles
-  static constexpr int N_BAR = 1 + 2 * kA3KStages + 2 * kA3VStages + 2 + 2 + 4 + 4;
-  static constexpr int TOTAL = BAR + N_BAR * 8 + 16;
+  static constexpr int N_BAR = 2 * kA3KStages + 2 * kA3VStages + 2 + 2 + 2 + 2 + 4 + 4 + 2 + 4;
+  static constexpr int ITEM = BAR + N_BAR * 8;                  // int [2]: the item ring
+  static constexpr int TOTAL = ITEM + 16 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
+
+struct AttItem {
+  int q0, n_a, n_b, n_max, col0;
+  long long row0;
+};
+
+__device__ __forceinline__ AttItem att_item(const AttParams& P, int idx, int n_qb) {
+  // item order: (sequence, head) major, query blocks of a head heaviest first
+  const int qb = n_qb - 1 - idx % n_qb;
+  const int sh = idx / n_qb;
+  const int head = sh % P.n_heads, seq = sh / P.n_heads;
+  AttItem it;
+  it.q0 = qb * 2 * kAttTile;
+  const int n_keys = (P.seq_len + kA3Keys - 1) / kA3Keys;   // steps that hold any key of the sequence
+  it.n_a = min(4 * qb + 2, n_keys);                          // causal: tile A (rows q0 .. q0 + 127) sees keys < q0 + 128
+  it.n_b = it.q0 + kAttTile < P.seq_len ? min(4 * qb + 4, n_keys) : 0;   // tile B two steps more (none if it lies past the end)
+  it.n_max = max(it.n_a, it.n_b);
+  it.row0 = (long long)seq * P.seq_len;
+  it.col0 = head * kAttTile;
+  return it;
+}
 
 template <bool F16, int PP, bool LAZY>
 __global__ void __launch_bounds__(kAttThreads, 1) attention3_kernel(const __grid_constant__ AttParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Att3Smem::BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;
+  uint64_t* k_full = bars;
   uint64_t* k_empty = k_full + kA3KStages;
   uint64_t* v_full = k_empty + kA3KStages;
   uint64_t* v_empty = v_full + kA3VStages;
-  uint64_t* s_full = v_empty + kA3VStages;   // [2]     MMA -> softmax of tile t: S_t(j) is in TMEM
-  uint64_t* s_empty = s_full + 2;            // [2]     softmax -> MMA: S_t(j) has been copied to registers
-  uint64_t* p_full = s_empty + 2;            // [2][2]  softmax -> MMA: P_t(j) is in TMEM buffer j & 1 (O_t rescaled if the maximum grew)
-  uint64_t* pv_done = p_full + 4;            // [2][2]  MMA -> softmax: O_t += P_t(j) V_j has completed (buffer j & 1 is free)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Att3Smem::N_BAR);
+  uint64_t* q_full = v_empty + kA3VStages;   // [2]     TMA -> Q K warp: Q_t of the item has landed
+  uint64_t* q_empty = q_full + 2;            // [2]     Q K warp -> TMA: the last score MMA of the item has read Q_t
+  uint64_t* s_full = q_empty + 2;            // [2]     Q K warp -> softmax of tile t: S_t is in TMEM
+  uint64_t* s_empty = s_full + 2;            // [2]     softmax -> Q K warp: S_t has been copied to registers
+  uint64_t* p_full = s_empty + 2;            // [2][2]  softmax -> P V warp: P_t is in TMEM buffer b (O_t rescaled if the maximum grew)
+  uint64_t* pv_done = p_full + 4;            // [2][2]  P V warp -> softmax: O_t += P_t V has completed (buffer b is free)
+  uint64_t* o_empty = pv_done + 4;           // [2]     softmax -> P V warp: O_t of the finished item has been read out
+  uint64_t* it_full = o_empty + 2;           // [2]     scheduler -> everyone: item ring slot filled
+  uint64_t* it_empty = it_full + 2;          // [2]     everyone -> scheduler: slot read
+  volatile int* s_item = reinterpret_cast<volatile int*>(smem + Att3Smem::ITEM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Att3Smem::ITEM + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int life = (P.dbg && blockIdx.y == 0 && blockIdx.z == 0) ? (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1)) : -1;
-  if (life >= 0 && threadIdx.x == 0) g_att_dbg2[life][0] = clock64();
-  const int qb = (int)gridDim.x - 1 - (int)blockIdx.x, head = blockIdx.y, seq = blockIdx.z;  // heaviest query blocks first
-  const int q0 = qb * 2 * kAttTile;
-  const bool valid_b = q0 + kAttTile < P.seq_len;
-  const int n_keys = (P.seq_len + kA3Keys - 1) / kA3Keys;   // steps that hold any key of the sequence
-  const int n_a = min(4 * qb + 2, n_keys);                 // causal: tile A (rows q0 .. q0 + 127) sees keys < q0 + 128 = steps 0 .. 4 qb + 1
-  const int n_b = valid_b ? min(4 * qb + 4, n_keys) : 0;   //         tile B two steps more
-  const int n_max = max(n_a, n_b);
-  const long long row0 = (long long)seq * P.seq_len;
-  const int col0 = head * kAttTile;
+  const int n_qb = (P.seq_len + 2 * kAttTile - 1) / (2 * kAttTile);
+  const int n_items = P.n_items;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&P.tmQ);
@@ -216,7 +244,6 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention3_kernel(const __grid
     tma_prefetch_desc(&P.tmV);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
     for (int st = 0; st < kA3KStages; ++st) {
       mbar_init(&k_full[st], 1);
       mbar_init(&k_empty[st], 1);
@@ -226,8 +253,13 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention3_kernel(const __grid
       mbar_init(&v_empty[st], 1);
     }
     for (int t = 0; t < 2; ++t) {
+      mbar_init(&q_full[t], 1);
+      mbar_init(&q_empty[t], 1);
       mbar_init(&s_full[t], 1);
       mbar_init(&s_empty[t], 4);
+      mbar_init(&o_empty[t], 4);
+      mbar_init(&it_full[t], 1);
+      mbar_init(&it_empty[t], kA3Consumers);
       for (int b = 0; b < 2; ++b) {
         mbar_init(&p_full[2 * t + b], 4);
         mbar_init(&pv_done[2 * t + b], 1);
@@ -240,52 +272,76 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention3_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (life >= 0 && threadIdx.x == 0) g_att_dbg2[life][1] = clock64();
+
+  // every consumer warp walks the same item sequence: n-th item from ring slot n & 1
+  auto next_item = [&](int n) -> int {
+    mbar_wait(&it_full[n & 1], (uint32_t)((n >> 1) & 1));
+    const int idx = s_item[n & 1];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&it_empty[n & 1]);
+    return idx;
+  };
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0) {
-      // TMA producer: whole warp converged, one elected lane issues.  Q_A, Q_B, then K_0, and (K_{j+1}, V_j) per step —
-      // the order the MMA warps consume them in.
-      if (elect_one()) {
-        mbar_expect_tx(q_full, 2 * kAttTileBytes);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          uint8_t* qd = smem + Att3Smem::Q + t * kAttTileBytes;
-          tma_load_2d(&P.tmQ, q_full, qd, col0, (int)(row0 + q0 + t * kAttTile));
-          tma_load_2d(&P.tmQ, q_full, qd + kAttHalfBytes, col0 + 64, (int)(row0 + q0 + t * kAttTile));
+    if (warp == 3) {
+      // ===== scheduler: hands out item ids (a sentinel >= n_items ends every role's loop)
+      if (lane == 0) {
+        for (int n = 0;; ++n) {
+          if (n >= 2) mbar_wait(&it_empty[n & 1], (uint32_t)(((n >> 1) - 1) & 1));
+          const int idx = (int)atomicAdd(P.counter, 1u);
+          s_item[n & 1] = idx;
+          mbar_arrive(&it_full[n & 1]);   // release: the slot is written before the arrive is observed
+          if (idx >= n_items) break;
         }
       }
-      __syncwarp();
-      auto load_kv = [&](bool is_v, int j) {
+    } else if (warp == 0) {
+      // ===== TMA producer: whole warp converged, one elected lane issues.  Per item: Q_A, Q_B (once the score MMAs of the
+      // previous item are through with them), K_0, then (K_{j+1}, V_j) per step — the order the MMA warps consume them in.
+      int kc = 0, vc = 0;   // K / V tiles loaded so far (ring position and phase keep counting across items)
+      auto load_kv = [&](bool is_v, const AttItem& it, int j) {
+        int& c = is_v ? vc : kc;
         const int stages = is_v ? kA3VStages : kA3KStages;
-        const int st = j % stages;
+        const int st = c % stages;
         uint64_t* full = is_v ? &v_full[st] : &k_full[st];
-        mbar_wait(is_v ? &v_empty[st] : &k_empty[st], (uint32_t)(((j / stages) & 1) ^ 1));
+        mbar_wait(is_v ? &v_empty[st] : &k_empty[st], (uint32_t)(((c / stages) & 1) ^ 1));
         if (elect_one()) {
           mbar_expect_tx(full, kA3KvBytes);
           uint8_t* d = smem + (is_v ? Att3Smem::V : Att3Smem::K) + st * kA3KvBytes;
-          const int krow = (int)(row0 + (long long)j * kA3Keys);
+          const int krow = (int)(it.row0 + (long long)j * kA3Keys);
           const CUtensorMap* tm = is_v ? &P.tmV : &P.tmK;
-          tma_load_2d(tm, full, d, col0, krow);
-          tma_load_2d(tm, full, d + kA3KvBytes / 2, col0 + 64, krow);
+          tma_load_2d(tm, full, d, it.col0, krow);
+          tma_load_2d(tm, full, d + kA3KvBytes / 2, it.col0 + 64, krow);
         }
         __syncwarp();
+        ++c;
       };
-      load_kv(false, 0);
-      for (int j = 0; j < n_max; ++j) {
-        if (j + 1 < n_max) load_kv(false, j + 1);
-        load_kv(true, j);
+      for (int n = 0;; ++n) {
+        const int idx = next_item(n);
+        if (idx >= n_items) break;
+        const AttItem it = att_item(P, idx, n_qb);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (n > 0) mbar_wait(&q_empty[t], (uint32_t)((n - 1) & 1));
+          if (elect_one()) {
+            mbar_expect_tx(&q_full[t], kAttTileBytes);
+            uint8_t* qd = smem + Att3Smem::Q + t * kAttTileBytes;
+            tma_load_2d(&P.tmQ, &q_full[t], qd, it.col0, (int)(it.row0 + it.q0 + t * kAttTile));
+            tma_load_2d(&P.tmQ, &q_full[t], qd + kAttHalfBytes, it.col0 + 64, (int)(it.row0 + it.q0 + t * kAttTile));
+          }
+          __syncwarp();
+        }
+        load_kv(false, it, 0);
+        for (int j = 0; j < it.n_max; ++j) {
+          if (j + 1 < it.n_max) load_kv(false, it, j + 1);
+          load_kv(true, it, j);
+        }
       }
     } else if (warp == 1) {
-      // Score MMAs of BOTH tiles (whole warp converged, one elected lane issues):  S_t = Q_t K_{j+1}^T as soon as the softmax of
-      // tile t has taken S_t(j) out of TMEM.  Splitting the MMA work by KIND (this warp: Q K^T, warp 2: P V) rather than by
-      // tile matters: a warp that issues both kinds for one tile serialises two barrier waits (~150 cycles each, completed or
-      // not) and two issue blocks per step — 1450 cycles per step with the softmax arithmetic switched off, against 1024 of
-      // tensor work (profiles/r02_attention.txt).
+      // ===== score MMAs of both tiles (whole warp converged, one elected lane issues):  S_t = Q_t K_j^T as soon as the softmax
+      // of tile t has taken the previous S_t out of TMEM
       const uint64_t kd0 = umma_smem_desc(smem_u32(smem + Att3Smem::K));
       const uint32_t idesc_qk = P.idesc_qk;
-      const bool dbg = P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
       auto issue_qk = [&](int t, int kst) {  // M 128, N 64, K 16 x 8; elected lane only
         const uint64_t qd = umma_smem_desc(smem_u32(smem + Att3Smem::Q + t * kAttTileBytes));
         const uint64_t kd = kd0 + (uint64_t)(kst * (kA3KvBytes >> 4));
@@ -299,64 +355,80 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention3_kernel(const __grid
       };
       int kst = 0;
       uint32_t kph = 0;
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_max; ++j) {  // scores of step j (j = 0: nothing to wait for but the operands)
-        if (dbg && j < 64) g_att_dbg[2][j][0] = clock64();
-        mbar_wait(&k_full[kst], kph);
-        if (dbg && j < 64) g_att_dbg[2][j][1] = clock64();
+      int sc[2] = {0, 0};   // score tiles issued so far per tile (s_empty phase of the previous one = sc - 1)
+      for (int n = 0;; ++n) {
+        const int idx = next_item(n);
+        if (idx >= n_items) break;
+        const AttItem it = att_item(P, idx, n_qb);
+        mbar_wait(&q_full[0], (uint32_t)(n & 1));
+        mbar_wait(&q_full[1], (uint32_t)(n & 1));
+        for (int j = 0; j < it.n_max; ++j) {
+          mbar_wait(&k_full[kst], kph);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (j < (t == 0 ? n_a : n_b)) {
-            if (j > 0) mbar_wait(&s_empty[t], (uint32_t)((j - 1) & 1));
-            tc_fence_after();
-            if (elect_one()) issue_qk(t, kst);
-            __syncwarp();
+          for (int t = 0; t < 2; ++t) {
+            const int n_t = t == 0 ? it.n_a : it.n_b;
+            if (j < n_t) {
+              if (sc[t] > 0) mbar_wait(&s_empty[t], (uint32_t)((sc[t] - 1) & 1));
+              tc_fence_after();
+              if (elect_one()) {
+                issue_qk(t, kst);
+                if (j == n_t - 1) umma_commit(&q_empty[t]);   // Q_t may be overwritten once these MMAs have read it
+              }
+              __syncwarp();
+              ++sc[t];
+            }
           }
-          if (dbg && j < 64) g_att_dbg[2][j][2 + t] = clock64();
+          if (elect_one()) umma_commit(&k_empty[kst]);
+          __syncwarp();
+          if (++kst == kA3KStages) {
+            kst = 0;
+            kph ^= 1u;
+          }
         }
-        if (elect_one()) umma_commit(&k_empty[kst]);
-        __syncwarp();
-        if (dbg && j < 64) g_att_dbg[2][j][4] = clock64();
-        if (++kst == kA3KStages) {
-          kst = 0;
-          kph ^= 1u;
+        if (it.n_b == 0) {  // tile B lies past the end of the sequence: nothing read its Q
+          if (elect_one()) umma_commit(&q_empty[1]);
+          __syncwarp();
         }
       }
-    } else if (warp == 2) {
-      // P V MMAs of both tiles:  O_t (+)= P_t(j) V_j, P from TMEM buffer j & 1 (8 columns = 16 keys per MMA)
+    } else {
+      // ===== P V MMAs of both tiles:  O_t (+)= P_t V_j, P from TMEM buffer b (8 columns = 16 keys per MMA)
       const uint64_t vd0 = umma_smem_desc_mn(smem_u32(smem + Att3Smem::V), kA3KvBytes / 2);
       const uint32_t idesc_pv = P.idesc_pv;
-      const bool dbg = P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
       int vst = 0;
       uint32_t vph = 0;
-      for (int j = 0; j < n_max; ++j) {
-        if (dbg && j < 64) g_att_dbg[3][j][0] = clock64();
-        mbar_wait(&v_full[vst], vph);
-        if (dbg && j < 64) g_att_dbg[3][j][1] = clock64();
+      int pc[2] = {0, 0};   // P tiles consumed so far per tile: buffer pc & 1, phase pc >> 1
+      for (int n = 0;; ++n) {
+        const int idx = next_item(n);
+        if (idx >= n_items) break;
+        const AttItem it = att_item(P, idx, n_qb);
+        for (int j = 0; j < it.n_max; ++j) {
+          mbar_wait(&v_full[vst], vph);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (j < (t == 0 ? n_a : n_b)) {
-            mbar_wait(&p_full[2 * t + (j & 1)], (uint32_t)((j >> 1) & 1));
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t vd = vd0 + (uint64_t)(vst * (kA3KvBytes >> 4));
-              const uint32_t tile_tm = tmem_base + (uint32_t)t * kA3TileCols;
+          for (int t = 0; t < 2; ++t) {
+            if (j < (t == 0 ? it.n_a : it.n_b)) {
+              if (j == 0 && n > 0) mbar_wait(&o_empty[t], (uint32_t)((n - 1) & 1));   // the previous item's O_t has been read out
+              const int b = pc[t] & 1;
+              mbar_wait(&p_full[2 * t + b], (uint32_t)((pc[t] >> 1) & 1));
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t vd = vd0 + (uint64_t)(vst * (kA3KvBytes >> 4));
+                const uint32_t tile_tm = tmem_base + (uint32_t)t * kA3TileCols;
 #pragma unroll
-              for (int kk = 0; kk < kA3Keys / 16; ++kk)
-                umma_f16_ts(tile_tm + kA3ColO, tile_tm + kA3ColP + (uint32_t)((j & 1) * 32 + kk * 8), vd + (uint64_t)(kk * (2048 >> 4)),
-                            idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-              umma_commit(&pv_done[2 * t + (j & 1)]);
+                for (int kk = 0; kk < kA3Keys / 16; ++kk)
+                  umma_f16_ts(tile_tm + kA3ColO, tile_tm + kA3ColP + (uint32_t)(b * 32 + kk * 8), vd + (uint64_t)(kk * (2048 >> 4)),
+                              idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&pv_done[2 * t + b]);
+              }
+              __syncwarp();
+              ++pc[t];
             }
-            __syncwarp();
           }
-          if (dbg && j < 64) g_att_dbg[3][j][2 + t] = clock64();
-        }
-        if (elect_one()) umma_commit(&v_empty[vst]);
-        __syncwarp();
-        if (dbg && j < 64) g_att_dbg[3][j][4] = clock64();
-        if (++vst == kA3VStages) {
-          vst = 0;
-          vph ^= 1u;
+          if (elect_one()) umma_commit(&v_empty[vst]);
+          __syncwarp();
+          if (++vst == kA3VStages) {
+            vst = 0;
+            vph ^= 1u;
+          }
         }
       }
     }
@@ -365,152 +437,142 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention3_kernel(const __grid
     const int t = (warp - 4) >> 2;      // 0: tile A, 1: tile B
     const int q = warp & 3;             // TMEM lane quadrant (hardware: warp id % 4)
     const int r = q * 32 + lane;        // query row inside the tile = TMEM lane
-    const int n_t = t == 0 ? n_a : n_b;
-    const int qrow = q0 + t * kAttTile + r;   // query position inside the sequence
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)t * kA3TileCols;
     const uint32_t p_tmem = s_tmem + kA3ColP, o_tmem = s_tmem + kA3ColO;
     const uint64_t scale2 = pk2(P.scale_log2, P.scale_log2);
-    float m_used = -INFINITY, l_run = 0.0f;
-    const bool dbg = P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && lane == 0;
-    for (int j = 0; j < n_t; ++j) {
-      if (dbg && j < 64) g_att_dbg[t][j][0] = clock64();
-      mbar_wait(&s_full[t], (uint32_t)(j & 1));
-      tc_fence_after();
-      if (dbg && j < 64) g_att_dbg[t][j][1] = clock64();
-      if (life >= 0 && j == 0 && t == 0 && q == 0 && lane == 0) g_att_dbg2[life][2] = clock64();
-      uint32_t sv[kA3Keys];
-      tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-      tmem_ld_32x32(s_tmem + 32u, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[t]);  // the score columns are free for Q K_{j+1}^T
-      if (dbg && j < 64) g_att_dbg[t][j][2] = clock64();
-      if (P.dbg & 2) {  // development: no softmax arithmetic (wrong results) — what the MMA side alone sustains
-        if (j >= 2) mbar_wait(&pv_done[2 * t + (j & 1)], (uint32_t)(((j >> 1) - 1) & 1));
-        tmem_st_32x32(p_tmem + (uint32_t)((j & 1) * 32), *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+    int c = 0;   // steps of this tile so far, all items: S phase c & 1, P buffer c & 1 with phase c >> 1
+    for (int n = 0;; ++n) {
+      const int idx = next_item(n);
+      if (idx >= n_items) break;
+      const AttItem it = att_item(P, idx, n_qb);
+      const int n_t = t == 0 ? it.n_a : it.n_b;
+      const int qrow = it.q0 + t * kAttTile + r;   // query position inside the sequence
+      float m_used = -INFINITY, l_run = 0.0f;
+      for (int j = 0; j < n_t; ++j, ++c) {
+        mbar_wait(&s_full[t], (uint32_t)(c & 1));
+        tc_fence_after();
+        uint32_t sv[kA3Keys];
+        tmem_ld_32x32(s_tmem, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld_32x32(s_tmem + 32u, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[t]);  // the score columns are free for the next Q K^T
+        const int key0 = j * kA3Keys;
+        if (key0 + kA3Keys - 1 > it.q0 + t * kAttTile + q * 32) {  // warp-uniform: some key of the step lies after some query of this warp
+#pragma unroll
+          for (int cc = 0; cc < kA3Keys; ++cc)
+            if (key0 + cc > qrow) sv[cc] = 0xff800000u;  // -inf
+        }
+        float mx8[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) mx8[cc] = max3(__uint_as_float(sv[cc]), __uint_as_float(sv[cc + 8]), __uint_as_float(sv[cc + 16]));
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) mx8[cc] = max3(mx8[cc], __uint_as_float(sv[cc + 24]), __uint_as_float(sv[cc + 32]));
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) mx8[cc] = max3(mx8[cc], __uint_as_float(sv[cc + 40]), __uint_as_float(sv[cc + 48]));
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) mx8[cc] = fmaxf(mx8[cc], __uint_as_float(sv[cc + 56]));
+        const float mx = max3(max3(mx8[0], mx8[1], mx8[2]), max3(mx8[3], mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]));
+        // key 0 is visible to every row, so the running maximum is finite from the first step on; a later step may be
+        // masked entirely for a row (mx = -inf): it neither moves the maximum nor adds to the sum
+        const float m_tile = mx * P.scale_log2;
+        const bool grow = LAZY ? (m_tile > m_used + 8.0f) : (m_tile > m_used);
+        float alpha = 1.0f;
+        if (grow) {
+          alpha = ex2_approx(m_used - m_tile);  // first step: exp2(-inf) = 0
+          m_used = m_tile;
+          l_run *= alpha;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          // rescale this thread's row of O in place (rare: the maximum is lazy); every earlier P V must have landed first
+          mbar_wait(&pv_done[2 * t + ((c - 1) & 1)], (uint32_t)(((c - 1) >> 1) & 1));
+          tc_fence_after();
+          const uint64_t a2 = pk2(alpha, alpha);
+#pragma unroll
+          for (int cc = 0; cc < kAttTile; cc += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(o_tmem + (uint32_t)cc, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              float a, b;
+              upk2(mul2(pk2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), a2), a, b);
+              v[e] = __float_as_uint(a);
+              v[e + 1] = __float_as_uint(b);
+            }
+            tmem_st_32x32(o_tmem + (uint32_t)cc, v);
+          }
+        }
+        // p = exp2(s * scale - m): fp32 row sum, 16-bit pairs
+        const uint64_t negm2 = pk2(-m_used, -m_used);
+        uint64_t l2[4] = {0ull, 0ull, 0ull, 0ull};
+        uint32_t w[kA3Keys / 2];
+#pragma unroll
+        for (int k = 0; k < kA3Keys / 2; ++k) {
+          const uint64_t x = fma2(pk2(__uint_as_float(sv[2 * k]), __uint_as_float(sv[2 * k + 1])), scale2, negm2);
+          float p0, p1;
+          if ((k & 3) < PP) {
+            exp2_poly2(x, p0, p1);
+          } else {
+            float x0, x1;
+            upk2(x, x0, x1);
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+          }
+          l2[k & 3] = add2(l2[k & 3], pk2(p0, p1));
+          w[k] = pack2<F16>(p0, p1);
+        }
+        float la, lb;
+        upk2(add2(add2(l2[0], l2[1]), add2(l2[2], l2[3])), la, lb);
+        l_run += la + lb;
+        // P buffer c & 1 was last read by the P V of step c - 2 (possibly the previous item's)
+        if (c >= 2) mbar_wait(&pv_done[2 * t + (c & 1)], (uint32_t)(((c >> 1) - 1) & 1));
+        tmem_st_32x32(p_tmem + (uint32_t)((c & 1) * 32), w);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[2 * t + (j & 1)]);
-        if (dbg && j < 64) g_att_dbg[t][j][7] = clock64();
-        l_run = 1.0f;
-        continue;
+        if (lane == 0) mbar_arrive(&p_full[2 * t + (c & 1)]);
       }
-      const int key0 = j * kA3Keys;
-      if (key0 + kA3Keys - 1 > q0 + t * kAttTile + q * 32) {  // warp-uniform: some key of the step lies after some query of this warp
-#pragma unroll
-        for (int c = 0; c < kA3Keys; ++c)
-          if (key0 + c > qrow) sv[c] = 0xff800000u;  // -inf
-      }
-      float mx8[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) mx8[c] = max3(__uint_as_float(sv[c]), __uint_as_float(sv[c + 8]), __uint_as_float(sv[c + 16]));
-#pragma unroll
-      for (int c = 0; c < 8; ++c) mx8[c] = max3(mx8[c], __uint_as_float(sv[c + 24]), __uint_as_float(sv[c + 32]));
-#pragma unroll
-      for (int c = 0; c < 8; ++c) mx8[c] = max3(mx8[c], __uint_as_float(sv[c + 40]), __uint_as_float(sv[c + 48]));
-#pragma unroll
-      for (int c = 0; c < 8; ++c) mx8[c] = fmaxf(mx8[c], __uint_as_float(sv[c + 56]));
-      const float mx = max3(max3(mx8[0], mx8[1], mx8[2]), max3(mx8[3], mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]));
-      // key 0 is visible to every row, so the running maximum is finite from the first step on; a later step may be
-      // masked entirely for a row (mx = -inf): it neither moves the maximum nor adds to the sum
-      const float m_tile = mx * P.scale_log2;
-      const bool grow = LAZY ? (m_tile > m_used + 8.0f) : (m_tile > m_used);
-      float alpha = 1.0f;
-      if (grow) {
-        alpha = ex2_approx(m_used - m_tile);  // first step: exp2(-inf) = 0
-        m_used = m_tile;
-        l_run *= alpha;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        // rescale this thread's row of O in place (rare: the maximum is lazy); every earlier P V must have landed first
-        mbar_wait(&pv_done[2 * t + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+      if (n_t > 0) {
+        // all P V of this tile have completed (the tensor pipe completes them in order): normalise by the row sum, store
+        const float inv = 1.0f / l_run;
+        mbar_wait(&pv_done[2 * t + ((c - 1) & 1)], (uint32_t)(((c - 1) >> 1) & 1));
         tc_fence_after();
-        const uint64_t a2 = pk2(alpha, alpha);
+        const bool ok = qrow < P.seq_len;
+        const long long tt = it.row0 + qrow;
+        const long long orow = (ok && P.out_rowmap) ? (long long)P.out_rowmap[tt] : tt;
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(P.out) + (orow * P.ld_out + it.col0) * 2);
 #pragma unroll
-        for (int c = 0; c < kAttTile; c += 32) {
+        for (int cc = 0; cc < kAttTile; cc += 32) {
           uint32_t v[32];
-          tmem_ld_32x32(o_tmem + (uint32_t)c, v);
+          tmem_ld_32x32(o_tmem + (uint32_t)cc, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float a, b;
-            upk2(mul2(pk2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])), a2), a, b);
-            v[e] = __float_as_uint(a);
-            v[e + 1] = __float_as_uint(b);
+          if (cc + 32 == kAttTile) {  // O_t is in registers: the next item's first P V may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_empty[t]);
           }
-          tmem_st_32x32(o_tmem + (uint32_t)c, v);
-        }
-      }
-      if (dbg && j < 64) g_att_dbg[t][j][3] = clock64();
-      // p = exp2(s * scale - m): fp32 row sum, 16-bit pairs
-      const uint64_t negm2 = pk2(-m_used, -m_used);
-      uint64_t l2[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t w[kA3Keys / 2];
+          if (ok) {
 #pragma unroll
-      for (int k = 0; k < kA3Keys / 2; ++k) {
-        const uint64_t x = fma2(pk2(__uint_as_float(sv[2 * k]), __uint_as_float(sv[2 * k + 1])), scale2, negm2);
-        float p0, p1;
-        if ((k & 3) < PP) {
-          exp2_poly2(x, p0, p1);
-        } else {
-          float x0, x1;
-          upk2(x, x0, x1);
-          p0 = ex2_approx(x0);
-          p1 = ex2_approx(x1);
+            for (int e = 0; e < 32; e += 8)
+              dst[(cc + e) >> 3] = make_uint4(pack2<F16>(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv),
+                                              pack2<F16>(__uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv),
+                                              pack2<F16>(__uint_as_float(v[e + 4]) * inv, __uint_as_float(v[e + 5]) * inv),
+                                              pack2<F16>(__uint_as_float(v[e + 6]) * inv, __uint_as_float(v[e + 7]) * inv));
+          }
         }
-        l2[k & 3] = add2(l2[k & 3], pk2(p0, p1));
-        w[k] = pack2<F16>(p0, p1);
-      }
-      float la, lb;
-      upk2(add2(add2(l2[0], l2[1]), add2(l2[2], l2[3])), la, lb);
-      l_run += la + lb;
-      if (dbg && j < 64) g_att_dbg[t][j][4] = clock64();
-      // P buffer j & 1 was last read by P V(j - 2)
-      if (j >= 2) mbar_wait(&pv_done[2 * t + (j & 1)], (uint32_t)(((j >> 1) - 1) & 1));
-      if (dbg && j < 64) g_att_dbg[t][j][5] = clock64();
-      tmem_st_32x32(p_tmem + (uint32_t)((j & 1) * 32), w);
-      tmem_st_wait();
-      tc_fence_before();
-      if (dbg && j < 64) g_att_dbg[t][j][6] = clock64();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[2 * t + (j & 1)]);
-      if (dbg && j < 64) g_att_dbg[t][j][7] = clock64();
-    }
-    if (life >= 0 && q == 0 && lane == 0) g_att_dbg2[life][3 + t] = clock64();
-    if (n_t > 0) {
-      // all P V of this tile have completed (the tensor pipe completes them in order): normalise by the row sum, store
-      const float inv = 1.0f / l_run;
-      mbar_wait(&pv_done[2 * t + ((n_t - 1) & 1)], (uint32_t)(((n_t - 1) >> 1) & 1));
-      tc_fence_after();
-      const bool ok = qrow < P.seq_len;
-      const long long tt = row0 + qrow;
-      const long long orow = (ok && P.out_rowmap) ? (long long)P.out_rowmap[tt] : tt;
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(P.out) + (orow * P.ld_out + col0) * 2);
-#pragma unroll
-      for (int c = 0; c < kAttTile; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(o_tmem + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (ok) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 8)
-            dst[(c + e) >> 3] = make_uint4(pack2<F16>(__uint_as_float(v[e]) * inv, __uint_as_float(v[e + 1]) * inv),
-                                           pack2<F16>(__uint_as_float(v[e + 2]) * inv, __uint_as_float(v[e + 3]) * inv),
-                                           pack2<F16>(__uint_as_float(v[e + 4]) * inv, __uint_as_float(v[e + 5]) * inv),
-                                           pack2<F16>(__uint_as_float(v[e + 6]) * inv, __uint_as_float(v[e + 7]) * inv));
-        }
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[t]);   // keeps the per-item phase of o_empty in step for a tile without work
       }
     }
   }
-  if (life >= 0 && warp == 4 && lane == 0) g_att_dbg2[life][5] = clock64();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
-  if (life >= 0 && threadIdx.x == 32) g_att_dbg2[life][6] = clock64();
 }
 
 }  // namespace mc
@@ -518,7 +580,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention3_kernel(const __grid
 using namespace mc;
 
 template <bool F16, int PP, bool LAZY>
-static cudaError_t launch_attention(const AttParams& P, dim3 grid, cudaStream_t stream) {
+static cudaError_t launch_attention(const AttParams& P, int grid, cudaStream_t stream) {
   static bool configured[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -529,6 +591,18 @@ static cudaError_t launch_attention(const AttParams& P, dim3 grid, cudaStream_t 
   }
   attention3_kernel<F16, PP, LAZY><<<grid, kAttThreads, Att3Smem::DYN_BYTES, stream>>>(P);
   return cudaGetLastError();
+}
+
+// work counters: 64 per device, handed out round-robin (launches in flight on different streams never share one); each is
+// zeroed on the launch stream right before its launch
+static unsigned int* attention_counter() {
+  static unsigned int* counters[64] = {};
+  static std::atomic<unsigned int> next{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!counters[dev] && cudaMalloc(&counters[dev], 64 * sizeof(unsigned int)) != cudaSuccess) counters[dev] = nullptr;
+  return counters[dev] ? counters[dev] + (next.fetch_add(1) & 63u) : nullptr;
 }
 
 extern "C" int mc_attention_causal_tuned(const void* q, const void* k, const void* v, void* out, int64_t ld_qkv, int64_t ld_out,
@@ -543,6 +617,8 @@ extern "C" int mc_attention_causal_tuned(const void* q, const void* k, const voi
   MC_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) == 0, "attention: pointers must be 16-byte aligned");
   const long long tokens = (long long)batch * seq_len;
   MC_REQUIRE(tokens < (1LL << 31), "attention: too many tokens");
+  const long long items = (long long)batch * n_heads * ((seq_len + 2 * kAttTile - 1) / (2 * kAttTile));
+  MC_REQUIRE(items < (1LL << 30), "attention: too many work items");
   AttParams P;
   memset(&P, 0, sizeof(P));
   // Q: 128-row boxes; K / V: 64-row boxes (one step)
@@ -556,6 +632,7 @@ extern "C" int mc_attention_causal_tuned(const void* q, const void* k, const voi
   P.seq_len = seq_len;
   P.n_heads = n_heads;
   P.is_f16 = dtype == MC_F16;
+  P.n_items = (int)items;
   P.scale_log2 = softmax_scale * 1.4426950408889634f;
   // instruction descriptors: D = F32, A/B = bf16 / fp16, N >> 3 at bit 17 (64 keys for the scores, 128 head-dim columns for
   // P V), M = 128 (>> 4 at bit 24); bit 16 = B operand MN-major (the V tile is [keys, head_dim] with head_dim contiguous)
@@ -563,11 +640,15 @@ extern "C" int mc_attention_causal_tuned(const void* q, const void* k, const voi
   const unsigned int common = (1u << 4) | (fmt << 7) | (fmt << 10) | ((unsigned)(kAttTile >> 4) << 24);
   P.idesc_qk = common | ((unsigned)(kA3Keys >> 3) << 17);
   P.idesc_pv = common | ((unsigned)(kAttTile >> 3) << 17) | (1u << 16);
-  P.dbg = (tuning >> 9) & 3;   // bit 9: timeline, bit 10: skip the softmax arithmetic (timing experiment, wrong results)
   cudaStream_t st = (cudaStream_t)stream;
+  P.counter = attention_counter();
+  MC_REQUIRE(P.counter != nullptr, "attention: no device memory for the work counter");
+  MC_CUDA_OK(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), st));
+  const int sms = sm_count();
+  MC_REQUIRE(sms > 0, "no CUDA device");
+  const int grid = (int)std::min<long long>(items, sms);
   // bits 4-7 = 1 + pairs out of 4 whose exp2 runs on the FMA pipe (0 = default), bit 8 = rescale on every new maximum
-  dim3 grid((seq_len + 2 * kAttTile - 1) / (2 * kAttTile), n_heads, batch);
-  const int pp = ((tuning >> 4) & 0xf) ? ((tuning >> 4) & 0xf) - 1 : 1;
+  const int pp = ((tuning >> 4) & 0xf) ? ((tuning >> 4) & 0xf) - 1 : 0;
   const bool eager = (tuning >> 8) & 1;
   const bool f16 = dtype == MC_F16;
   cudaError_t e = cudaErrorInvalidValue;
@@ -586,14 +667,6 @@ extern "C" int mc_attention_causal_tuned(const void* q, const void* k, const voi
   }
 #undef MC_ATT
   if (e != cudaSuccess) return fail(MC_ERR_CUDA, "attention launch failed: %s", cudaGetErrorString(e));
-  return MC_OK;
-}
-
-extern "C" int mc_attention_debug_read(long long* host_out, size_t bytes) {
-  MC_REQUIRE(host_out && bytes >= sizeof(long long) * 4 * 64 * 8, "debug_read: buffer too small");
-  MC_CUDA_OK(cudaMemcpyFromSymbol(host_out, g_att_dbg, sizeof(long long) * 4 * 64 * 8));
-  if (bytes >= sizeof(long long) * (4 * 64 * 8 + 16))
-    MC_CUDA_OK(cudaMemcpyFromSymbol(host_out + 4 * 64 * 8, g_att_dbg2, sizeof(long long) * 16));
   return MC_OK;
 }
 
