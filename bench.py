@@ -736,7 +736,7 @@ def prefill_spot_check(model, cfg_name: str, device):
     return res
 
 
-def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materialize=None):
+def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materialize=None, with_decode: bool = False):
     """Composed prefill, batch-sharded (every rank holds a full replica and its own requests; no collective on the timed
     path).  Returns the result dict (rank 0) with tokens/s, roofline of the routed-linear kernel, e2e and verification."""
     from modelcompose_b200 import _cabi
@@ -782,16 +782,26 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
     step_flops = (flops["total"] - (flops["lora"] if model.materialize else 0.0)) * batch
     achieved = lin_flops / (lin_ms * 1e-3) / 1e12
 
-    # ---- e2e through the public forward API: pinned host ids/features -> device, last-position logits -> host, per step
+    # ---- e2e through the public forward API, fed the way the reference's eval loader feeds its model (collator -> batch ->
+    # forward, multimodal_dataset.py:141-214): per-request instances -> data.bucket_by_length (equal spliced length: the
+    # reference's batched inference raises on ragged batches) -> data.FeatureCollator -> data.PinnedBatch (pinned staging);
+    # every timed step copies the staged batch host -> device, runs forward and reads the last-position logits back
+    from modelcompose_b200 import data as DT
+    from modelcompose_b200 import synthetic as syn
+    instances = [{"input_ids": ids_h[i], "modal_inputs": {m: v[i] for m, v in feats_h.items()}} for i in range(batch)]
+    rows_per_block = {m: syn.MODAL_TOKENS[m] + 10 for m in feats_h}
+    groups = list(DT.bucket_by_length(instances, batch, rows_per_block))
+    assert len(groups) == 1 and len(groups[0]) == batch, "synthetic requests share one layout: one bucket expected"
+    collated = DT.FeatureCollator(pad_token_id=0, model_max_length=ids_h.shape[1])([instances[i] for i in groups[0]])
+    staged = DT.PinnedBatch().load(collated)
     last = torch.empty((batch, model.config.vocab_size), dtype=torch.bfloat16).pin_memory()
-    h2d = ids_h.numel() * 8 + mask_h.numel() * 8 + sum(v.numel() * 2 for v in feats_h.values())
+    h2d = sum(v.numel() * v.element_size() for v in staged._batch.values()) + \
+        sum(v.numel() * v.element_size() for v in staged._modal.values())
     d2h = last.numel() * 2
 
     def step_e2e():
-        i = ids_h.to(device, non_blocking=True)
-        m = mask_h.to(device, non_blocking=True)
-        f = {k: v.to(device, non_blocking=True) for k, v in feats_h.items()}
-        o = model.forward(i, m, modal_inputs=f)
+        b = staged.to(device)
+        o = model.forward(b["input_ids"], b["attention_mask"], modal_inputs=b["modal_inputs"])
         last.copy_(o.logits[:, -1, :], non_blocking=True)
         torch.cuda.synchronize()
     step_e2e()
@@ -842,8 +852,8 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
                      "algorithmic_tflop_per_step": round(lin_flops / 1e12, 2), "frac_of_burst_peak": round(achieved / peak_burst, 4),
                      "whole_step_tflops": round(step_flops / (ms_per_step * 1e-3) / 1e12, 1)},
         "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e_steps, "api": "MultimodalLlamaForCausalLM.forward(input_ids, attention_mask, modal_inputs=...) from pinned host "
-                "buffers; last-position logits copied back", "timer": "host wall clock incl. synchronize, max over ranks"},
+                "steps": e_steps, "api": "data.bucket_by_length -> data.FeatureCollator -> data.PinnedBatch (pinned host staging) -> "
+                "MultimodalLlamaForCausalLM.forward(input_ids, attention_mask, modal_inputs=...); last-position logits copied back", "timer": "host wall clock incl. synchronize, max over ranks"},
         "gpu_launches": int(launches) * world,
         "attention": "mc::attention3_kernel (tcgen05, P / O in TMEM)" if __import__("modelcompose_b200.model", fromlist=["x"]).ATTENTION_NATIVE
                      else "library call (cuDNN via torch SDPA)",
@@ -851,9 +861,170 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
                          "collective": "ncclAllGather of request 0 last-position logits, outside the timed region" if world > 1 else None},
         "clocks": clocks.summary(),
     }
+    if with_decode:
+        res["decode"] = run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, world, dist, barrier)
     del model
     torch.cuda.empty_cache()
     return res
+
+
+def hbm_peak():
+    return measured_peaks()
+
+
+def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, world, dist, barrier, steps: int = 64):
+    """Decode steps after the config's prefill (generation loop of modelcompose/eval/model_multimodal_qa_loader.py:93-102 over
+    multimodal_arch.py:290-293 / multimodal_llama.py:436-438): one new token per request per step against the key/value cache,
+    default adapter on every row.  A step = one replay of the captured graph (embedding gather, 32 layers of stream-K skinny
+    linears + split-KV attention, lm_head, greedy argmax).  HBM-bound: the roofline is weight + cache bytes over copy bandwidth."""
+    from modelcompose_b200 import _cabi
+    from modelcompose_b200 import decode as DC
+    batch = ids_d.shape[0]
+    warmup = max(3, min(args.warmup, 5))
+    out = model.forward(ids_d, mask_d, modal_inputs=feats_d, use_cache=True, last_logits_only=True, cache_extra=2 * (steps + warmup) + 16)
+    cache = out.past_key_values
+    S0 = cache.length
+    cache.prefill_mask = None
+    model._rope_tables(cache.capacity)
+    dws = model._decode_workspace(cache)
+    first = torch.empty(batch, dtype=torch.int64, device=device)
+    DC.argmax_rows(out.logits[:, -1, :].contiguous(), None, first)
+    dws.ids.copy_(first)
+    dws.pos.fill_(cache.length)
+    for _ in range(warmup):   # eager step, capture, replays
+        dws.run()
+        cache.length += 1
+    assert dws.graph is not None, "the decode step must run as a captured graph"
+    barrier()
+    n0 = _cabi.LAUNCHES
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    len0 = cache.length
+    with ClockSampler(device.index) as clocks:
+        t0.record()
+        for _ in range(steps):
+            dws.run()
+        t1.record()
+        barrier()
+    cache.length += steps
+    launches = _cabi.LAUNCHES - n0
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    value = batch * world / (ms_per_step * 1e-3)
+    avg_len = len0 + (steps + 1) / 2.0
+    w_bytes, kv_bytes = dws.weight_bytes, dws.cache_bytes(1) * avg_len
+    # the dominant kernel alone: the skinny linears launched one by one with CUDA events around each (same buffers, no graph)
+    ev = []
+    dws_e = DC.DecodeWorkspace(model, cache, None, use_graph=False)
+    dws_e.ids.copy_(dws.ids)
+    dws_e.pos.fill_(cache.length)
+    orig = DC.SkinnyLaunch.run
+
+    def timed_run(self):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(self)
+        b.record()
+        ev.append((a, b))
+    DC.SkinnyLaunch.run = timed_run
+    try:
+        for _ in range(2):
+            dws_e.run()
+            dws_e.pos.fill_(cache.length)   # same position again: the cache entry is simply rewritten
+    finally:
+        DC.SkinnyLaunch.run = orig
+    torch.cuda.synchronize()
+    lin_ms = sum(a.elapsed_time(b) for a, b in ev) / 2
+    del dws_e
+    # ---- e2e: a streaming server's step — the new token ids come from pinned host memory, the step's greedy tokens go back
+    ids_host = torch.empty((batch, 1), dtype=torch.int64).pin_memory()
+    tok_host = torch.empty(batch, dtype=torch.int64).pin_memory()
+    ids_host.copy_(dws.next64.cpu()[:, None])
+    e_steps = min(steps, 32)
+    torch.cuda.synchronize()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e_steps):
+        o = model.forward(ids_host.to(device, non_blocking=True), None, past_key_values=cache, use_cache=True)
+        tok_host.copy_(dws.next64, non_blocking=True)
+        torch.cuda.synchronize()
+        ids_host[:, 0] = tok_host
+    dt = time.perf_counter() - w0
+    te = torch.tensor([dt], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = batch * world / (float(te.item()) / e_steps)
+    finite = bool(torch.isfinite(o.logits).all())
+    # ---- untimed parity check on the bench's own weights: decode steps of a short probe batch vs the prefill of the extended
+    # sequence (the prefill path itself is checked against the oracle in this run).  The bar (that of tests/test_decode_gpu.py)
+    # is applied to a 2-layer view of the model (same full-width weights): the two paths round at the same points but sum in a
+    # different order, and 32 random-init layers amplify those last-bit differences, so the full-depth numbers are reported
+    # next to it with a sanity bar only.
+    check = None
+    if rank == 0:
+        import copy
+        from modelcompose_b200 import splice as SP
+        from modelcompose_b200 import synthetic as syn
+        _, _, merged, present, _ = PREFILL_CONFIGS[cfg_name]
+        g = torch.Generator().manual_seed(91)
+        pids = syn.make_prompt_ids(2, present, 16, model.config.vocab_size, 92, SP.MODAL_TOKEN_INDEXES, 6).to(device)
+        pf = {m: torch.randn((2, 12 + 5 * i, syn.MODAL_FEATURE_DIM[m]), generator=g).to(torch.bfloat16).to(device) for i, m in enumerate(present)}
+
+        def probe(mdl):
+            gen = mdl.generate(pids, modal_inputs=pf, max_new_tokens=4, do_sample=False)
+            full = mdl.forward(gen, torch.ones_like(gen), modal_inputs=pf)
+            Sp = full.logits.shape[1]
+            o1 = mdl.forward(pids, torch.ones_like(pids), modal_inputs=pf, use_cache=True, cache_extra=8)
+            c2 = o1.past_key_values
+            worst, cosm, scale = 0.0, 1.0, 0.0
+            for i in range(3):
+                tok = gen[:, pids.shape[1] + i:pids.shape[1] + i + 1]
+                od = mdl.forward(tok, None, past_key_values=c2, modal_inputs=pf)
+                a, b = od.logits[:, 0].float().flatten(), full.logits[:, Sp - 4 + i, :].float().flatten()
+                worst, scale = max(worst, (a - b).abs().max().item()), max(scale, b.abs().max().item())
+                cosm = min(cosm, torch.nn.functional.cosine_similarity(a, b, dim=0).item())
+            return worst, scale, cosm
+        shallow = copy.copy(model)
+        shallow.layers, shallow._ws, shallow._dws, shallow._proj_cache = model.layers[:2], {}, None, {}
+        w2, s2, c2_ = probe(shallow)
+        del shallow
+        w32, s32, c32 = probe(model)
+        ok = w2 <= 2.0 ** -5 * s2 and c2_ >= 0.9995 and c32 >= 0.99
+        check = {"what": "logits of 3 decode steps of a 2-request probe vs the prefill of the extended sequence (same weights)",
+                 "layers_2": {"max_abs": round(w2, 5), "scale": round(s2, 4), "cosine": round(c2_, 7)},
+                 "all_layers": {"max_abs": round(w32, 5), "scale": round(s32, 4), "cosine": round(c32, 7)},
+                 "bar": "2-layer view: max_abs <= 2^-5 * scale and cosine >= 0.9995; full depth: cosine >= 0.99 (last-bit "
+                        "differences amplified by 32 random-init layers)", "ok": bool(ok)}
+        if not ok:
+            raise SystemExit(f"PARITY FAILURE (decode {cfg_name}): {json.dumps(check)}")
+    peak, peak_src = hbm_peak()
+    achieved = (w_bytes + kv_bytes) / (ms_per_step * 1e-3) / 1e9
+    lin_achieved = w_bytes / (lin_ms * 1e-3) / 1e9
+    return {
+        "metric": "composed-decode tokens/s", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
+        "data": "synthetic", "vs_baseline": None,
+        "config": {"workload": PREFILL_CONFIGS[cfg_name][0] + " — decode steps after that prefill", "requests_per_gpu": batch,
+                   "context_tokens": [int(len0), int(len0 + steps)], "prompt_tokens_after_splice": int(S0),
+                   "linear_form": "materialised W_eff of the default group" if model.materialize else
+                   "base weight + low-rank branch of the default group (rank %d)" % (dws.t[0].shape[1] if dws.t else 0),
+                   "l2": "weights %.1f GB + cache %.1f GB per step, far larger than L2" % (w_bytes / 1e9, kv_bytes / 1e9),
+                   "step": "one CUDA-graph replay: embedding gather, 32 layers, final norm, lm_head, greedy argmax"},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": int(w_bytes + kv_bytes), "weight_bytes": int(w_bytes), "kv_cache_bytes": int(kv_bytes),
+                     "kernel": "mc::skinny_streamk_kernel (stream-K skinny linears: cp.async.bulk ring -> ldmatrix -> mma.sync)",
+                     "kernel_ms_per_step": round(lin_ms, 4), "kernel_share_of_step": round(lin_ms / ms_per_step, 4),
+                     "kernel_achieved_GBps_on_weight_bytes": round(lin_achieved, 1), "kernel_frac": round(lin_achieved / peak, 4),
+                     "kernel_timing": "event pairs around every skinny-linear launch of an ungraphed step (includes launch gaps)"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s", "h2d_bytes_per_step": int(batch * 8), "d2h_bytes_per_step": int(batch * 8),
+                "steps": e_steps, "api": "MultimodalLlamaForCausalLM.forward(input_ids [B,1] from pinned host memory, past_key_values=cache); "
+                "greedy tokens copied back and synchronised every step", "timer": "host wall clock incl. synchronize, max over ranks"},
+        "gpu_launches": int(launches) * world, "launches_per_step": dws.launches_per_step(),
+        "verification": {"finite_logits": finite, "decode_vs_prefill_check": check},
+        "clocks": clocks.summary(),
+    }
 
 
 def cpu_prefill_layer_rate(cfg_name: str, max_seconds: float = 25.0):
@@ -910,7 +1081,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "merge", "prefill", "ties"],
+    ap.add_argument("--workload", default="all", choices=["all", "merge", "prefill", "ties", "decode"],
                     help="all (default): the merge line (BASELINE config 2) carrying the prefill result under \"prefill\"; "
                          "merge / prefill: that workload alone as the primary line")
     ap.add_argument("--prefill-config", default="c3", choices=sorted(PREFILL_CONFIGS))
@@ -967,24 +1138,33 @@ def main():
         torch.cuda.empty_cache()
         if line is not None and world == 1 and not args.no_e2e:
             line["ties"] = run_ties(device)  # the other merge strategy family of the CLI, one GPU
-    if args.workload in ("all", "prefill") and not args.no_e2e:
+    if args.workload in ("all", "prefill", "decode") and not args.no_e2e:
         configs = [(args.prefill_config, args.materialize)]
         if nested:
             configs += [(c, args.materialize) for c in ("c4", "c5") if c != args.prefill_config]
             configs += [(args.prefill_config, not args.materialize)]   # the other evaluation form of the linears, same config
         for i, (cfg_name, mat) in enumerate(configs):
-            pre = run_prefill(args, device, rank, world, dist, barrier, cfg_name, materialize=mat)
+            # decode steps after the prefill of the first config (both evaluation forms of it when nested)
+            with_decode = args.workload == "decode" or (args.workload == "all" and cfg_name == args.prefill_config)
+            pre = run_prefill(args, device, rank, world, dist, barrier, cfg_name, materialize=mat, with_decode=with_decode)
             if rank == 0:
                 # CPU baseline on rank 0 at N=1 only (under torchrun the other ranks would wait on it), first config only
                 pre["cpu_baseline"] = (cpu_prefill_layer_rate(cfg_name, max_seconds=15.0)
                                        if world == 1 and not args.no_cpu_baseline and i == 0 else None)
-                if args.workload == "prefill" and i == 0:
+                dec = pre.pop("decode", None)
+                suffix = ""
+                if mat != args.materialize:
+                    suffix = "_materialized" if mat else "_branch"
+                if args.workload == "decode" and i == 0:
+                    line = dec
+                    line["prefill"] = pre
+                elif args.workload == "prefill" and i == 0:
                     line = pre
                 elif line is not None:
                     key = "prefill" if i == 0 and args.workload == "all" else "prefill_" + cfg_name
-                    if mat != args.materialize:
-                        key += "_materialized" if mat else "_branch"
-                    line[key] = pre
+                    line[key + suffix] = pre
+                    if dec is not None:
+                        line["decode" + ("" if i == 0 else "_" + cfg_name) + suffix] = dec
     if rank == 0 and line is not None:
         emit(line)
     if world > 1:

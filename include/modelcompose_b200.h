@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MC_ABI_VERSION 2
+#define MC_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MC_API __attribute__((visibility("default")))
@@ -359,6 +359,87 @@ MC_API int mc_rmsnorm(const void* x, const void* weight, void* out, int64_t rows
                float eps, int dtype, mc_stream_t stream);
 MC_API int mc_rope(void* q, void* k, const void* cos_table, const void* sin_table, int64_t tokens, int seq_len, int pos_offset,
             int n_heads, int head_dim, int64_t ldq, int64_t ldk, int dtype, mc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode step (one new token per sequence against a key/value cache): the generation loop behind
+ *   modelcompose/model/multimodal_arch.py:290-293          (cache present: no splice, mask rebuilt over past + 1)
+ *   modelcompose/model/language_model/multimodal_llama.py:436-438  (modality masks dropped: every row takes the default
+ *                                                           adapter), :274-312 (attention with past_key_value), :747-767
+ *   (prepare_inputs_for_generation).  With M = batch <= 64 rows every linear is a stream over its weight matrix (HBM-bound),
+ * so the step runs on its own kernels instead of the 128-row tcgen05 tiles of the prefill.
+ * ---------------------------------------------------------------------------------------------- */
+#define MC_SKINNY_MAX_PROBLEMS 4
+#define MC_SKINNY_MAX_M 64
+
+typedef enum mc_skinny_epilogue {
+  MC_SKINNY_EPI_NONE = 0,
+  MC_SKINNY_EPI_RESIDUAL = 1, /* + residual[m,n] (fp32 add, one rounding; may run in place) */
+  MC_SKINNY_EPI_COLSCALE = 2, /* acc * col_scale[n] in fp32 before rounding: the LoRA down-projection T = s * (x A^T) */
+  MC_SKINNY_EPI_SILU_MUL = 3  /* dual problem: C = silu(gate) * up with gate = A0 B0^T + A1 B1^T, up = A0 B0u^T + A1u B1u^T;
+                                 gate, silu(gate) and up each rounded to the storage dtype before the product — the rounding
+                                 points of multimodal_llama.py:381-388 and of the prefill's MC_LINEAR_EPI_SILU_MUL */
+} mc_skinny_epilogue;
+
+typedef struct mc_skinny_desc {
+  int32_t M, N, K0, K1;          /* M <= MC_SKINNY_MAX_M; K0, K1, N multiples of 8; K1 = 0: no second product */
+  const void* A0; int64_t lda0;  /* device [M, K0] activations */
+  const void* B0; int64_t ldb0;  /* device [N, K0] weights (nn.Linear layout) */
+  const void* A1; int64_t lda1;  /* device [M, K1] rank-space activations of the default adapter group, or NULL */
+  const void* B1; int64_t ldb1;  /* device [N, K1] (columns of B_all of that group) */
+  const void* B0u;               /* SILU_MUL only: second weight matrix [N, K0] (leading dimension ldb0) */
+  const void* A1u;               /* SILU_MUL only, K1 > 0: [M, K1] (leading dimension lda1) */
+  const void* B1u;               /* SILU_MUL only, K1 > 0: [N, K1] (leading dimension ldb1) */
+  void* C; int64_t ldc;          /* device [M, N] */
+  const void* residual; int64_t ldr;
+  const float* col_scale;        /* device fp32 [N] (COLSCALE) */
+  int32_t epilogue;              /* mc_skinny_epilogue */
+} mc_skinny_desc_t;
+
+typedef struct mc_skinny_plan mc_skinny_plan_t;
+
+/* C = epilogue(A0 B0^T + A1 B1^T) for 1..MC_SKINNY_MAX_PROBLEMS problems in ONE launch (q/k/v share a launch).
+ * Default kernel: persistent stream-K — every SM owns an equal span of (block of 64 weight rows, 128-element K chunk)
+ * iterations whatever N and K are; weight and activation boxes are staged by TMA (cp.async.bulk.tensor + mbarrier ring, ~170 KB
+ * in flight per SM; the plan holds the tensor maps), fragments are read with ldmatrix, mma.sync.m16n8k16 accumulates in fp32;
+ * row blocks shared by several CTAs are combined through the workspace by the last CTA to arrive, in CTA order (deterministic).
+ * tuning bit 4 selects the register kernel instead (weight rows streamed with 128-bit loads straight into MMA fragments, K split
+ * over the warps of a CTA), bit 5 32-row blocks, bits 0-3 = 1 16-row CTAs of the register kernel.
+ * The plan stays valid while the pointers in `desc` do (decode buffers are static, plans are built once per cache).
+ * workspace: device memory of mc_skinny_workspace_bytes() bytes, ZEROED once by the caller and then left alone (the kernel
+ * restores it); launches that may run concurrently need separate workspaces. */
+MC_API size_t mc_skinny_workspace_bytes(void);
+MC_API int mc_skinny_plan_create(mc_skinny_plan_t** plan, const mc_skinny_desc_t* desc, int n_problems, int dtype, int tuning);
+MC_API int mc_skinny_plan_run(const mc_skinny_plan_t* plan, void* workspace, size_t workspace_bytes, mc_stream_t stream);
+/* weight bytes one run streams (the HBM roofline's numerator) */
+MC_API int64_t mc_skinny_plan_bytes(const mc_skinny_plan_t* plan);
+MC_API int mc_skinny_plan_destroy(mc_skinny_plan_t* plan);
+
+/* Rotary embedding of the new token's q and k (rounding points of mc_rope) and append of k / v to the cache.
+ * q, k_new, v_new: device [batch, n_heads * head_dim] (projection outputs, q is rotated in place); caches: device
+ * [batch, n_heads, capacity, head_dim] (the transformers-4.31 past_key_value layout with room to grow: the keys of one
+ * (sequence, head) are one contiguous stream); d_pos: DEVICE int32 scalar = number of tokens already cached = position of the new
+ * token (read at run time, so a captured CUDA graph replays across steps); cos / sin tables [positions, head_dim]. */
+MC_API int mc_decode_rope_append(void* q, const void* k_new, const void* v_new, int64_t ld_qkv, void* k_cache, void* v_cache,
+                          int64_t capacity, const int32_t* d_pos, const void* cos_table, const void* sin_table, int batch,
+                          int n_heads, int head_dim, int dtype, mc_stream_t stream);
+
+/* Attention of one query token per sequence over the cached keys [0, *d_pos] (the new token included — call after
+ * mc_decode_rope_append): softmax(q k^T * softmax_scale) v in fp32 (multimodal_llama.py:295-312 with q_len = 1).
+ * key_mask: device uint8 [batch, ld_mask] or NULL; key j of sequence b takes part iff key_mask[b, j] != 0 (padded prompts).
+ * The keys are cut into n_splits ranges per (sequence, head) that run as separate CTAs and are combined by the last one to
+ * finish, in split order (deterministic); scratch: device fp32 [batch * n_heads * n_splits * (head_dim + 2)], counters: device
+ * int32 [batch * n_heads], zero before the first call (the kernel leaves them zero).  head_dim must be 128. */
+MC_API int mc_decode_attention(const void* q, const void* k_cache, const void* v_cache, int64_t capacity, const int32_t* d_pos,
+                        const uint8_t* key_mask, int64_t ld_mask, void* out, int64_t ld_q, int64_t ld_out, int batch,
+                        int n_heads, int head_dim, float softmax_scale, int n_splits, float* scratch, int32_t* counters,
+                        int dtype, mc_stream_t stream);
+
+/* out[m] = index of the largest logit of row m (first index on ties), as int32 and / or int64: the greedy sampler of
+ * generate() (HF greedy_search behind modelcompose/eval/model_multimodal_qa_loader.py:93-102), kept on the device so a decode
+ * step needs no host round trip.  d_counter (device int32 or NULL) is incremented by one: the position counter of a captured
+ * decode loop (mc_decode_rope_append / mc_decode_attention read it as d_pos in the next step). */
+MC_API int mc_argmax_rows(const void* logits, int64_t ld, int rows, int cols, int32_t* out_i32, int64_t* out_i64,
+                   int32_t* d_counter, int dtype, mc_stream_t stream);
 
 #ifdef __cplusplus
 }

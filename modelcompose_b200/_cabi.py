@@ -61,6 +61,14 @@ SIGNATURES = {
     "mc_gather_rows": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp]),
     "mc_rmsnorm": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, C.c_float, _i, _vp]),
     "mc_rope": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i64, _i64, _i, _vp]),
+    "mc_skinny_workspace_bytes": (_sz, []),
+    "mc_skinny_plan_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i]),
+    "mc_skinny_plan_run": (_i, [_vp, _vp, _sz, _vp]),
+    "mc_skinny_plan_bytes": (_i64, [_vp]),
+    "mc_skinny_plan_destroy": (_i, [_vp]),
+    "mc_decode_rope_append": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "mc_decode_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, C.c_float, _i, _vp, _vp, _i, _vp]),
+    "mc_argmax_rows": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
 }
 
 
@@ -100,7 +108,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.mc_abi_version() != 2:
+        if handle.mc_abi_version() != 3:
             raise McError("libmodelcompose_b200.so ABI version mismatch; rebuild")
         _LIB = handle
     return _LIB

@@ -66,6 +66,7 @@ struct alignas(64) LinParams {
   int n_prob, total_tiles, is_f16;
   unsigned int idesc;
   int group_m;  // tile rasterisation: group_m M-tiles share a sweep over N (keeps the operand working set in L2)
+  int epi_staged;  // 1: NONE / RESIDUAL / SILU_MUL epilogues go through the shared-memory transpose (coalesced global accesses)
   int compact;  // 1: every CTA first compacts the (M tile, N tile) pairs that survive routing and owns every grid-th of them
   // Segmented launch (grouped GEMM over materialised per-group weights): the rows of every problem are cut into n_seg
   // consecutive segments whose boundaries live in DEVICE memory (seg_start[0 .. n_seg], written per batch by the host code
@@ -359,13 +360,99 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
   }
 }
 
+constexpr int kEpiStageBytes = 32 * 32 * 4;  // per epilogue warp: one 32-row x 32-column fp32 chunk
+
+// NONE / RESIDUAL / SILU_MUL epilogues with COALESCED global accesses.  In epilogue_tile a thread owns an output row, so every
+// warp-level 16-byte load / store touches 32 different rows (32 lines): at 512 x 256 pair tiles the address-divergent accesses
+// of the eight epilogue warps, not the TMEM reads or the arithmetic, are what the non-overlapped epilogue costs (~17 k cycles per
+// tile for a plain store, ~38 k with the SiLU(gate) operand, against 65 k cycles of MMAs at K = 4096).  Here every 32 x 32 fp32
+// chunk is transposed through 4 KB of shared memory per warp (16-byte units XOR-swizzled by row: conflict-free both ways): a
+// pass then covers 8 rows x 64 contiguous bytes, i.e. 8 lines per instruction instead of 32, for the operand loads (issued one
+// chunk ahead) and the stores.  Arithmetic and rounding points are those of epilogue_tile (bit-identical results).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_staged(const LinProblem& pr, bool is_f16, uint32_t taddr, int row0, int lane, int m_end,
+                                                     int n0, float* stage) {
+  const int epi = pr.epilogue;
+  const bool has_aux = epi == MC_LINEAR_EPI_RESIDUAL || epi == MC_LINEAR_EPI_SILU_MUL;
+  const int piece = lane & 3;
+  char* cptr[4];
+  const char* rptr[4];
+  bool ok[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + 8 * i + (lane >> 2);
+    ok[i] = r < m_end;
+    const int orow = (pr.c_rowmap && ok[i]) ? pr.c_rowmap[r] : r;
+    cptr[i] = reinterpret_cast<char*>(pr.C) + ((long long)orow * pr.ldc + n0 + piece * 8) * 2;
+    rptr[i] = reinterpret_cast<const char*>(pr.residual) + ((long long)r * pr.ldr + n0 + piece * 8) * 2;
+  }
+  uint4 aux[4], aux_next[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    aux[i] = make_uint4(0u, 0u, 0u, 0u);
+    aux_next[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (has_aux && ok[i] && n0 + piece * 8 < pr.N) aux[i] = *reinterpret_cast<const uint4*>(rptr[i]);
+  }
+  float* my_row = stage + lane * 32;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    if (n0 + c >= pr.N) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + (uint32_t)c, v);
+    if (has_aux) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c + 32 < BN && ok[i] && n0 + c + 32 + piece * 8 < pr.N) aux_next[i] = *reinterpret_cast<const uint4*>(rptr[i] + (c + 32) * 2);
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = 8 * i + (lane >> 2);
+      const float4 lo = *reinterpret_cast<const float4*>(stage + rr * 32 + (((2 * piece) ^ (rr & 7)) << 2));
+      const float4 hi = *reinterpret_cast<const float4*>(stage + rr * 32 + (((2 * piece + 1) ^ (rr & 7)) << 2));
+      if (ok[i] && n0 + c + piece * 8 < pr.N) {
+        float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        if (epi == MC_LINEAR_EPI_RESIDUAL) {
+          float r[8];
+          unpack8(aux[i], is_f16, r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += r[e];
+        } else if (epi == MC_LINEAR_EPI_SILU_MUL) {
+          float g[8], sg[8], up[8];
+          unpack8(aux[i], is_f16, g);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sg[e] = __fdividef(g[e], 1.0f + __expf(-g[e]));
+          const uint4 sgr = pack8(sg, is_f16), upr = pack8(f, is_f16);
+          unpack8(sgr, is_f16, sg);
+          unpack8(upr, is_f16, up);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = sg[e] * up[e];
+        }
+        *reinterpret_cast<uint4*>(cptr[i] + c * 2) = pack8(f, is_f16);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aux[i] = aux_next[i];
+  }
+}
+
+__device__ __forceinline__ bool epilogue_is_staged(const LinParams& P, const LinProblem& pr) {
+  return P.epi_staged && (pr.epilogue == MC_LINEAR_EPI_NONE || pr.epilogue == MC_LINEAR_EPI_RESIDUAL || pr.epilogue == MC_LINEAR_EPI_SILU_MUL);
+}
+
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int EPI_OFFSET = (BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 127) & ~127;  // 4 epilogue warps x 4 KB transpose buffers
+  static constexpr int TOTAL = EPI_OFFSET + 4 * kEpiStageBytes;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for the manual 1024-byte alignment
 };
 
@@ -534,7 +621,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_kernel(const __grid_consta
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN>(pr, is_f16, taddr, row, t.m_end, n0);
+      if (epilogue_is_staged(P, pr))
+        epilogue_tile_staged<BN>(pr, is_f16, taddr, t.m0 + q * 32, lane, t.m_end, n0, reinterpret_cast<float*>(smem + L::EPI_OFFSET + q * kEpiStageBytes));
+      else
+        epilogue_tile<BN>(pr, is_f16, taddr, row, t.m_end, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -618,7 +708,8 @@ struct SmemLayout2 {
   static constexpr int B_BYTES = 128 * kBK * 2;    // this CTA's 128 rows (N) of the 256-column B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 2) * 8 + 16;
+  static constexpr int EPI_OFFSET = (BAR_OFFSET + (2 * STAGES + 2) * 8 + 16 + 127) & ~127;  // 8 epilogue warps x 4 KB transpose buffers
+  static constexpr int TOTAL = EPI_OFFSET + 8 * kEpiStageBytes;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
@@ -772,7 +863,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) linear
       mbar_wait(tfull_bar, t_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN);
-      epilogue_tile<BN>(pr, is_f16, taddr, row, t.m_end, t.nt * BN);
+      if (epilogue_is_staged(P, pr))
+        epilogue_tile_staged<BN>(pr, is_f16, taddr, row - lane, lane, t.m_end, t.nt * BN,
+                                 reinterpret_cast<float*>(smem + L::EPI_OFFSET + (warp - 4) * kEpiStageBytes));
+      else
+        epilogue_tile<BN>(pr, is_f16, taddr, row, t.m_end, t.nt * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -803,7 +898,8 @@ struct SmemLayout3 {
   static constexpr int B_BYTES = 128 * kBK * 2;   // this CTA's 128 (of 256) B rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int EPI_OFFSET = (BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 127) & ~127;
+  static constexpr int TOTAL = EPI_OFFSET + 4 * kEpiStageBytes;
   static constexpr int DYN_BYTES = TOTAL + 1024;
 };
 
@@ -942,7 +1038,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-      epilogue_tile<BN>(pr, is_f16, taddr, row, pr.M, t.nt * BN);
+      if (epilogue_is_staged(P, pr))
+        epilogue_tile_staged<BN>(pr, is_f16, taddr, row - lane, lane, pr.M, t.nt * BN,
+                                 reinterpret_cast<float*>(smem + L::EPI_OFFSET + (warp & 3) * kEpiStageBytes));
+      else
+        epilogue_tile<BN>(pr, is_f16, taddr, row, pr.M, t.nt * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1280,6 +1380,7 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     p->params.compact = ok ? 1 : 0;
   }
   p->params.is_f16 = dtype == MC_F16;
+  p->params.epi_staged = ((tuning >> 17) & 1) ? 0 : 1;  // tuning bit 17: row-per-thread epilogue everywhere (the round-1 form)
   // instruction descriptor: D = F32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12: 0 = F16, 1 = BF16), both K-major,
   // N >> 3 at bit 17, M >> 4 at bit 24
   const unsigned int fmt = dtype == MC_F16 ? 0u : 1u;

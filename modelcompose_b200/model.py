@@ -24,6 +24,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _cabi
+from . import decode as DC
 from . import linear as LN
 from . import materialize as MZ
 from . import splice as SP
@@ -153,6 +154,9 @@ class CausalLMOutputWithPast:
     modal_id: Optional[torch.Tensor] = None  # extra: uint8 [B, S'] routing ids (0 = default)
 
 
+DECODE_GRAPH = os.environ.get("MC_DECODE_GRAPH", "1") != "0"    # 0: launch the decode step's kernels one by one (development)
+DECODE_NATIVE = os.environ.get("MC_DECODE_NATIVE", "1") != "0"  # 0: decode through the prefill kernels at M = batch (development)
+
 LINEARS = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
 
 
@@ -171,26 +175,28 @@ class _Layer:
 
 
 class KVCache:
-    """Key/value cache of one batch: per layer ``[B, capacity, heads, head_dim]`` (keys stored after RoPE, as
-    transformers 4.31 caches them, multimodal_llama.py:284-289).  Returned as ``past_key_values`` when ``use_cache``."""
+    """Key/value cache of one batch: per layer ``[B, heads, capacity, head_dim]`` (keys stored after RoPE, as transformers 4.31
+    caches them, multimodal_llama.py:284-289) — the reference's ``past_key_value`` layout with room to grow, so the keys of
+    one (sequence, head) are one contiguous stream for the decode attention.  Returned as ``past_key_values`` when ``use_cache``."""
 
     def __init__(self, n_layers: int, B: int, capacity: int, n_heads: int, head_dim: int, dtype, device):
-        self.k = [torch.empty((B, capacity, n_heads, head_dim), dtype=dtype, device=device) for _ in range(n_layers)]
-        self.v = [torch.empty((B, capacity, n_heads, head_dim), dtype=dtype, device=device) for _ in range(n_layers)]
+        self.k = [torch.empty((B, n_heads, capacity, head_dim), dtype=dtype, device=device) for _ in range(n_layers)]
+        self.v = [torch.empty((B, n_heads, capacity, head_dim), dtype=dtype, device=device) for _ in range(n_layers)]
         self.length = 0
         self.capacity = capacity
+        self.prefill_mask = None
 
     def grow(self, capacity: int) -> None:
         for lst in (self.k, self.v):
             for i, t in enumerate(lst):
-                n = torch.empty((t.shape[0], capacity) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
-                n[:, :self.length].copy_(t[:, :self.length])
+                n = torch.empty((t.shape[0], t.shape[1], capacity, t.shape[3]), dtype=t.dtype, device=t.device)
+                n[:, :, :self.length].copy_(t[:, :, :self.length])
                 lst[i] = n
         self.capacity = capacity
 
     def legacy(self):
         """transformers-4.31 layout: tuple over layers of (k, v) ``[B, heads, length, head_dim]`` views."""
-        return tuple((k[:, :self.length].transpose(1, 2), v[:, :self.length].transpose(1, 2)) for k, v in zip(self.k, self.v))
+        return tuple((k[:, :, :self.length], v[:, :, :self.length]) for k, v in zip(self.k, self.v))
 
     def __len__(self):
         return len(self.k)
@@ -437,6 +443,7 @@ class MultimodalLlamaForCausalLM:
         self._ws: Dict[Tuple[int, int], _Workspace] = {}
         self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._proj_cache: Dict[tuple, tuple] = {}
+        self._dws: Optional["DC.DecodeWorkspace"] = None
 
     # ------------------------------------------------------------------------------------------ construction helpers
     def _local_tokens(self, sd, kind: str, n_default: int):
@@ -568,11 +575,11 @@ class MultimodalLlamaForCausalLM:
             _cabi.count_launch()
         q, k, v = (t.view(B, S, nH, D) for t in (ws.q, ws.k, ws.v))
         if cache is not None:
-            cache.k[layer_idx][:, past:past + S].copy_(k)
-            cache.v[layer_idx][:, past:past + S].copy_(v)
+            cache.k[layer_idx][:, :, past:past + S].copy_(k.transpose(1, 2))
+            cache.v[layer_idx][:, :, past:past + S].copy_(v.transpose(1, 2))
         F = torch.nn.functional
         if past > 0:
-            kk, vv = cache.k[layer_idx][:, :past + S], cache.v[layer_idx][:, :past + S]
+            kk, vv = cache.k[layer_idx][:, :, :past + S], cache.v[layer_idx][:, :, :past + S]  # [B, heads, L, D]
             mask = None
             if not full or S > 1:
                 neg = torch.finfo(self.dtype).min
@@ -581,8 +588,7 @@ class MultimodalLlamaForCausalLM:
                     mask = mask + torch.full((S, past + S), neg, dtype=self.dtype, device=self.device).triu(past + 1)[None, None]
                 if not full:
                     mask = (mask + (~attention_mask.bool())[:, None, None, :].to(self.dtype) * neg).clamp_min(neg)
-            o = F.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), attn_mask=mask,
-                                               scale=1.0 / math.sqrt(D)).transpose(1, 2)
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), kk, vv, attn_mask=mask, scale=1.0 / math.sqrt(D)).transpose(1, 2)
         elif full and D == 128 and ATTENTION_NATIVE:
             # own tcgen05 kernel: reads the projection outputs in place and writes straight into buffer (modality-major) order
             LN.attention_causal(ws.q, ws.k, ws.v, ws.attn, B, S, nH, 1.0 / math.sqrt(D),
@@ -601,7 +607,7 @@ class MultimodalLlamaForCausalLM:
 
     def prefill(self, inputs_embeds: torch.Tensor, modal_id: Optional[torch.Tensor], attention_mask=None,
                 use_cache: bool = False, output_hidden_states: bool = False, past_key_values: Optional[KVCache] = None,
-                last_logits_only: bool = False):
+                last_logits_only: bool = False, cache_extra: int = 128):
         """MultimodalLlamaModel.forward + lm_head (:488-619, :720) on (spliced) embeddings; returns (logits, cache, hidden).
         With ``past_key_values`` this is the decode step: ``inputs_embeds`` holds the new token(s) only, every row takes
         the default adapter (``modal_id`` None — the reference drops the modality masks when a cache is present, :436-438)."""
@@ -614,7 +620,7 @@ class MultimodalLlamaForCausalLM:
             if past + S > cache.capacity:
                 cache.grow(max(past + S, cache.capacity * 2))
         elif use_cache:
-            cache = KVCache(len(self.layers), B, S + 128, nH, H // nH, self.dtype, self.device)
+            cache = KVCache(len(self.layers), B, S + max(1, int(cache_extra)), nH, H // nH, self.dtype, self.device)
         self._rope_tables(past + S)  # before the workspace: its plans point at the tables
         key = (B, S)
         if key not in self._ws:
@@ -662,9 +668,32 @@ class MultimodalLlamaForCausalLM:
         ws.lm_head.run()
         return ws.logits.view(B, S, -1), cache, (tuple(hidden) if output_hidden_states else None)
 
+    def _decode_native(self, ids, cache, output_hidden_states) -> bool:
+        D = self.config.hidden_size // self.config.num_attention_heads
+        return (DECODE_NATIVE and ids.dim() == 2 and ids.shape[1] == 1 and ids.shape[0] <= DC.MAX_M and D == 128
+                and not output_hidden_states and cache.length > 0)
+
+    def _decode_workspace(self, cache: "KVCache", attention_mask=None) -> "DC.DecodeWorkspace":
+        """The decode step's buffers / launches / graph for this cache (rebuilt when the cache was reallocated).  Padded
+        positions of the prompt are taken from ``attention_mask`` (or the mask the prefill stored) when the workspace is
+        built; every later position is attended to, as HF generate's appended ones columns have it."""
+        dws = self._dws
+        if dws is None or not dws.matches(cache) or dws.rope_ptr != self._rope[0].data_ptr():
+            mask = attention_mask if attention_mask is not None else getattr(cache, "prefill_mask", None)
+            key_mask = None
+            if mask is not None and not bool(mask.all()):
+                key_mask = torch.ones((mask.shape[0], cache.capacity), dtype=torch.uint8, device=self.device)
+                n = min(mask.shape[1], cache.capacity)
+                key_mask[:, :n] = (mask[:, :n] != 0).to(torch.uint8)
+            self._dws = None  # release the old graph and buffers first
+            dws = DC.DecodeWorkspace(self, cache, key_mask, use_graph=DECODE_GRAPH)
+            dws.rope_ptr = self._rope[0].data_ptr()
+            self._dws = dws
+        return dws
+
     def forward(self, input_ids=None, attention_mask=None, past_key_values=None, inputs_embeds=None, labels=None,
                 use_cache=None, output_attentions=None, output_hidden_states=None, modal_inputs=None, return_dict=None,
-                last_logits_only: bool = False):
+                last_logits_only: bool = False, cache_extra: int = 128):
         """Reference signature (multimodal_llama.py:676-688).  ``past_key_values`` (a ``KVCache`` returned by an earlier
         call with ``use_cache=True``) selects the decode step: new tokens only, default adapter, no splice (:290-293)."""
         if output_attentions:
@@ -678,6 +707,17 @@ class MultimodalLlamaForCausalLM:
             if attention_mask is not None and modal_inputs is not None and ids.shape[1] == 1:
                 # multimodal_arch.py:291-292: the mask is rebuilt as all ones over past + 1
                 attention_mask = torch.ones((ids.shape[0], past_key_values.length + 1), dtype=attention_mask.dtype, device=self.device)
+            if self._decode_native(ids, past_key_values, output_hidden_states):
+                # one token per sequence, batch <= 64: the graph-captured HBM-bound step of modelcompose_b200/decode.py
+                cache = past_key_values
+                if cache.length + 1 > cache.capacity:
+                    cache.grow(max(cache.length + 1, cache.capacity * 2))
+                self._rope_tables(cache.length + 1)
+                dws = self._decode_workspace(cache, attention_mask)
+                logits = dws.step(ids, cache.length).view(ids.shape[0], 1, -1)
+                cache.length += 1
+                out = CausalLMOutputWithPast(logits=logits, past_key_values=cache)
+                return (logits, cache) if return_dict is False else out
             r = SP.splice(ids, None, None, self.embed_tokens, {})  # embedding lookup of the new tokens
             logits, kv, hidden = self.prefill(r.inputs_embeds, None, attention_mask, True, bool(output_hidden_states), past_key_values)
             out = CausalLMOutputWithPast(logits=logits, past_key_values=kv, hidden_states=hidden)
@@ -701,7 +741,9 @@ class MultimodalLlamaForCausalLM:
             if self.config.lora_strategy not in ("modal", "modal+language"):  # :703-704
                 modal_id = None
         logits, kv, hidden = self.prefill(inputs_embeds, modal_id, attention_mask, bool(use_cache), bool(output_hidden_states),
-                                          last_logits_only=last_logits_only and labels is None)
+                                          last_logits_only=last_logits_only and labels is None, cache_extra=cache_extra)
+        if kv is not None:
+            kv.prefill_mask = attention_mask  # spliced mask of the prompt (padded positions stay masked in the decode steps)
         loss = None
         if labels is not None:  # :723-733
             shift_logits = logits[..., :-1, :].contiguous().view(-1, self.config.vocab_size)
@@ -727,15 +769,20 @@ class MultimodalLlamaForCausalLM:
         B = ids.shape[0]
         if attention_mask is None:
             attention_mask = torch.ones_like(ids)
-        out = self.forward(ids, attention_mask.to(self.device), modal_inputs=modal_inputs, use_cache=True, last_logits_only=True)
+        out = self.forward(ids, attention_mask.to(self.device), modal_inputs=modal_inputs, use_cache=True, last_logits_only=True,
+                           cache_extra=max_new_tokens + 1)
         cache = out.past_key_values
         logits = out.logits[:, -1, :]
         text_mask = attention_mask.to(self.device)
         done = torch.zeros(B, dtype=torch.bool, device=self.device)
         pad = pad_token_id if pad_token_id is not None else (eos_token_id if eos_token_id is not None else 0)
+        greedy = not (do_sample and temperature > 0)
+        D = self.config.hidden_size // self.config.num_attention_heads
+        native = DECODE_NATIVE and B <= DC.MAX_M and D == 128
+        dws = None
         new_tokens = []
         for step in range(max_new_tokens):
-            if do_sample and temperature > 0:
+            if not greedy:
                 probs = torch.softmax(logits.float() / temperature, dim=-1)
                 if top_p is not None and top_p < 1.0:
                     sp, si = probs.sort(dim=-1, descending=True)
@@ -744,9 +791,13 @@ class MultimodalLlamaForCausalLM:
                     probs = torch.zeros_like(probs).scatter_(1, si, sp)
                     probs = probs / probs.sum(-1, keepdim=True)
                 nxt = torch.multinomial(probs, 1, generator=generator).squeeze(1)
+            elif dws is not None:
+                nxt = dws.next64.clone()  # the step's own argmax (mc_argmax_rows inside the graph)
             else:
-                nxt = logits.argmax(-1)
-            nxt = torch.where(done, torch.full_like(nxt, pad), nxt)
+                nxt = torch.empty(B, dtype=torch.int64, device=self.device)
+                DC.argmax_rows(logits.contiguous(), None, nxt)
+            if eos_token_id is not None:
+                nxt = torch.where(done, torch.full_like(nxt, pad), nxt)
             new_tokens.append(nxt)
             if eos_token_id is not None:
                 done = done | (nxt == eos_token_id)
@@ -754,6 +805,24 @@ class MultimodalLlamaForCausalLM:
                     break
             if step + 1 == max_new_tokens:
                 break
+            if native:
+                # graph-captured decode step (modelcompose_b200/decode.py): with modal inputs every cached position is attended
+                # to (multimodal_arch.py:291-292); text-only batches keep the prompt's padded positions masked (HF generate
+                # appends ones to the caller's mask).  The graph's own argmax already wrote the next ids and advanced the
+                # position; only sampled / eos-padded tokens have to be written over them.
+                if dws is None:
+                    self._rope_tables(cache.capacity)
+                    if modal_inputs:
+                        cache.prefill_mask = None
+                    dws = self._decode_workspace(cache)
+                    dws.ids.copy_(nxt)
+                    dws.pos.fill_(cache.length)
+                elif not greedy or eos_token_id is not None:
+                    dws.ids.copy_(nxt)
+                dws.run()
+                cache.length += 1
+                logits = dws.logits
+                continue
             if modal_inputs:
                 # multimodal_arch.py:291-292: with modal inputs the mask is rebuilt as all ones over past + 1
                 step_mask = torch.ones((B, cache.length + 1), dtype=attention_mask.dtype, device=self.device)

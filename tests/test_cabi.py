@@ -31,7 +31,7 @@ def test_ctypes_table_matches_header(built_lib):
     from modelcompose_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_symbols()
     lib = _cabi.lib()
-    assert lib.mc_abi_version() == 2
+    assert lib.mc_abi_version() == 3
 
 
 def test_argument_validation_without_gpu(built_lib):

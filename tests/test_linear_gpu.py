@@ -119,6 +119,30 @@ def test_silu_mul_epilogue_matches_separate_ops():
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("tuning", [0, 1, 3, 4])
+@pytest.mark.parametrize("M,N,K", [(300, 688, 256), (1030, 520, 128), (77, 264, 72), (512, 256, 64)])
+def test_staged_epilogue_is_bit_identical_to_row_per_thread(dtype, tuning, M, N, K):
+    """The coalesced (shared-memory transposed) NONE / RESIDUAL / SILU_MUL epilogues against the row-per-thread form
+    (tuning bit 17) on every kernel, ragged M / N tails, scattered output rows."""
+    x, W = rnd((M, K), dtype, 11).cuda(), rnd((N, K), dtype, 12, 0.2).cuda()
+    res = rnd((M, N), dtype, 13).cuda()
+    perm = torch.randperm(M, generator=torch.Generator().manual_seed(14)).to(torch.int32).cuda()
+    for epi, rowmap in ((LN.EPI_NONE, None), (LN.EPI_RESIDUAL, None), (LN.EPI_SILU_MUL, None), (LN.EPI_NONE, perm)):
+        outs = []
+        for bit in (0, 1 << 17):
+            out = res.clone() if epi != LN.EPI_NONE else torch.full((M, N), 7.0, dtype=dtype, device="cuda")
+            LN.LinearPlan([LN.Problem(x, W, out, residual=out if epi != LN.EPI_NONE else None, epilogue=epi, c_rowmap=rowmap)],
+                          tuning=tuning | bit).run()
+            outs.append(out)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), (epi, tuning, rowmap is not None)
+    ref = x.float() @ W.float().t()
+    plain = torch.empty((M, N), dtype=dtype, device="cuda")
+    LN.LinearPlan([LN.Problem(x, W, plain)], tuning=tuning).run()
+    check(plain, ref, dtype, "staged plain epilogue")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("D,tuning", [(128, 0), (64, 0), (64, 1), (128, 3), (128, 4), (64, 4)])
 def test_rope_epilogue_bit_exact_vs_separate_kernel(dtype, D, tuning):
     """q/k projection with RoPE in the epilogue == projection followed by mc_rope == oracle apply_rope on the rounded projection."""
