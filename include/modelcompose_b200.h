@@ -402,8 +402,11 @@ typedef struct mc_skinny_plan mc_skinny_plan_t;
  * iterations whatever N and K are; weight and activation boxes are staged by TMA (cp.async.bulk.tensor + mbarrier ring, ~170 KB
  * in flight per SM; the plan holds the tensor maps), fragments are read with ldmatrix, mma.sync.m16n8k16 accumulates in fp32;
  * row blocks shared by several CTAs are combined through the workspace by the last CTA to arrive, in CTA order (deterministic).
- * tuning bit 4 selects the register kernel instead (weight rows streamed with 128-bit loads straight into MMA fragments, K split
- * over the warps of a CTA), bit 5 32-row blocks, bits 0-3 = 1 16-row CTAs of the register kernel.
+ * tuning (development / A-B): bit 4 selects the register kernel instead (weight rows streamed with 128-bit loads straight into
+ * MMA fragments, K split over the warps of a CTA), bit 5 32-row blocks, bit 7 forces 128-element K chunks (default: 256 when the
+ * ring keeps three stages), bit 12 fills the ring with cp.async from four producer warps instead of TMA, bits 8-11 cap the ring
+ * depth, bit 6 makes the consumers skip the arithmetic (pipeline ceiling; results are garbage), bits 0-3 = 1: 16-row CTAs of
+ * the register kernel.
  * The plan stays valid while the pointers in `desc` do (decode buffers are static, plans are built once per cache).
  * workspace: device memory of mc_skinny_workspace_bytes() bytes, ZEROED once by the caller and then left alone (the kernel
  * restores it); launches that may run concurrently need separate workspaces. */
@@ -433,6 +436,13 @@ MC_API int mc_decode_attention(const void* q, const void* k_cache, const void* v
                         const uint8_t* key_mask, int64_t ld_mask, void* out, int64_t ld_q, int64_t ld_out, int batch,
                         int n_heads, int head_dim, float softmax_scale, int n_splits, float* scratch, int32_t* counters,
                         int dtype, mc_stream_t stream);
+
+/* Launch mode of the CALLING THREAD for the decode-chain entry points (mc_gather_rows, mc_rmsnorm, mc_skinny_plan_run,
+ * mc_decode_rope_append, mc_decode_attention, mc_argmax_rows): bit 0 = programmatic dependent launch — each kernel may become
+ * resident while its predecessor in the stream still runs, prefetches what does not depend on it (the skinny-linear kernel its
+ * first ring of weight tiles) and waits (griddepcontrol.wait) before touching anything a predecessor writes.  Only for a chain
+ * in which EVERY kernel is one of the above (the decode step); returns the previous mode.  Captured CUDA graphs keep the edges. */
+MC_API int mc_set_launch_mode(int flags);
 
 /* out[m] = index of the largest logit of row m (first index on ties), as int32 and / or int64: the greedy sampler of
  * generate() (HF greedy_search behind modelcompose/eval/model_multimodal_qa_loader.py:93-102), kept on the device so a decode

@@ -21,6 +21,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+int& launch_mode() {
+  static thread_local int mode = 0;
+  return mode;
+}
+
 int sm_count() {
   static std::mutex mu;
   static int cache[64];
@@ -40,6 +45,12 @@ int sm_count() {
 extern "C" int mc_abi_version(void) { return MC_ABI_VERSION; }
 
 extern "C" const char* mc_last_error(void) { return mc::last_error().c_str(); }
+
+extern "C" int mc_set_launch_mode(int flags) {
+  const int old = mc::launch_mode();
+  mc::launch_mode() = flags;
+  return old;
+}
 
 extern "C" int mc_device_info(char* name, size_t cap, int* sms, int* cc) {
   int dev = 0;

@@ -33,6 +33,32 @@ int fail(int code, const char* fmt, ...);
 // per-device SM count (cached)
 int sm_count();
 
+// ---- programmatic dependent launch (decode chain) ---------------------------------------------
+// mc_set_launch_mode(1) makes the decode-chain entry points of the calling thread launch their kernels with
+// cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's CTAs may then become resident while its predecessor in the
+// stream is still running (every kernel of the chain calls griddepcontrol.launch_dependents first thing), run whatever does
+// not depend on the predecessor — barrier setup, descriptor fetch, and in the skinny-linear kernel the first ring of WEIGHT
+// loads — and block in griddepcontrol.wait before touching anything a predecessor writes.  Without the attribute both
+// instructions are no-ops, so the same kernels serve the ordinary launches.
+int& launch_mode();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (launch_mode() & 1) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline size_t dtype_size(int dt) { return dt == MC_F32 ? 4 : 2; }
 inline bool dtype_valid(int dt) { return dt == MC_F32 || dt == MC_F16 || dt == MC_BF16; }
 
@@ -92,6 +118,9 @@ __device__ __forceinline__ void st_stream(Vec<32>* p, const Vec<32>& v) {
                "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
                : "memory");
 }
+
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- device: scalar conversions with defined rounding ---------------------------------------
 template <typename T>

@@ -173,6 +173,8 @@ template <int RT, int NT, bool F16>
 __global__ void __launch_bounds__(kSkThreads) skinny_linear_kernel(const __grid_constant__ SkParams P) {
   extern __shared__ float sk_red[];  // [kSkWarps][8 NT][16 RT + 1]
   constexpr int FT = 16 * RT, MT = 8 * NT, LDR = FT + 1;
+  griddep_launch_dependents();
+  griddep_wait();
   int p = 0, first = 0;
   while (p < P.n_prob - 1 && (int)blockIdx.x >= P.prob[p].cta_end) {
     first = P.prob[p].cta_end;
@@ -259,8 +261,8 @@ __global__ void __launch_bounds__(kSkThreads) skinny_linear_kernel(const __grid_
 // row block their partial sums meet in shared memory.  A row block whose K range is shared by several CTAs goes through a
 // scratch tile per CTA; the last CTA to arrive adds the partial tiles in CTA order (deterministic) and runs the epilogue.
 constexpr int kS2Consumers = 8;
-constexpr int kS2Threads = (kS2Consumers + 1) * 32;
-constexpr int kS2KC = 128;     // K elements per chunk = two 64-element TMA boxes
+constexpr int kS2Producers = 4;  // producer warps (cp.async path; the TMA path uses one lane of the first)
+constexpr int kS2Threads = (kS2Consumers + kS2Producers) * 32;
 constexpr int kS2MaxStages = 12;
 constexpr int kS2TileFloats = MC_SKINNY_MAX_M * 64;  // scratch tile: [M][R] fp32, R <= 64
 
@@ -279,6 +281,7 @@ struct alignas(64) S2Params {
   int n_prob, total_iters, span, stages, xslots, stage_bytes;
   int nh;          // 64-element TMA boxes per K chunk (2: 128-element chunks, 4: 256)
   int copy_only;   // profiling aid: consumers release the stages without reading them (pipeline ceiling)
+  int use_tma;     // 1: stages filled by TMA tensor loads (one lane issues); 0: by cp.async from four producer warps
   float* scratch;  // [grid][2][kS2TileFloats]
   int* counters;   // [total row blocks], zero between launches
 };
@@ -311,6 +314,12 @@ __device__ __forceinline__ void s2_advance(const S2Params& P, S2Iter& w) {
   }
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
@@ -342,9 +351,10 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int it0 = min((int)blockIdx.x * P.span, P.total_iters), it1 = min(it0 + P.span, P.total_iters);
+  griddep_launch_dependents();  // decode chain: the next kernel may become resident as soon as every CTA of this one runs
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(full + s, 1);
+      mbar_init(full + s, P.use_tma ? 1 : kS2Producers * 32);
       mbar_init(empty + s, kS2Consumers);
     }
     fence_barrier_init();
@@ -352,13 +362,14 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
   __syncthreads();
   if (it0 >= it1) return;
 
-  if (warp == kS2Consumers) {
-    // ------------------------------------------------------------------------------------------------ producer
-    S2Iter w = s2_locate(P, it0);
-    for (int it = it0, i = 0; it < it1; ++it, ++i) {
-      const int s = i % P.stages;
-      const uint32_t ph = (uint32_t)(i / P.stages) & 1u;
-      mbar_wait(empty + s, ph ^ 1u);
+  if (warp >= kS2Consumers) {
+    // ------------------------------------------------------------------------------------------------ producers
+    if (P.use_tma && warp != kS2Consumers) return;
+    const int pt = threadIdx.x - kS2Consumers * 32;  // 0 .. 127 (cp.async path)
+    const int ppr = 8 * P.nh;                         // 16-byte pieces per row of a stage
+    // fills stage ii % stages with iteration `w`; parts: 1 = weights (+ the barrier's byte count), 2 = activations, 3 = both
+    auto fill = [&](int ii, const S2Iter& w, int parts) {
+      const int s = ii % P.stages;
       const S2Problem& q = P.prob[w.p];
       const SkProblem& pr = q.pr;
       const bool dual = pr.epilogue == MC_SKINNY_EPI_SILU_MUL;
@@ -368,28 +379,79 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
       const int halves = min(P.nh, (K - k0 + 63) >> 6);
       const int F = dual ? R / 2 : R, n0 = w.rb * F;
       const int nx = (dual && phase) ? 2 : 1;
-      if (elect_one()) {
-        unsigned char* st = ring + (size_t)s * P.stage_bytes;
-        mbar_expect_tx(full + s, (uint32_t)halves * (W_HALF + (uint32_t)nx * X_HALF));
-        for (int h = 0; h < halves; ++h) {
-          const int k = k0 + 64 * h;
-          if (dual) {
-            tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
-            tma_load_2d(phase ? &q.tmB1u : &q.tmB0u, full + s, st + h * W_HALF + W_HALF / 2, k, n0);
-          } else {
-            tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
+      unsigned char* st = ring + (size_t)s * P.stage_bytes;
+      if (P.use_tma) {
+        if (elect_one()) {
+          if (parts & 1) mbar_expect_tx(full + s, (uint32_t)halves * (W_HALF + (uint32_t)nx * X_HALF));
+          for (int h = 0; h < halves; ++h) {
+            const int k = k0 + 64 * h;
+            if (parts & 1) {
+              if (dual) {
+                tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
+                tma_load_2d(phase ? &q.tmB1u : &q.tmB0u, full + s, st + h * W_HALF + W_HALF / 2, k, n0);
+              } else {
+                tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
+              }
+            }
+            if (parts & 2) {
+              tma_load_2d(phase ? &q.tmA1 : &q.tmA0, full + s, st + X_BASE + h * X_HALF, k, 0);
+              if (nx == 2) tma_load_2d(&q.tmA1u, full + s, st + X_BASE + X_SLOT + h * X_HALF, k, 0);
+            }
           }
-          tma_load_2d(phase ? &q.tmA1 : &q.tmA0, full + s, st + X_BASE + h * X_HALF, k, 0);
-          if (nx == 2) tma_load_2d(&q.tmA1u, full + s, st + X_BASE + X_SLOT + h * X_HALF, k, 0);
         }
+        __syncwarp();
+      } else {
+        // LSU path (A/B only, 3-4x slower): 16-byte cp.async pieces written in the layout TMA's 128-byte swizzle would produce
+        // (unit ^= row & 7).  Rows past N / M and pieces past K are zero-filled (src-size 0).
+        const uint32_t st_u32 = smem_u32(st);
+        const long long ldw = phase ? pr.ldb1 : pr.ldb0, ldx = phase ? pr.lda1 : pr.lda0;
+        for (int pc = pt; pc < R * ppr; pc += kS2Producers * 32) {
+          const int r = pc / ppr, u16 = pc % ppr, h = u16 >> 3, u = u16 & 7;
+          const bool second = dual && r >= R / 2;
+          const char* wb = second ? (phase ? pr.B1u : pr.B0u) : (phase ? pr.B1 : pr.B0);
+          const int row = n0 + (dual ? r % (R / 2) : r), k = k0 + u16 * 8;
+          const bool ok = row < pr.N && k < K;
+          const char* src = ok ? wb + row * ldw + 2ll * k : wb;
+          cp_async16(st_u32 + (uint32_t)h * W_HALF + (uint32_t)r * 128u + (uint32_t)((u ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+        }
+        for (int pc = pt; pc < nx * MT * ppr; pc += kS2Producers * 32) {
+          const int slot = pc / (MT * ppr), rem = pc % (MT * ppr);
+          const int m = rem / ppr, u16 = rem % ppr, h = u16 >> 3, u = u16 & 7;
+          const char* xb = slot ? pr.A1u : (phase ? pr.A1 : pr.A0);
+          const int k = k0 + u16 * 8;
+          const bool ok = m < pr.M && k < K;
+          const char* src = ok ? xb + m * ldx + 2ll * k : xb;
+          cp_async16(st_u32 + X_BASE + (uint32_t)slot * X_SLOT + (uint32_t)h * X_HALF + (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) << 4),
+                     src, ok ? 16u : 0u);
+        }
+        cp_async_arrive(full + s);  // arrives once this thread's copies above have landed
       }
-      __syncwarp();
+    };
+    // Weights do not depend on the predecessor kernel: in the TMA path the first ring of weight boxes is requested BEFORE
+    // griddepcontrol.wait (under programmatic dependent launch this CTA may be running while the previous kernel of the decode
+    // chain still is), the activation boxes of those stages right after it.
+    const int pre = P.use_tma ? min(P.stages, it1 - it0) : 0;
+    S2Iter w = s2_locate(P, it0);
+    for (int i = 0; i < pre; ++i) {
+      fill(i, w, 1);
+      s2_advance(P, w);
+    }
+    griddep_wait();
+    w = s2_locate(P, it0);
+    for (int i = 0; i < pre; ++i) {
+      fill(i, w, 2);
+      s2_advance(P, w);
+    }
+    for (int i = pre; i < it1 - it0; ++i) {
+      mbar_wait(empty + i % P.stages, ((uint32_t)(i / P.stages) & 1u) ^ 1u);
+      fill(i, w, 3);
       s2_advance(P, w);
     }
     return;
   }
 
   // -------------------------------------------------------------------------------------------------- consumers
+  griddep_wait();
   const int tp = warp % TP, kp = warp / TP, g = lane >> 2, t = lane & 3;
   const int tid = threadIdx.x;  // 0 .. 255
   float acc[2][NT][4];
@@ -564,6 +626,8 @@ __global__ void __launch_bounds__(256)
 decode_rope_append_kernel(T* __restrict__ q, const T* __restrict__ k_new, const T* __restrict__ v_new, long long ld,
                           T* __restrict__ k_cache, T* __restrict__ v_cache, long long capacity, const int* __restrict__ d_pos,
                           const T* __restrict__ cos_t, const T* __restrict__ sin_t, int batch, int n_heads, int head_dim) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int half = head_dim >> 1, vec = half >> 3;
   const int total = batch * n_heads * vec;
   const int pos = *d_pos;
@@ -619,6 +683,8 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const __gr
   __shared__ float sm_acc[8][kDaD];
   __shared__ float sm_m[8], sm_l[8];
   __shared__ int sm_last;
+  griddep_launch_dependents();
+  griddep_wait();
   const int bh = blockIdx.x, b = bh / P.n_heads, h = bh % P.n_heads, split = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, l16 = lane & 15, hw = tid >> 4;
   const int L = *P.d_pos + 1;
@@ -758,6 +824,8 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const T* __restrict__ 
                                                           long long* __restrict__ out_i64, int* __restrict__ counter) {
   __shared__ float sv[8];
   __shared__ int si[8];
+  griddep_launch_dependents();
+  griddep_wait();
   const T* row = logits + (long long)blockIdx.x * ld;
   float best = -INFINITY;
   int idx = 0x7fffffff;
@@ -823,8 +891,7 @@ static cudaError_t launch_skinny(const SkParams& P, int grid, cudaStream_t strea
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  skinny_linear_kernel<RT, NT, F16><<<grid, kSkThreads, smem, stream>>>(P);
-  return cudaGetLastError();
+  return launch_kernel(skinny_linear_kernel<RT, NT, F16>, dim3(grid), dim3(kSkThreads), smem, stream, P);
 }
 
 template <int RT, bool F16>
@@ -847,8 +914,7 @@ static cudaError_t launch_streamk(const S2Params& P, int grid, size_t smem, cuda
     if (e != cudaSuccess) return e;
     configured[dev] = true;
   }
-  skinny_streamk_kernel<RT, NT, F16><<<grid, kS2Threads, smem, stream>>>(P);
-  return cudaGetLastError();
+  return launch_kernel(skinny_streamk_kernel<RT, NT, F16>, dim3(grid), dim3(kS2Threads), smem, stream, P);
 }
 
 template <int RT, bool F16>
@@ -957,8 +1023,16 @@ extern "C" int mc_skinny_plan_create(mc_skinny_plan_t** out, const mc_skinny_des
     const int R = 16 * p->rt2, MT = 8 * p->nt;
     S2Params& Q = p->sk;
     Q.n_prob = n_problems;
-    Q.nh = ((tuning >> 7) & 1) ? 4 : 2;          // tuning bit 7: 256-element K chunks
+    // K chunk: 256 elements (four TMA boxes per operand and stage: 512 contiguous bytes per weight row) when the ring still gets
+    // three stages, else 128; tuning bit 7 forces 128.  Measured (profiles/r02_decode.txt): 256 is 10-20 % faster at M <= 32.
     Q.copy_only = (tuning >> 6) & 1;              // tuning bit 6: profiling aid, results are garbage
+    Q.use_tma = ((tuning >> 12) & 1) ? 0 : 1;     // tuning bit 12: cp.async producer warps instead of TMA (slower: kept for A/B)
+    Q.xslots = dual_k1 ? 2 : 1;
+    {
+      const size_t fixed256 = 1024 + 256 + (size_t)kS2Consumers * MT * 33 * 4 + (size_t)MT * (R + 1) * 4;
+      const size_t stage256 = 4 * (size_t)(R * 128 + Q.xslots * MT * 128);
+      Q.nh = (!((tuning >> 7) & 1) && (227 * 1024 - fixed256) / stage256 >= 3) ? 4 : 2;
+    }
     const int kc_elems = 64 * Q.nh;
     int iters = 0, rbs = 0;
     for (int i = 0; i < n_problems && rc == MC_OK; ++i) {
@@ -988,7 +1062,6 @@ extern "C" int mc_skinny_plan_create(mc_skinny_plan_t** out, const mc_skinny_des
       return rc;
     }
     Q.total_iters = iters;
-    Q.xslots = dual_k1 ? 2 : 1;
     Q.stage_bytes = Q.nh * (R * 128 + Q.xslots * MT * 128);
     const size_t fixed = 1024 + 256 + (size_t)kS2Consumers * MT * 33 * 4 + (size_t)MT * (R + 1) * 4;
     Q.stages = (int)std::min<size_t>(kS2MaxStages, (227 * 1024 - fixed) / Q.stage_bytes);
@@ -1048,14 +1121,14 @@ extern "C" int mc_decode_rope_append(void* q, const void* k_new, const void* v_n
   const int total = batch * n_heads * (head_dim / 16);
   const int grid = (total + 255) / 256;
   if (dtype == MC_BF16)
-    decode_rope_append_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (__nv_bfloat16*)q, (const __nv_bfloat16*)k_new, (const __nv_bfloat16*)v_new, ld_qkv, (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache,
-        capacity, d_pos, (const __nv_bfloat16*)cos_table, (const __nv_bfloat16*)sin_table, batch, n_heads, head_dim);
+    MC_CUDA_OK(launch_kernel(decode_rope_append_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (__nv_bfloat16*)q,
+                             (const __nv_bfloat16*)k_new, (const __nv_bfloat16*)v_new, (long long)ld_qkv, (__nv_bfloat16*)k_cache,
+                             (__nv_bfloat16*)v_cache, (long long)capacity, (const int*)d_pos, (const __nv_bfloat16*)cos_table,
+                             (const __nv_bfloat16*)sin_table, batch, n_heads, head_dim));
   else
-    decode_rope_append_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (__half*)q, (const __half*)k_new, (const __half*)v_new, ld_qkv, (__half*)k_cache, (__half*)v_cache, capacity, d_pos,
-        (const __half*)cos_table, (const __half*)sin_table, batch, n_heads, head_dim);
-  MC_CUDA_OK(cudaGetLastError());
+    MC_CUDA_OK(launch_kernel(decode_rope_append_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (__half*)q, (const __half*)k_new,
+                             (const __half*)v_new, (long long)ld_qkv, (__half*)k_cache, (__half*)v_cache, (long long)capacity,
+                             (const int*)d_pos, (const __half*)cos_table, (const __half*)sin_table, batch, n_heads, head_dim));
   return MC_OK;
 }
 
@@ -1077,9 +1150,8 @@ extern "C" int mc_decode_attention(const void* q, const void* k_cache, const voi
   P.n_heads = n_heads; P.n_splits = n_splits;
   P.scale_log2e = softmax_scale * 1.4426950408889634f;
   const dim3 grid((unsigned)(batch * n_heads), (unsigned)n_splits);
-  if (dtype == MC_BF16) decode_attention_kernel<__nv_bfloat16><<<grid, kDaThreads, 0, (cudaStream_t)stream>>>(P);
-  else decode_attention_kernel<__half><<<grid, kDaThreads, 0, (cudaStream_t)stream>>>(P);
-  MC_CUDA_OK(cudaGetLastError());
+  if (dtype == MC_BF16) MC_CUDA_OK(launch_kernel(decode_attention_kernel<__nv_bfloat16>, grid, dim3(kDaThreads), 0, (cudaStream_t)stream, P));
+  else MC_CUDA_OK(launch_kernel(decode_attention_kernel<__half>, grid, dim3(kDaThreads), 0, (cudaStream_t)stream, P));
   return MC_OK;
 }
 
@@ -1090,9 +1162,10 @@ extern "C" int mc_argmax_rows(const void* logits, int64_t ld, int rows, int cols
   MC_REQUIRE(rows >= 0 && cols >= 1 && ld >= cols && ld % 8 == 0 && ((uintptr_t)logits & 15) == 0, "argmax: bad shape or alignment");
   if (rows == 0) return MC_OK;
   if (dtype == MC_BF16)
-    argmax_rows_kernel<__nv_bfloat16><<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, ld, cols, out_i32, (long long*)out_i64, d_counter);
+    MC_CUDA_OK(launch_kernel(argmax_rows_kernel<__nv_bfloat16>, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)logits,
+                             (long long)ld, cols, (int*)out_i32, (long long*)out_i64, (int*)d_counter));
   else
-    argmax_rows_kernel<__half><<<rows, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, ld, cols, out_i32, (long long*)out_i64, d_counter);
-  MC_CUDA_OK(cudaGetLastError());
+    MC_CUDA_OK(launch_kernel(argmax_rows_kernel<__half>, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __half*)logits, (long long)ld,
+                             cols, (int*)out_i32, (long long*)out_i64, (int*)d_counter));
   return MC_OK;
 }

@@ -16,6 +16,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__ out, long long rows, int hidden,
                long long ldx, long long ldo, float eps) {
+  griddep_launch_dependents();  // decode chain (mc_set_launch_mode): no-ops in an ordinary launch
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   const int n_vec = hidden >> 3;
@@ -103,6 +105,8 @@ rope_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ cos_t, c
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const char* __restrict__ src, long long ld_src, char* __restrict__ dst, long long ld_dst,
                    const int* __restrict__ index, long long rows, int n_vec) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
@@ -134,9 +138,8 @@ extern "C" int mc_gather_rows(const void* src, int64_t ld_src_bytes, void* dst, 
   const int sms = sm_count();
   MC_REQUIRE(sms > 0, "no CUDA device");
   const int grid = (int)std::min<long long>((rows + 7) / 8, (long long)sms * 32);
-  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const char*)src, ld_src_bytes, (char*)dst, ld_dst_bytes, index, rows,
-                                                             row_bytes / 16);
-  MC_CUDA_OK(cudaGetLastError());
+  MC_CUDA_OK(launch_kernel(gather_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const char*)src, (long long)ld_src_bytes,
+                           (char*)dst, (long long)ld_dst_bytes, (const int*)index, (long long)rows, row_bytes / 16));
   return MC_OK;
 }
 
@@ -151,12 +154,11 @@ extern "C" int mc_rmsnorm(const void* x, const void* weight, void* out, int64_t 
   MC_REQUIRE(sms > 0, "no CUDA device");
   const int grid = (int)std::min<long long>((rows + 7) / 8, (long long)sms * 32);
   if (dtype == MC_BF16)
-    rmsnorm_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)weight,
-                                                                         (__nv_bfloat16*)out, rows, hidden, ldx, ldo, eps);
+    MC_CUDA_OK(launch_kernel(rmsnorm_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x,
+                             (const __nv_bfloat16*)weight, (__nv_bfloat16*)out, (long long)rows, hidden, (long long)ldx, (long long)ldo, eps));
   else
-    rmsnorm_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)x, (const __half*)weight, (__half*)out, rows,
-                                                                   hidden, ldx, ldo, eps);
-  MC_CUDA_OK(cudaGetLastError());
+    MC_CUDA_OK(launch_kernel(rmsnorm_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (const __half*)weight,
+                             (__half*)out, (long long)rows, hidden, (long long)ldx, (long long)ldo, eps));
   return MC_OK;
 }
 

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -26,6 +27,9 @@ from . import linear as LN
 
 SK_NONE, SK_RESIDUAL, SK_COLSCALE, SK_SILU_MUL = 0, 1, 2, 3
 MAX_M = 64
+# programmatic dependent launch along the decode chain (mc_set_launch_mode): every kernel of the step may start while its
+# predecessor still runs and the skinny linears prefetch their first ring of weights before they wait for it; 0 = plain launches
+PDL = os.environ.get("MC_DECODE_PDL", "1") != "0"
 
 
 class SkinnyDesc(C.Structure):
@@ -158,6 +162,7 @@ class DecodeWorkspace:
         self.cache_ptrs = tuple(t.data_ptr() for t in cache.k)
         self.key_mask = key_mask  # uint8 [B, capacity] or None
         self.use_graph = use_graph
+        self.pdl = PDL
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.warm = 0
 
@@ -170,9 +175,10 @@ class DecodeWorkspace:
         self.q, self.k, self.v, self.attn = buf(B, H), buf(B, H), buf(B, H), buf(B, H)
         self.act = buf(B, I)
         self.logits = buf(B, V)
-        # split the keys of a (sequence, head) over CTAs until every SM has ~4 of them
+        # split the keys of a (sequence, head) over CTAs so that ONE wave fills the GPU: 7 CTAs of the attention kernel fit an SM
+        # (72 registers x 128 threads), and a count just under 7 x SMs measured best (B = 32: 1 split, 16: 2, 8: 3-4, 1: 32)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        self.n_splits = max(1, min(16, -(-4 * sms // (B * nH)), max(1, self.capacity // 256)))
+        self.n_splits = max(1, min(32, (7 * sms) // (B * nH), max(1, self.capacity // 64)))
         self.att_scratch = buf(B * nH * self.n_splits * (D + 2), dtype=torch.float32)
         self.att_counters = buf(B * nH, dtype=torch.int32)
         ws = skinny_workspace(dev)
@@ -243,6 +249,13 @@ class DecodeWorkspace:
 
     def _enqueue(self) -> None:
         """All launches of one step on the current stream (this is what the graph records)."""
+        prev = _cabi.lib().mc_set_launch_mode(1 if self.pdl else 0)
+        try:
+            self._enqueue_chain()
+        finally:
+            _cabi.lib().mc_set_launch_mode(prev)
+
+    def _enqueue_chain(self) -> None:
         m = self.model
         LN.gather_rows(m.embed_tokens, self.ids, self.x)
         for li, (layer, L) in enumerate(zip(m.layers, self.launches)):

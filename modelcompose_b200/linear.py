@@ -24,6 +24,10 @@ K_BLOCK = 64
 
 
 _PROFILE = None  # list of (start, end) CUDA events around every linear launch while profiling is on
+# development switch: 1 = row-per-thread epilogues everywhere (tuning bit 17), the round-1 form, for A/B runs against the
+# coalesced shared-memory-transposed NONE / RESIDUAL / SILU_MUL epilogues
+import os as _os
+EPI_ROWWISE = _os.environ.get("MC_LINEAR_EPI_ROWWISE", "0") != "0"
 
 
 def start_profile() -> None:
@@ -158,8 +162,8 @@ class LinearPlan:
                 d.c_rowmap = p.c_rowmap.data_ptr()
             self._keep.append(p)
         self._h = C.c_void_p()
-        _cabi.check(_cabi.lib().mc_linear_plan_create(C.byref(self._h), descs, len(problems), _cabi.dtype_code(dtype), tuning),
-                    "mc_linear_plan_create")
+        _cabi.check(_cabi.lib().mc_linear_plan_create(C.byref(self._h), descs, len(problems), _cabi.dtype_code(dtype),
+                                                      int(tuning) | ((1 << 17) if EPI_ROWWISE else 0)), "mc_linear_plan_create")
 
     @property
     def flops(self) -> float:

@@ -36,7 +36,7 @@ def rnd(shape, g, dtype, std=1.0):
 
 # ------------------------------------------------------------------------------------------------------ skinny linear
 @pytest.mark.parametrize("key", list(DTYPES))
-@pytest.mark.parametrize("tuning", [0, 16, 17, 32])
+@pytest.mark.parametrize("tuning", [0, 16, 17, 32, 128, 4096, 4096 | 128])
 @pytest.mark.parametrize("M,N,K0,K1", [(1, 64, 128, 0), (5, 200, 256, 64), (8, 4096, 1024, 384), (16, 136, 688, 48), (17, 256, 4096, 0),
                                        (32, 512, 2048, 384), (33, 328, 640, 128), (64, 1024, 1024, 64), (3, 72, 72, 24)])
 def test_skinny_linear_vs_fp32(key, tuning, M, N, K0, K1):
@@ -66,7 +66,7 @@ def test_skinny_linear_vs_fp32(key, tuning, M, N, K0, K1):
 
 
 @pytest.mark.parametrize("key", list(DTYPES))
-@pytest.mark.parametrize("tuning", [0, 16, 32])
+@pytest.mark.parametrize("tuning", [0, 16, 32, 128, 4096])
 @pytest.mark.parametrize("M,N,K0,K1", [(4, 96, 256, 0), (32, 11008, 4096, 384), (20, 688, 256, 16), (64, 344, 512, 64)])
 def test_skinny_dual_silu_mul(key, tuning, M, N, K0, K1):
     """gate/up in one launch: silu(gate) * up with gate, silu(gate), up each rounded to the storage dtype (the prefill's rounding points)."""
@@ -97,7 +97,7 @@ def test_skinny_multi_problem_qkv_and_kernel_agreement():
     ts = [rnd((M, R0), g, dt) for _ in range(3)]
     Bs = [rnd((H, R0), g, dt, R0 ** -0.5) for _ in range(3)]
     outs = {}
-    for tuning in (0, 16, 32):
+    for tuning in (0, 16, 32, 128, 4096):
         o = [torch.empty((M, H), dtype=dt, device="cuda") for _ in range(3)]
         DC.SkinnyLaunch([dict(A0=x, B0=Ws[i], A1=ts[i], B1=Bs[i], C=o[i]) for i in range(3)], tuning).run()
         outs[tuning] = o
@@ -263,6 +263,27 @@ def test_decode_graph_equals_eager_and_prefill_kernel_path(golden, monkeypatch):
         monkeypatch.undo()
     assert torch.equal(outs["graph"], outs["eager"])
     logits_close(outs["graph"], outs["prefill-kernels"], "bf16", "decode kernels vs the prefill kernels at M = batch")
+
+
+def test_programmatic_dependent_launch_is_bit_identical(golden, monkeypatch):
+    """The decode chain launched with programmatic dependent launch (kernels overlap their predecessors' tails, weights
+    prefetched before griddepcontrol.wait) against plain stream-ordered launches: same bits, graph and eager."""
+    dtype = torch.bfloat16
+    ids, feats = _prompt(4, dtype, seed=6)
+    outs = {}
+    for pdl in (True, False):
+        for graph in (True, False):
+            monkeypatch.setattr(DC, "PDL", pdl)
+            monkeypatch.setattr(MD, "DECODE_GRAPH", graph)
+            model = d128_model(golden, dtype)
+            outs[(pdl, graph)] = model.generate(ids, modal_inputs=feats, max_new_tokens=12, do_sample=False)
+            logits = model._dws.logits.clone()
+            outs[(pdl, graph, "logits")] = logits
+            assert model._dws.pdl == pdl and (model._dws.graph is not None) == graph
+            monkeypatch.undo()
+    for graph in (True, False):
+        assert torch.equal(outs[(True, graph)], outs[(False, graph)])
+        assert torch.equal(outs[(True, graph, "logits")], outs[(False, graph, "logits")])
 
 
 def test_padded_text_only_batch_keeps_pads_masked(golden):

@@ -36,8 +36,7 @@ def main():
     Wg, Wu = [w(I, H) for _ in range(n)], [w(I, H) for _ in range(n)]
     Wd = [w(H, I) for _ in range(n)]
     Wo = [w(H, H) for _ in range(3 * n)]
-    tunings = [("default", 0), ("copy-only", 64), ("kc256", 128), ("kc256 copy-only", 192), ("4 stages", 4 << 8), ("2 stages", 2 << 8),
-               ("4 stages copy-only", (4 << 8) | 64), ("R32", 32), ("register", 16)]
+    tunings = [("tma kc256 (default)", 0), ("tma kc128", 128), ("tma kc256 copy-only", 64), ("cp.async kc256", 4096), ("register", 16)]
     for M in (1, 16, 32, 64):
         x, xi = w(M, H), w(M, I)
         act, y = torch.empty((M, I), dtype=dt, device=dev), torch.empty((M, H), dtype=dt, device=dev)
@@ -55,7 +54,7 @@ def main():
             ls = [DC.SkinnyLaunch([dict(A0=x, B0=Wo[c], C=y)], tuning) for c in range(3 * n)]
             ms = timed(ls)
             row.append(f"o[4096x4096] {ls[0].bytes / ms / 1e6:6.0f} ({ms * 1e3:.1f} us)")
-            print(f"M={M:2d} {name:20s} | " + " | ".join(row) + "  GB/s", flush=True)
+            print(f"M={M:2d} {name:26s} | " + " | ".join(row) + "  GB/s", flush=True)
 
 
 if __name__ == "__main__":
