@@ -771,6 +771,12 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
     tokens = batch * S_out * world
     value = tokens / (ms_per_step * 1e-3)
 
+    if os.environ.get("MC_BENCH_NVTX"):  # profiling aid: one step inside an NVTX range (ncu --nvtx --nvtx-include "mc_prefill_step/")
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("mc_prefill_step")
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
     # ---- dominant kernel: the routed/grouped linear launches, timed with CUDA events on the launching stream
     LN.start_profile()
     for _ in range(2):
@@ -914,6 +920,13 @@ def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, worl
     value = batch * world / (ms_per_step * 1e-3)
     avg_len = len0 + (steps + 1) / 2.0
     w_bytes, kv_bytes = dws.weight_bytes, dws.cache_bytes(1) * avg_len
+    if os.environ.get("MC_BENCH_NVTX"):  # profiling aid: one decode step inside an NVTX range (ncu --nvtx --nvtx-include "mc_decode_step/")
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("mc_decode_step")
+        dws.run()
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        cache.length += 1
     # the dominant kernel alone: the skinny linears launched one by one with CUDA events around each (same buffers, no graph)
     ev = []
     dws_e = DC.DecodeWorkspace(model, cache, None, use_graph=False)

@@ -282,6 +282,7 @@ struct alignas(64) S2Params {
   int nh;          // 64-element TMA boxes per K chunk (2: 128-element chunks, 4: 256)
   int copy_only;   // profiling aid: consumers release the stages without reading them (pipeline ceiling)
   int use_tma;     // 1: stages filled by TMA tensor loads (one lane issues); 0: by cp.async from four producer warps
+  int x_lsu;       // TMA mode: 1 = the ACTIVATION boxes come through the LSU (cp.async from producer warps 1-3), TMA carries weights only
   float* scratch;  // [grid][2][kS2TileFloats]
   int* counters;   // [total row blocks], zero between launches
 };
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
   griddep_launch_dependents();  // decode chain: the next kernel may become resident as soon as every CTA of this one runs
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(full + s, P.use_tma ? 1 : kS2Producers * 32);
+      mbar_init(full + s, P.use_tma ? (P.x_lsu ? 1 + (kS2Producers - 1) * 32 : 1) : kS2Producers * 32);
       mbar_init(empty + s, kS2Consumers);
     }
     fence_barrier_init();
@@ -364,7 +365,41 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
 
   if (warp >= kS2Consumers) {
     // ------------------------------------------------------------------------------------------------ producers
-    if (P.use_tma && warp != kS2Consumers) return;
+    if (P.use_tma && warp != kS2Consumers) {
+      if (!P.x_lsu) return;
+      // ---- activation loaders (warps 1-3 of the producer group; tuning bit 14, an experiment kept for A/B): the x boxes of every
+      // stage through cp.async so that TMA carries weights only.  At M = 32 a third of the TMA bytes are activations re-read from
+      // L2 for every row block — but moving them to the LSU measured 12-20 % SLOWER (profiles/r02_decode.txt).
+      griddep_wait();
+      const int xt = threadIdx.x - (kS2Consumers + 1) * 32;  // 0 .. 95
+      constexpr int XT = (kS2Producers - 1) * 32;
+      const int ppr = 8 * P.nh, lg_ppr = P.nh == 4 ? 5 : 4;   // 16-byte pieces per activation row and stage (16 or 32)
+      S2Iter w = s2_locate(P, it0);
+      for (int i = 0; i < it1 - it0; ++i) {
+        const int s = i % P.stages;
+        mbar_wait(empty + s, ((uint32_t)(i / P.stages) & 1u) ^ 1u);
+        const S2Problem& q = P.prob[w.p];
+        const SkProblem& pr = q.pr;
+        const bool phase = w.kc >= q.nkc0;
+        const int kc = phase ? w.kc - q.nkc0 : w.kc, K = phase ? pr.K1 : pr.K0;
+        const int k0 = kc * KC;
+        const int nx = (pr.epilogue == MC_SKINNY_EPI_SILU_MUL && phase) ? 2 : 1;
+        const long long ldx = phase ? pr.lda1 : pr.lda0;
+        const uint32_t st_u32 = smem_u32(ring + (size_t)s * P.stage_bytes) + X_BASE;
+        for (int slot = 0; slot < nx; ++slot) {
+          const char* xb = slot ? pr.A1u : (phase ? pr.A1 : pr.A0);
+          for (int pc = xt; pc < pr.M * ppr; pc += XT) {
+            const int m = pc >> lg_ppr, u16 = pc & (ppr - 1), h = u16 >> 3, u = u16 & 7, k = k0 + u16 * 8;
+            const bool ok = k < K;  // past K: zeros (they meet the zeros TMA filled into the weight box)
+            cp_async16(st_u32 + (uint32_t)slot * X_SLOT + (uint32_t)h * X_HALF + (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) << 4),
+                       ok ? xb + m * ldx + 2ll * k : xb, ok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive(full + s);
+        s2_advance(P, w);
+      }
+      return;
+    }
     const int pt = threadIdx.x - kS2Consumers * 32;  // 0 .. 127 (cp.async path)
     const int ppr = 8 * P.nh;                         // 16-byte pieces per row of a stage
     // fills stage ii % stages with iteration `w`; parts: 1 = weights (+ the barrier's byte count), 2 = activations, 3 = both
@@ -382,7 +417,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
       unsigned char* st = ring + (size_t)s * P.stage_bytes;
       if (P.use_tma) {
         if (elect_one()) {
-          if (parts & 1) mbar_expect_tx(full + s, (uint32_t)halves * (W_HALF + (uint32_t)nx * X_HALF));
+          if (parts & 1) mbar_expect_tx(full + s, (uint32_t)halves * (W_HALF + (P.x_lsu ? 0u : (uint32_t)nx * X_HALF)));
           for (int h = 0; h < halves; ++h) {
             const int k = k0 + 64 * h;
             if (parts & 1) {
@@ -393,7 +428,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
                 tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
               }
             }
-            if (parts & 2) {
+            if ((parts & 2) && !P.x_lsu) {
               tma_load_2d(phase ? &q.tmA1 : &q.tmA0, full + s, st + X_BASE + h * X_HALF, k, 0);
               if (nx == 2) tma_load_2d(&q.tmA1u, full + s, st + X_BASE + X_SLOT + h * X_HALF, k, 0);
             }
@@ -1019,6 +1054,8 @@ extern "C" int mc_skinny_plan_create(mc_skinny_plan_t** out, const mc_skinny_des
       delete p;
       return fail(MC_ERR_CUDA, "no CUDA device");
     }
+    // row block: 64 weight rows; tuning bit 5: 32.  (128-row blocks — half the activation bytes per weight byte, but a ring of
+    // 2-4 stages — measured 10-25 % slower at M >= 16: profiles/r02_decode.txt)
     p->rt2 = ((tuning >> 5) & 1) ? 2 : 4;
     const int R = 16 * p->rt2, MT = 8 * p->nt;
     S2Params& Q = p->sk;
@@ -1027,6 +1064,7 @@ extern "C" int mc_skinny_plan_create(mc_skinny_plan_t** out, const mc_skinny_des
     // three stages, else 128; tuning bit 7 forces 128.  Measured (profiles/r02_decode.txt): 256 is 10-20 % faster at M <= 32.
     Q.copy_only = (tuning >> 6) & 1;              // tuning bit 6: profiling aid, results are garbage
     Q.use_tma = ((tuning >> 12) & 1) ? 0 : 1;     // tuning bit 12: cp.async producer warps instead of TMA (slower: kept for A/B)
+    Q.x_lsu = (tuning >> 14) & 1;                 // tuning bit 14: activation boxes through cp.async instead of TMA (measured slower)
     Q.xslots = dual_k1 ? 2 : 1;
     {
       const size_t fixed256 = 1024 + 256 + (size_t)kS2Consumers * MT * 33 * 4 + (size_t)MT * (R + 1) * 4;

@@ -36,7 +36,8 @@ def main():
     Wg, Wu = [w(I, H) for _ in range(n)], [w(I, H) for _ in range(n)]
     Wd = [w(H, I) for _ in range(n)]
     Wo = [w(H, H) for _ in range(3 * n)]
-    tunings = [("tma kc256 (default)", 0), ("tma kc128", 128), ("tma kc256 copy-only", 64), ("cp.async kc256", 4096), ("register", 16)]
+    tunings = [("W tma + x lsu (default)", 0), ("W tma + x tma", 1 << 14), ("R128, x lsu", 1 << 13), ("R128, x tma", (1 << 13) | (1 << 14)),
+               ("default copy-only", 64), ("register", 16)]
     for M in (1, 16, 32, 64):
         x, xi = w(M, H), w(M, I)
         act, y = torch.empty((M, I), dtype=dt, device=dev), torch.empty((M, H), dtype=dt, device=dev)
