@@ -1027,7 +1027,8 @@ def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, worl
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                      "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": int(w_bytes + kv_bytes), "weight_bytes": int(w_bytes), "kv_cache_bytes": int(kv_bytes),
-                     "kernel": "mc::skinny_streamk_kernel (stream-K skinny linears: cp.async.bulk ring -> ldmatrix -> mma.sync)",
+                     "kernel": "mc::skinny_streamk_kernel (persistent stream-K skinny linears: TMA box ring -> ldmatrix -> mma.sync.m16n8k16); attention: "
+                               "mc::decode_attention_kernel (split-KV, 16 lanes per key)",
                      "kernel_ms_per_step": round(lin_ms, 4), "kernel_share_of_step": round(lin_ms / ms_per_step, 4),
                      "kernel_achieved_GBps_on_weight_bytes": round(lin_achieved, 1), "kernel_frac": round(lin_achieved / peak, 4),
                      "kernel_timing": "event pairs around every skinny-linear launch of an ungraphed step (includes launch gaps)"},

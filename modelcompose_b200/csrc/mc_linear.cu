@@ -362,10 +362,6 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
 
 constexpr int kEpiStageBytes = 32 * 32 * 4;  // per epilogue warp: one 32-row x 32-column fp32 chunk
 
-template <int BN>
-__device__ __forceinline__ void epilogue_rope_staged(const LinProblem& pr, bool is_f16, uint32_t taddr, int row0, int lane, int m_end, int n0,
-                                                     float* stage);
-
 // NONE / RESIDUAL / SILU_MUL epilogues with COALESCED global accesses.  In epilogue_tile a thread owns an output row, so every
 // warp-level 16-byte load / store touches 32 different rows (32 lines): at 512 x 256 pair tiles the address-divergent accesses
 // of the eight epilogue warps, not the TMEM reads or the arithmetic, are what the non-overlapped epilogue costs (~17 k cycles per
@@ -377,10 +373,6 @@ template <int BN>
 __device__ __forceinline__ void epilogue_tile_staged(const LinProblem& pr, bool is_f16, uint32_t taddr, int row0, int lane, int m_end,
                                                      int n0, float* stage) {
   const int epi = pr.epilogue;
-  if (epi == MC_LINEAR_EPI_ROPE) {
-    epilogue_rope_staged<BN>(pr, is_f16, taddr, row0, lane, m_end, n0, stage);
-    return;
-  }
   const bool has_aux = epi == MC_LINEAR_EPI_RESIDUAL || epi == MC_LINEAR_EPI_SILU_MUL;
   const int piece = lane & 3;
   char* cptr[4];
@@ -449,107 +441,11 @@ __device__ __forceinline__ void epilogue_tile_staged(const LinProblem& pr, bool 
   }
 }
 
-// ROPE epilogue in the coalesced form: per head, the 32-column chunk c of the first half and its partner chunk c + D/2 go through the
-// warp's transpose buffer one after the other; in the coalesced domain (pass = 8 rows x 64 contiguous bytes) a lane holds both
-// values of its 8 rotation pairs, reads cos / sin of its row's position coalesced as well, and stores the two rotated pieces.
-// Same op sequence and rounding points as epilogue_tile's ROPE branch (bit-identical; tests/test_linear_gpu.py).
-template <int BN>
-__device__ __forceinline__ void epilogue_rope_staged(const LinProblem& pr, bool is_f16, uint32_t taddr, int row0, int lane, int m_end, int n0,
-                                                     float* stage) {
-  const int D = pr.rope_head_dim, half = D >> 1;
-  const int piece = lane & 3;
-  char* cptr[4];
-  const char* cosr[4];
-  bool ok[4];
-  const long long sin_minus_cos = reinterpret_cast<const char*>(pr.rope_sin) - reinterpret_cast<const char*>(pr.rope_cos);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = row0 + 8 * i + (lane >> 2);
-    ok[i] = r < m_end;
-    const int orow = (pr.c_rowmap && ok[i]) ? pr.c_rowmap[r] : r;
-    const int pos = (pr.rope_pos ? *pr.rope_pos : 0) + orow % pr.rope_seq_len;
-    cptr[i] = reinterpret_cast<char*>(pr.C) + ((long long)orow * pr.ldc + n0 + piece * 8) * 2;
-    cosr[i] = reinterpret_cast<const char*>(pr.rope_cos) + ((long long)pos * D + piece * 8) * 2;
-  }
-  float* my_row = stage + lane * 32;
-#pragma unroll 1
-  for (int h0 = 0; h0 < BN; h0 += D) {
-    if (n0 + h0 >= pr.N) break;  // warp-uniform (N is a multiple of head_dim)
-#pragma unroll 1
-    for (int c = 0; c < half; c += 32) {
-      uint32_t lo[32], hi[32];
-      tmem_ld_32x32(taddr + (uint32_t)(h0 + c), lo);
-      tmem_ld_32x32(taddr + (uint32_t)(h0 + half + c), hi);
-      tmem_ld_wait();
-      uint4 x1p[4];  // first-half values of this lane's pairs, already rounded to the storage dtype (the first thing RoPE does with them)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 2)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-      // cos / sin of this lane's rows (coalesced: 64 contiguous bytes per row and table), in flight while the transposes run
-      uint4 cv[4], sv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        cv[i] = make_uint4(0u, 0u, 0u, 0u);
-        sv[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (ok[i]) {
-          cv[i] = *reinterpret_cast<const uint4*>(cosr[i] + c * 2);
-          sv[i] = *reinterpret_cast<const uint4*>(cosr[i] + sin_minus_cos + c * 2);
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = 8 * i + (lane >> 2);
-        const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + (((2 * piece) ^ (rr & 7)) << 2));
-        const float4 b = *reinterpret_cast<const float4*>(stage + rr * 32 + (((2 * piece + 1) ^ (rr & 7)) << 2));
-        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        x1p[i] = pack8(f, is_f16);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 2)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = 8 * i + (lane >> 2);
-        const float4 a = *reinterpret_cast<const float4*>(stage + rr * 32 + (((2 * piece) ^ (rr & 7)) << 2));
-        const float4 b = *reinterpret_cast<const float4*>(stage + rr * 32 + (((2 * piece + 1) ^ (rr & 7)) << 2));
-        if (ok[i]) {
-          float x2[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          float x1[8], cs[8], sn[8], o1[8], o2[8], p1[8], p2[8], p3[8], p4[8];
-          unpack8(x1p[i], is_f16, x1);  // the linear's output, rounded to the storage dtype
-          unpack8(pack8(x2, is_f16), is_f16, x2);
-          unpack8(cv[i], is_f16, cs);
-          unpack8(sv[i], is_f16, sn);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            p1[e] = x1[e] * cs[e];
-            p2[e] = -x2[e] * sn[e];
-            p3[e] = x2[e] * cs[e];
-            p4[e] = x1[e] * sn[e];
-          }
-          unpack8(pack8(p1, is_f16), is_f16, p1);
-          unpack8(pack8(p2, is_f16), is_f16, p2);
-          unpack8(pack8(p3, is_f16), is_f16, p3);
-          unpack8(pack8(p4, is_f16), is_f16, p4);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            o1[e] = p1[e] + p2[e];
-            o2[e] = p3[e] + p4[e];
-          }
-          *reinterpret_cast<uint4*>(cptr[i] + (h0 + c) * 2) = pack8(o1, is_f16);
-          *reinterpret_cast<uint4*>(cptr[i] + (h0 + c + half) * 2) = pack8(o2, is_f16);
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
+// (A coalesced form of the ROPE epilogue — both halves of a rotation pair through the transpose buffer, cos / sin read coalesced —
+// was tried in round 2: bit-identical, but no gain on the q/k/v launch inside the step and, through register pressure in the
+// CTA-pair kernel (168 registers, spills), a loss on its other epilogues; profiles/r02_epilogue_ab.txt.  ROPE stays row-per-thread.)
 __device__ __forceinline__ bool epilogue_is_staged(const LinParams& P, const LinProblem& pr) {
-  return P.epi_staged && (pr.epilogue == MC_LINEAR_EPI_NONE || pr.epilogue == MC_LINEAR_EPI_RESIDUAL || pr.epilogue == MC_LINEAR_EPI_SILU_MUL ||
-                          pr.epilogue == MC_LINEAR_EPI_ROPE);
+  return P.epi_staged && (pr.epilogue == MC_LINEAR_EPI_NONE || pr.epilogue == MC_LINEAR_EPI_RESIDUAL || pr.epilogue == MC_LINEAR_EPI_SILU_MUL);
 }
 
 template <int BN, int STAGES>
