@@ -622,7 +622,10 @@ def run_ties(device, steps: int = 10, K: int = 20, func: str = "mean"):
                       "elements_per_source": d, "algorithmic_bytes": plan.algorithmic_bytes,
                       "passes": "1 sampling pass over 1/32 of the data + 1 counting pass + 1 merge pass over 3 sources, fp32 output"},
            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4),
-                        "traffic": None, "peak_source": peak_src, "kernel": "whole mc_ties_plan_run (sample, bracket, count, select, merge, fix-up)"},
+                        "traffic": measured_traffic("mc_ties_plan_run", 1, plan.algorithmic_bytes),
+                        "traffic_unit": "DRAM read+write bytes of one plan run summed over its kernels (ncu capture, profiles/traffic.json), scaled by "
+                                        "this run's algorithmic bytes",
+                        "peak_source": peak_src, "kernel": "whole mc_ties_plan_run (sample, bracket, count, select, merge, fix-up)"},
            "stats": st, "gpu_launches": 11 * steps}
     del plan, srcs, outs
     torch.cuda.empty_cache()
@@ -969,6 +972,13 @@ def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, worl
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = batch * world / (float(te.item()) / e_steps)
     finite = bool(torch.isfinite(o.logits).all())
+    # request 0 is the same on every rank and every kernel is deterministic: its decode logits must agree bit for bit (untimed)
+    verified = None
+    if world > 1:
+        probe0 = o.logits[0, 0, :].float().contiguous()
+        gathered = [torch.empty_like(probe0) for _ in range(world)]
+        dist.all_gather(gathered, probe0)
+        verified = all(torch.equal(g_, gathered[0]) for g_ in gathered)
     # ---- untimed parity check on the bench's own weights: decode steps of a short probe batch vs the prefill of the extended
     # sequence (the prefill path itself is checked against the oracle in this run).  The bar (that of tests/test_decode_gpu.py)
     # is applied to a 2-layer view of the model (same full-width weights): the two paths round at the same points but sum in a
@@ -1025,7 +1035,11 @@ def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, worl
                    "l2": "weights %.1f GB + cache %.1f GB per step, far larger than L2" % (w_bytes / 1e9, kv_bytes / 1e9),
                    "step": "one CUDA-graph replay: embedding gather, 32 layers, final norm, lm_head, greedy argmax"},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": (lambda a, b: None if a is None or b is None else int(a + b))(
+                         measured_traffic("mc::skinny_streamk_kernel", world, int(w_bytes)), measured_traffic("mc::decode_attention_kernel", world, int(kv_bytes))),
+                     "traffic_unit": "DRAM bytes per step: weight bytes x (traffic / algorithmic) of the ncu capture of the stream-K kernel + cache bytes x "
+                                     "that of the attention kernel (profiles/traffic.json)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_step": int(w_bytes + kv_bytes), "weight_bytes": int(w_bytes), "kv_cache_bytes": int(kv_bytes),
                      "kernel": "mc::skinny_streamk_kernel (persistent stream-K skinny linears: TMA box ring -> ldmatrix -> mma.sync.m16n8k16); attention: "
                                "mc::decode_attention_kernel (split-KV, 16 lanes per key)",
@@ -1036,7 +1050,9 @@ def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, worl
                 "steps": e_steps, "api": "MultimodalLlamaForCausalLM.forward(input_ids [B,1] from pinned host memory, past_key_values=cache); "
                 "greedy tokens copied back and synchronised every step", "timer": "host wall clock incl. synchronize, max over ranks"},
         "gpu_launches": int(launches) * world, "launches_per_step": dws.launches_per_step(),
-        "verification": {"finite_logits": finite, "decode_vs_prefill_check": check},
+        "verification": {"finite_logits": finite, "decode_vs_prefill_check": check, "probe_request_identical_across_ranks": verified,
+                         "collective": "ncclAllGather of request 0's decode logits after %d steps, outside the timed region" % (warmup + steps + e_steps)
+                         if world > 1 else None},
         "clocks": clocks.summary(),
     }
 

@@ -320,6 +320,17 @@ MC_API double mc_linear_plan_flops(const mc_linear_plan_t* plan);
 MC_API int mc_linear_plan_destroy(mc_linear_plan_t* plan);
 /* mtile_mask[t] = OR over rows of 128-row tile t of (1 << row_group[row]). */
 MC_API int mc_route_tile_masks(const uint8_t* d_row_group, int M, uint32_t* d_mtile_mask, mc_stream_t stream);
+/* Same with every tile of an aligned run of `coarsen` (1, 2 or 4) tiles carrying the union of the run: the CTA-pair kernels skip LoRA
+ * k-blocks per 256 / 512 rows, so the down-projection must have produced (zeros in) the rank columns of every group of the run. */
+MC_API int mc_route_tile_masks_coarse(const uint8_t* d_row_group, int M, uint32_t* d_mtile_mask, int coarsen, mc_stream_t stream);
+/* Modality-major row order of a batch (the order the routed / grouped linears run in: every 128-row tile holds one adapter
+ * group): a STABLE counting sort of the T = B * S' rows by routing group.  d_modal_id: device uint8 [T], the ids the splice emits
+ * (mc_splice_run: 0 = text, 1 + i = i-th spliced modality); lut: HOST uint8 [n_lut <= 16] mapping those ids to routing groups of
+ * the model (NULL = identity); outputs (device): perm[i] = sequence-order row held at buffer row i, inv_perm[t] = buffer row of
+ * sequence row t, row_group[i] = group of buffer row i, seg_start[0 .. n_groups] = first buffer row of every group (the
+ * segment table of the grouped GEMM), group_seq[t] (or NULL) = routing group of sequence row t.  One launch, no host sync. */
+MC_API int mc_route_permutation(const uint8_t* d_modal_id, int T, const uint8_t* lut, int n_lut, int n_groups, int32_t* d_perm,
+                         int32_t* d_inv_perm, uint8_t* d_row_group, int32_t* d_seg_start, uint8_t* d_group_seq, mc_stream_t stream);
 /* out = silu(gate) * up, elementwise over [rows, cols] (multimodal_llama.py:381-388; act rounded to the storage
  * dtype before the product, as the reference's separate ops do). */
 MC_API int mc_silu_mul(const void* gate, const void* up, void* out, int64_t rows, int cols, int64_t ld_gate, int64_t ld_up,

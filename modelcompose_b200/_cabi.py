@@ -55,6 +55,8 @@ SIGNATURES = {
     "mc_linear_plan_flops": (C.c_double, [_vp]),
     "mc_linear_plan_destroy": (_i, [_vp]),
     "mc_route_tile_masks": (_i, [_vp, _i, _vp, _vp]),
+    "mc_route_tile_masks_coarse": (_i, [_vp, _i, _vp, _i, _vp]),
+    "mc_route_permutation": (_i, [_vp, _i, C.c_char_p, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mc_silu_mul": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _i64, _i, _vp]),
     "mc_attention_causal": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i, C.c_float, _i, _vp]),
     "mc_attention_causal_tuned": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _i, _i, _i, _i, C.c_float, _i, _i, _vp]),

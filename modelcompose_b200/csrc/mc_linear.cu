@@ -250,35 +250,46 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float x1[8], x2[8], cs[8], sn[8], o1[8], o2[8], p1[8], p2[8], p3[8], p4[8];
+            // Packed 16-bit arithmetic reproduces the eager ops bit for bit: a product of two 16-bit floats is exact in fp32, so
+            // "fp32 product rounded to the storage dtype" is the single rounding of HMUL2; a sum of two 16-bit floats is exact in
+            // fp32 unless the exponents differ by more than 16, where both roundings return the larger operand, so HADD2 equals
+            // "fp32 sum rounded" (the _rn intrinsics keep ptxas from contracting product and sum into an FMA, which would skip the
+            // product's rounding).  6 packed instructions per element pair instead of ~20 fp32 operations and six conversions.
+            float x1[8], x2[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               x1[e] = __uint_as_float(lo[8 * j + e]);
               x2[e] = __uint_as_float(hi[8 * j + e]);
             }
-            unpack8(pack8(x1, is_f16), is_f16, x1);  // the linear's output, rounded to the storage dtype
-            unpack8(pack8(x2, is_f16), is_f16, x2);
-            unpack8(cv[j], is_f16, cs);
-            unpack8(sv[j], is_f16, sn);
+            const uint4 a = pack8(x1, is_f16), b = pack8(x2, is_f16);  // the linear's output, rounded to the storage dtype
+            uint4 o1, o2;
+            const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+            const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
+            const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cv[j]);
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sv[j]);
+            uint32_t* o1w = reinterpret_cast<uint32_t*>(&o1);
+            uint32_t* o2w = reinterpret_cast<uint32_t*>(&o2);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              p1[e] = x1[e] * cs[e];
-              p2[e] = -x2[e] * sn[e];
-              p3[e] = x2[e] * cs[e];
-              p4[e] = x1[e] * sn[e];
-            }
-            unpack8(pack8(p1, is_f16), is_f16, p1);
-            unpack8(pack8(p2, is_f16), is_f16, p2);
-            unpack8(pack8(p3, is_f16), is_f16, p3);
-            unpack8(pack8(p4, is_f16), is_f16, p4);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              o1[e] = p1[e] + p2[e];
-              o2[e] = p3[e] + p4[e];
+            for (int w = 0; w < 4; ++w) {
+              if (is_f16) {
+                const __half2 xa = *reinterpret_cast<const __half2*>(&aw[w]), xb = *reinterpret_cast<const __half2*>(&bw[w]);
+                const __half2 c2 = *reinterpret_cast<const __half2*>(&cw[w]), s2 = *reinterpret_cast<const __half2*>(&sw[w]);
+                const __half2 r1 = __hadd2_rn(__hmul2_rn(xa, c2), __hneg2(__hmul2_rn(xb, s2)));  // x1*cos + (-x2)*sin; _rn: never contracted into an FMA
+                const __half2 r2 = __hadd2_rn(__hmul2_rn(xb, c2), __hmul2_rn(xa, s2));           // x2*cos + x1*sin
+                o1w[w] = *reinterpret_cast<const uint32_t*>(&r1);
+                o2w[w] = *reinterpret_cast<const uint32_t*>(&r2);
+              } else {
+                const __nv_bfloat162 xa = *reinterpret_cast<const __nv_bfloat162*>(&aw[w]), xb = *reinterpret_cast<const __nv_bfloat162*>(&bw[w]);
+                const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&cw[w]), s2 = *reinterpret_cast<const __nv_bfloat162*>(&sw[w]);
+                const __nv_bfloat162 r1 = __hadd2_rn(__hmul2_rn(xa, c2), __hneg2(__hmul2_rn(xb, s2)));
+                const __nv_bfloat162 r2 = __hadd2_rn(__hmul2_rn(xb, c2), __hmul2_rn(xa, s2));
+                o1w[w] = *reinterpret_cast<const uint32_t*>(&r1);
+                o2w[w] = *reinterpret_cast<const uint32_t*>(&r2);
+              }
             }
             const int col = n0 + h0 + c + 8 * j;
-            *reinterpret_cast<uint4*>(crow + (long long)col * 2) = pack8(o1, is_f16);
-            *reinterpret_cast<uint4*>(crow + (long long)(col + half) * 2) = pack8(o2, is_f16);
+            *reinterpret_cast<uint4*>(crow + (long long)col * 2) = o1;
+            *reinterpret_cast<uint4*>(crow + (long long)(col + half) * 2) = o2;
           }
         }
       }
@@ -1065,15 +1076,96 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear3
 
 // ---- routing helpers ------------------------------------------------------------------------------------
 // mask[t] = OR over the rows of 128-row tile t of (1 << group[row])
-__global__ void route_tile_mask_kernel(const unsigned char* __restrict__ group, int M, unsigned int* __restrict__ mask, int n_tiles) {
+// coarsen = 2 / 4: every tile of an aligned run of 2 / 4 tiles gets the union of the run (the CTA-pair kernels skip LoRA k-blocks per
+// 256 / 512 rows)
+__global__ void route_tile_mask_kernel(const unsigned char* __restrict__ group, int M, unsigned int* __restrict__ mask, int n_tiles, int coarsen) {
   const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (tile >= n_tiles) return;
   unsigned int m = 0;
-  for (int r = tile * kBM + lane; r < min(M, (tile + 1) * kBM); r += 32) m |= 1u << (group[r] & 31);
+  const int first = tile / coarsen * coarsen;
+  for (int r = first * kBM + lane; r < min(M, (first + coarsen) * kBM); r += 32) m |= 1u << (group[r] & 31);
 #pragma unroll
   for (int d = 16; d; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
   if (lane == 0) mask[tile] = m;
+}
+
+// Modality-major row order of a batch: a STABLE counting sort of the T rows by routing group, one CTA.  Every thread owns a
+// contiguous run of rows (so the order inside a group is the sequence order), counts its rows per group, the per-group counts are
+// scanned over the threads, and a second walk over the run places the rows.  Replaces a library radix sort + bincount + cumsum +
+// two index kernels per batch.  lut (in parameter space) maps the splice's modality ids to routing groups.
+constexpr int kRouteThreads = 1024;
+constexpr int kRouteMaxGroups = MC_LINEAR_MAX_SEGMENTS;
+struct RouteLut {
+  unsigned char g[16];
+};
+__global__ void __launch_bounds__(kRouteThreads) route_permutation_kernel(const unsigned char* __restrict__ modal_id, int T, RouteLut lut, int n_groups,
+                                                                          int* __restrict__ perm, int* __restrict__ inv_perm,
+                                                                          unsigned char* __restrict__ row_group, int* __restrict__ seg_start,
+                                                                          unsigned char* __restrict__ group_seq) {
+  __shared__ int warp_tot[kRouteMaxGroups][32];
+  __shared__ int group_base[kRouteMaxGroups + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (T + kRouteThreads - 1) / kRouteThreads;
+  const int t0 = min(tid * per, T), t1 = min(t0 + per, T);
+  int cnt[kRouteMaxGroups];
+#pragma unroll
+  for (int g = 0; g < kRouteMaxGroups; ++g) cnt[g] = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int g = lut.g[modal_id[t] & 15];
+#pragma unroll
+    for (int k = 0; k < kRouteMaxGroups; ++k) cnt[k] += (g == k);
+  }
+  int start[kRouteMaxGroups];  // exclusive prefix of this thread's count inside the group
+#pragma unroll
+  for (int g = 0; g < kRouteMaxGroups; ++g) {
+    int v = cnt[g];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += o;
+    }
+    if (lane == 31) warp_tot[g][warp] = v;
+    start[g] = v - cnt[g];
+  }
+  __syncthreads();
+  if (warp < kRouteMaxGroups) {  // warp g scans the 32 warp totals of group g
+    int v = warp_tot[warp][lane];
+    const int own = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += o;
+    }
+    warp_tot[warp][lane] = v - own;
+    if (lane == 31) group_base[warp + 1] = v;  // total of the group
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int g = 0; g < kRouteMaxGroups; ++g) {
+      const int n = group_base[g + 1];
+      group_base[g] = acc;
+      acc += n;
+    }
+    group_base[kRouteMaxGroups] = acc;
+    for (int g = 0; g <= n_groups; ++g) seg_start[g] = group_base[min(g, kRouteMaxGroups)];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < kRouteMaxGroups; ++g) start[g] += group_base[g] + warp_tot[g][warp];
+  for (int t = t0; t < t1; ++t) {
+    const int g = lut.g[modal_id[t] & 15];
+    int pos = 0;
+#pragma unroll
+    for (int k = 0; k < kRouteMaxGroups; ++k) {
+      if (g == k) pos = start[k]++;
+    }
+    perm[pos] = t;
+    inv_perm[t] = pos;
+    row_group[pos] = (unsigned char)g;
+    if (group_seq) group_seq[t] = (unsigned char)g;
+  }
 }
 
 // out[i] = silu(gate[i]) * up[i]   (multimodal_llama.py:381-388: act_fn(gate_proj(x)) * up_proj(x)); rounding points
@@ -1416,10 +1508,32 @@ extern "C" int mc_linear_plan_destroy(mc_linear_plan_t* p) {
   return MC_OK;
 }
 
-extern "C" int mc_route_tile_masks(const uint8_t* d_row_group, int M, uint32_t* d_mtile_mask, mc_stream_t stream) {
+extern "C" int mc_route_tile_masks_coarse(const uint8_t* d_row_group, int M, uint32_t* d_mtile_mask, int coarsen, mc_stream_t stream) {
   MC_REQUIRE(d_row_group && d_mtile_mask && M >= 1, "route masks: NULL pointer or M < 1");
+  MC_REQUIRE(coarsen == 1 || coarsen == 2 || coarsen == 4, "route masks: coarsen must be 1, 2 or 4");
   const int n_tiles = (M + kBM - 1) / kBM;
-  route_tile_mask_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_row_group, M, d_mtile_mask, n_tiles);
+  route_tile_mask_kernel<<<(n_tiles + 7) / 8, 256, 0, (cudaStream_t)stream>>>(d_row_group, M, d_mtile_mask, n_tiles, coarsen);
+  MC_CUDA_OK(cudaGetLastError());
+  return MC_OK;
+}
+
+extern "C" int mc_route_tile_masks(const uint8_t* d_row_group, int M, uint32_t* d_mtile_mask, mc_stream_t stream) {
+  return mc_route_tile_masks_coarse(d_row_group, M, d_mtile_mask, 1, stream);
+}
+
+extern "C" int mc_route_permutation(const uint8_t* d_modal_id, int T, const uint8_t* lut, int n_lut, int n_groups, int32_t* d_perm,
+                                    int32_t* d_inv_perm, uint8_t* d_row_group, int32_t* d_seg_start, uint8_t* d_group_seq, mc_stream_t stream) {
+  MC_REQUIRE(d_modal_id && d_perm && d_inv_perm && d_row_group && d_seg_start && T >= 1, "route permutation: NULL pointer or T < 1");
+  MC_REQUIRE(n_groups >= 1 && n_groups <= kRouteMaxGroups && n_lut >= 0 && n_lut <= 16, "route permutation: n_groups outside [1, %d] or n_lut > 16",
+             kRouteMaxGroups);
+  RouteLut l;
+  for (int i = 0; i < 16; ++i) {
+    int g = (lut != nullptr && i < n_lut) ? (int)lut[i] : (lut == nullptr ? i : 0);
+    MC_REQUIRE(!(lut != nullptr && i < n_lut) || g < n_groups, "route permutation: lut[%d] = %d is not a routing group (< %d)", i, g, n_groups);
+    l.g[i] = (unsigned char)(g < n_groups ? g : 0);  // ids the splice never produces for this model
+  }
+  route_permutation_kernel<<<1, kRouteThreads, 0, (cudaStream_t)stream>>>(d_modal_id, T, l, n_groups, d_perm, d_inv_perm, d_row_group, d_seg_start,
+                                                                          d_group_seq);
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
 }

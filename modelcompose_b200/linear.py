@@ -201,16 +201,34 @@ def route_tile_masks(row_group: torch.Tensor, out: Optional[torch.Tensor] = None
     n = (M + TILE_M - 1) // TILE_M
     if out is None:
         out = torch.empty(n, dtype=torch.int32, device=row_group.device)
-    _cabi.check(_cabi.lib().mc_route_tile_masks(row_group.data_ptr(), M, out.data_ptr(), _cabi.current_stream_ptr()),
+    if coarsen not in (1, 2, 4):
+        raise ValueError("coarsen must be 1, 2 or 4")
+    _cabi.check(_cabi.lib().mc_route_tile_masks_coarse(row_group.data_ptr(), M, out.data_ptr(), int(coarsen), _cabi.current_stream_ptr()),
                 "mc_route_tile_masks")
     _cabi.count_launch()
-    if coarsen > 1:
-        m = torch.nn.functional.pad(out, (0, (-n) % coarsen)).view(-1, coarsen)
-        union = m[:, 0]
-        for i in range(1, coarsen):
-            union = union | m[:, i]
-        out.copy_(union[:, None].expand(-1, coarsen).reshape(-1)[:n])
     return out
+
+
+def route_permutation(modal_id: torch.Tensor, lut: Optional[Sequence[int]], n_groups: int, perm: torch.Tensor, inv_perm: torch.Tensor,
+                      row_group: torch.Tensor, seg_start: torch.Tensor, group_seq: Optional[torch.Tensor] = None) -> None:
+    """Stable counting sort of the batch's rows by routing group (``mc_route_permutation``): fills ``perm`` / ``inv_perm`` (int32
+    [T]), ``row_group`` (uint8 [T], buffer order), ``seg_start`` (int32 [n_groups + 1]) and optionally ``group_seq`` (uint8 [T],
+    the routing group of every sequence-order row).  ``lut`` maps the splice's modality ids to routing groups (None = identity)."""
+    T = modal_id.numel()
+    if modal_id.dtype != torch.uint8 or not modal_id.is_cuda or not modal_id.is_contiguous():
+        raise ValueError("modal_id must be a contiguous CUDA uint8 tensor")
+    for t, dt, n, what in ((perm, torch.int32, T, "perm"), (inv_perm, torch.int32, T, "inv_perm"), (row_group, torch.uint8, T, "row_group"),
+                           (seg_start, torch.int32, n_groups + 1, "seg_start")):
+        if t.dtype != dt or t.numel() != n or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"{what} must be a contiguous CUDA {dt} tensor with {n} elements")
+    if group_seq is not None and (group_seq.dtype != torch.uint8 or group_seq.numel() != T or not group_seq.is_contiguous()):
+        raise ValueError("group_seq must be a contiguous CUDA uint8 tensor with one entry per row")
+    lut_b = None if lut is None else bytes(int(x) for x in lut)
+    _cabi.check(_cabi.lib().mc_route_permutation(modal_id.data_ptr(), T, lut_b, 0 if lut is None else len(lut_b), int(n_groups),
+                                                 perm.data_ptr(), inv_perm.data_ptr(), row_group.data_ptr(), seg_start.data_ptr(),
+                                                 None if group_seq is None else group_seq.data_ptr(), _cabi.current_stream_ptr()),
+                "mc_route_permutation")
+    _cabi.count_launch()
 
 
 def attention_causal(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, batch: int, seq_len: int,

@@ -255,9 +255,11 @@ class _Workspace:
         self.logits_last = buf(B, V)
         self.lm_head_last = LN.LinearPlan([LN.Problem(self.xn_last, model.lm_head, self.logits_last)], tuning=1)
 
-    def set_routing(self, modal_id: Optional[torch.Tensor]) -> None:
-        """Routing ids of this batch (sequence order, ``[B, S]`` uint8 or None = all default) -> row permutation, per-row
-        groups in buffer order, per-tile group masks."""
+    def set_routing(self, modal_id: Optional[torch.Tensor], lut: Optional[Sequence[int]] = None) -> Optional[torch.Tensor]:
+        """Routing of this batch: ``modal_id`` ``[B, S]`` uint8 in sequence order (None = all default) with ``lut`` mapping its
+        values to routing groups (None = they are routing groups already) -> row permutation, per-row groups in buffer order,
+        segment table / per-tile group masks.  Returns the routing groups in sequence order (``[B, S]`` uint8) or None."""
+        n_groups = self.seg_start.numel() - 1
         if modal_id is None:
             self.row_group.zero_()
             if self.permute and not self.perm_is_identity:
@@ -265,22 +267,21 @@ class _Workspace:
                 self.inv_perm.copy_(self.perm)
                 self.perm_is_identity = True
             self.seg_start[1:] = self.T
+            group_seq = None
         elif self.permute:
-            gseq = modal_id.reshape(-1)
-            order = torch.sort(gseq, stable=True).indices  # tiny (T uint8 keys); stable keeps sequence order inside a group
-            self.perm.copy_(order)
-            self.inv_perm[order] = torch.arange(self.T, dtype=torch.int32, device=self.perm.device)
-            self.row_group.copy_(gseq[order])
+            # stable counting sort by group on the device (mc_route_permutation): one launch, no host synchronisation
+            group_seq = torch.empty((self.B, self.S), dtype=torch.uint8, device=self.perm.device)
+            LN.route_permutation(modal_id.reshape(-1).contiguous(), lut, n_groups, self.perm, self.inv_perm, self.row_group, self.seg_start,
+                                 group_seq.view(-1))
             self.perm_is_identity = False
-            if self.dense:  # rows of group g: [seg_start[g], seg_start[g + 1]) — stays on the device, the kernels read it
-                counts = torch.bincount(gseq.int(), minlength=self.seg_start.numel() - 1)
-                self.seg_start[1:] = torch.cumsum(counts, 0).to(torch.int32)
         else:
             if self.dense:
                 raise ValueError("the materialised form needs rows grouped by modality: route in modality-major order")
-            self.row_group.view(self.B, self.S).copy_(modal_id)
+            group_seq = modal_id if lut is None else torch.tensor(list(lut), dtype=torch.uint8, device=modal_id.device)[modal_id.long()]
+            self.row_group.view(self.B, self.S).copy_(group_seq)
         if not self.dense:
             LN.route_tile_masks(self.row_group, self.mtile, coarsen={3: 4, 4: 2}.get(self.up_tuning & 0xff, 1))
+        return group_seq
 
     def last_rows(self) -> torch.Tensor:
         """int32 [B]: buffer row holding the last position of every sequence."""
@@ -607,7 +608,7 @@ class MultimodalLlamaForCausalLM:
 
     def prefill(self, inputs_embeds: torch.Tensor, modal_id: Optional[torch.Tensor], attention_mask=None,
                 use_cache: bool = False, output_hidden_states: bool = False, past_key_values: Optional[KVCache] = None,
-                last_logits_only: bool = False, cache_extra: int = 128):
+                last_logits_only: bool = False, cache_extra: int = 128, modal_lut: Optional[Sequence[int]] = None):
         """MultimodalLlamaModel.forward + lm_head (:488-619, :720) on (spliced) embeddings; returns (logits, cache, hidden).
         With ``past_key_values`` this is the decode step: ``inputs_embeds`` holds the new token(s) only, every row takes
         the default adapter (``modal_id`` None — the reference drops the modality masks when a cache is present, :436-438)."""
@@ -632,7 +633,7 @@ class MultimodalLlamaForCausalLM:
         if ws.pos_value != past:
             ws.pos.fill_(past)
             ws.pos_value = past
-        ws.set_routing(modal_id)
+        self._last_group_seq = ws.set_routing(modal_id, modal_lut)
         ws.load_rows(inputs_embeds.reshape(B * S, H), ws.x)
         full = attention_mask is None or bool(attention_mask.all())  # one host sync per call, not per layer
         hidden = []
@@ -732,16 +733,20 @@ class MultimodalLlamaForCausalLM:
                           None if labels is None else labels.to(self.device).contiguous(), self.embed_tokens, feats, pre, suf,
                           list(modal_inputs.keys()) if modal_inputs else None)
             inputs_embeds, attention_mask, labels = r.inputs_embeds, r.attention_mask, r.labels
+            modal_lut = None
             if r.modal_names:
-                # splice ids follow the order of `feats`; routing ids follow self.modal_names (0 = default)
-                lut = torch.zeros(SP.MAX_MODAL + 1, dtype=torch.uint8, device=self.device)
+                # splice ids follow the order of `feats`; routing ids follow self.modal_names (0 = default): the mapping rides into
+                # the permutation kernel as a 16-entry table
+                modal_lut = [0] * (SP.MAX_MODAL + 1)
                 for i, m in enumerate(r.modal_names):
-                    lut[1 + i] = self.modal_names.index(m)
-                modal_id = lut[r.modal_id.long()]
+                    modal_lut[1 + i] = self.modal_names.index(m)
+                modal_id = r.modal_id
             if self.config.lora_strategy not in ("modal", "modal+language"):  # :703-704
-                modal_id = None
+                modal_id, modal_lut = None, None
         logits, kv, hidden = self.prefill(inputs_embeds, modal_id, attention_mask, bool(use_cache), bool(output_hidden_states),
-                                          last_logits_only=last_logits_only and labels is None, cache_extra=cache_extra)
+                                          last_logits_only=last_logits_only and labels is None, cache_extra=cache_extra,
+                                          modal_lut=modal_lut if input_ids is not None else None)
+        modal_id = self._last_group_seq  # routing groups in sequence order (the splice's ids mapped through the table)
         if kv is not None:
             kv.prefill_mask = attention_mask  # spliced mask of the prompt (padded positions stay masked in the decode steps)
         loss = None

@@ -304,6 +304,23 @@ def test_routed_up_launch_on_pair_kernels_is_bit_identical(dtype, up_tuning, run
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("T,n_groups,lut", [(1, 1, None), (1000, 4, None), (31360, 4, [0, 2, 1, 3, 0, 0, 0]), (57104, 5, [0, 4, 3, 2, 1, 0, 0]), (777, 8, None)])
+def test_route_permutation_is_a_stable_sort_by_group(T, n_groups, lut):
+    g = torch.Generator().manual_seed(T)
+    n_ids = n_groups if lut is None else 5
+    ids = torch.randint(0, n_ids, (T,), generator=g).to(torch.uint8).cuda()
+    perm, inv = torch.empty(T, dtype=torch.int32, device="cuda"), torch.empty(T, dtype=torch.int32, device="cuda")
+    rg, seq = torch.empty(T, dtype=torch.uint8, device="cuda"), torch.empty(T, dtype=torch.uint8, device="cuda")
+    seg = torch.empty(n_groups + 1, dtype=torch.int32, device="cuda")
+    LN.route_permutation(ids, lut, n_groups, perm, inv, rg, seg, seq)
+    groups = ids.long().cpu() if lut is None else torch.tensor(lut)[ids.long().cpu()]
+    order = torch.sort(groups, stable=True).indices
+    assert torch.equal(perm.cpu().long(), order) and torch.equal(seq.cpu().long(), groups)
+    assert torch.equal(inv.cpu().long()[order], torch.arange(T)) and torch.equal(rg.cpu().long(), groups[order])
+    counts = torch.bincount(groups, minlength=n_groups)
+    assert torch.equal(seg.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]))
+
+
 def test_route_tile_masks():
     mid = make_modal_id(1000, 3, 5)
     got = LN.route_tile_masks(mid.cuda()).cpu()
@@ -312,6 +329,13 @@ def test_route_tile_masks():
         for g in mid[t * 128:(t + 1) * 128].unique().tolist():
             want |= 1 << g
         assert got[t].item() == want
+    for coarsen in (2, 4):  # every tile of an aligned run carries the union of the run
+        c = LN.route_tile_masks(mid.cuda(), coarsen=coarsen).cpu()
+        for t in range(got.numel()):
+            want = 0
+            for u in range(t // coarsen * coarsen, min(got.numel(), t // coarsen * coarsen + coarsen)):
+                want |= got[u].item()
+            assert c[t].item() == want, (coarsen, t)
 
 
 @pytest.mark.parametrize("key", ["torch.bfloat16", "torch.float16"])
