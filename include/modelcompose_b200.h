@@ -415,10 +415,8 @@ typedef struct mc_skinny_plan mc_skinny_plan_t;
  * row blocks shared by several CTAs are combined through the workspace by the last CTA to arrive, in CTA order (deterministic).
  * tuning (development / A-B): bit 4 selects the register kernel instead (weight rows streamed with 128-bit loads straight into
  * MMA fragments, K split over the warps of a CTA), bit 5 32-row blocks, bit 7 forces 128-element K chunks (default: 256 when the
- * ring keeps three stages), bit 12 fills the ring with cp.async from four producer warps instead of TMA, bit 14 only the
- * activation boxes (both measured slower), bits 8-11 cap the ring
- * depth, bit 6 makes the consumers skip the arithmetic (pipeline ceiling; results are garbage), bits 0-3 = 1: 16-row CTAs of
- * the register kernel.
+ * ring keeps three stages), bits 8-11 cap the ring depth, bit 6 makes the
+ * consumers skip the arithmetic (pipeline ceiling; results are garbage), bits 0-3 = 1: 16-row CTAs of the register kernel.
  * The plan stays valid while the pointers in `desc` do (decode buffers are static, plans are built once per cache).
  * workspace: device memory of mc_skinny_workspace_bytes() bytes, ZEROED once by the caller and then left alone (the kernel
  * restores it); launches that may run concurrently need separate workspaces. */

@@ -261,8 +261,7 @@ __global__ void __launch_bounds__(kSkThreads) skinny_linear_kernel(const __grid_
 // row block their partial sums meet in shared memory.  A row block whose K range is shared by several CTAs goes through a
 // scratch tile per CTA; the last CTA to arrive adds the partial tiles in CTA order (deterministic) and runs the epilogue.
 constexpr int kS2Consumers = 8;
-constexpr int kS2Producers = 4;  // producer warps (cp.async path; the TMA path uses one lane of the first)
-constexpr int kS2Threads = (kS2Consumers + kS2Producers) * 32;
+constexpr int kS2Threads = (kS2Consumers + 1) * 32;  // 8 consumer warps + the producer warp (one elected lane issues the TMA loads)
 constexpr int kS2MaxStages = 12;
 constexpr int kS2TileFloats = MC_SKINNY_MAX_M * 64;  // scratch tile: [M][R] fp32, R <= 64
 
@@ -281,8 +280,6 @@ struct alignas(64) S2Params {
   int n_prob, total_iters, span, stages, xslots, stage_bytes;
   int nh;          // 64-element TMA boxes per K chunk (2: 128-element chunks, 4: 256)
   int copy_only;   // profiling aid: consumers release the stages without reading them (pipeline ceiling)
-  int use_tma;     // 1: stages filled by TMA tensor loads (one lane issues); 0: by cp.async from four producer warps
-  int x_lsu;       // TMA mode: 1 = the ACTIVATION boxes come through the LSU (cp.async from producer warps 1-3), TMA carries weights only
   float* scratch;  // [grid][2][kS2TileFloats]
   int* counters;   // [total row blocks], zero between launches
 };
@@ -315,12 +312,6 @@ __device__ __forceinline__ void s2_advance(const S2Params& P, S2Iter& w) {
   }
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
@@ -355,7 +346,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
   griddep_launch_dependents();  // decode chain: the next kernel may become resident as soon as every CTA of this one runs
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(full + s, P.use_tma ? (P.x_lsu ? 1 + (kS2Producers - 1) * 32 : 1) : kS2Producers * 32);
+      mbar_init(full + s, 1);
       mbar_init(empty + s, kS2Consumers);
     }
     fence_barrier_init();
@@ -363,46 +354,11 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
   __syncthreads();
   if (it0 >= it1) return;
 
-  if (warp >= kS2Consumers) {
-    // ------------------------------------------------------------------------------------------------ producers
-    if (P.use_tma && warp != kS2Consumers) {
-      if (!P.x_lsu) return;
-      // ---- activation loaders (warps 1-3 of the producer group; tuning bit 14, an experiment kept for A/B): the x boxes of every
-      // stage through cp.async so that TMA carries weights only.  At M = 32 a third of the TMA bytes are activations re-read from
-      // L2 for every row block — but moving them to the LSU measured 12-20 % SLOWER (profiles/r02_decode.txt).
-      griddep_wait();
-      const int xt = threadIdx.x - (kS2Consumers + 1) * 32;  // 0 .. 95
-      constexpr int XT = (kS2Producers - 1) * 32;
-      const int ppr = 8 * P.nh, lg_ppr = P.nh == 4 ? 5 : 4;   // 16-byte pieces per activation row and stage (16 or 32)
-      S2Iter w = s2_locate(P, it0);
-      for (int i = 0; i < it1 - it0; ++i) {
-        const int s = i % P.stages;
-        mbar_wait(empty + s, ((uint32_t)(i / P.stages) & 1u) ^ 1u);
-        const S2Problem& q = P.prob[w.p];
-        const SkProblem& pr = q.pr;
-        const bool phase = w.kc >= q.nkc0;
-        const int kc = phase ? w.kc - q.nkc0 : w.kc, K = phase ? pr.K1 : pr.K0;
-        const int k0 = kc * KC;
-        const int nx = (pr.epilogue == MC_SKINNY_EPI_SILU_MUL && phase) ? 2 : 1;
-        const long long ldx = phase ? pr.lda1 : pr.lda0;
-        const uint32_t st_u32 = smem_u32(ring + (size_t)s * P.stage_bytes) + X_BASE;
-        for (int slot = 0; slot < nx; ++slot) {
-          const char* xb = slot ? pr.A1u : (phase ? pr.A1 : pr.A0);
-          for (int pc = xt; pc < pr.M * ppr; pc += XT) {
-            const int m = pc >> lg_ppr, u16 = pc & (ppr - 1), h = u16 >> 3, u = u16 & 7, k = k0 + u16 * 8;
-            const bool ok = k < K;  // past K: zeros (they meet the zeros TMA filled into the weight box)
-            cp_async16(st_u32 + (uint32_t)slot * X_SLOT + (uint32_t)h * X_HALF + (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) << 4),
-                       ok ? xb + m * ldx + 2ll * k : xb, ok ? 16u : 0u);
-          }
-        }
-        cp_async_arrive(full + s);
-        s2_advance(P, w);
-      }
-      return;
-    }
-    const int pt = threadIdx.x - kS2Consumers * 32;  // 0 .. 127 (cp.async path)
-    const int ppr = 8 * P.nh;                         // 16-byte pieces per row of a stage
-    // fills stage ii % stages with iteration `w`; parts: 1 = weights (+ the barrier's byte count), 2 = activations, 3 = both
+  if (warp == kS2Consumers) {
+    // ------------------------------------------------------------------------------------------------ producer (one lane issues)
+    // fills stage ii % stages with iteration `w`; parts: 1 = weight boxes (+ the barrier's byte count), 2 = activation boxes, 3 = both.
+    // (Two other ways to fill the ring were measured and dropped, profiles/r02_decode.txt: 16-byte cp.async from four producer warps,
+    // 3-4x slower, and activations by cp.async with weights on TMA, 12-20 % slower.)
     auto fill = [&](int ii, const S2Iter& w, int parts) {
       const int s = ii % P.stages;
       const S2Problem& q = P.prob[w.p];
@@ -415,57 +371,30 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
       const int F = dual ? R / 2 : R, n0 = w.rb * F;
       const int nx = (dual && phase) ? 2 : 1;
       unsigned char* st = ring + (size_t)s * P.stage_bytes;
-      if (P.use_tma) {
-        if (elect_one()) {
-          if (parts & 1) mbar_expect_tx(full + s, (uint32_t)halves * (W_HALF + (P.x_lsu ? 0u : (uint32_t)nx * X_HALF)));
-          for (int h = 0; h < halves; ++h) {
-            const int k = k0 + 64 * h;
-            if (parts & 1) {
-              if (dual) {
-                tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
-                tma_load_2d(phase ? &q.tmB1u : &q.tmB0u, full + s, st + h * W_HALF + W_HALF / 2, k, n0);
-              } else {
-                tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
-              }
-            }
-            if ((parts & 2) && !P.x_lsu) {
-              tma_load_2d(phase ? &q.tmA1 : &q.tmA0, full + s, st + X_BASE + h * X_HALF, k, 0);
-              if (nx == 2) tma_load_2d(&q.tmA1u, full + s, st + X_BASE + X_SLOT + h * X_HALF, k, 0);
+      if (elect_one()) {
+        if (parts & 1) mbar_expect_tx(full + s, (uint32_t)halves * (W_HALF + (uint32_t)nx * X_HALF));
+        for (int h = 0; h < halves; ++h) {
+          const int k = k0 + 64 * h;
+          if (parts & 1) {
+            if (dual) {
+              tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
+              tma_load_2d(phase ? &q.tmB1u : &q.tmB0u, full + s, st + h * W_HALF + W_HALF / 2, k, n0);
+            } else {
+              tma_load_2d(phase ? &q.tmB1 : &q.tmB0, full + s, st + h * W_HALF, k, n0);
             }
           }
+          if (parts & 2) {
+            tma_load_2d(phase ? &q.tmA1 : &q.tmA0, full + s, st + X_BASE + h * X_HALF, k, 0);
+            if (nx == 2) tma_load_2d(&q.tmA1u, full + s, st + X_BASE + X_SLOT + h * X_HALF, k, 0);
+          }
         }
-        __syncwarp();
-      } else {
-        // LSU path (A/B only, 3-4x slower): 16-byte cp.async pieces written in the layout TMA's 128-byte swizzle would produce
-        // (unit ^= row & 7).  Rows past N / M and pieces past K are zero-filled (src-size 0).
-        const uint32_t st_u32 = smem_u32(st);
-        const long long ldw = phase ? pr.ldb1 : pr.ldb0, ldx = phase ? pr.lda1 : pr.lda0;
-        for (int pc = pt; pc < R * ppr; pc += kS2Producers * 32) {
-          const int r = pc / ppr, u16 = pc % ppr, h = u16 >> 3, u = u16 & 7;
-          const bool second = dual && r >= R / 2;
-          const char* wb = second ? (phase ? pr.B1u : pr.B0u) : (phase ? pr.B1 : pr.B0);
-          const int row = n0 + (dual ? r % (R / 2) : r), k = k0 + u16 * 8;
-          const bool ok = row < pr.N && k < K;
-          const char* src = ok ? wb + row * ldw + 2ll * k : wb;
-          cp_async16(st_u32 + (uint32_t)h * W_HALF + (uint32_t)r * 128u + (uint32_t)((u ^ (r & 7)) << 4), src, ok ? 16u : 0u);
-        }
-        for (int pc = pt; pc < nx * MT * ppr; pc += kS2Producers * 32) {
-          const int slot = pc / (MT * ppr), rem = pc % (MT * ppr);
-          const int m = rem / ppr, u16 = rem % ppr, h = u16 >> 3, u = u16 & 7;
-          const char* xb = slot ? pr.A1u : (phase ? pr.A1 : pr.A0);
-          const int k = k0 + u16 * 8;
-          const bool ok = m < pr.M && k < K;
-          const char* src = ok ? xb + m * ldx + 2ll * k : xb;
-          cp_async16(st_u32 + X_BASE + (uint32_t)slot * X_SLOT + (uint32_t)h * X_HALF + (uint32_t)m * 128u + (uint32_t)((u ^ (m & 7)) << 4),
-                     src, ok ? 16u : 0u);
-        }
-        cp_async_arrive(full + s);  // arrives once this thread's copies above have landed
       }
+      __syncwarp();
     };
-    // Weights do not depend on the predecessor kernel: in the TMA path the first ring of weight boxes is requested BEFORE
-    // griddepcontrol.wait (under programmatic dependent launch this CTA may be running while the previous kernel of the decode
-    // chain still is), the activation boxes of those stages right after it.
-    const int pre = P.use_tma ? min(P.stages, it1 - it0) : 0;
+    // Weights do not depend on the predecessor kernel: the first ring of weight boxes is requested BEFORE griddepcontrol.wait (under
+    // programmatic dependent launch this CTA may be running while the previous kernel of the decode chain still is), the
+    // activation boxes of those stages right after it.
+    const int pre = min(P.stages, it1 - it0);
     S2Iter w = s2_locate(P, it0);
     for (int i = 0; i < pre; ++i) {
       fill(i, w, 1);
@@ -1063,13 +992,12 @@ extern "C" int mc_skinny_plan_create(mc_skinny_plan_t** out, const mc_skinny_des
     // K chunk: 256 elements (four TMA boxes per operand and stage: 512 contiguous bytes per weight row) when the ring still gets
     // three stages, else 128; tuning bit 7 forces 128.  Measured (profiles/r02_decode.txt): 256 is 10-20 % faster at M <= 32.
     Q.copy_only = (tuning >> 6) & 1;              // tuning bit 6: profiling aid, results are garbage
-    Q.use_tma = ((tuning >> 12) & 1) ? 0 : 1;     // tuning bit 12: cp.async producer warps instead of TMA (slower: kept for A/B)
-    Q.x_lsu = (tuning >> 14) & 1;                 // tuning bit 14: activation boxes through cp.async instead of TMA (measured slower)
+    const size_t budget = 227 * 1024;
     Q.xslots = dual_k1 ? 2 : 1;
     {
       const size_t fixed256 = 1024 + 256 + (size_t)kS2Consumers * MT * 33 * 4 + (size_t)MT * (R + 1) * 4;
       const size_t stage256 = 4 * (size_t)(R * 128 + Q.xslots * MT * 128);
-      Q.nh = (!((tuning >> 7) & 1) && (227 * 1024 - fixed256) / stage256 >= 3) ? 4 : 2;
+      Q.nh = (!((tuning >> 7) & 1) && (budget - fixed256) / stage256 >= 3) ? 4 : 2;
     }
     const int kc_elems = 64 * Q.nh;
     int iters = 0, rbs = 0;
@@ -1102,7 +1030,7 @@ extern "C" int mc_skinny_plan_create(mc_skinny_plan_t** out, const mc_skinny_des
     Q.total_iters = iters;
     Q.stage_bytes = Q.nh * (R * 128 + Q.xslots * MT * 128);
     const size_t fixed = 1024 + 256 + (size_t)kS2Consumers * MT * 33 * 4 + (size_t)MT * (R + 1) * 4;
-    Q.stages = (int)std::min<size_t>(kS2MaxStages, (227 * 1024 - fixed) / Q.stage_bytes);
+    Q.stages = (int)std::min<size_t>(kS2MaxStages, (budget - fixed) / Q.stage_bytes);
     if ((tuning >> 8) & 0xf) Q.stages = std::min(Q.stages, (tuning >> 8) & 0xf);  // tuning bits 8-11: cap the ring depth
     if (Q.stages < 2) {
       delete p;

@@ -36,7 +36,7 @@ def rnd(shape, g, dtype, std=1.0):
 
 # ------------------------------------------------------------------------------------------------------ skinny linear
 @pytest.mark.parametrize("key", list(DTYPES))
-@pytest.mark.parametrize("tuning", [0, 16, 17, 32, 128, 4096, 4096 | 128, 1 << 14])
+@pytest.mark.parametrize("tuning", [0, 16, 17, 32, 128, 3 << 8])
 @pytest.mark.parametrize("M,N,K0,K1", [(1, 64, 128, 0), (5, 200, 256, 64), (8, 4096, 1024, 384), (16, 136, 688, 48), (17, 256, 4096, 0),
                                        (32, 512, 2048, 384), (33, 328, 640, 128), (64, 1024, 1024, 64), (3, 72, 72, 24)])
 def test_skinny_linear_vs_fp32(key, tuning, M, N, K0, K1):
@@ -66,7 +66,7 @@ def test_skinny_linear_vs_fp32(key, tuning, M, N, K0, K1):
 
 
 @pytest.mark.parametrize("key", list(DTYPES))
-@pytest.mark.parametrize("tuning", [0, 16, 32, 128, 4096, 1 << 14])
+@pytest.mark.parametrize("tuning", [0, 16, 32, 128])
 @pytest.mark.parametrize("M,N,K0,K1", [(4, 96, 256, 0), (32, 11008, 4096, 384), (20, 688, 256, 16), (64, 344, 512, 64)])
 def test_skinny_dual_silu_mul(key, tuning, M, N, K0, K1):
     """gate/up in one launch: silu(gate) * up with gate, silu(gate), up each rounded to the storage dtype (the prefill's rounding points)."""
@@ -97,7 +97,7 @@ def test_skinny_multi_problem_qkv_and_kernel_agreement():
     ts = [rnd((M, R0), g, dt) for _ in range(3)]
     Bs = [rnd((H, R0), g, dt, R0 ** -0.5) for _ in range(3)]
     outs = {}
-    for tuning in (0, 16, 32, 128, 4096):
+    for tuning in (0, 16, 32, 128):
         o = [torch.empty((M, H), dtype=dt, device="cuda") for _ in range(3)]
         DC.SkinnyLaunch([dict(A0=x, B0=Ws[i], A1=ts[i], B1=Bs[i], C=o[i]) for i in range(3)], tuning).run()
         outs[tuning] = o

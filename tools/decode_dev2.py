@@ -36,8 +36,7 @@ def main():
     Wg, Wu = [w(I, H) for _ in range(n)], [w(I, H) for _ in range(n)]
     Wd = [w(H, I) for _ in range(n)]
     Wo = [w(H, H) for _ in range(3 * n)]
-    tunings = [("W tma + x lsu (default)", 0), ("W tma + x tma", 1 << 14), ("R128, x lsu", 1 << 13), ("R128, x tma", (1 << 13) | (1 << 14)),
-               ("default copy-only", 64), ("register", 16)]
+    tunings = [("stream-K, 256-element chunks (default)", 0), ("128-element chunks", 128), ("copy-only", 64), ("4 stages", 4 << 8), ("register", 16)]
     for M in (1, 16, 32, 64):
         x, xi = w(M, H), w(M, I)
         act, y = torch.empty((M, I), dtype=dt, device=dev), torch.empty((M, H), dtype=dt, device=dev)
