@@ -286,6 +286,41 @@ def test_programmatic_dependent_launch_is_bit_identical(golden, monkeypatch):
         assert torch.equal(outs[(True, graph, "logits")], outs[(False, graph, "logits")])
 
 
+def test_cache_growth_rebuilds_the_decode_workspace(golden):
+    """forward(past_key_values=...) past the cache's capacity: the cache is reallocated, the captured graph (which bakes the cache
+    addresses) is rebuilt, and the logits equal those of a run whose cache was large enough from the start."""
+    dtype = torch.bfloat16
+    model = d128_model(golden, dtype)
+    ids, feats = _prompt(2, dtype, seed=4)
+    runs = {}
+    for extra in (2, 64):
+        o1 = model.forward(ids, torch.ones_like(ids), modal_inputs=feats, use_cache=True, cache_extra=extra)
+        cache, tok, logits = o1.past_key_values, o1.logits[:, -1].argmax(-1), []
+        cap0 = cache.capacity
+        for _ in range(6):
+            o = model.forward(tok[:, None], None, past_key_values=cache, modal_inputs=feats)
+            logits.append(o.logits[:, 0].clone())
+            tok = o.logits[:, 0].argmax(-1)
+        runs[extra] = torch.stack(logits)
+        assert (cache.capacity > cap0) == (extra == 2)
+    assert torch.equal(runs[2], runs[64])
+
+
+def test_sampling_and_eos_on_the_native_decode_path(golden):
+    dtype = torch.bfloat16
+    model = d128_model(golden, dtype)
+    ids, feats = _prompt(3, dtype, seed=3)
+    greedy = model.generate(ids, modal_inputs=feats, max_new_tokens=5, do_sample=False)
+    eos = int(greedy[0, ids.shape[1] + 1])  # row 0 emits it at its second step
+    out = model.generate(ids, modal_inputs=feats, max_new_tokens=5, do_sample=False, eos_token_id=eos, pad_token_id=0)
+    assert torch.equal(out[0, :ids.shape[1] + 2], greedy[0, :ids.shape[1] + 2]) and (out[0, ids.shape[1] + 2:] == 0).all()
+    a = model.generate(ids, modal_inputs=feats, max_new_tokens=4, do_sample=True, temperature=0.8, top_p=0.9,
+                       generator=torch.Generator(device="cuda").manual_seed(5))
+    b = model.generate(ids, modal_inputs=feats, max_new_tokens=4, do_sample=True, temperature=0.8, top_p=0.9,
+                       generator=torch.Generator(device="cuda").manual_seed(5))
+    assert a.shape == (3, ids.shape[1] + 4) and torch.equal(a, b)
+
+
 def test_padded_text_only_batch_keeps_pads_masked(golden):
     """HF generate appends ones to the caller's mask: the padded prompt positions stay masked in every decode step."""
     dtype = torch.bfloat16
