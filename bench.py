@@ -872,7 +872,10 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
                    if model.materialize else "base weight + low-rank branch of the token's group (the reference's form)",
                    "algorithmic_tflop_per_step_per_gpu": round(step_flops / 1e12, 2)},
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak_sus, "unit": "TFLOP/s",
-                     "frac": round(achieved / peak_sus, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(achieved / peak_sus, 4), "traffic": step_traffic(cfg_name, model.materialize),
+                     "traffic_unit": "DRAM read+write bytes of ALL kernels of one step of this config (NVTX-scoped ncu capture, "
+                                     "profiles/r02_prefill_traffic.txt); null for configs without a capture",
+                     "peak_source": peak_src,
                      "kernel": up_kernel + " (routed LoRA linears, projector, lm_head)",
                      "launches_per_step": lin_n // 2, "kernel_ms_per_step": round(lin_ms, 3),
                      "kernel_share_of_step": round(lin_ms / ms_per_step, 4),
@@ -893,6 +896,17 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
     del model
     torch.cuda.empty_cache()
     return res
+
+
+def step_traffic(cfg_name: str, materialized: bool):
+    """DRAM bytes of one whole prefill step from the committed NVTX-scoped ncu capture of that config, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        d = json.load(f)
+    v = d.get(f"prefill step {cfg_name} {'materialized' if materialized else 'branch'}")
+    return None if v is None else int(v["dram_bytes"])
 
 
 def hbm_peak():
