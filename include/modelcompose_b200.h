@@ -447,8 +447,18 @@ MC_API int mc_decode_attention(const void* q, const void* k_cache, const void* v
                         int n_heads, int head_dim, float softmax_scale, int n_splits, float* scratch, int32_t* counters,
                         int dtype, mc_stream_t stream);
 
+/* mc_decode_rope_append + mc_decode_attention in ONE launch: q / k_new / v_new are the raw projection outputs [batch, ld_qkv] (q is
+ * NOT modified); every CTA rotates q and k_new of its (sequence, head) itself (rounding points of mc_rope), the CTA whose key range
+ * holds the new position *d_pos appends k / v to the caches, and the new key is taken from shared memory instead of being read back.
+ * Same result as the two separate calls, bit for bit; one launch less per layer of a decode step. */
+MC_API int mc_decode_attention_fused(const void* q, const void* k_new, const void* v_new, int64_t ld_qkv, void* k_cache, void* v_cache,
+                              int64_t capacity, const int32_t* d_pos, const void* cos_table, const void* sin_table,
+                              const uint8_t* key_mask, int64_t ld_mask, void* out, int64_t ld_out, int batch, int n_heads,
+                              int head_dim, float softmax_scale, int n_splits, float* scratch, int32_t* counters, int dtype,
+                              mc_stream_t stream);
+
 /* Launch mode of the CALLING THREAD for the decode-chain entry points (mc_gather_rows, mc_rmsnorm, mc_skinny_plan_run,
- * mc_decode_rope_append, mc_decode_attention, mc_argmax_rows): bit 0 = programmatic dependent launch — each kernel may become
+ * mc_decode_rope_append, mc_decode_attention, mc_decode_attention_fused, mc_argmax_rows): bit 0 = programmatic dependent launch — each kernel may become
  * resident while its predecessor in the stream still runs, prefetches what does not depend on it (the skinny-linear kernel its
  * first ring of weight tiles) and waits (griddepcontrol.wait) before touching anything a predecessor writes.  Only for a chain
  * in which EVERY kernel is one of the above (the decode step); returns the previous mode.  Captured CUDA graphs keep the edges. */

@@ -70,6 +70,8 @@ SIGNATURES = {
     "mc_skinny_plan_destroy": (_i, [_vp]),
     "mc_decode_rope_append": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mc_decode_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, C.c_float, _i, _vp, _vp, _i, _vp]),
+    "mc_decode_attention_fused": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, C.c_float, _i, _vp, _vp,
+                                       _i, _vp]),
     "mc_argmax_rows": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "mc_set_launch_mode": (_i, [_i]),
 }

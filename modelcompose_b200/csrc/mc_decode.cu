@@ -517,16 +517,19 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
       }
       bool run_epilogue = complete;
       if (!complete) {
-        __threadfence();
+        // Publish the partial tile and count the arrival.  ONE thread fences: the CTA barrier orders every consumer's stores before
+        // thread 0's fence, and the fence is cumulative, so they are visible at GPU scope before the counter moves (a fence in all
+        // 256 threads cost ~2 us per split row block: two per CTA and launch).  Same on the reading side: atomic, fence, barrier.
         consumer_bar();
         if (tid == 0) {
           const int c_first = a_j / P.span, c_last = (b_j - 1) / P.span;
+          __threadfence();
           *flag = atomicAdd(P.counters + rb_global, 1) == c_last - c_first;
+          __threadfence();
         }
         consumer_bar();
         run_epilogue = *flag != 0;
         if (run_epilogue) {
-          __threadfence();
           const int c_first = a_j / P.span, c_last = (b_j - 1) / P.span;
           for (int idx = tid; idx < pr.M * R; idx += kS2Consumers * 32) {
             float v = 0.f;
@@ -633,6 +636,14 @@ struct DaParams {
   long long capacity, ld_mask, ld_q, ld_out;  // ld_q / ld_out in bytes
   int n_heads, n_splits;
   float scale_log2e;
+  // fused form (mc_decode_attention_fused): q / k_new / v_new are the raw projection outputs; the kernel rotates q and k_new itself
+  // (rounding points of mc_rope), the CTA whose key range holds the new position appends k / v to the cache, and that key is read
+  // from shared memory rather than back from the cache
+  const char* k_new;
+  const char* v_new;
+  const char* cos_t;
+  const char* sin_t;
+  int fused;
 };
 
 template <typename T>
@@ -656,15 +667,53 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const __gr
   chunk = (chunk + 8 * kDaUnroll - 1) / (8 * kDaUnroll) * (8 * kDaUnroll);
   const int start = split * chunk, end = min(L, start + chunk);
 
-  float qf[8];
-  unpack8f<T>(*reinterpret_cast<const uint4*>(P.q + b * P.ld_q + (h * kDaD + l16 * 8) * 2ll), qf);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) qf[e] *= P.scale_log2e;
   // caches are [batch, heads, capacity, D]: the keys of one (sequence, head) are one contiguous stream, 512 B per warp-level load
   const long long key_stride = kDaD * 2;
-  const char* kb = P.k_cache + (long long)bh * P.capacity * kDaD * 2 + l16 * 16;
-  const char* vb = P.v_cache + (long long)bh * P.capacity * kDaD * 2 + l16 * 16;
+  char* kc_row = const_cast<char*>(P.k_cache) + (long long)bh * P.capacity * kDaD * 2;
+  char* vc_row = const_cast<char*>(P.v_cache) + (long long)bh * P.capacity * kDaD * 2;
+  const char* kb = kc_row + l16 * 16;
+  const char* vb = vc_row + l16 * 16;
   const unsigned char* mrow = P.key_mask ? P.key_mask + b * P.ld_mask : nullptr;
+  const int pos = L - 1;
+  __shared__ __align__(16) T s_q[kDaD], s_k[kDaD], s_v[kDaD];
+  float qf[8];
+  if (P.fused) {
+    // RoPE of the new token's q and k for this (sequence, head): thread i < 64 rotates the pair (i, i + 64) with every product and
+    // the sum rounded to the storage dtype (the eager ops of the reference, as rope8 / mc_rope); threads 64 .. 127 copy v
+    const long long off = b * P.ld_q + h * kDaD * 2ll;
+    if (tid < kDaD / 2) {
+      const T* qp = reinterpret_cast<const T*>(P.q + off);
+      const T* kp = reinterpret_cast<const T*>(P.k_new + off);
+      const T* cr = reinterpret_cast<const T*>(P.cos_t) + (long long)pos * kDaD;
+      const T* sr = reinterpret_cast<const T*>(P.sin_t) + (long long)pos * kDaD;
+      const float cl = to_f32<T>(cr[tid]), ch = to_f32<T>(cr[tid + kDaD / 2]), sl = to_f32<T>(sr[tid]), sh = to_f32<T>(sr[tid + kDaD / 2]);
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const T* xp = which ? kp : qp;
+        const float x1 = to_f32<T>(xp[tid]), x2 = to_f32<T>(xp[tid + kDaD / 2]);
+        const T p1 = from_f32<T>(x1 * cl), p2 = from_f32<T>(-x2 * sl), p3 = from_f32<T>(x2 * ch), p4 = from_f32<T>(x1 * sh);
+        T* dst = which ? s_k : s_q;
+        dst[tid] = from_f32<T>(to_f32<T>(p1) + to_f32<T>(p2));
+        dst[tid + kDaD / 2] = from_f32<T>(to_f32<T>(p3) + to_f32<T>(p4));
+      }
+    } else {
+      const T* vp = reinterpret_cast<const T*>(P.v_new + off);
+      const int i = (tid - kDaD / 2) * 2;
+      s_v[i] = vp[i];
+      s_v[i + 1] = vp[i + 1];
+    }
+    __syncthreads();
+    if (pos >= start && pos < end && tid < 32) {  // append: 16 lanes x 16 bytes each for k and v
+      const int i = (tid & 15) * 8;
+      if (tid < 16) *reinterpret_cast<uint4*>(kc_row + pos * key_stride + i * 2) = *reinterpret_cast<const uint4*>(s_k + i);
+      else *reinterpret_cast<uint4*>(vc_row + pos * key_stride + i * 2) = *reinterpret_cast<const uint4*>(s_v + i);
+    }
+    unpack8f<T>(*reinterpret_cast<const uint4*>(s_q + l16 * 8), qf);
+  } else {
+    unpack8f<T>(*reinterpret_cast<const uint4*>(P.q + b * P.ld_q + (h * kDaD + l16 * 8) * 2ll), qf);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) qf[e] *= P.scale_log2e;
 
   float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
@@ -680,8 +729,13 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const __gr
       blk.ok[u] = j < end && (mrow == nullptr || mrow[j] != 0);
       blk.kv[u] = blk.vv[u] = make_uint4(0u, 0u, 0u, 0u);
       if (j < end) {
-        blk.kv[u] = ld_w16(kb + j * key_stride);
-        blk.vv[u] = ld_w16(vb + j * key_stride);
+        if (P.fused && j == pos) {  // the new token's own key: from shared memory, never back from the cache in the same launch
+          blk.kv[u] = *reinterpret_cast<const uint4*>(s_k + l16 * 8);
+          blk.vv[u] = *reinterpret_cast<const uint4*>(s_v + l16 * 8);
+        } else {
+          blk.kv[u] = ld_w16(kb + j * key_stride);
+          blk.vv[u] = ld_w16(vb + j * key_stride);
+        }
       }
     }
   };
@@ -762,12 +816,14 @@ __global__ void __launch_bounds__(kDaThreads) decode_attention_kernel(const __gr
     part[kDaD] = gm;
     part[kDaD + 1] = lsum;
   }
-  __threadfence();
   __syncthreads();
-  if (tid == 0) sm_last = atomicAdd(P.counters + bh, 1) == P.n_splits - 1;
+  if (tid == 0) {  // one thread fences: the barrier orders the CTA's stores before it, and the fence is cumulative
+    __threadfence();
+    sm_last = atomicAdd(P.counters + bh, 1) == P.n_splits - 1;
+    __threadfence();
+  }
   __syncthreads();
   if (!sm_last) return;
-  __threadfence();
   const float* all = P.scratch + (long long)bh * P.n_splits * (kDaD + 2);
   float tm = -INFINITY;
   for (int sp = 0; sp < P.n_splits; ++sp) tm = fmaxf(tm, __ldcg(all + sp * (kDaD + 2) + kDaD));
@@ -1098,10 +1154,10 @@ extern "C" int mc_decode_rope_append(void* q, const void* k_new, const void* v_n
   return MC_OK;
 }
 
-extern "C" int mc_decode_attention(const void* q, const void* k_cache, const void* v_cache, int64_t capacity, const int32_t* d_pos,
-                                   const uint8_t* key_mask, int64_t ld_mask, void* out, int64_t ld_q, int64_t ld_out, int batch,
-                                   int n_heads, int head_dim, float softmax_scale, int n_splits, float* scratch, int32_t* counters,
-                                   int dtype, mc_stream_t stream) {
+static int decode_attention_launch(const void* q, const void* k_new, const void* v_new, const void* cos_table, const void* sin_table, int fused,
+                                   const void* k_cache, const void* v_cache, int64_t capacity, const int32_t* d_pos, const uint8_t* key_mask,
+                                   int64_t ld_mask, void* out, int64_t ld_q, int64_t ld_out, int batch, int n_heads, int head_dim,
+                                   float softmax_scale, int n_splits, float* scratch, int32_t* counters, int dtype, mc_stream_t stream) {
   MC_REQUIRE(q && k_cache && v_cache && d_pos && out, "decode attention: NULL pointer");
   MC_REQUIRE(dtype == MC_BF16 || dtype == MC_F16, "decode attention: dtype must be bf16 or fp16");
   MC_REQUIRE(head_dim == kDaD, "decode attention: head_dim must be %d", kDaD);
@@ -1109,16 +1165,38 @@ extern "C" int mc_decode_attention(const void* q, const void* k_cache, const voi
   MC_REQUIRE(n_splits == 1 || (scratch && counters), "decode attention: n_splits > 1 needs scratch and counters");
   MC_REQUIRE(key_mask == nullptr || ld_mask >= capacity, "decode attention: ld_mask must cover the capacity");
   MC_REQUIRE((((uintptr_t)q | (uintptr_t)k_cache | (uintptr_t)v_cache) & 15) == 0 && ld_q % 8 == 0, "decode attention: q / caches must be 16-byte aligned");
+  MC_REQUIRE(!fused || (k_new && v_new && cos_table && sin_table && (((uintptr_t)k_new | (uintptr_t)v_new) & 15) == 0),
+             "decode attention: the fused form needs k_new, v_new and the cos / sin tables");
   DaParams P;
+  memset(&P, 0, sizeof(P));
   P.q = (const char*)q; P.k_cache = (const char*)k_cache; P.v_cache = (const char*)v_cache; P.key_mask = key_mask;
   P.out = (char*)out; P.scratch = scratch; P.counters = counters; P.d_pos = d_pos;
   P.capacity = capacity; P.ld_mask = ld_mask; P.ld_q = ld_q * 2; P.ld_out = ld_out * 2;
   P.n_heads = n_heads; P.n_splits = n_splits;
   P.scale_log2e = softmax_scale * 1.4426950408889634f;
+  P.k_new = (const char*)k_new; P.v_new = (const char*)v_new; P.cos_t = (const char*)cos_table; P.sin_t = (const char*)sin_table;
+  P.fused = fused;
   const dim3 grid((unsigned)(batch * n_heads), (unsigned)n_splits);
   if (dtype == MC_BF16) MC_CUDA_OK(launch_kernel(decode_attention_kernel<__nv_bfloat16>, grid, dim3(kDaThreads), 0, (cudaStream_t)stream, P));
   else MC_CUDA_OK(launch_kernel(decode_attention_kernel<__half>, grid, dim3(kDaThreads), 0, (cudaStream_t)stream, P));
   return MC_OK;
+}
+
+extern "C" int mc_decode_attention(const void* q, const void* k_cache, const void* v_cache, int64_t capacity, const int32_t* d_pos,
+                                   const uint8_t* key_mask, int64_t ld_mask, void* out, int64_t ld_q, int64_t ld_out, int batch,
+                                   int n_heads, int head_dim, float softmax_scale, int n_splits, float* scratch, int32_t* counters,
+                                   int dtype, mc_stream_t stream) {
+  return decode_attention_launch(q, nullptr, nullptr, nullptr, nullptr, 0, k_cache, v_cache, capacity, d_pos, key_mask, ld_mask, out, ld_q, ld_out,
+                                 batch, n_heads, head_dim, softmax_scale, n_splits, scratch, counters, dtype, stream);
+}
+
+extern "C" int mc_decode_attention_fused(const void* q, const void* k_new, const void* v_new, int64_t ld_qkv, void* k_cache, void* v_cache,
+                                         int64_t capacity, const int32_t* d_pos, const void* cos_table, const void* sin_table,
+                                         const uint8_t* key_mask, int64_t ld_mask, void* out, int64_t ld_out, int batch, int n_heads,
+                                         int head_dim, float softmax_scale, int n_splits, float* scratch, int32_t* counters, int dtype,
+                                         mc_stream_t stream) {
+  return decode_attention_launch(q, k_new, v_new, cos_table, sin_table, 1, k_cache, v_cache, capacity, d_pos, key_mask, ld_mask, out, ld_qkv,
+                                 ld_out, batch, n_heads, head_dim, softmax_scale, n_splits, scratch, counters, dtype, stream);
 }
 
 extern "C" int mc_argmax_rows(const void* logits, int64_t ld, int rows, int cols, int32_t* out_i32, int64_t* out_i64,

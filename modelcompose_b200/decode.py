@@ -30,6 +30,8 @@ MAX_M = 64
 # programmatic dependent launch along the decode chain (mc_set_launch_mode): every kernel of the step may start while its
 # predecessor still runs and the skinny linears prefetch their first ring of weights before they wait for it; 0 = plain launches
 PDL = os.environ.get("MC_DECODE_PDL", "1") != "0"
+# RoPE of the new q / k and the cache append inside the attention launch (mc_decode_attention_fused); 0 = two launches (A/B switch)
+FUSED_ROPE = os.environ.get("MC_DECODE_FUSED_ROPE", "1") != "0"
 
 
 class SkinnyDesc(C.Structure):
@@ -163,6 +165,7 @@ class DecodeWorkspace:
         self.key_mask = key_mask  # uint8 [B, capacity] or None
         self.use_graph = use_graph
         self.pdl = PDL
+        self.fused_rope = FUSED_ROPE
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.warm = 0
 
@@ -196,14 +199,14 @@ class DecodeWorkspace:
                           epilogue=SK_COLSCALE) for i, n in enumerate(names)]
             return SkinnyLaunch(probs, tuning, ws)
 
-        def up(layer, names, src, outs, residual=None):
+        def up(layer, names, src, outs, residual=None, tune=tuning):
             probs = []
             for i, (n, o) in enumerate(zip(names, outs)):
                 p = dict(A0=src, B0=W(layer, n), C=o, epilogue=SK_RESIDUAL if residual is not None else SK_NONE, residual=residual)
                 if R0:
                     p.update(A1=self.t[i], B1=layer.ad[n].B_all[:, :R0])
                 probs.append(p)
-            return SkinnyLaunch(probs, tuning, ws)
+            return SkinnyLaunch(probs, tune, ws)
 
         for layer in model.layers:
             L = {}
@@ -213,7 +216,9 @@ class DecodeWorkspace:
                 L["down_gu"] = down(layer, ("gate_proj", "up_proj"), self.xn)
                 L["down_d"] = down(layer, ("down_proj",), self.act)
             L["qkv"] = up(layer, ("q_proj", "k_proj", "v_proj"), self.xn, (self.q, self.k, self.v))
-            L["o"] = up(layer, ("o_proj",), self.attn, (self.x,), residual=self.x)
+            # o_proj (33.5 MB): the register kernel beats the stream-K kernel on launches this small (16.5 vs 22 us at M = 32: every CTA
+            # of the stream-K schedule would share both its row blocks with a neighbour), profiles/r02_decode.txt
+            L["o"] = up(layer, ("o_proj",), self.attn, (self.x,), residual=self.x, tune=tuning | 16)
             gu = dict(A0=self.xn, B0=W(layer, "gate_proj"), B0u=W(layer, "up_proj"), C=self.act, epilogue=SK_SILU_MUL)
             if R0:
                 gu.update(A1=self.t[0], B1=layer.ad["gate_proj"].B_all[:, :R0], A1u=self.t[1], B1u=layer.ad["up_proj"].B_all[:, :R0])
@@ -236,10 +241,19 @@ class DecodeWorkspace:
         m, lib, dtc, st = self.model, _cabi.lib(), _cabi.dtype_code(self.model.dtype), _cabi.current_stream_ptr()
         cos, sin = m._rope
         kc, vc = self.cache.k[li], self.cache.v[li]
+        km = self.key_mask
+        if self.fused_rope:
+            _cabi.check(lib.mc_decode_attention_fused(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.q.stride(0), kc.data_ptr(),
+                                                      vc.data_ptr(), self.capacity, self.pos.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                                                      None if km is None else km.data_ptr(), 0 if km is None else km.stride(0),
+                                                      self.attn.data_ptr(), self.attn.stride(0), self.B, self.nH, self.D,
+                                                      1.0 / math.sqrt(self.D), self.n_splits, self.att_scratch.data_ptr(),
+                                                      self.att_counters.data_ptr(), dtc, st), "mc_decode_attention_fused")
+            _cabi.count_launch()
+            return
         _cabi.check(lib.mc_decode_rope_append(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.q.stride(0), kc.data_ptr(),
                                               vc.data_ptr(), self.capacity, self.pos.data_ptr(), cos.data_ptr(), sin.data_ptr(),
                                               self.B, self.nH, self.D, dtc, st), "mc_decode_rope_append")
-        km = self.key_mask
         _cabi.check(lib.mc_decode_attention(self.q.data_ptr(), kc.data_ptr(), vc.data_ptr(), self.capacity, self.pos.data_ptr(),
                                             None if km is None else km.data_ptr(), 0 if km is None else km.stride(0),
                                             self.attn.data_ptr(), self.q.stride(0), self.attn.stride(0), self.B, self.nH, self.D,
@@ -280,7 +294,7 @@ class DecodeWorkspace:
         argmax_rows(self.logits, self.ids, self.next64, self.pos)
 
     def launches_per_step(self) -> int:
-        per_layer = len(self.launches[0]) + 4 if self.launches else 0
+        per_layer = len(self.launches[0]) + (3 if self.fused_rope else 4) if self.launches else 0
         return 1 + per_layer * len(self.launches) + 3
 
     def run(self) -> None:

@@ -135,6 +135,7 @@ def test_decode_rope_append_and_attention(key, B, nH, L, splits, masked):
     cap = L + 7
     kc, vc = rnd((B, nH, cap, D), g, dt), rnd((B, nH, cap, D), g, dt)   # [batch, heads, capacity, D]
     q, k, v = rnd((B, nH * D), g, dt), rnd((B, nH * D), g, dt), rnd((B, nH * D), g, dt)
+    q_raw = q.clone()
     cos, sin = _rope_tables(cap + 8, D, dt)
     pos = torch.tensor([L - 1], dtype=torch.int32, device="cuda")
     # reference RoPE through the library's own prefill op (bit-exact expected: same rounding points)
@@ -159,6 +160,17 @@ def test_decode_rope_append_and_attention(key, B, nH, L, splits, masked):
                                             None if mask is None else mask.data_ptr(), 0 if mask is None else cap, out.data_ptr(),
                                             nH * D, nH * D, B, nH, D, 1.0 / math.sqrt(D), splits, scratch.data_ptr(), counters.data_ptr(),
                                             _cabi.dtype_code(dt), st), "decode_attention")
+    assert int(counters.abs().sum()) == 0
+    # the fused launch (RoPE + append + attention) from the raw q / k / v: same cache contents and output, bit for bit
+    kc2, vc2 = kc.clone(), vc.clone()
+    kc2[:, :, L - 1], vc2[:, :, L - 1] = 7.0, -7.0
+    out2 = torch.empty_like(out)
+    q_raw_in = q_raw.clone()
+    _cabi.check(lib.mc_decode_attention_fused(q_raw.data_ptr(), k.data_ptr(), v.data_ptr(), nH * D, kc2.data_ptr(), vc2.data_ptr(), cap, pos.data_ptr(),
+                                              cos.data_ptr(), sin.data_ptr(), None if mask is None else mask.data_ptr(), 0 if mask is None else cap,
+                                              out2.data_ptr(), nH * D, B, nH, D, 1.0 / math.sqrt(D), splits, scratch.data_ptr(), counters.data_ptr(),
+                                              _cabi.dtype_code(dt), st), "decode_attention_fused")
+    assert torch.equal(kc2, kc) and torch.equal(vc2, vc) and torch.equal(out2, out) and torch.equal(q_raw, q_raw_in)
     assert int(counters.abs().sum()) == 0
     qf = q.float().view(B, nH, 1, D)
     kf, vf = kc[:, :, :L].float(), vc[:, :, :L].float()
@@ -319,6 +331,23 @@ def test_sampling_and_eos_on_the_native_decode_path(golden):
     b = model.generate(ids, modal_inputs=feats, max_new_tokens=4, do_sample=True, temperature=0.8, top_p=0.9,
                        generator=torch.Generator(device="cuda").manual_seed(5))
     assert a.shape == (3, ids.shape[1] + 4) and torch.equal(a, b)
+
+
+def test_fused_rope_attention_launch_is_bit_identical_in_the_loop(golden, monkeypatch):
+    dtype = torch.bfloat16
+    ids, feats = _prompt(4, dtype, seed=12)
+    outs = {}
+    for fused in (True, False):
+        monkeypatch.setattr(DC, "FUSED_ROPE", fused)
+        model = d128_model(golden, dtype)
+        outs[fused] = (model.generate(ids, modal_inputs=feats, max_new_tokens=10, do_sample=False), model._dws.logits.clone(),
+                       [k.clone() for k in model._dws.cache.k])
+        assert model._dws.fused_rope == fused
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    n = outs[True][0].shape[1]
+    for a, b in zip(outs[True][2], outs[False][2]):
+        L = model._dws.cache.length
+        assert torch.equal(a[:, :, :L], b[:, :, :L])
 
 
 def test_padded_text_only_batch_keeps_pads_masked(golden):
