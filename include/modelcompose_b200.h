@@ -423,6 +423,12 @@ typedef struct mc_skinny_plan mc_skinny_plan_t;
 MC_API size_t mc_skinny_workspace_bytes(void);
 MC_API int mc_skinny_plan_create(mc_skinny_plan_t** plan, const mc_skinny_desc_t* desc, int n_problems, int dtype, int tuning);
 MC_API int mc_skinny_plan_run(const mc_skinny_plan_t* plan, void* workspace, size_t workspace_bytes, mc_stream_t stream);
+/* Fuses the RMSNorm that PRODUCES the plan's activations into its launch: before the products, dst[rows, hidden] =
+ * rmsnorm(src) * weight is computed (one warp per row, exactly the arithmetic of mc_rmsnorm) while the first ring of weight tiles is
+ * already in flight; the problems of the plan are expected to read dst as their A0.  Stream-K kernel only.  Removes one launch
+ * (>= 5.5 us inside a captured graph) per norm of the decode step. */
+MC_API int mc_skinny_plan_set_norm(mc_skinny_plan_t* plan, const void* src, int64_t ld_src, const void* weight, void* dst, int64_t ld_dst,
+                            int rows, int hidden, float eps);
 /* weight bytes one run streams (the HBM roofline's numerator) */
 MC_API int64_t mc_skinny_plan_bytes(const mc_skinny_plan_t* plan);
 MC_API int mc_skinny_plan_destroy(mc_skinny_plan_t* plan);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "mc_skinny_plan_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i]),
     "mc_skinny_plan_run": (_i, [_vp, _vp, _sz, _vp]),
     "mc_skinny_plan_bytes": (_i64, [_vp]),
+    "mc_skinny_plan_set_norm": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _i, C.c_float]),
     "mc_skinny_plan_destroy": (_i, [_vp]),
     "mc_decode_rope_append": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "mc_decode_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, C.c_float, _i, _vp, _vp, _i, _vp]),

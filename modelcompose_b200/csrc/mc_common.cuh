@@ -141,4 +141,42 @@ __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2hal
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// One row of LlamaRMSNorm by ONE warp (fp32 variance, x * rsqrt(var + eps) rounded to the storage dtype, then weight * that, rounded
+// again): the body of rmsnorm_kernel (mc_ops.cu), shared with the skinny-linear kernel that computes the norm under its weight ramp.
+template <typename T>
+__device__ __forceinline__ void rmsnorm_row(const T* __restrict__ x_row, const T* __restrict__ w, T* __restrict__ out_row, int hidden, float eps,
+                                            int lane) {
+  const int n_vec = hidden >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x_row);
+  float ss = 0.f;
+  for (int i = lane; i < n_vec; i += 32) {
+    const uint4 u = xr[i];
+    const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float f = to_f32<T>(e[k]);
+      ss += f * f;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+  const float inv = rsqrtf(ss / (float)hidden + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out_row);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  for (int i = lane; i < n_vec; i += 32) {
+    const uint4 u = xr[i];  // second read hits L1/L2
+    const uint4 wu = wr[i];
+    const T* e = reinterpret_cast<const T*>(&u);
+    const T* we = reinterpret_cast<const T*>(&wu);
+    uint4 o;
+    T* oe = reinterpret_cast<T*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const T h = from_f32<T>(to_f32<T>(e[k]) * inv);
+      oe[k] = from_f32<T>(to_f32<T>(we[k]) * to_f32<T>(h));
+    }
+    orow[i] = o;
+  }
+}
+
 }  // namespace mc

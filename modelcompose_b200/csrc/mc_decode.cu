@@ -282,6 +282,15 @@ struct alignas(64) S2Params {
   int copy_only;   // profiling aid: consumers release the stages without reading them (pipeline ceiling)
   float* scratch;  // [grid][2][kS2TileFloats]
   int* counters;   // [total row blocks], zero between launches
+  // optional: the launch first computes norm_dst = rmsnorm(norm_src) * norm_w ([norm_rows, norm_hidden], one warp per row, the
+  // arithmetic of mc_rmsnorm) — the activations its problems read as A0 — while the first ring of weight boxes is in flight
+  const char* norm_src;
+  const char* norm_w;
+  char* norm_dst;
+  long long norm_lds, norm_ldd;  // bytes
+  int norm_rows, norm_hidden;
+  float norm_eps;
+  int* norm_cnt;   // [2]: CTAs that finished the norm, CTAs that finished the launch; zero between launches
 };
 
 struct S2Iter {  // position of the walk through the iteration space
@@ -352,7 +361,39 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
     fence_barrier_init();
   }
   __syncthreads();
-  if (it0 >= it1) return;
+  // fused RMSNorm (optional): every CTA's consumer warps take rows blockIdx.x * 8 + warp, + 8 * gridDim.x, ...; each CTA then counts
+  // that owns rows counts itself on norm_cnt[0] (one thread fences after the CTA barrier), and the producers hold the ACTIVATION boxes back
+  // until all of those have arrived (the weight boxes of the first ring are already in flight by then).  Generic-proxy stores, async-proxy (TMA)
+  // reads: the reader issues fence.proxy.async after the acquire.
+  auto norm_phase = [&]() {
+    if (P.norm_rows <= 0 || warp >= kS2Consumers) return;
+    griddep_wait();
+    for (int row = (int)blockIdx.x * kS2Consumers + warp; row < P.norm_rows; row += (int)gridDim.x * kS2Consumers) {
+      if constexpr (F16)
+        rmsnorm_row<__half>(reinterpret_cast<const __half*>(P.norm_src + row * P.norm_lds), reinterpret_cast<const __half*>(P.norm_w),
+                            reinterpret_cast<__half*>(P.norm_dst + row * P.norm_ldd), P.norm_hidden, P.norm_eps, lane);
+      else
+        rmsnorm_row<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(P.norm_src + row * P.norm_lds), reinterpret_cast<const __nv_bfloat16*>(P.norm_w),
+                                   reinterpret_cast<__nv_bfloat16*>(P.norm_dst + row * P.norm_ldd), P.norm_hidden, P.norm_eps, lane);
+    }
+    if ((int)blockIdx.x * kS2Consumers >= P.norm_rows) return;  // only the CTAs that own rows arrive (the producers wait for exactly those)
+    consumer_bar();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(P.norm_cnt, 1);
+    }
+  };
+  auto norm_exit = [&]() {  // the last CTA to finish the launch re-arms the two counters (every producer has passed its wait by then)
+    if (P.norm_rows > 0 && threadIdx.x == 0 && atomicAdd(P.norm_cnt + 1, 1) == (int)gridDim.x - 1) {
+      P.norm_cnt[0] = 0;
+      P.norm_cnt[1] = 0;
+    }
+  };
+  if (it0 >= it1) {
+    norm_phase();
+    norm_exit();
+    return;
+  }
 
   if (warp == kS2Consumers) {
     // ------------------------------------------------------------------------------------------------ producer (one lane issues)
@@ -401,6 +442,16 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
       s2_advance(P, w);
     }
     griddep_wait();
+    if (P.norm_rows > 0) {
+      if (lane == 0) {
+        const int owners = min((int)gridDim.x, (P.norm_rows + kS2Consumers - 1) / kS2Consumers);
+        while (*reinterpret_cast<volatile int*>(P.norm_cnt) < owners) {
+        }
+        __threadfence();
+      }
+      __syncwarp();
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
     w = s2_locate(P, it0);
     for (int i = 0; i < pre; ++i) {
       fill(i, w, 2);
@@ -416,6 +467,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
 
   // -------------------------------------------------------------------------------------------------- consumers
   griddep_wait();
+  norm_phase();
   const int tp = warp % TP, kp = warp / TP, g = lane >> 2, t = lane & 3;
   const int tid = threadIdx.x;  // 0 .. 255
   float acc[2][NT][4];
@@ -563,6 +615,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) skinny_streamk_kernel(const __g
     }
     s2_advance(P, w);
   }
+  norm_exit();
 }
 
 // ================================================================================================ RoPE + cache append
@@ -1078,7 +1131,7 @@ extern "C" int mc_skinny_plan_create(mc_skinny_plan_t** out, const mc_skinny_des
       if (rc == MC_OK && d.K1 > 0 && dual) rc = encode_operand(&q.tmB1u, d.B1u, d.N, d.K1, d.ldb1, F, dtype);
       if (rc == MC_OK && d.K1 > 0 && dual) rc = encode_operand(&q.tmA1u, d.A1u, d.M, d.K1, d.lda1, MT, dtype);
     }
-    if (rc == MC_OK && rbs > kS2MaxRowBlocks) rc = fail(MC_ERR_INVALID, "skinny linear: %d row blocks exceed the workspace (%d)", rbs, kS2MaxRowBlocks);
+    if (rc == MC_OK && rbs > kS2MaxRowBlocks - 2) rc = fail(MC_ERR_INVALID, "skinny linear: %d row blocks exceed the workspace (%d)", rbs, kS2MaxRowBlocks - 2);
     if (rc != MC_OK) {
       delete p;
       return rc;
@@ -1108,6 +1161,7 @@ extern "C" int mc_skinny_plan_run(const mc_skinny_plan_t* p, void* workspace, si
                "skinny linear: workspace missing, smaller than mc_skinny_workspace_bytes() or misaligned");
     S2Params Q = p->sk;
     Q.counters = (int*)workspace;
+    Q.norm_cnt = Q.counters + kS2MaxRowBlocks - 2;  // the last two counters (row blocks use at most kS2MaxRowBlocks - 2)
     Q.scratch = (float*)((char*)workspace + (size_t)kS2MaxRowBlocks * sizeof(int));
     if (p->rt2 == 2) e = p->f16 ? launch_streamk_nt<2, true>(Q, p->nt, p->grid, p->smem, (cudaStream_t)stream)
                                 : launch_streamk_nt<2, false>(Q, p->nt, p->grid, p->smem, (cudaStream_t)stream);
@@ -1121,6 +1175,25 @@ extern "C" int mc_skinny_plan_run(const mc_skinny_plan_t* p, void* workspace, si
                : launch_skinny_nt<2, false>(p->reg, p->reg_ctas, p->nt, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) return fail(MC_ERR_CUDA, "skinny linear launch failed: %s", cudaGetErrorString(e));
+  return MC_OK;
+}
+
+extern "C" int mc_skinny_plan_set_norm(mc_skinny_plan_t* p, const void* src, int64_t ld_src, const void* weight, void* dst, int64_t ld_dst,
+                                       int rows, int hidden, float eps) {
+  MC_REQUIRE(p != nullptr, "skinny plan is NULL");
+  MC_REQUIRE(p->streamk, "skinny linear: the fused RMSNorm needs the stream-K kernel (not tuning bit 4)");
+  MC_REQUIRE(src && weight && dst && rows >= 1 && rows <= MC_SKINNY_MAX_M && hidden >= 8 && hidden % 8 == 0 && ld_src >= hidden &&
+                 ld_dst >= hidden && ld_src % 8 == 0 && ld_dst % 8 == 0, "skinny linear: bad RMSNorm shape");
+  MC_REQUIRE((((uintptr_t)src | (uintptr_t)weight | (uintptr_t)dst) & 15) == 0, "skinny linear: RMSNorm pointers must be 16-byte aligned");
+  S2Params& Q = p->sk;
+  Q.norm_src = (const char*)src;
+  Q.norm_w = (const char*)weight;
+  Q.norm_dst = (char*)dst;
+  Q.norm_lds = ld_src * 2;
+  Q.norm_ldd = ld_dst * 2;
+  Q.norm_rows = rows;
+  Q.norm_hidden = hidden;
+  Q.norm_eps = eps;
   return MC_OK;
 }
 

@@ -20,39 +20,8 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
   griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int n_vec = hidden >> 3;
-  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
-    float ss = 0.f;
-    for (int i = lane; i < n_vec; i += 32) {
-      const uint4 u = xr[i];
-      const T* e = reinterpret_cast<const T*>(&u);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float f = to_f32<T>(e[k]);
-        ss += f * f;
-      }
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
-    const float inv = rsqrtf(ss / (float)hidden + eps);
-    uint4* orow = reinterpret_cast<uint4*>(out + row * ldo);
-    const uint4* wr = reinterpret_cast<const uint4*>(w);
-    for (int i = lane; i < n_vec; i += 32) {
-      const uint4 u = xr[i];  // second read hits L1/L2
-      const uint4 wu = wr[i];
-      const T* e = reinterpret_cast<const T*>(&u);
-      const T* we = reinterpret_cast<const T*>(&wu);
-      uint4 o;
-      T* oe = reinterpret_cast<T*>(&o);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const T h = from_f32<T>(to_f32<T>(e[k]) * inv);
-        oe[k] = from_f32<T>(to_f32<T>(we[k]) * to_f32<T>(h));
-      }
-      orow[i] = o;
-    }
-  }
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps)
+    rmsnorm_row<T>(x + row * ldx, w, out + row * ldo, hidden, eps, lane);
 }
 
 // One thread rotates 8 element pairs (i, i + D/2) of one head of q or k.

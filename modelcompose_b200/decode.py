@@ -32,6 +32,11 @@ MAX_M = 64
 PDL = os.environ.get("MC_DECODE_PDL", "1") != "0"
 # RoPE of the new q / k and the cache append inside the attention launch (mc_decode_attention_fused); 0 = two launches (A/B switch)
 FUSED_ROPE = os.environ.get("MC_DECODE_FUSED_ROPE", "1") != "0"
+# 1 = the RMSNorms of the step inside the skinny launch that consumes them (mc_skinny_plan_set_norm: bit-identical, 65 launches fewer).
+# Default 0: measured 2-3 % SLOWER (7.50 vs 7.29 ms materialised, profiles/r02_decode.txt step 11) — with programmatic dependent launch the
+# separate rmsnorm kernel already runs under the next launch's weight prefetch, while the in-kernel norm puts a cross-CTA wait in front
+# of the activation loads.
+FUSED_NORM = os.environ.get("MC_DECODE_FUSED_NORM", "0") != "0"
 
 
 class SkinnyDesc(C.Structure):
@@ -120,6 +125,15 @@ class SkinnyLaunch:
                                                       self.tuning), "mc_skinny_plan_create")
         assert int(_cabi.lib().mc_skinny_plan_bytes(self._h)) == self.bytes
 
+    def set_norm(self, src: torch.Tensor, weight: torch.Tensor, dst: torch.Tensor, eps: float) -> None:
+        """The launch first computes ``dst = rmsnorm(src) * weight`` (the activations its problems read) under its weight ramp."""
+        s_, d_ = _m(src, "norm src", self.dtype), _m(dst, "norm dst", self.dtype)
+        if tuple(s_.shape) != tuple(d_.shape) or weight.dtype != self.dtype or weight.numel() != s_.shape[1] or not weight.is_cuda:
+            raise ValueError("skinny linear: RMSNorm src / dst / weight do not match")
+        self.keep_norm = (src, weight, dst)
+        _cabi.check(_cabi.lib().mc_skinny_plan_set_norm(self._h, s_.data_ptr(), s_.stride(0), weight.data_ptr(), d_.data_ptr(), d_.stride(0),
+                                                        s_.shape[0], s_.shape[1], float(eps)), "mc_skinny_plan_set_norm")
+
     def run(self) -> None:
         _cabi.check(_cabi.lib().mc_skinny_plan_run(self._h, self.ws.data_ptr(), self.ws.numel(), _cabi.current_stream_ptr()),
                     "mc_skinny_plan_run")
@@ -166,6 +180,7 @@ class DecodeWorkspace:
         self.use_graph = use_graph
         self.pdl = PDL
         self.fused_rope = FUSED_ROPE
+        self.fused_norm = FUSED_NORM
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.warm = 0
 
@@ -224,9 +239,15 @@ class DecodeWorkspace:
                 gu.update(A1=self.t[0], B1=layer.ad["gate_proj"].B_all[:, :R0], A1u=self.t[1], B1u=layer.ad["up_proj"].B_all[:, :R0])
             L["gu"] = SkinnyLaunch([gu], tuning, ws)
             L["d"] = up(layer, ("down_proj",), self.act, (self.x,), residual=self.x)
+            if self.fused_norm:  # the first launch that reads xn computes it: input_layernorm -> q/k/v side, post_attention_layernorm -> MLP side
+                eps = float(cfg.rms_norm_eps)
+                L["down_qkv" if R0 else "qkv"].set_norm(self.x, layer.ln1, self.xn, eps)
+                L["down_gu" if R0 else "gu"].set_norm(self.x, layer.ln2, self.xn, eps)
             self.launches.append(L)
             self.weight_bytes += sum(v.bytes for v in L.values())
         self.lm_head = SkinnyLaunch([dict(A0=self.xn, B0=model.lm_head, C=self.logits)], tuning, ws)
+        if self.fused_norm:
+            self.lm_head.set_norm(self.x, model.norm, self.xn, float(cfg.rms_norm_eps))
         self.weight_bytes += self.lm_head.bytes
 
     # ---------------------------------------------------------------------------------------------------------------
@@ -273,7 +294,8 @@ class DecodeWorkspace:
         m = self.model
         LN.gather_rows(m.embed_tokens, self.ids, self.x)
         for li, (layer, L) in enumerate(zip(m.layers, self.launches)):
-            m._rmsnorm(self.x, layer.ln1, self.xn)
+            if not self.fused_norm:
+                m._rmsnorm(self.x, layer.ln1, self.xn)
             if "down_qkv" in L:
                 L["down_qkv"].run()
             L["qkv"].run()
@@ -281,21 +303,23 @@ class DecodeWorkspace:
             if "down_o" in L:
                 L["down_o"].run()
             L["o"].run()
-            m._rmsnorm(self.x, layer.ln2, self.xn)
+            if not self.fused_norm:
+                m._rmsnorm(self.x, layer.ln2, self.xn)
             if "down_gu" in L:
                 L["down_gu"].run()
             L["gu"].run()
             if "down_d" in L:
                 L["down_d"].run()
             L["d"].run()
-        m._rmsnorm(self.x, m.norm, self.xn)
+        if not self.fused_norm:
+            m._rmsnorm(self.x, m.norm, self.xn)
         self.lm_head.run()
         # greedy sampler + hand-over: next ids into the gather index of the next step, position counter + 1
         argmax_rows(self.logits, self.ids, self.next64, self.pos)
 
     def launches_per_step(self) -> int:
-        per_layer = len(self.launches[0]) + (3 if self.fused_rope else 4) if self.launches else 0
-        return 1 + per_layer * len(self.launches) + 3
+        per_layer = len(self.launches[0]) + (1 if self.fused_rope else 2) + (0 if self.fused_norm else 2) if self.launches else 0
+        return 1 + per_layer * len(self.launches) + (2 if self.fused_norm else 3)
 
     def run(self) -> None:
         """One decode step from the state in ``ids`` / ``pos``; leaves logits, next ids (``ids`` / ``next64``) and ``pos`` + 1."""

@@ -333,16 +333,20 @@ def test_sampling_and_eos_on_the_native_decode_path(golden):
     assert a.shape == (3, ids.shape[1] + 4) and torch.equal(a, b)
 
 
-def test_fused_rope_attention_launch_is_bit_identical_in_the_loop(golden, monkeypatch):
+@pytest.mark.parametrize("what", ["FUSED_ROPE", "FUSED_NORM"])
+@pytest.mark.parametrize("materialize", [False, True])
+def test_fused_rope_attention_launch_is_bit_identical_in_the_loop(golden, monkeypatch, what, materialize):
+    """RoPE + append inside the attention launch, and the RMSNorms inside the skinny launches that consume them, against the
+    separate launches: same tokens, logits and cache contents, bit for bit."""
     dtype = torch.bfloat16
     ids, feats = _prompt(4, dtype, seed=12)
     outs = {}
     for fused in (True, False):
-        monkeypatch.setattr(DC, "FUSED_ROPE", fused)
-        model = d128_model(golden, dtype)
+        monkeypatch.setattr(DC, what, fused)
+        model = d128_model(golden, dtype, materialize)
         outs[fused] = (model.generate(ids, modal_inputs=feats, max_new_tokens=10, do_sample=False), model._dws.logits.clone(),
                        [k.clone() for k in model._dws.cache.k])
-        assert model._dws.fused_rope == fused
+        assert getattr(model._dws, what.lower()) == fused
     assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
     n = outs[True][0].shape[1]
     for a, b in zip(outs[True][2], outs[False][2]):
