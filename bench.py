@@ -644,7 +644,7 @@ def run_ties(device, steps: int = 10, K: int = 20, func: str = "mean"):
                         "traffic_unit": "DRAM read+write bytes of one plan run summed over its kernels (ncu capture, profiles/traffic.json), scaled by "
                                         "this run's algorithmic bytes",
                         "peak_source": peak_src, "kernel": "whole mc_ties_plan_run (sample, bracket, count, select, merge, fix-up)"},
-           "stats": st, "gpu_launches": 11 * steps}
+           "stats": st, "gpu_launches": 6 * steps}  # sample + bracket, count + window select, full-range pass (no-op), merge, fix-up, re-merge (no-op)
     del plan, srcs, outs
     torch.cuda.empty_cache()
     return res

@@ -4,12 +4,12 @@
 // scripts/model_composition/merge_unimodal_modelcompose.py:59-64,75-85 (`ties-*`, `convert-drop-*`).
 //
 // Roofline: HBM.  Every pass streams the sources once with 128-bit L1::no_allocate loads:
-//   select   bf16 / fp16: ties_sample_kernel (1/32 of the data, 2^15 shared-memory bins) -> ties_bracket_kernel (key bracket of
-//            the k-th magnitude) -> ties_count_kernel (one pass: SIMD ">= t" counters per bin boundary of the bracket) ->
-//            ties_window_select_kernel; a bracket miss, small inputs and fp32 take the full-range radix passes
-//            (ties_hist_kernel -> ties_select_kernel, 1 pass of 15 bits or 3 passes of 11+10+10 bits)
+//   select   bf16 / fp16: ties_sample_kernel (1/32 .. 1/256 of the data, 2^15 shared-memory bins; its last CTA per source turns the
+//            sample into the key bracket of the k-th magnitude) -> ties_count_kernel (one pass: SIMD ">= t" counters per bin boundary
+//            of the bracket; its last CTA per source picks the bin); a bracket miss, small inputs and fp32 take the full-range radix
+//            passes (ties_hist_kernel, whose last CTA per source selects the digit; 1 pass of 15 bits or 3 passes of 11+10+10 bits)
 //   merge    ties_merge_kernel, speculative majority +1, census of elected signs (mc_ties_kernels.cuh)
-//   fix      ties_finalize_kernel decides: nothing / ties_fix_kernel over the listed majority-dependent elements / a dense
+//   fix      ties_fix_kernel decides from the census: nothing / recompute the listed majority-dependent elements / a dense
 //            re-merge (list overflow, or MAX with a negative majority); the unused kernels exit at once
 // Algorithmic bytes per element = (passes + 1) * n_src * sizeof(src) + sizeof(dst)  (bf16, 3 sources, sum: 14 B).
 #include <algorithm>
@@ -32,13 +32,96 @@ __device__ __forceinline__ unsigned int magnitude_key<__nv_bfloat16>(__nv_bfloat
   return (unsigned int)(__bfloat16_as_ushort(v) & 0x7fffu);
 }
 
+// True in exactly one CTA of the launch per source: the one that arrives last, after every CTA's global atomics on the
+// histogram are visible.  Call with all threads; the counter is back at 0 when the launch ends.
+__device__ __forceinline__ bool ties_last_cta_of_source(TiesState* st, int src, unsigned int n_ctas) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&st->done[src], 1u);
+    s_last = prev == n_ctas - 1u;
+    if (s_last) st->done[src] = 0u;
+  }
+  __syncthreads();
+  const bool last = s_last != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+// Inclusive scan of one value per thread over a 1024-thread CTA: shuffles inside the warps, one pass over the 32 warp totals.
+__device__ __forceinline__ unsigned long long ties_scan_1024(unsigned long long local, unsigned long long* s_warp /* [33] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long x = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  __syncthreads();  // s_warp may still be read by an earlier call
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = s_warp[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += y;
+    }
+    s_warp[lane] = w;
+    if (lane == 31) s_warp[32] = w;  // grand total
+  }
+  __syncthreads();
+  return x + (warp ? s_warp[warp - 1] : 0ull);
+}
+
+// The last CTA of a source in ties_hist_kernel: find the bin holding rank k_rem, append it to the prefix, clear the histogram for the next pass.
+// `key_kind` on the last pass turns the finished key into the threshold value: 0 fp32 bits, 1 fp16 bits, 2 bf16 bits.
+__device__ __forceinline__ void ties_select_cta(unsigned long long* gh, TiesState* st, int src, int bits, int last, int key_kind) {
+  __shared__ unsigned long long s_warp[33];
+  const int tid = threadIdx.x;
+  const int nbins = 1 << bits;
+  const int per = nbins >= 1024 ? nbins / 1024 : 1;
+  const int b0 = tid * per;
+  unsigned long long local = 0ull;
+  if (b0 < nbins)
+    for (int i = 0; i < per; ++i) local += __ldcg(gh + b0 + i);
+  const unsigned long long incl = ties_scan_1024(local, s_warp), excl = incl - local;
+  const unsigned long long k = st->k_rem[src];
+  if (b0 < nbins && excl < k && k <= incl) {
+    unsigned long long cum = excl;
+    int b = b0;
+    for (int i = 0; i < per; ++i) {
+      const unsigned long long c = __ldcg(gh + b0 + i);
+      if (cum + c >= k) {
+        b = b0 + i;
+        break;
+      }
+      cum += c;
+    }
+    const unsigned int key = (st->prefix[src] << bits) | (unsigned int)b;
+    st->prefix[src] = key;
+    st->k_rem[src] = k - cum;
+    if (last) {
+      float thr;
+      if (key_kind == 0) thr = __uint_as_float(key);
+      else if (key_kind == 1) thr = __half2float(__ushort_as_half((unsigned short)key));
+      else thr = __uint_as_float(key << 16);
+      st->thr[src] = thr;
+    }
+  }
+  __syncthreads();
+  if (b0 < nbins)
+    for (int i = 0; i < per; ++i) gh[b0 + i] = 0ull;
+}
+
 // Histogram of digit ((key >> shift) & (2^bits - 1)) over the elements of source blockIdx.y whose higher key bits equal
 // the prefix found by the earlier passes.  One shared-memory histogram per CTA (<= 128 KB), flushed with 64-bit global
 // atomics; CTAs take super-chunks of 4 chunks so every thread has four 128-bit loads in flight.
 template <typename S>
 __global__ void __launch_bounds__(kTiesHistThreads, 1)
-ties_hist_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, const TiesState* __restrict__ st,
-                 unsigned long long* __restrict__ ghist, int shift, int bits, int hi_shift) {
+ties_hist_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, TiesState* st,
+                 unsigned long long* __restrict__ ghist, int shift, int bits, int hi_shift, int last, int key_kind) {
   extern __shared__ unsigned int s_hist[];
   constexpr int E = 16 / sizeof(S);
   constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
@@ -97,75 +180,30 @@ ties_hist_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict
     const unsigned int c = s_hist[i];
     if (c) atomicAdd(gh + i, (unsigned long long)c);
   }
+  if (ties_last_cta_of_source(st, src, gridDim.x)) ties_select_cta(gh, st, src, bits, last, key_kind);
 }
 
+__device__ __forceinline__ void ties_init_source(TiesState* st, int i, unsigned long long kth) {
+  st->k_rem[i] = kth;
+  st->prefix[i] = 0u;
+  st->thr[i] = 0.0f;
+  st->win_lo[i] = 0u;
+  st->win_hi[i] = 0u;
+  st->below[i] = 0ull;
+}
+__device__ __forceinline__ void ties_init_globals(TiesState* st, int need_full) {
+  st->need_full = need_full;
+  st->n_pos = st->n_neg = st->n_zero = st->n_amb = 0ull;
+  st->majority = 1;
+  st->need_fix = 0;
+  st->fix_count = 0u;
+}
+
+// Start of a run without the sampling pass (the sampled path resets the state in ties_sample_kernel).
 __global__ void ties_init_kernel(TiesState* st, unsigned long long kth, int n_src, int need_full) {
   const int i = threadIdx.x;
-  if (i < MC_MERGE_MAX_SRC) {
-    st->k_rem[i] = i < n_src ? kth : 0ull;
-    st->prefix[i] = 0u;
-    st->thr[i] = 0.0f;
-    st->win_lo[i] = 0u;
-    st->win_hi[i] = 0u;
-    st->below[i] = 0ull;
-  }
-  if (i == 0) st->need_full = need_full;
-  if (i == 0) {
-    st->n_pos = st->n_neg = st->n_zero = st->n_amb = 0ull;
-    st->majority = 1;
-    st->need_fix = 0;
-    st->fix_count = 0u;
-  }
-}
-
-// One CTA per source: find the bin holding rank k_rem, append it to the prefix, clear the histogram for the next pass.
-// `key_kind` on the last pass turns the finished key into the threshold value: 0 fp32 bits, 1 fp16 bits, 2 bf16 bits.
-__global__ void __launch_bounds__(1024) ties_select_kernel(unsigned long long* __restrict__ ghist, TiesState* st, int bits, int last, int key_kind) {
-  __shared__ unsigned long long s_part[1024];
-  if (!st->need_full) return;
-  const int src = blockIdx.x, tid = threadIdx.x;
-  const int nbins = 1 << bits;
-  const int per = nbins >= 1024 ? nbins / 1024 : 1;
-  unsigned long long* gh = ghist + (size_t)src * nbins;
-  const int b0 = tid * per;
-  unsigned long long local = 0ull;
-  if (b0 < nbins)
-    for (int i = 0; i < per; ++i) local += gh[b0 + i];
-  s_part[tid] = local;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan over the per-thread partial sums
-    const unsigned long long add = tid >= off ? s_part[tid - off] : 0ull;
-    __syncthreads();
-    s_part[tid] += add;
-    __syncthreads();
-  }
-  const unsigned long long k = st->k_rem[src];
-  const unsigned long long incl = s_part[tid], excl = incl - local;
-  if (b0 < nbins && excl < k && k <= incl) {
-    unsigned long long cum = excl;
-    int b = b0;
-    for (int i = 0; i < per; ++i) {
-      const unsigned long long c = gh[b0 + i];
-      if (cum + c >= k) {
-        b = b0 + i;
-        break;
-      }
-      cum += c;
-    }
-    const unsigned int key = (st->prefix[src] << bits) | (unsigned int)b;
-    st->prefix[src] = key;
-    st->k_rem[src] = k - cum;
-    if (last) {
-      float thr;
-      if (key_kind == 0) thr = __uint_as_float(key);
-      else if (key_kind == 1) thr = __half2float(__ushort_as_half((unsigned short)key));
-      else thr = __uint_as_float(key << 16);
-      st->thr[src] = thr;
-    }
-  }
-  __syncthreads();
-  if (b0 < nbins)
-    for (int i = 0; i < per; ++i) gh[b0 + i] = 0ull;
+  if (i < MC_MERGE_MAX_SRC) ties_init_source(st, i, i < n_src ? kth : 0ull);
+  if (i == 0) ties_init_globals(st, need_full);
 }
 
 // ---- sampled bracket (bf16 / fp16) --------------------------------------------------------------------------------
@@ -183,58 +221,29 @@ __device__ __forceinline__ float key_to_float<__nv_bfloat16>(unsigned int key) {
 template <>
 __device__ __forceinline__ float key_to_float<float>(unsigned int key) { return __uint_as_float(key); }
 
-template <typename S>
-__global__ void __launch_bounds__(kTiesHistThreads, 1)
-ties_sample_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, const TiesState* __restrict__ st,
-                   unsigned long long* __restrict__ ghist) {
-  extern __shared__ unsigned int s_hist[];
-  if (st->need_full) return;
-  constexpr int E = 16 / sizeof(S);
-  constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
-  constexpr int NB = 1 << 15;
-  const int src = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < NB; i += kTiesHistThreads) s_hist[i] = 0u;
-  __syncthreads();
-  for (int c0 = blockIdx.x * 32; c0 < nchunks; c0 += gridDim.x * 32) {
-    const int c = c0 + warp;
-    if (c >= nchunks) continue;
-    const MergeChunk ch = chunks[c];
-    const MergeSeg* sg = segs + ch.seg;
-    const long long base = (long long)ch.idx * CHUNK;
-    const long long n = min((long long)CHUNK, sg->numel - base);
-    const int granule = (int)(((unsigned int)c * 7u) % (unsigned int)kTiesSampleEvery);  // which 512 B of the chunk
-    const long long first = (long long)(granule * 32 + lane) * E;
-    const S* p = reinterpret_cast<const S*>(sg->src[src]) + base;
-    if (sg->aligned && first + E <= n) {
-      const Vec<16> v = ld_stream(reinterpret_cast<const Vec<16>*>(p + first));
-#pragma unroll
-      for (int e = 0; e < E; ++e) atomicAdd(&s_hist[magnitude_key<S>(reinterpret_cast<const S*>(&v)[e])], 1u);
-    } else {
-      for (long long i = first; i < min(first + E, n); ++i) atomicAdd(&s_hist[magnitude_key<S>(p[i])], 1u);
-    }
-  }
-  __syncthreads();
-  unsigned long long* gh = ghist + (size_t)src * NB;
-  for (int i = threadIdx.x; i < NB; i += kTiesHistThreads) {
-    const unsigned int c = s_hist[i];
-    if (c) atomicAdd(gh + i, (unsigned long long)c);
-  }
-}
-
-// One CTA per source over the 2^15-bin sample histogram: bins holding the sample ranks t - margin and t + margin, where
-// t = k * n_sample / d.  Clears the histogram for the counting pass.
-__global__ void __launch_bounds__(1024) ties_bracket_kernel(unsigned long long* __restrict__ ghist, TiesState* st, unsigned long long kth,
-                                                            unsigned long long d_total) {
-  extern __shared__ unsigned int s_cnt[];  // 2^15 sample counts, padded (+1 word per 32) so a thread's 32 bins are conflict-free
-  __shared__ unsigned long long s_part[1024];
+// The last sampling CTA of a source, over its 2^15-bin sample histogram: bins holding the sample ranks t - margin and t + margin,
+// where t = k * n_sample / d.  Clears the histogram for the counting pass.  s_cnt: 2^15 + 2^10 words of shared memory.
+__device__ __forceinline__ void ties_bracket_cta(unsigned long long* gh, TiesState* st, int src, unsigned long long kth,
+                                                 unsigned long long d_total, unsigned int* s_cnt) {
+  // s_cnt: the sample counts, padded (+1 word per 32) so a thread's 32 bins are conflict-free
+  __shared__ unsigned long long s_warp[33];
   __shared__ unsigned int s_lo, s_hi;
-  if (st->need_full) return;
   constexpr int NB = 1 << 15, PER = NB / 1024;
-  const int src = blockIdx.x, tid = threadIdx.x;
-  unsigned long long* gh = ghist + (size_t)src * NB;
-  for (int b = tid; b < NB; b += 1024) {  // coalesced read, cleared for the counting pass on the way
-    s_cnt[b + (b >> 5)] = (unsigned int)gh[b];
-    gh[b] = 0ull;
+  const int tid = threadIdx.x;
+  {  // coalesced read in two batches of 16 independent loads per thread, cleared for the counting pass on the way
+    constexpr int BATCH = 16;
+#pragma unroll
+    for (int b0 = 0; b0 < NB; b0 += 1024 * BATCH) {
+      unsigned long long g[BATCH];
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) g[i] = __ldcg(gh + b0 + i * 1024 + tid);
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        const int b = b0 + i * 1024 + tid;
+        s_cnt[b + (b >> 5)] = (unsigned int)g[i];
+        gh[b] = 0ull;
+      }
+    }
   }
   if (tid == 0) {
     s_lo = 0u;
@@ -244,19 +253,12 @@ __global__ void __launch_bounds__(1024) ties_bracket_kernel(unsigned long long* 
   unsigned long long local = 0ull;
 #pragma unroll
   for (int i = 0; i < PER; ++i) local += s_cnt[tid * (PER + 1) + i];
-  s_part[tid] = local;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const unsigned long long add = tid >= off ? s_part[tid - off] : 0ull;
-    __syncthreads();
-    s_part[tid] += add;
-    __syncthreads();
-  }
-  const float n_s = (float)s_part[1023];
+  const unsigned long long incl = ties_scan_1024(local, s_warp);
+  const float n_s = (float)s_warp[32];
   const float q = (float)((double)kth / (double)d_total);
   const float t = q * n_s, margin = 6.0f * sqrtf(n_s * q * (1.0f - q)) + 64.0f;
   const float r_lo = t - margin, r_hi = t + margin;  // sample ranks (1-based) that bracket the k-th element
-  unsigned long long cum = s_part[tid] - local;
+  unsigned long long cum = incl - local;
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     const unsigned int c = s_cnt[tid * (PER + 1) + i];
@@ -269,18 +271,107 @@ __global__ void __launch_bounds__(1024) ties_bracket_kernel(unsigned long long* 
   }
   __syncthreads();
   if (tid == 0) {
-    // a bracket wider than the window is clipped: the select notices if the rank lies beyond it and asks for the full passes
+    // this source's part of the run state starts here.  A bracket wider than the window is clipped (no samples at all: bins
+    // 0 .. window - 1): the window select notices if the rank lies beyond it and asks for the full passes
+    ties_init_source(st, src, kth);
     st->win_lo[src] = s_lo;
     st->win_hi[src] = min(s_hi, s_lo + (unsigned int)kTiesWindowBins - 1u);
-    if (n_s < 1.0f) atomicExch(&st->need_full, 1);
   }
+}
+
+// First kernel of a sampled run: CTA (0, 0) resets the run-wide part of the device state (nothing in this launch reads it), the
+// last CTA of each source that source's part.  Each warp takes
+// four chunks per trip — descriptors, then the four 512-byte granules, then the shared-memory atomics — so four DRAM round
+// trips overlap instead of following one another.
+template <typename S>
+__global__ void __launch_bounds__(kTiesHistThreads, 1)
+ties_sample_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, int nchunks, TiesState* st,
+                   unsigned long long* __restrict__ ghist, unsigned long long kth, unsigned long long d_total, int every) {
+  extern __shared__ unsigned int s_hist[];
+  constexpr int E = 16 / sizeof(S);
+  constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
+  constexpr int NB = 1 << 15;
+  constexpr int U = 4;
+  const int src = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ties_init_globals(st, 0);
+  for (int i = threadIdx.x; i < NB; i += kTiesHistThreads) s_hist[i] = 0u;
+  __syncthreads();
+  // `every`: only every `every`-th chunk contributes its granule (large inputs: 2^21 samples per source bracket the rank as
+  // tightly as 2^25 would — the bracket is 1-3 bins of the dtype either way — and the shared-memory atomics bound this pass)
+  const int nsel = (nchunks + every - 1) / every;
+  for (int c0 = blockIdx.x * 32 * U; c0 < nsel; c0 += gridDim.x * 32 * U) {
+    const S* ptr[U];
+    long long first[U], n[U];
+    bool vec_ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int c = (c0 + u * 32 + warp) * every;
+      ptr[u] = nullptr;
+      if (c >= nchunks) continue;
+      const MergeChunk ch = chunks[c];
+      const MergeSeg* sg = segs + ch.seg;
+      const long long base = (long long)ch.idx * CHUNK;
+      n[u] = min((long long)CHUNK, sg->numel - base);
+      const int granule = (int)(((unsigned int)c * 7u) % (unsigned int)kTiesSampleEvery);  // which 512 B of the chunk
+      first[u] = (long long)(granule * 32 + lane) * E;
+      ptr[u] = reinterpret_cast<const S*>(sg->src[src]) + base;
+      vec_ok[u] = sg->aligned && first[u] + E <= n[u];
+    }
+    Vec<16> v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (ptr[u] != nullptr && vec_ok[u]) v[u] = ld_stream(reinterpret_cast<const Vec<16>*>(ptr[u] + first[u]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ptr[u] == nullptr) continue;
+      if (vec_ok[u]) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) atomicAdd(&s_hist[magnitude_key<S>(reinterpret_cast<const S*>(&v[u])[e])], 1u);
+      } else {
+        for (long long i = first[u]; i < min(first[u] + E, n[u]); ++i) atomicAdd(&s_hist[magnitude_key<S>(ptr[u][i])], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long* gh = ghist + (size_t)src * NB;
+  for (int i = threadIdx.x; i < NB; i += kTiesHistThreads) {
+    const unsigned int c = s_hist[i];
+    if (c) atomicAdd(gh + i, (unsigned long long)c);
+  }
+  if (ties_last_cta_of_source(st, src, gridDim.x)) ties_bracket_cta(gh, st, src, kth, d_total, s_hist);
+}
+
+// The last counting CTA of a source: the bin of the bracket that holds rank k - below; a rank outside the bracket requests the
+// full passes.  Cleans the bracket's bins for whatever pass comes next.
+template <typename S>
+__device__ __forceinline__ void ties_window_select_cta(unsigned long long* gh /* this source's 2^15 bins */, TiesState* st, int src,
+                                                       unsigned long long kth) {
+  const unsigned int lo = st->win_lo[src], hi = st->win_hi[src];
+  if (threadIdx.x == 0) {
+    const unsigned long long below = *reinterpret_cast<volatile unsigned long long*>(&st->below[src]);
+    bool found = false;
+    if (kth > below) {
+      unsigned long long cum = below;
+      for (unsigned int b = lo; b <= hi; ++b) {
+        cum += __ldcg(gh + b);
+        if (cum >= kth) {
+          st->thr[src] = key_to_float<S>(b);
+          found = true;
+          break;
+        }
+      }
+    }
+    if (!found) atomicExch(&st->need_full, 1);
+  }
+  __syncthreads();
+  for (unsigned int b = lo + threadIdx.x; b <= hi; b += blockDim.x) gh[b] = 0ull;
 }
 
 // The streaming pass: keys below the bracket are counted, keys inside it histogrammed (a few bins, rarely hit).
 template <typename S>
 __global__ void __launch_bounds__(kTiesCountThreads, 4)
 ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, const void* const* __restrict__ vec,
-                  int nchunks, TiesState* st, unsigned long long* __restrict__ ghist) {
+                  int nchunks, TiesState* st, unsigned long long* __restrict__ ghist, unsigned long long kth) {
   __shared__ unsigned int s_win[kTiesWindowBins];
   __shared__ unsigned int s_below;
   if (st->need_full) return;
@@ -440,53 +531,7 @@ ties_count_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
     const unsigned int cnt = s_win[i];
     if (cnt) atomicAdd(gh + i, (unsigned long long)cnt);
   }
-}
-
-// One CTA per source: the bin of the bracket that holds rank k - below; a rank outside the bracket requests the full passes.
-template <typename S>
-__global__ void __launch_bounds__(1024) ties_window_select_kernel(unsigned long long* __restrict__ ghist, TiesState* st, unsigned long long kth) {
-  __shared__ int s_miss;
-  const int src = blockIdx.x, tid = threadIdx.x;
-  // need_full may be raised by another source's CTA of this launch: every CTA still cleans its own bins
-  const bool active = st->need_full == 0;
-  const unsigned int lo = st->win_lo[src], hi = st->win_hi[src];
-  unsigned long long* gh = ghist + (size_t)src * (1 << 15);
-  if (tid == 0) s_miss = 0;
-  __syncthreads();
-  if (active && tid == 0) {
-    const unsigned long long below = st->below[src];
-    bool found = false;
-    if (kth > below) {
-      unsigned long long cum = below;
-      for (unsigned int b = lo; b <= hi; ++b) {
-        cum += gh[b];
-        if (cum >= kth) {
-          st->thr[src] = key_to_float<S>(b);
-          found = true;
-          break;
-        }
-      }
-    }
-    if (!found) s_miss = 1;
-  }
-  __syncthreads();
-  for (unsigned int b = lo + tid; b <= hi; b += 1024) gh[b] = 0ull;
-  if (tid == 0 && s_miss) atomicExch(&st->need_full, 1);
-}
-
-__global__ void ties_finalize_kernel(TiesState* st, int func, unsigned long long total) {
-  const unsigned long long p = st->n_pos, n = st->n_neg;
-  st->n_zero = total - p - n - st->n_amb;
-  const int majority = p > n ? 1 : (p < n ? -1 : 0);
-  st->majority = majority;
-  // the speculative pass used +1: wrong wherever survivors cancel exactly (listed: sparse fix-up), and MAX writes
-  // -0 (0 * -1) into every element without survivors when the majority is negative (dense re-merge)
-  int fix = 0;
-  if (majority != 1) {
-    if (func == MC_TIES_MAX && majority == -1 && st->n_zero > 0ull) fix = 2;
-    else if (st->n_amb > 0ull) fix = st->fix_count <= kTiesFixCapacity ? 1 : 2;
-  }
-  st->need_fix = fix;
+  if (ties_last_cta_of_source(st, src, gridDim.x)) ties_window_select_cta<S>(ghist + (size_t)src * (1 << 15), st, src, kth);
 }
 
 static TiesKernels pick_ties(int sdt, int n_src, int func) {
@@ -584,6 +629,7 @@ extern "C" int mc_ties_plan_create(mc_ties_plan_t** out, int n_tensors, int n_sr
   cudaError_t e = cudaGetDevice(&p->device);
   if (e == cudaSuccess && p->sms <= 0) e = cudaErrorNoDevice;
   if (e == cudaSuccess) e = cudaMalloc(&p->d_state, sizeof(TiesState));
+  if (e == cudaSuccess) e = cudaMemset(p->d_state, 0, sizeof(TiesState));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_hist, (size_t)n_src * kHistBinsMax * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_fix, (size_t)kTiesFixCapacity * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_metrics, sizeof(TiesMetricSums));
@@ -627,25 +673,27 @@ static int enqueue_select(const mc_ties_plan_t* p, int64_t kth, cudaStream_t s) 
   // 16-bit dtypes with enough data: sampled bracket + one counting pass; otherwise (and on a bracket miss, decided on
   // the device) the full-range radix select, most significant digit first.  Unneeded kernels exit at once.
   const bool sampled = p->src_dtype != MC_F32 && p->nchunks >= 1024;
-  ties_init_kernel<<<1, 32, 0, s>>>(p->d_state, (unsigned long long)kth, p->n_src, sampled ? 0 : 1);
+  if (!sampled) ties_init_kernel<<<1, 32, 0, s>>>(p->d_state, (unsigned long long)kth, p->n_src, 1);
   if (sampled) {
-    const size_t smem = ((size_t)1 << 15) * sizeof(unsigned int);
+    // 2^15 sample bins; the bracket step of the last CTA re-reads them in a padded layout (+1 word per 32)
     const size_t bsmem = (((size_t)1 << 15) + 1024) * sizeof(unsigned int);
-    MC_CUDA_OK(cudaFuncSetAttribute(ties_bracket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-    dim3 sgrid(std::max(1, std::min((p->nchunks + 31) / 32, p->sms / p->n_src)), p->n_src);
+    // one 512-byte granule of every `every`-th chunk: >= 2^13 chunks (2^21 samples) per source once the input is large enough
+    const int every = std::max(1, std::min(8, p->nchunks >> 13));
+    const int nsel = (p->nchunks + every - 1) / every;
+    dim3 sgrid(std::max(1, std::min((nsel + 127) / 128, p->sms / p->n_src)), p->n_src);
     dim3 cgrid(std::max(1, std::min((p->nchunks + 1) / 2, p->sms * 4 / p->n_src)), p->n_src);
     if (p->src_dtype == MC_F16) {
-      MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ties_sample_kernel<__half><<<sgrid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
-      ties_bracket_kernel<<<p->n_src, 1024, bsmem, s>>>(p->d_hist, p->d_state, (unsigned long long)kth, (unsigned long long)p->total_elems);
-      ties_count_kernel<__half><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_hist);
-      ties_window_select_kernel<__half><<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, (unsigned long long)kth);
+      MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+      ties_sample_kernel<__half><<<sgrid, kTiesHistThreads, bsmem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
+                                                                          (unsigned long long)kth, (unsigned long long)p->total_elems, every);
+      ties_count_kernel<__half><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_hist,
+                                                                   (unsigned long long)kth);
     } else {
-      MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ties_sample_kernel<__nv_bfloat16><<<sgrid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist);
-      ties_bracket_kernel<<<p->n_src, 1024, bsmem, s>>>(p->d_hist, p->d_state, (unsigned long long)kth, (unsigned long long)p->total_elems);
-      ties_count_kernel<__nv_bfloat16><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_hist);
-      ties_window_select_kernel<__nv_bfloat16><<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, (unsigned long long)kth);
+      MC_CUDA_OK(cudaFuncSetAttribute(ties_sample_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+      ties_sample_kernel<__nv_bfloat16><<<sgrid, kTiesHistThreads, bsmem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
+                                                                          (unsigned long long)kth, (unsigned long long)p->total_elems, every);
+      ties_count_kernel<__nv_bfloat16><<<cgrid, kTiesCountThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_hist,
+                                                                   (unsigned long long)kth);
     }
   }
   struct Pass { int shift, bits, hi_shift; };
@@ -662,17 +710,16 @@ static int enqueue_select(const mc_ties_plan_t* p, int64_t kth, cudaStream_t s) 
     if (p->src_dtype == MC_F32) {
       MC_CUDA_OK(cudaFuncSetAttribute(ties_hist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ties_hist_kernel<float><<<grid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
-                                                                    passes[i].shift, passes[i].bits, passes[i].hi_shift);
+                                                                    passes[i].shift, passes[i].bits, passes[i].hi_shift, i == n_pass - 1, key_kind);
     } else if (p->src_dtype == MC_F16) {
       MC_CUDA_OK(cudaFuncSetAttribute(ties_hist_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ties_hist_kernel<__half><<<grid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
-                                                                     passes[i].shift, passes[i].bits, passes[i].hi_shift);
+                                                                     passes[i].shift, passes[i].bits, passes[i].hi_shift, i == n_pass - 1, key_kind);
     } else {
       MC_CUDA_OK(cudaFuncSetAttribute(ties_hist_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ties_hist_kernel<__nv_bfloat16><<<grid, kTiesHistThreads, smem, s>>>(p->d_segs, p->d_chunks, p->nchunks, p->d_state, p->d_hist,
-                                                                            passes[i].shift, passes[i].bits, passes[i].hi_shift);
+                                                                            passes[i].shift, passes[i].bits, passes[i].hi_shift, i == n_pass - 1, key_kind);
     }
-    ties_select_kernel<<<p->n_src, 1024, 0, s>>>(p->d_hist, p->d_state, passes[i].bits, i == n_pass - 1, key_kind);
   }
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
@@ -691,15 +738,18 @@ extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, 
   cudaStream_t s = (cudaStream_t)stream;
   const int rc = enqueue_select(p, kth, s);
   if (rc != MC_OK) return rc;
-  // L2 prefetch distance of the merge pass: one generation of resident CTAs (MC_TIES_PREFETCH=0 turns it off, a
-  // development switch for the ncu comparison)
+  // L2 prefetch distance of the merge pass, in chunks (= CTAs) ahead: a quarter of a generation of resident CTAs — one SM
+  // count; swept on B200 in profiles/r02_ties.txt (longer leads lose the lines again before the demand loads arrive).
+  // MC_TIES_PREFETCH=n overrides it (0 turns the prefetch off), a development switch for the ncu comparison.
   static const int pf_env = [] { const char* e = getenv("MC_TIES_PREFETCH"); return e ? atoi(e) : -1; }();
-  const int pf_dist = pf_env >= 0 ? pf_env : p->sms * 4;
+  const int pf_dist = pf_env >= 0 ? pf_env : p->sms;
   fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 0, pf_dist);
-  ties_finalize_kernel<<<1, 1, 0, s>>>(p->d_state, func, (unsigned long long)p->total_elems);
-  fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix);
-  // dense re-merge: a grid-stride launch that is small when it turns out to be a no-op
-  fn.merge<<<std::min(p->nchunks, p->sms * 16), kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 1, 0);
+  fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix,
+                                                                                (unsigned long long)p->total_elems);
+  // dense re-merge: one generation of resident CTAs striding over the chunks (each asks L2 for its own next chunk while it works on
+  // the current one); a no-op launch of that size costs next to nothing
+  const int rgrid = std::min(p->nchunks, p->sms * 4);
+  fn.merge<<<rgrid, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 1, pf_env == 0 ? 0 : rgrid);
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
 }

@@ -19,6 +19,9 @@ struct TiesState {
   unsigned int win_lo[MC_MERGE_MAX_SRC], win_hi[MC_MERGE_MAX_SRC];
   unsigned long long below[MC_MERGE_MAX_SRC];
   int need_full;                               // 1: run the full-range histogram passes (fp32, small inputs, bracket miss)
+  // CTAs of the current launch that have flushed their counts for a source: the last one runs the per-source step that follows
+  // (bracket / window select / radix select) in the same launch, and puts the counter back to 0
+  unsigned int done[MC_MERGE_MAX_SRC];
 };
 
 constexpr int kTiesChunkBytes = 16384;  // one chunk = 1024 16-byte vectors of every source
@@ -103,21 +106,23 @@ __device__ __forceinline__ float rcp_approx(float a) {
 }
 
 // Packed trim of one 32-bit word (two 16-bit values): entries with |x| < thr become +0, the others keep their bits.
-// thr2 holds the threshold (a value of the dtype: it is the k-th |x| of the data) in both halves.
+// thr2 holds the threshold (a value of the dtype: it is the k-th |x| of the data) in both halves.  Two instructions per
+// word: HSET2.LT with the |.| operand modifier, then w & ~mask.  ptxas only folds the modifier into the fp16 form of HSET2
+// (for bf16 it materialises |w| with an extra instruction), so bf16 pairs are compared AS fp16 bit patterns: both formats
+// are sign-magnitude with the exponent above the mantissa, hence the magnitudes order like their bit patterns in either.
+// The exception is a pattern whose magnitude bits are >= 0x7c01, a NaN to the fp16 compare, which answers false: the
+// value is kept — right whenever the threshold itself is below 0x7c00 (bf16 2^121), which ties_fast_threshold checks
+// (the kernel takes the scalar path of the unaligned tails otherwise).
 template <typename S>
 __device__ __forceinline__ uint32_t trim_word(uint32_t w, uint32_t thr2) {
-  const uint32_t a = w & 0x7fff7fffu;
-  if constexpr (std::is_same<S, __nv_bfloat16>::value) {
-    __nv_bfloat162_raw ra, rt;
-    ra.x = (unsigned short)a; ra.y = (unsigned short)(a >> 16);
-    rt.x = (unsigned short)thr2; rt.y = (unsigned short)(thr2 >> 16);
-    return w & __hge2_mask(__nv_bfloat162(ra), __nv_bfloat162(rt));
-  } else {
-    __half2_raw ra, rt;
-    ra.x = (unsigned short)a; ra.y = (unsigned short)(a >> 16);
-    rt.x = (unsigned short)thr2; rt.y = (unsigned short)(thr2 >> 16);
-    return w & __hge2_mask(__half2(ra), __half2(rt));
-  }
+  __half2_raw ra, rt;
+  ra.x = (unsigned short)w; ra.y = (unsigned short)(w >> 16);
+  rt.x = (unsigned short)thr2; rt.y = (unsigned short)(thr2 >> 16);
+  return w & ~__hlt2_mask(__habs2(__half2(ra)), __half2(rt));
+}
+template <typename S>
+__device__ __forceinline__ bool ties_fast_threshold(uint32_t thr2) {
+  return !std::is_same<S, __nv_bfloat16>::value || (thr2 & 0xffffu) < 0x7c00u;
 }
 template <typename S>
 __device__ __forceinline__ uint32_t pack_thr(float thr) {
@@ -146,22 +151,24 @@ __device__ __forceinline__ uint32_t pack_thr(float thr) {
 //   * survivors that cancel exactly (class 3) are acc == 0 with a non-empty candidate, for either default sign:
 //     amb = [sum k > 0] (1 - p - n);
 //   * MAX keeps the running maximum of k instead of the sum; (max k) * sigma is exact and keeps torch's -0.
-// p, n, amb come back as 0.0 / 1.0 so that the census is three float adds per element.
-template <int NSRC, typename S, typename D, int FUNC, bool TRIMMED = false>
-__device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float (&thr)[NSRC], float mh, float& p, float& n, float& amb) {
-  static_assert(sizeof(S) == 2, "16-bit sources");
+// p, n, some (and amb in the scalar form) come back as 0.0 / 1.0, so the census of the vector path is three FFMAs per element
+// (ties_chunk_fast).
+// Election half of the element function on already trimmed entries m: the kept sum (or running max) ksum >= +0, the number of
+// kept non-zero entries cnt (MEAN only), the elected sign sg = +-1, the census indicators p = [acc > 0], n = [acc < 0] and
+// some = [a kept entry is non-zero].  DEFPOS: the default sign is known to be + (the speculative pass), so hs = 0.5 - n.
+template <int NSRC, int FUNC, bool DEFPOS>
+__device__ __forceinline__ void ties_elect_fast(const float (&m)[NSRC], float mh, float& ksum, float& cnt, float& sg, float& p, float& n,
+                                                float& some) {
   const float inf = __int_as_float(0x7f800000);
-  float m[NSRC];
-#pragma unroll
-  for (int s = 0; s < NSRC; ++s) m[s] = TRIMMED ? in[s] : __fmul_rn(in[s], fabsf(in[s]) >= thr[s] ? 1.0f : 0.0f);
   float acc = m[0];
 #pragma unroll
   for (int s = 1; s < NSRC; ++s) acc = __fadd_rn(acc, m[s]);
   p = mul_sat(acc, inf);
   n = mul_sat(acc, -inf);
-  const float hs = __fmaf_rn(-n, __fadd_rn(0.5f, mh), __fmaf_rn(p, __fsub_rn(0.5f, mh), mh));
-  const float sg = __fadd_rn(hs, hs);
-  float ksum = 0.0f, cnt = 0.0f;
+  const float hs = DEFPOS ? __fsub_rn(0.5f, n) : __fmaf_rn(-n, __fadd_rn(0.5f, mh), __fmaf_rn(p, __fsub_rn(0.5f, mh), mh));
+  sg = __fadd_rn(hs, hs);
+  ksum = 0.0f;
+  cnt = 0.0f;
 #pragma unroll
   for (int s = 0; s < NSRC; ++s) {
     const float k = __fmaf_rn(0.5f, fabsf(m[s]), __fmul_rn(m[s], hs));
@@ -171,15 +178,46 @@ __device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float 
       cnt = s == 0 ? one : __fadd_rn(cnt, one);
     }
   }
-  const float some = FUNC == MC_TIES_MEAN ? mul_sat(cnt, 1.0f) : mul_sat(ksum, inf);  // [a kept entry != 0]
-  amb = __fmaf_rn(-some, __fadd_rn(p, n), some);
-  if (FUNC == MC_TIES_SUM) return from_f32<D>(__fmaf_rn(ksum, sg, 0.0f));
-  if (FUNC == MC_TIES_MAX) return from_f32<D>(__fmul_rn(ksum, sg));  // a 16-bit value already; (+0) * -1 = -0 as torch
-  const float x = to_f32<S>(from_f32<S>(ksum));  // >= +0: the sign goes on last
-  const float c = fmaxf(cnt, 1.0f), r = rcp_approx(c);
+  some = FUNC == MC_TIES_MEAN ? mul_sat(cnt, 1.0f) : mul_sat(ksum, inf);
+}
+
+// MEAN: x = the kept sum after its 16-bit rounding (>= +0), c = #kept.  c = 0 comes with x = 0: r = inf, q0 = q1 = NaN and
+// min(NaN, 0) = 0, so no max(c, 1) is needed; fma(., sg, +0) puts the sign on and turns -0 into the reference's +0.
+template <typename D>
+__device__ __forceinline__ D ties_mean_quotient(float x, float c, float sg) {
+  const float r = rcp_approx(c);
   const float q0 = __fmul_rn(x, r);
   const float q1 = __fmaf_rn(__fmaf_rn(-q0, c, x), r, q0);
   return from_f32<D>(__fmaf_rn(fminf(q1, x), sg, 0.0f));
+}
+
+// float32 values of a and b after rounding to the 16-bit dtype S: one packed conversion for the pair
+template <typename S>
+__device__ __forceinline__ void round_pair(float a, float b, float& xa, float& xb) {
+  if constexpr (std::is_same<S, __nv_bfloat16>::value) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+    xa = __uint_as_float(u << 16);
+    xb = __uint_as_float(u & 0xffff0000u);
+  } else {
+    const float2 f = __half22float2(__floats2half2_rn(a, b));
+    xa = f.x;
+    xb = f.y;
+  }
+}
+
+template <int NSRC, typename S, typename D, int FUNC>
+__device__ __forceinline__ D ties_one_fast(const float (&in)[NSRC], const float (&thr)[NSRC], float mh, float& p, float& n, float& amb) {
+  static_assert(sizeof(S) == 2, "16-bit sources");
+  float m[NSRC];
+#pragma unroll
+  for (int s = 0; s < NSRC; ++s) m[s] = __fmul_rn(in[s], fabsf(in[s]) >= thr[s] ? 1.0f : 0.0f);
+  float ksum, cnt, sg, some;
+  ties_elect_fast<NSRC, FUNC, false>(m, mh, ksum, cnt, sg, p, n, some);
+  amb = __fmaf_rn(-some, __fadd_rn(p, n), some);
+  if (FUNC == MC_TIES_SUM) return from_f32<D>(__fmaf_rn(ksum, sg, 0.0f));
+  if (FUNC == MC_TIES_MAX) return from_f32<D>(__fmul_rn(ksum, sg));  // a 16-bit value already; (+0) * -1 = -0 as torch
+  return ties_mean_quotient<D>(to_f32<S>(from_f32<S>(ksum)), cnt, sg);
 }
 
 template <typename S, int FUNC>
@@ -207,8 +245,84 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned int byt
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// One whole, aligned chunk of 16-bit sources on the fast element function: 4 vectors per source per thread, trimmed two
+// values per instruction on the packed words before they are widened, elements taken in pairs so that MEAN's 16-bit
+// rounding of the kept sum is one packed conversion.  ONE basic block (ptxas sinks loads whose first use sits in a later
+// block).  The census (DEFPOS, the speculative pass, only) is kept as one BIT per element in float accumulators — three FFMAs
+// per element, mask += indicator * 2^bit, 16 elements per mask so the sums stay exact — for p = [sum > 0], n = [sum < 0] and
+// some = [a kept entry is non-zero]; per 16 elements the counts are two popcounts and the class-3 elements (survivors cancel
+// exactly: a kept entry and no elected sign) are the bits of some & ~(p | n), returned in amb_bits for the caller's rare path.
+template <int NSRC, typename S, typename D, int FUNC, bool DEFPOS>
+__device__ __forceinline__ void ties_chunk_fast(const void* const* __restrict__ row, const uint32_t (&thr2)[NSRC], float mh, float majority,
+                                                unsigned int& c_pos, unsigned int& c_neg, unsigned int (&amb_bits)[2]) {
+  constexpr int E = 16 / sizeof(S);
+  constexpr int VPT = 4;
+  static_assert(E == 8 && VPT == 4, "two masks of 16 bits");
+  using VS = Vec<16>;
+  using VD = Vec<E * sizeof(D)>;
+  VS v[NSRC][VPT];
+#pragma unroll
+  for (int s = 0; s < NSRC; ++s) {
+    const VS* p = reinterpret_cast<const VS*>(row[s]) + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) v[s][j] = ld_stream(p + j * kTiesMergeThreads);
+  }
+  VD* q = reinterpret_cast<VD*>(const_cast<void*>(row[NSRC])) + threadIdx.x;
+  float m_pos = 0.0f, m_neg = 0.0f, m_some = 0.0f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    VD o;
+    D* oe = reinterpret_cast<D*>(&o);
+#pragma unroll
+    for (int s = 0; s < NSRC; ++s) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) v[s][j].w[w] = trim_word<S>(v[s][j].w[w], thr2[s]);
+    }
+#pragma unroll
+    for (int e = 0; e < E; e += 2) {
+      float ksum[2], cnt[2], sg[2], pn[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float in[NSRC];
+#pragma unroll
+        for (int s = 0; s < NSRC; ++s) in[s] = vec_elem_f32<S>(v[s][j], e + h);
+        float p, n, some;
+        ties_elect_fast<NSRC, FUNC, DEFPOS>(in, mh, ksum[h], cnt[h], sg[h], p, n, some);
+        if (DEFPOS) {
+          const float bit = (float)(1 << ((j & 1) * E + e + h));
+          m_pos = __fmaf_rn(p, bit, m_pos);
+          m_neg = __fmaf_rn(n, bit, m_neg);
+          m_some = __fmaf_rn(some, bit, m_some);
+        }
+        pn[h] = FUNC == MC_TIES_MAX && !DEFPOS ? p + n : 1.0f;
+      }
+      if (FUNC == MC_TIES_MEAN) {
+        float x[2];
+        round_pair<S>(ksum[0], ksum[1], x[0], x[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) oe[e + h] = ties_mean_quotient<D>(x[h], cnt[h], sg[h]);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          oe[e + h] = FUNC == MC_TIES_SUM ? from_f32<D>(__fmaf_rn(ksum[h], sg[h], 0.0f)) : from_f32<D>(__fmul_rn(ksum[h], sg[h]));
+          // majority sign exactly 0 (see ties_one): MAX multiplies by sign 0 wherever no sign is elected
+          if (FUNC == MC_TIES_MAX && !DEFPOS && majority == 0.0f && pn[h] == 0.0f) oe[e + h] = from_f32<D>(0.0f);
+        }
+      }
+    }
+    st_stream(q + j * kTiesMergeThreads, o);
+    if (DEFPOS && (j & 1)) {
+      const unsigned int bp = (unsigned int)m_pos, bn = (unsigned int)m_neg;
+      c_pos += __popc(bp);
+      c_neg += __popc(bn);
+      amb_bits[j >> 1] = (unsigned int)m_some & ~(bp | bn);
+      m_pos = m_neg = m_some = 0.0f;
+    }
+  }
+}
+
 // mode 0: speculative merge with majority = +1, census of the elected signs, list of majority-dependent elements.
-// mode 1: dense re-merge with the real majority; exits at once unless ties_finalize_kernel asked for it (need_fix == 2).
+// mode 1: dense re-merge with the real majority; exits at once unless the fix-up kernel asked for it (need_fix == 2).
 template <int NSRC, typename S, typename D, int FUNC>
 __global__ void __launch_bounds__(kTiesMergeThreads)
 ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, const void* const* __restrict__ vec,
@@ -230,12 +344,15 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   constexpr bool kFast = TiesFast<S, FUNC>::value;
   const float mh = majority > 0.0f ? 0.5f : -0.5f;
   uint32_t thr2[NSRC];
+  bool fast_ok = kFast;
   if constexpr (kFast) {
 #pragma unroll
-    for (int s = 0; s < NSRC; ++s) thr2[s] = pack_thr<S>(thr[s]);
+    for (int s = 0; s < NSRC; ++s) {
+      thr2[s] = pack_thr<S>(thr[s]);
+      fast_ok = fast_ok && ties_fast_threshold<S>(thr2[s]);
+    }
   }
   unsigned int c_pos = 0u, c_neg = 0u, c_amb = 0u;  // elements without survivors are derived: total - pos - neg - amb
-  float f_pos = 0.0f, f_neg = 0.0f;                 // fast path: per-chunk census in float (<= 16 per chunk: exact)
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
     // ptxas sinks this long block's loads next to their first use (three 16-byte loads in flight per thread), so the
     // memory-level parallelism comes from L2 prefetches instead: one thread asks L2 for the whole chunk that the CTA
@@ -255,7 +372,32 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
         }
       }
     }
-    if (row[0] != nullptr) {
+    bool vector_path = row[0] != nullptr;
+    if constexpr (kFast) {
+      vector_path = vector_path && fast_ok;
+      if (vector_path) {
+        unsigned int amb_bits[2] = {0u, 0u};
+        if (mode == 0) {
+          ties_chunk_fast<NSRC, S, D, FUNC, true>(row, thr2, mh, majority, c_pos, c_neg, amb_bits);
+          if ((amb_bits[0] | amb_bits[1]) != 0u) {  // rare: append this thread's class-3 elements to the fix-up list
+#pragma unroll 1
+            for (int jp = 0; jp < 2; ++jp) {
+              unsigned int bits = jp == 0 ? amb_bits[0] : amb_bits[1];
+              while (bits) {
+                const int b = __ffs((int)bits) - 1;
+                bits &= bits - 1u;
+                c_amb += 1u;
+                const unsigned int slot = atomicAdd(&st->fix_count, 1u);
+                if (slot < kTiesFixCapacity)
+                  fix_list[slot] = ((unsigned long long)c << 32) | (unsigned int)(((jp * 2 + (b >> 3)) * kTiesMergeThreads + threadIdx.x) * E + (b & 7));
+              }
+            }
+          }
+        } else {
+          ties_chunk_fast<NSRC, S, D, FUNC, false>(row, thr2, mh, majority, c_pos, c_neg, amb_bits);
+        }
+      }
+    } else if (vector_path) {
       VS v[NSRC][VPT];
 #pragma unroll
       for (int s = 0; s < NSRC; ++s) {
@@ -264,51 +406,32 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
         for (int j = 0; j < VPT; ++j) v[s][j] = ld_stream(p + j * kTiesMergeThreads);
       }
       VD* q = reinterpret_cast<VD*>(const_cast<void*>(row[NSRC])) + threadIdx.x;
-      // Class-3 elements (rare) are collected as one bit per element in float accumulators (mask_j += amb * 2^e, an FFMA)
-      // and appended to the fix-up list after the sweep: the hot path is ONE basic block, so every load above issues
-      // before the first element is touched (ptxas sinks loads whose first use sits in a later block).
-      float amb_mask[VPT];
+      // Class-3 elements (rare) are collected as one bit per element and appended to the fix-up list after the sweep
+      unsigned int amb_mask[VPT];
+      unsigned int amb_any = 0u;
 #pragma unroll
       for (int j = 0; j < VPT; ++j) {
         VD o;
         D* oe = reinterpret_cast<D*>(&o);
-        amb_mask[j] = 0.0f;
-        if constexpr (kFast) {  // trim two values per instruction on the packed words, before they are widened
-#pragma unroll
-          for (int s = 0; s < NSRC; ++s) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) v[s][j].w[w] = trim_word<S>(v[s][j].w[w], thr2[s]);
-          }
-        }
+        amb_mask[j] = 0u;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
           float in[NSRC];
 #pragma unroll
           for (int s = 0; s < NSRC; ++s) in[s] = vec_elem_f32<S>(v[s][j], e);
-          if constexpr (kFast) {
-            float p, n, amb;
-            oe[e] = ties_one_fast<NSRC, S, D, FUNC, true>(in, thr, mh, p, n, amb);
-            if (FUNC == MC_TIES_MAX && majority == 0.0f && p == 0.0f && n == 0.0f) oe[e] = from_f32<D>(0.0f);  // sign 0 (see ties_one)
-            f_pos += p;
-            f_neg += n;
-            amb_mask[j] = __fmaf_rn(amb, (float)(1 << e), amb_mask[j]);
-          } else {
-            int cls;
-            oe[e] = ties_one<NSRC, S, D, FUNC>(in, thr, majority, cls);
-            c_pos += cls == 0;
-            c_neg += cls == 1;
-            amb_mask[j] += cls == 3 ? (float)(1 << e) : 0.0f;
-          }
+          int cls;
+          oe[e] = ties_one<NSRC, S, D, FUNC>(in, thr, majority, cls);
+          c_pos += cls == 0;
+          c_neg += cls == 1;
+          amb_mask[j] |= cls == 3 ? 1u << e : 0u;
         }
+        amb_any |= amb_mask[j];
         st_stream(q + j * kTiesMergeThreads, o);
       }
-      float amb_any = 0.0f;
-#pragma unroll
-      for (int j = 0; j < VPT; ++j) amb_any += amb_mask[j];
-      if (amb_any != 0.0f) {
+      if (amb_any != 0u) {
 #pragma unroll 1
         for (int j = 0; j < VPT; ++j) {
-          unsigned int bits = (unsigned int)amb_mask[j];
+          unsigned int bits = amb_mask[j];
           while (bits) {
             const int e = __ffs((int)bits) - 1;
             bits &= bits - 1u;
@@ -321,7 +444,8 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
           }
         }
       }
-    } else {
+    }
+    if (!vector_path) {
       const MergeChunk ch = chunks[c];
       const MergeSeg* sg = segs + ch.seg;
       const long long base = (long long)ch.idx * CHUNK;
@@ -344,11 +468,6 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
         }
       }
     }
-    if constexpr (kFast) {
-      c_pos += (unsigned int)f_pos;
-      c_neg += (unsigned int)f_neg;
-      f_pos = f_neg = 0.0f;
-    }
   }
   if (mode == 1) return;
   __shared__ unsigned int s_census[3];
@@ -369,18 +488,35 @@ ties_merge_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restric
   }
 }
 
-// Sparse fix-up: recompute the listed majority-dependent elements with the real majority (need_fix == 1).
+// After the speculative pass: the majority sign of the census, the decision between nothing / sparse fix-up / dense re-merge
+// (every CTA derives it from the same counters; CTA 0 records it for the re-merge launch and the statistics), and the sparse
+// fix-up itself: the listed majority-dependent elements recomputed with the real majority (need_fix == 1).
+// The speculative pass used +1: wrong wherever survivors cancel exactly (listed), and MAX writes -0 (0 * -1) into every
+// element without survivors when the majority is negative (dense re-merge).
 template <int NSRC, typename S, typename D, int FUNC>
 __global__ void __launch_bounds__(256)
-ties_fix_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, const TiesState* __restrict__ st,
-                const unsigned long long* __restrict__ fix_list) {
-  if (st->need_fix != 1) return;
+ties_fix_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict__ chunks, TiesState* st,
+                const unsigned long long* __restrict__ fix_list, unsigned long long total) {
+  const unsigned long long n_p = st->n_pos, n_n = st->n_neg, n_a = st->n_amb;
+  const unsigned int n = st->fix_count;
+  const unsigned long long n_zero = total - n_p - n_n - n_a;
+  const int maj = n_p > n_n ? 1 : (n_p < n_n ? -1 : 0);
+  int fix = 0;
+  if (maj != 1) {
+    if (FUNC == MC_TIES_MAX && maj == -1 && n_zero > 0ull) fix = 2;
+    else if (n_a > 0ull) fix = n <= kTiesFixCapacity ? 1 : 2;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->n_zero = n_zero;
+    st->majority = maj;
+    st->need_fix = fix;
+  }
+  if (fix != 1) return;
   constexpr int CHUNK = kTiesChunkBytes / sizeof(S);
-  const float majority = (float)st->majority;
+  const float majority = (float)maj;
   float thr[NSRC];
 #pragma unroll
   for (int s = 0; s < NSRC; ++s) thr[s] = st->thr[s];
-  const unsigned int n = st->fix_count;
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned long long packed = fix_list[i];
     const MergeChunk ch = chunks[(int)(packed >> 32)];
@@ -395,7 +531,7 @@ ties_fix_kernel(const MergeSeg* __restrict__ segs, const MergeChunk* __restrict_
 }
 
 typedef void (*ties_fn_t)(const MergeSeg*, const MergeChunk*, const void* const*, int, TiesState*, unsigned long long*, int, int);
-typedef void (*ties_fix_fn_t)(const MergeSeg*, const MergeChunk*, const TiesState*, const unsigned long long*);
+typedef void (*ties_fix_fn_t)(const MergeSeg*, const MergeChunk*, TiesState*, const unsigned long long*, unsigned long long);
 struct TiesKernels {
   ties_fn_t merge;
   ties_fix_fn_t fix;

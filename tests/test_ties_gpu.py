@@ -82,6 +82,36 @@ def test_device_plan_bit_exact(dtype, n_src, kind, K):
         plan.close()
 
 
+@pytest.mark.parametrize("K", [90, 20])
+def test_bf16_magnitudes_beyond_the_fp16_pattern_range(K):
+    """The packed trim compares bf16 pairs as fp16 bit patterns, which is only valid below 2^121 (pattern 0x7c00): values beyond
+    it are kept by the compare (right for any sane threshold), a THRESHOLD beyond it sends the kernel down its scalar path.
+    Sources with every magnitude in [2^120, 2^124): keeping the top 90 % puts the threshold below 2^121 with data on both sides
+    of it, keeping the top 20 % puts the threshold itself beyond."""
+    g = torch.Generator().manual_seed(5)
+    srcs = []
+    for _ in range(3):
+        lst = []
+        for n in SIZES:
+            mag = torch.exp2(120.0 + 4.0 * torch.rand(n, generator=g))
+            lst.append((mag * (torch.randint(0, 2, (n,), generator=g).float() * 2 - 1)).to(torch.bfloat16))
+        srcs.append(lst)
+    dev = [[t.cuda() for t in lst] for lst in srcs]
+    for func in ("sum", "mean", "max"):
+        odt = torch.float32 if func == "mean" else torch.bfloat16
+        outs = [torch.full((n,), 7.0, dtype=odt, device="cuda") for n in SIZES]
+        plan = M.TiesPlan(dev, outs)
+        plan.run(K, func)
+        st = plan.stats()
+        want, ost = oracle_merge(srcs, K, func)
+        assert st["thresholds"] == [float(x) for x in ost["thresholds"]]
+        assert (min(st["thresholds"]) >= 2.0 ** 121) == (K == 20) and (max(st["thresholds"]) < 2.0 ** 121) == (K == 90)
+        assert (st["n_pos"], st["n_neg"], st["n_ambiguous"]) == (ost["n_pos"], ost["n_neg"], ost["ambiguous"])
+        for t in range(len(SIZES)):
+            assert bits_equal(outs[t], want[t]), (func, K, t)
+        plan.close()
+
+
 def test_fix_pass_only_when_needed():
     """positive majority: the speculative pass is final; negative majority with cancellations: the listed elements are
     recomputed (1); MAX with a negative majority or an overflowing list: dense re-merge (2) — all bit-exact vs the oracle"""
