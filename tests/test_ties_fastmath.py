@@ -100,6 +100,8 @@ def emulate_fast(flat: torch.Tensor, thr, majority: float, func: str, packed_tri
             acc = (acc + m[s]).astype(F32)
         p, n = mul_sat(acc, INF), mul_sat(acc, -INF)
         hs = (-n * (F32(0.5) + mh) + (p * (F32(0.5) - mh) + mh)).astype(F32)   # every step exact
+        if majority > 0:   # the speculative pass (default sign +) computes it as 0.5 - n
+            assert np.array_equal(hs, (F32(0.5) - n).astype(F32))
         sg = (hs + hs).astype(F32)
         ksum = cnt = None
         for s in range(n_src):
@@ -118,8 +120,10 @@ def emulate_fast(flat: torch.Tensor, thr, majority: float, func: str, packed_tri
             out = torch.from_numpy(o).to(dt)
         else:
             xr = round_dt(ksum, dt)
-            c = np.maximum(cnt, F32(1))
-            q = np.fmin((xr / c).astype(F32), xr)           # the quotient itself is covered by the exhaustive test
+            assert not np.any((cnt == 0) & (xr != 0))       # nothing kept: the kept sum is +0 ...
+            with np.errstate(divide="ignore"):
+                q = np.fmin((xr / cnt).astype(F32), xr)     # ... 0 / 0 = NaN and fmin(NaN, 0) = 0: no max(cnt, 1) needed.  The quotient itself
+                                                            # is covered by the exhaustive test
             out = torch.from_numpy((q * sg + F32(0)).astype(F32))
     return out, p, n, amb
 
@@ -180,3 +184,22 @@ def test_packed_threshold_counter_has_no_cross_half_borrow():
                 # dp4a with 0x01010101 adds the four bytes: 0x80 per set flag
                 dp = (flags & 0xff) + ((flags >> 8) & 0xff) + ((flags >> 16) & 0xff) + ((flags >> 24) & 0xff)
                 assert np.array_equal(dp >> 7, (lo_keys >= t).astype(np.uint32) + (1 if hk >= t else 0))
+
+
+def test_bf16_trim_as_fp16_bit_patterns():
+    """trim_word compares bf16 pairs with the fp16 form of HSET2 (the one whose |.| operand modifier ptxas folds): for every magnitude
+    pattern and every threshold pattern below 0x7c00, "not (|x| < t) as fp16" equals "|x| >= t as bf16"; patterns from 0x7c01 up are
+    NaN to the fp16 compare and come out as kept, which is what bf16 says for finite values beyond 2^121 and for inf."""
+    mags = np.arange(0, 0x8000, dtype=np.uint16)
+    as_bf16 = (mags.astype(np.uint32) << 16).view(np.float32)
+    as_fp16 = mags.view(np.float16)
+    rng = np.random.default_rng(0)
+    thr = np.unique(np.concatenate([rng.integers(0, 0x7c00, 600), [0, 1, 0x3ff, 0x400, 0x7bff]]).astype(np.uint16))
+    with np.errstate(invalid="ignore"):
+        for t in thr:
+            t_bf16 = np.uint32(int(t) << 16).view(np.float32)
+            keep_ref = as_bf16 >= t_bf16                      # NaN patterns (> 0x7f80): False in the reference, see below
+            keep_dev = ~(as_fp16 < np.uint16(t).view(np.float16))
+            finite_or_inf = mags <= 0x7f80
+            assert np.array_equal(keep_ref[finite_or_inf], keep_dev[finite_or_inf]), hex(int(t))
+            assert keep_dev[~finite_or_inf].all()             # bf16 NaNs stay in the sum (the reference's x * mask keeps them NaN too)
