@@ -16,6 +16,7 @@ and replayed: no host synchronisation and no Python launch overhead between toke
 from __future__ import annotations
 
 import ctypes as C
+import gc
 import math
 import os
 from typing import List, Optional
@@ -334,9 +335,19 @@ class DecodeWorkspace:
                 return
             g = torch.cuda.CUDAGraph()
             n0 = _cabi.LAUNCHES
-            # capture WITHOUT executing: the recorded step is replayed right away
-            with torch.cuda.graph(g):
-                self._enqueue()
+            # capture WITHOUT executing: the recorded step is replayed right away.  A cudaFree invalidates a capture in progress, and
+            # the finalizers of plan objects (this package's and anyone's) issue one whenever the garbage collector decides to run
+            # them: collect what is pending first, keep the collector off for the few milliseconds of the capture, and let other
+            # threads' CUDA calls be (thread_local error mode).
+            gc.collect()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._enqueue()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             _cabi.LAUNCHES = n0
             self.graph = g
         self.graph.replay()
