@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "mc_ties_kernels.cuh"
@@ -746,10 +747,15 @@ extern "C" int mc_ties_plan_run(const mc_ties_plan_t* p, int64_t kth, int func, 
   fn.merge<<<p->nchunks, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 0, pf_dist);
   fn.fix<<<std::min(p->sms * 4, (int)(kTiesFixCapacity / 256)), 256, 0, s>>>(p->d_segs, p->d_chunks, p->d_state, p->d_fix,
                                                                                 (unsigned long long)p->total_elems);
-  // dense re-merge: one generation of resident CTAs striding over the chunks (each asks L2 for its own next chunk while it works on
-  // the current one); a no-op launch of that size costs next to nothing
-  const int rgrid = std::min(p->nchunks, p->sms * 4);
-  fn.merge<<<rgrid, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 1, pf_env == 0 ? 0 : rgrid);
+  // dense re-merge: a grid-stride launch that is small when it turns out to be a no-op (4.4 us); each CTA asks L2 for its own next
+  // chunk while it works on the current one (16 CTAs per SM x that lead: 0.604 ms against 0.613 without the prefetch and 0.646 with
+  // one generation of resident CTAs, 3 x 160 M max / negative majority)
+  // (MC_TIES_REMERGE="<CTAs per SM>,<prefetch distance in grids>": development switch for the sweep in profiles/r02_ties.txt)
+  static const int rm_mult = [] { const char* e = getenv("MC_TIES_REMERGE"); return e ? std::max(1, atoi(e)) : 16; }();
+  static const int rm_pf = [] { const char* e = getenv("MC_TIES_REMERGE"); const char* c = e ? strchr(e, ',') : nullptr; return c ? atoi(c + 1) : 1; }();
+  const int rgrid = std::min(p->nchunks, p->sms * rm_mult);
+  fn.merge<<<rgrid, kTiesMergeThreads, 0, s>>>(p->d_segs, p->d_chunks, p->d_vec, p->nchunks, p->d_state, p->d_fix, 1,
+                                              pf_env == 0 ? 0 : rgrid * rm_pf);
   MC_CUDA_OK(cudaGetLastError());
   return MC_OK;
 }
