@@ -197,7 +197,7 @@ class TiesPlan:
             for k in range(n_src):
                 _check_device_tensor(sources[k][t], src_dtype, numel, f"sources[{k}][{t}]")
         self._keep = (list(map(list, sources)), list(outputs) if outputs is not None else None)
-        self.n_src, self.n_tensors = n_src, n_t
+        self.n_src, self.n_tensors, self.src_dtype = n_src, n_t, src_dtype
         self._h = C.c_void_p()
         _cabi.check(_cabi.lib().mc_ties_plan_create(
             C.byref(self._h), n_t, n_src, _cabi.ptr_array([sources[k][t].data_ptr() for k in range(n_src) for t in range(n_t)]),
@@ -213,7 +213,9 @@ class TiesPlan:
     def run(self, K=20, func: str = "mean") -> None:
         _cabi.check(_cabi.lib().mc_ties_plan_run(self._h, ties_kth_rank(self.elements, K), TIES_FUNCS[func],
                                                  _cabi.current_stream_ptr()), "mc_ties_plan_run")
-        _cabi.count_launch(11)  # init, 4 sampled-select + 2..6 full-select (most exit at once), merge, finalize, fix, re-merge
+        # 16-bit sources: sample + bracket, count + select, full-range pass (exits at once), merge, fix-up, re-merge; fp32: init and three
+        # full-range passes instead of the first three
+        _cabi.count_launch(6 if self.src_dtype != torch.float32 else 7)
 
     def metrics(self, reset_thresh=50) -> dict:
         """Parameter-interference metrics of the plan's sources (reference calculate_metrics.py:26-37,53-64):
