@@ -380,9 +380,25 @@ class MultimodalLlamaForCausalLM:
         if dtype not in (torch.float16, torch.bfloat16):
             raise ValueError("inference dtype must be float16 (reference builder.py:185) or bfloat16")
         self.config, self.device, self.dtype = config, torch.device(device), dtype
-        if getattr(config, "rope_scaling", None) is not None:
-            raise NotImplementedError("rope_scaling (linear / dynamic NTK rotary embeddings, multimodal_llama.py:222-238) is not "
-                                      "implemented on this path: the composed vicuna checkpoints use plain RoPE")
+        # config.rope_scaling (multimodal_llama.py:190-203): "linear" divides the positions by the factor — a different table, nothing
+        # else changes.  "dynamic" (NTK) re-derives the base from the longest sequence seen so far, per call and per decode step,
+        # also for keys already in the cache: a table per step does not fit the captured decode step, so it is refused.
+        self.rope_linear_factor = 1.0
+        scaling_cfg = getattr(config, "rope_scaling", None)
+        if scaling_cfg is not None:
+            kind, factor = scaling_cfg.get("type"), float(scaling_cfg.get("factor", 1.0))
+            if kind == "linear":
+                if not factor >= 1.0:
+                    raise ValueError(f"rope_scaling factor must be >= 1, got {factor}")
+                self.rope_linear_factor = factor
+            elif kind == "dynamic":
+                raise NotImplementedError("rope_scaling type 'dynamic' (NTK, multimodal_llama.py:200-203) is not implemented on this path; "
+                                          "'linear' is")
+            else:
+                raise ValueError(f"Unknown RoPE scaling type {kind}")  # the reference's message (multimodal_llama.py:205)
+        if int(getattr(config, "pretraining_tp", 1) or 1) > 1:
+            raise NotImplementedError("pretraining_tp > 1 (sliced projections that bypass the adapters, multimodal_llama.py:222-237, "
+                                      ":323-326, :366-377) is not implemented on this path")
         if config.num_key_value_heads != config.num_attention_heads:
             raise NotImplementedError(f"grouped-query attention (num_key_value_heads {config.num_key_value_heads} != "
                                       f"num_attention_heads {config.num_attention_heads}) is not implemented on this path")
@@ -462,7 +478,7 @@ class MultimodalLlamaForCausalLM:
         return out
 
     def _rope_tables(self, seq_len: int):
-        """transformers 4.31 LlamaRotaryEmbedding: fp32 cache built on the host, cast to the model dtype on use.  The
+        """transformers 4.31 LlamaRotaryEmbedding / LlamaLinearScalingRotaryEmbedding: fp32 cache built on the host, cast to the model dtype on use.  The
         tables are referenced by the launch plans, so they only ever grow (in 4096-position steps) and growing drops the
         cached workspaces."""
         n = max(seq_len, self.config.max_position_embeddings)
@@ -472,6 +488,8 @@ class MultimodalLlamaForCausalLM:
             base = float(getattr(self.config, "rope_theta", 10000.0) or 10000.0)
             inv_freq = 1.0 / (base ** (torch.arange(0, D, 2).float() / D))
             t = torch.arange(n, dtype=inv_freq.dtype)
+            if self.rope_linear_factor != 1.0:
+                t = t / self.rope_linear_factor  # LlamaLinearScalingRotaryEmbedding
             freqs = torch.einsum("i,j->ij", t, inv_freq)
             emb = torch.cat((freqs, freqs), dim=-1)
             self._rope = (emb.cos().to(self.dtype).to(self.device).contiguous(),

@@ -80,11 +80,15 @@ def rms_norm(x, weight, eps):
     return weight * h.to(dt)
 
 
-def rope_cos_sin(head_dim, seq_len, dtype, base=10000.0, cache_dtype=torch.float32):
+def rope_cos_sin(head_dim, seq_len, dtype, base=10000.0, cache_dtype=torch.float32, linear_factor=1.0):
     """transformers 4.31 LlamaRotaryEmbedding: inv_freq fp32, emb = cat(freqs, freqs); the cos/sin cache is
-    stored in ``cache_dtype`` (``torch.get_default_dtype()`` at module construction) and cast to ``dtype`` on use."""
+    stored in ``cache_dtype`` (``torch.get_default_dtype()`` at module construction) and cast to ``dtype`` on use.
+    ``linear_factor``: LlamaLinearScalingRotaryEmbedding (config.rope_scaling = {"type": "linear", "factor": f},
+    multimodal_llama.py:193-199) divides the positions by f before the outer product."""
     inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2).float() / head_dim))
     t = torch.arange(seq_len, dtype=inv_freq.dtype)
+    if linear_factor != 1.0:
+        t = t / linear_factor
     freqs = torch.einsum("i,j->ij", t, inv_freq)
     emb = torch.cat((freqs, freqs), dim=-1)
     return emb.cos().to(cache_dtype).to(dtype), emb.sin().to(cache_dtype).to(dtype)
@@ -114,7 +118,8 @@ def causal_additive_mask(bsz, q_len, dtype, attention_mask_2d=None):
 
 
 # ----------------------------------------------------------------------------- A14 attention, A15 MLP, A16 layer/model
-def attention_forward(x, p: Dict[str, LinearParams], masks, modal_names, num_heads, position_ids, additive_mask):
+def attention_forward(x, p: Dict[str, LinearParams], masks, modal_names, num_heads, position_ids, additive_mask,
+                      rope_linear_factor=1.0):
     """:204-342 (no past_key_value, pretraining_tp == 1, num_key_value_heads == num_heads)."""
     bsz, q_len, hidden = x.shape
     hd = hidden // num_heads
@@ -129,7 +134,7 @@ def attention_forward(x, p: Dict[str, LinearParams], masks, modal_names, num_hea
     q = q.view(bsz, q_len, num_heads, hd).transpose(1, 2)
     k = k.view(bsz, q_len, num_heads, hd).transpose(1, 2)
     v = v.view(bsz, q_len, num_heads, hd).transpose(1, 2)
-    cos, sin = rope_cos_sin(hd, q_len, v.dtype)
+    cos, sin = rope_cos_sin(hd, q_len, v.dtype, linear_factor=rope_linear_factor)
     q, k = apply_rope(q, k, cos, sin, position_ids)
     w = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(hd)
     if additive_mask is not None:
@@ -153,10 +158,10 @@ def mlp_forward(x, p: Dict[str, LinearParams], masks, modal_names):
     return routed_sum(down, masks, x)
 
 
-def decoder_layer_forward(x, layer, masks, modal_names, num_heads, position_ids, additive_mask, eps):
+def decoder_layer_forward(x, layer, masks, modal_names, num_heads, position_ids, additive_mask, eps, rope_linear_factor=1.0):
     """:408-468.  ``layer``: dict with 'input_layernorm', 'post_attention_layernorm' (weights) and the 7 LinearParams."""
     h = rms_norm(x, layer["input_layernorm"], eps)
-    h = attention_forward(h, layer, masks, modal_names, num_heads, position_ids, additive_mask)
+    h = attention_forward(h, layer, masks, modal_names, num_heads, position_ids, additive_mask, rope_linear_factor)
     x = x + h
     h = rms_norm(x, layer["post_attention_layernorm"], eps)
     h = mlp_forward(h, layer, masks, modal_names)
@@ -164,7 +169,7 @@ def decoder_layer_forward(x, layer, masks, modal_names, num_heads, position_ids,
 
 
 def model_forward(inputs_embeds, layers, final_norm, lm_head, masks, modal_names, num_heads, eps,
-                  attention_mask_2d=None):
+                  attention_mask_2d=None, rope_linear_factor=1.0):
     """:526-545 (position ids, mask), :561-603 (layer loop, final norm), :720 (lm_head on all positions)."""
     bsz, q_len, _ = inputs_embeds.shape
     position_ids = torch.arange(q_len, dtype=torch.long).unsqueeze(0)
@@ -173,6 +178,6 @@ def model_forward(inputs_embeds, layers, final_norm, lm_head, masks, modal_names
     additive = causal_additive_mask(bsz, q_len, inputs_embeds.dtype, attention_mask_2d)
     h = inputs_embeds
     for layer in layers:
-        h = decoder_layer_forward(h, layer, masks, modal_names, num_heads, position_ids, additive, eps)
+        h = decoder_layer_forward(h, layer, masks, modal_names, num_heads, position_ids, additive, eps, rope_linear_factor)
     h = rms_norm(h, final_norm, eps)
     return F.linear(h, lm_head), h

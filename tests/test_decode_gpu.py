@@ -256,6 +256,27 @@ def test_decode_steps_vs_prefill_of_extended_sequence(golden, key, materialize):
         logits_close(o.logits[:, 0], full.logits[:, Sp - new + i, :], key, f"decode step {i} vs prefill")
 
 
+def test_decode_with_linear_rope_scaling(golden):
+    """config.rope_scaling "linear": the decode step reads the same scaled table as the prefill (decode vs prefill of the extended sequence)."""
+    dtype, key = torch.bfloat16, "bf16"
+    run = golden("merge_c1.pt")["runs"][STRATEGY_C1]
+    cfgd = dict(run["config"])
+    cfgd["num_attention_heads"] = cfgd["num_key_value_heads"] = 2
+    cfgd["rope_scaling"] = {"type": "linear", "factor": 4.0}
+    model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfgd), syn.make_base_llm(seed=1), run["state_dict"], device="cuda", dtype=dtype)
+    B, new = 2, 4
+    ids, feats = _prompt(B, dtype)
+    out_ids = model.generate(ids, modal_inputs=feats, max_new_tokens=new, do_sample=False)
+    full = model.forward(out_ids, torch.ones_like(out_ids), modal_inputs=feats)
+    Sp = full.logits.shape[1]
+    o1 = model.forward(ids, torch.ones_like(ids), modal_inputs=feats, use_cache=True, cache_extra=8)
+    cache = o1.past_key_values
+    for i in range(3):
+        tok = out_ids[:, ids.shape[1] + i:ids.shape[1] + i + 1]
+        o = model.forward(tok, torch.ones((B, cache.length + 1), dtype=torch.int64, device="cuda"), past_key_values=cache, modal_inputs=feats)
+        logits_close(o.logits[:, 0], full.logits[:, Sp - new + i, :], key, f"decode step {i} vs prefill, linear RoPE scaling")
+
+
 def test_decode_graph_equals_eager_and_prefill_kernel_path(golden, monkeypatch):
     dtype = torch.bfloat16
     ids, feats = _prompt(4, dtype, seed=5)

@@ -198,3 +198,27 @@ def test_prefill_layers_and_logits(golden, key):
     for layer in layers:
         h0 = XO.decoder_layer_forward(h0, layer, None, g["modal_names"], 4, pos, add, 1e-5)
     _close(h0, ref["hidden_nomask"], key)
+
+
+# ------------------------------------------------------------------------------------------- rope_scaling "linear"
+@pytest.mark.parametrize("factor", [2.0, 4.0, 3.0])
+def test_rope_linear_scaling_vs_transformers(factor):
+    """LlamaLinearScalingRotaryEmbedding (multimodal_llama.py:193-199 -> transformers 4.31, a pinned dependency of the reference that is
+    neither vendored under /root/reference nor installed here) divides the positions by the factor.  Anchor: the installed
+    transformers' "linear" rope initialisation, which scales inv_freq instead — the same table bit for bit when the factor is a
+    power of two ((t / f) * w == t * (w / f) in fp32), and up to the rounding of a ~10^3 rad argument otherwise."""
+    from transformers import LlamaConfig
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+    D, n = 128, 4096
+    cfg = LlamaConfig(hidden_size=4 * D, num_attention_heads=4, max_position_embeddings=n, rope_scaling={"rope_type": "linear", "factor": factor})
+    inv_freq, attention_scale = ROPE_INIT_FUNCTIONS["linear"](cfg, "cpu")
+    assert attention_scale == 1.0
+    freqs = torch.einsum("i,j->ij", torch.arange(n, dtype=torch.float32), inv_freq.float())
+    emb = torch.cat((freqs, freqs), dim=-1)
+    cos, sin = XO.rope_cos_sin(D, n, torch.float32, linear_factor=factor)
+    if factor in (2.0, 4.0):
+        assert torch.equal(cos, emb.cos()) and torch.equal(sin, emb.sin())
+    else:
+        assert (cos - emb.cos()).abs().max() < 1e-3 and (sin - emb.sin()).abs().max() < 1e-3
+    plain = XO.rope_cos_sin(D, n, torch.float32)[0]
+    assert torch.equal(cos[::int(factor)][: n // 4], plain[: n // 4]) if factor in (2.0, 4.0) else not torch.equal(cos, plain)

@@ -95,7 +95,8 @@ def oracle_forward(cfg: dict, base, sd, ids, attn, feats, dtype, n_heads):
     bmasks = {k: v.bool() for k, v in masks.items()}
     ordered = {m: bmasks.get(m, torch.zeros_like(bmasks["default"])) for m in modal_names}
     logits, _ = XO.model_forward(embeds, layers, cpu(base["model.norm.weight"]), cpu(base["lm_head.weight"]),
-                                 ordered, modal_names, n_heads, cfg["rms_norm_eps"])
+                                 ordered, modal_names, n_heads, cfg["rms_norm_eps"],
+                                 rope_linear_factor=float((cfg.get("rope_scaling") or {}).get("factor", 1.0)))
     return logits, bmasks, modal_names
 
 
@@ -116,6 +117,34 @@ def test_end_to_end_forward_vs_oracle(golden, key):
     assert out.logits.shape == logits.shape
     assert torch.equal(out.modal_id.cpu() == 1, bmasks["audio"]) and torch.equal(out.modal_id.cpu() == 2, bmasks["vision"])
     compare(out.logits, logits, key, "end-to-end logits")
+
+
+def test_rope_scaling_linear_vs_oracle_and_dynamic_refused(golden):
+    """config.rope_scaling = {"type": "linear", "factor": 4} (multimodal_llama.py:193-199): the positions are divided by the factor;
+    prefill vs the oracle, decode steps vs the prefill of the extended sequence.  "dynamic" is refused, unknown types get the reference's
+    ValueError."""
+    dtype, key = torch.bfloat16, "torch.bfloat16"
+    run = golden("merge_c1.pt")["runs"][STRATEGY_C1]
+    base = syn.make_base_llm(seed=1)
+    cfgd = dict(run["config"])
+    cfgd["rope_scaling"] = {"type": "linear", "factor": 4.0}
+    model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfgd), base, run["state_dict"], device="cuda", dtype=dtype)
+    plain = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(run["config"]), base, run["state_dict"], device="cuda", dtype=dtype)
+    g = torch.Generator().manual_seed(4)
+    B = 2
+    ids = syn.make_prompt_ids(B, ["vision", "audio"], 24, 1000, seed=5, modal_token_indexes=SO.MODAL_TOKEN_INDEXES, n_head=6)
+    feats = {"audio": torch.randn(B, 9, 48, generator=g).to(dtype), "vision": torch.randn(B, 14, 64, generator=g).to(dtype)}
+    attn = torch.ones_like(ids)
+    dev_feats = {k: v.cuda() for k, v in feats.items()}
+    out = model.forward(ids.cuda(), attn.cuda(), modal_inputs=dev_feats)
+    logits, _, _ = oracle_forward(cfgd, base, run["state_dict"], ids, attn, feats, dtype, 4)
+    compare(out.logits, logits, key, "logits with linear RoPE scaling")
+    unscaled = plain.forward(ids.cuda(), attn.cuda(), modal_inputs=dev_feats).logits
+    assert (out.logits.float() - unscaled.float()).abs().max() > 8 * MAXABS[key] * logits.abs().max()  # the table matters at these positions
+    for bad, exc in (({"type": "dynamic", "factor": 2.0}, NotImplementedError), ({"type": "yarn", "factor": 2.0}, ValueError)):
+        cfgd["rope_scaling"] = bad
+        with pytest.raises(exc):
+            MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfgd), base, run["state_dict"], device="cuda", dtype=dtype)
 
 
 def test_modality_major_row_order_is_bit_identical(golden, monkeypatch):
