@@ -577,7 +577,7 @@ def run_merge_e2e(args, job: MergeJob, seeds, weights, device, world, barrier, d
 
 
 # ------------------------------------------------------------------------------------------------ TIES workload
-def run_ties(device, steps: int = 10, K: int = 20, func: str = "mean"):
+def run_ties(device, steps: int = 10, K: int = 20, func: str = "mean", e2e: bool = True):
     """TIES merge (`--strategy ties-mean -K 20`, reference ties_merging.py:161-179) of the shared `default` adapters of
     three vicuna-7B DAMC checkpoints: 3 sources x 448 LoRA tensors = 319,815,680 bf16 elements per source, N(0, 0.02) /
     U(+-1/sqrt(in)) random init on the device.  One GPU (the trim threshold and the majority sign are global statistics).
@@ -645,6 +645,42 @@ def run_ties(device, steps: int = 10, K: int = 20, func: str = "mean"):
                                         "this run's algorithmic bytes",
                         "peak_source": peak_src, "kernel": "whole mc_ties_plan_run (sample, bracket, count, select, merge, fix-up)"},
            "stats": st, "gpu_launches": 6 * steps}  # sample + bracket, count + window select, full-range pass (no-op), merge, fix-up, re-merge (no-op)
+    if e2e:
+        # the same merge through the host-buffer entry point the CLI uses (mc_ties_host: sources in pinned host memory -> device
+        # slabs -> plan -> outputs back in pinned host memory); every call allocates and frees its device memory, as the CLI's does
+        import time
+        def arena(tensors, dtype):
+            flat = torch.empty(sum(t.numel() for t in tensors), dtype=dtype, pin_memory=True)
+            views, pos = [], 0
+            for t in tensors:
+                views.append(flat[pos:pos + t.numel()].view(t.shape))
+                pos += t.numel()
+            return views
+        h_srcs = []
+        for lst in srcs:
+            views = arena(lst, torch.bfloat16)
+            for v, t in zip(views, lst):
+                v.copy_(t)
+            h_srcs.append(views)
+        h_outs = arena(outs, outs[0].dtype)
+        torch.cuda.synchronize()
+        times = []
+        for it in range(4):   # first call: context / allocator warm-up
+            t0 = time.perf_counter()
+            _, hst = M.ties_merge_host_tensors(h_srcs, K, func, outputs=h_outs)
+            times.append(time.perf_counter() - t0)
+        for j in (0, len(shapes) // 2, len(shapes) - 1):
+            if not torch.equal(h_outs[j].view(torch.int32 if h_outs[j].dtype == torch.float32 else torch.int16),
+                               outs[j].cpu().view(torch.int32 if outs[j].dtype == torch.float32 else torch.int16)):
+                raise SystemExit(f"PARITY FAILURE: host-buffer TIES output tensor {j} differs from the device-resident run")
+        if hst["thresholds"] != st["thresholds"]:
+            raise SystemExit("PARITY FAILURE: host-buffer TIES thresholds differ from the device-resident run")
+        sec = sum(times[1:]) / len(times[1:])
+        res["e2e"] = {"value": round(plan.algorithmic_bytes / sec / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": 3 * d * 2,
+                      "d2h_bytes_per_step": d * outs[0].element_size(), "ms_per_step": round(sec * 1e3, 2),
+                      "what": "merge.ties_merge_host_tensors (mc_ties_host) on pinned host tensors: H2D of the 3 sources, plan, kernels, D2H of the "
+                              "outputs, device memory allocated and freed inside the call; wall clock around the synchronous call, 3 calls"}
+        del h_srcs, h_outs
     del plan, srcs, outs
     torch.cuda.empty_cache()
     return res
@@ -1179,7 +1215,7 @@ def main():
     line = None
     if args.workload == "ties":
         if rank == 0:
-            emit(run_ties(device))
+            emit(run_ties(device, e2e=not args.no_e2e))
         if world > 1:
             barrier()
             dist.destroy_process_group()

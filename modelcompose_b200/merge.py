@@ -267,16 +267,25 @@ def _promoted_sources(tensor_lists: Sequence[Sequence[torch.Tensor]], names: Opt
 
 
 def ties_merge_host_tensors(tensor_lists: Sequence[Sequence[torch.Tensor]], K=20, func: str = "mean",
-                            names: Optional[Sequence[str]] = None):
+                            names: Optional[Sequence[str]] = None, outputs: Optional[Sequence[torch.Tensor]] = None):
     """TIES-merge HOST tensors through the GPU (``mc_ties_host``).  ``tensor_lists[s][t]``: CPU tensors, same shapes across
-    sources; mixed dtypes are promoted to one (as the reference's flatten does).  Returns (new CPU tensors, stats dict);
-    float32 outputs for ``mean``."""
+    sources; mixed dtypes are promoted to one (as the reference's flatten does).  Returns (CPU tensors, stats dict);
+    float32 outputs for ``mean``.  ``outputs``: write into these CPU tensors (e.g. pinned ones) instead of new ones."""
     if not torch.cuda.is_available():
         raise _cabi.McError("merging tensors needs a CUDA device (modelcompose_b200 has no CPU fallback)")
     n_src, n_t = len(tensor_lists), len(tensor_lists[0])
     srcs, src_dtype = _promoted_sources(tensor_lists, names)
     out_dtype = torch.float32 if func == "mean" else src_dtype
-    outs = [torch.empty(t.shape, dtype=out_dtype) for t in srcs[0]]
+    if outputs is None:
+        outs = [torch.empty(t.shape, dtype=out_dtype) for t in srcs[0]]
+    else:
+        outs = list(outputs)
+        if len(outs) != n_t:
+            raise ValueError("one output per tensor")
+        for ti, (o, t) in enumerate(zip(outs, srcs[0])):
+            if o.is_cuda or o.dtype != out_dtype or o.shape != t.shape or not o.is_contiguous():
+                raise ValueError(f"outputs[{ti}]: need a contiguous CPU tensor of {out_dtype} {tuple(t.shape)}, "
+                                 f"got {o.dtype} {tuple(o.shape)}")
     d = sum(o.numel() for o in outs)
     st = _cabi.TiesStats()
     _cabi.check(_cabi.lib().mc_ties_host(

@@ -139,8 +139,13 @@ def test_rope_scaling_linear_vs_oracle_and_dynamic_refused(golden):
     out = model.forward(ids.cuda(), attn.cuda(), modal_inputs=dev_feats)
     logits, _, _ = oracle_forward(cfgd, base, run["state_dict"], ids, attn, feats, dtype, 4)
     compare(out.logits, logits, key, "logits with linear RoPE scaling")
+    # the tables themselves: bit-identical to the oracle's scaled table, not the plain one; and the logits moved
+    D, n = 64, 256
+    want_cos, want_sin = XO.rope_cos_sin(D, n, dtype, linear_factor=4.0)
+    assert torch.equal(model._rope[0][:n].cpu(), want_cos) and torch.equal(model._rope[1][:n].cpu(), want_sin)
+    assert not torch.equal(model._rope[0][:n].cpu(), XO.rope_cos_sin(D, n, dtype)[0])
     unscaled = plain.forward(ids.cuda(), attn.cuda(), modal_inputs=dev_feats).logits
-    assert (out.logits.float() - unscaled.float()).abs().max() > 8 * MAXABS[key] * logits.abs().max()  # the table matters at these positions
+    assert not torch.equal(out.logits, unscaled)
     for bad, exc in (({"type": "dynamic", "factor": 2.0}, NotImplementedError), ({"type": "yarn", "factor": 2.0}, ValueError)):
         cfgd["rope_scaling"] = bad
         with pytest.raises(exc):

@@ -289,6 +289,26 @@ def test_unaligned_and_fused_tensors():
             assert bits_equal(o, w)
 
 
+def test_host_tensor_entry_point_with_caller_outputs():
+    """merge.ties_merge_host_tensors (mc_ties_host): new CPU outputs and caller-provided pinned outputs hold the same bits as the
+    device-resident plan; wrong outputs are refused."""
+    srcs = make_sources(3, [8192, 40000, 17], torch.bfloat16, seed=3, kind="gauss")
+    for func in ("sum", "mean"):
+        odt = torch.float32 if func == "mean" else torch.bfloat16
+        want, ost = oracle_merge(srcs, 20, func)
+        got, st = M.ties_merge_host_tensors(srcs, 20, func)
+        mine = [torch.empty(t.shape, dtype=odt, pin_memory=True) for t in srcs[0]]
+        got2, st2 = M.ties_merge_host_tensors(srcs, 20, func, outputs=mine)
+        assert all(a is b for a, b in zip(got2, mine)) and st == st2
+        assert st["thresholds"] == [float(x) for x in ost["thresholds"]]
+        for t in range(3):
+            assert bits_equal(got[t], want[t]) and bits_equal(mine[t], want[t]), (func, t)
+    with pytest.raises(ValueError):
+        M.ties_merge_host_tensors(srcs, 20, "mean", outputs=[torch.empty(t.shape, dtype=torch.bfloat16) for t in srcs[0]])
+    with pytest.raises(ValueError):
+        M.ties_merge_host_tensors(srcs, 20, "sum", outputs=[torch.empty(8192, dtype=torch.bfloat16)])
+
+
 def test_do_merging_matches_reference_fixture(golden):
     g = golden("ties.pt")
     for case in g["vectors"]:
