@@ -269,7 +269,8 @@ typedef enum mc_linear_epilogue {
   MC_LINEAR_EPI_SILU_MUL = 5,  /* silu(residual[m,n]) * acc: `residual` holds the stored gate_proj output, the product
                                   is the up_proj problem's result (multimodal_llama.py:381-388); may run in place */
   MC_LINEAR_EPI_ROPE = 6       /* rotary embedding of the q / k projection outputs (multimodal_llama.py:281-282), same
-                                  rounding points as mc_rope; head_dim in {64,128,256} dividing N and the N tile */
+                                  rounding points as mc_rope; head_dim in {64,128,256} dividing N and the N tile; C, rope_cos and
+                                  rope_sin 32-byte aligned and ldc a multiple of 16 (the epilogue moves 32-byte vectors) */
 } mc_linear_epilogue;
 
 typedef struct mc_linear_desc {

@@ -238,58 +238,57 @@ __device__ __forceinline__ void epilogue_tile(const LinProblem& pr, bool is_f16,
         uint32_t lo[32], hi[32];
         tmem_ld_32x32(taddr + (uint32_t)(h0 + c), lo);
         tmem_ld_32x32(taddr + (uint32_t)(h0 + half + c), hi);
-        uint4 cv[4], sv[4];
+        // cos / sin and the two output halves move as 32-byte vectors (one full sector per thread and instruction: the rows of a warp
+        // are 32 different lines either way, 16-byte accesses took two instructions and two L2 requests per sector)
+        Vec<32> cv[2], sv[2];
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            cv[j] = *reinterpret_cast<const uint4*>(cosr + (c + 8 * j) * 2);
-            sv[j] = *reinterpret_cast<const uint4*>(sinr + (c + 8 * j) * 2);
+          for (int j = 0; j < 2; ++j) {
+            cv[j] = *reinterpret_cast<const Vec<32>*>(cosr + (c + 16 * j) * 2);
+            sv[j] = *reinterpret_cast<const Vec<32>*>(sinr + (c + 16 * j) * 2);
           }
         }
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             // Packed 16-bit arithmetic reproduces the eager ops bit for bit: a product of two 16-bit floats is exact in fp32, so
             // "fp32 product rounded to the storage dtype" is the single rounding of HMUL2; a sum of two 16-bit floats is exact in
             // fp32 unless the exponents differ by more than 16, where both roundings return the larger operand, so HADD2 equals
             // "fp32 sum rounded" (the _rn intrinsics keep ptxas from contracting product and sum into an FMA, which would skip the
             // product's rounding).  6 packed instructions per element pair instead of ~20 fp32 operations and six conversions.
-            float x1[8], x2[8];
+            Vec<32> o1, o2;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              x1[e] = __uint_as_float(lo[8 * j + e]);
-              x2[e] = __uint_as_float(hi[8 * j + e]);
-            }
-            const uint4 a = pack8(x1, is_f16), b = pack8(x2, is_f16);  // the linear's output, rounded to the storage dtype
-            uint4 o1, o2;
-            const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
-            const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
-            const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cv[j]);
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sv[j]);
-            uint32_t* o1w = reinterpret_cast<uint32_t*>(&o1);
-            uint32_t* o2w = reinterpret_cast<uint32_t*>(&o2);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < 8; ++w) {
+              const int e = 16 * j + 2 * w;
+              uint32_t aw, bw;  // the linear's output, rounded to the storage dtype
               if (is_f16) {
-                const __half2 xa = *reinterpret_cast<const __half2*>(&aw[w]), xb = *reinterpret_cast<const __half2*>(&bw[w]);
-                const __half2 c2 = *reinterpret_cast<const __half2*>(&cw[w]), s2 = *reinterpret_cast<const __half2*>(&sw[w]);
+                const __half2 ha = __floats2half2_rn(__uint_as_float(lo[e]), __uint_as_float(lo[e + 1]));
+                const __half2 hb = __floats2half2_rn(__uint_as_float(hi[e]), __uint_as_float(hi[e + 1]));
+                aw = *reinterpret_cast<const uint32_t*>(&ha);
+                bw = *reinterpret_cast<const uint32_t*>(&hb);
+                const __half2 xa = *reinterpret_cast<const __half2*>(&aw), xb = *reinterpret_cast<const __half2*>(&bw);
+                const __half2 c2 = *reinterpret_cast<const __half2*>(&cv[j].w[w]), s2 = *reinterpret_cast<const __half2*>(&sv[j].w[w]);
                 const __half2 r1 = __hadd2_rn(__hmul2_rn(xa, c2), __hneg2(__hmul2_rn(xb, s2)));  // x1*cos + (-x2)*sin; _rn: never contracted into an FMA
                 const __half2 r2 = __hadd2_rn(__hmul2_rn(xb, c2), __hmul2_rn(xa, s2));           // x2*cos + x1*sin
-                o1w[w] = *reinterpret_cast<const uint32_t*>(&r1);
-                o2w[w] = *reinterpret_cast<const uint32_t*>(&r2);
+                o1.w[w] = *reinterpret_cast<const uint32_t*>(&r1);
+                o2.w[w] = *reinterpret_cast<const uint32_t*>(&r2);
               } else {
-                const __nv_bfloat162 xa = *reinterpret_cast<const __nv_bfloat162*>(&aw[w]), xb = *reinterpret_cast<const __nv_bfloat162*>(&bw[w]);
-                const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&cw[w]), s2 = *reinterpret_cast<const __nv_bfloat162*>(&sw[w]);
+                const __nv_bfloat162 ha = __floats2bfloat162_rn(__uint_as_float(lo[e]), __uint_as_float(lo[e + 1]));
+                const __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(hi[e]), __uint_as_float(hi[e + 1]));
+                aw = *reinterpret_cast<const uint32_t*>(&ha);
+                bw = *reinterpret_cast<const uint32_t*>(&hb);
+                const __nv_bfloat162 xa = *reinterpret_cast<const __nv_bfloat162*>(&aw), xb = *reinterpret_cast<const __nv_bfloat162*>(&bw);
+                const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&cv[j].w[w]), s2 = *reinterpret_cast<const __nv_bfloat162*>(&sv[j].w[w]);
                 const __nv_bfloat162 r1 = __hadd2_rn(__hmul2_rn(xa, c2), __hneg2(__hmul2_rn(xb, s2)));
                 const __nv_bfloat162 r2 = __hadd2_rn(__hmul2_rn(xb, c2), __hmul2_rn(xa, s2));
-                o1w[w] = *reinterpret_cast<const uint32_t*>(&r1);
-                o2w[w] = *reinterpret_cast<const uint32_t*>(&r2);
+                o1.w[w] = *reinterpret_cast<const uint32_t*>(&r1);
+                o2.w[w] = *reinterpret_cast<const uint32_t*>(&r2);
               }
             }
-            const int col = n0 + h0 + c + 8 * j;
-            *reinterpret_cast<uint4*>(crow + (long long)col * 2) = o1;
-            *reinterpret_cast<uint4*>(crow + (long long)(col + half) * 2) = o2;
+            const int col = n0 + h0 + c + 16 * j;
+            *reinterpret_cast<Vec<32>*>(crow + (long long)col * 2) = o1;
+            *reinterpret_cast<Vec<32>*>(crow + (long long)(col + half) * 2) = o2;
           }
         }
       }
@@ -1353,8 +1352,9 @@ extern "C" int mc_linear_plan_create(mc_linear_plan_t** out, const mc_linear_des
     PLAN_REQUIRE(d.epilogue != MC_LINEAR_EPI_ROPE ||
                      (d.rope_cos && d.rope_sin && d.rope_seq_len >= 1 && d.rope_head_dim >= 64 && d.rope_head_dim % 64 == 0 &&
                       bn % d.rope_head_dim == 0 && d.N % d.rope_head_dim == 0 &&
-                      (((uintptr_t)d.rope_cos | (uintptr_t)d.rope_sin) & 15) == 0),
-                 "problem %d: ROPE epilogue needs cos/sin tables, seq_len >= 1 and a head_dim in {64, 128, 256} dividing N and the tile", i);
+                      (((uintptr_t)d.rope_cos | (uintptr_t)d.rope_sin | (uintptr_t)d.C) & 31) == 0 && d.ldc % 16 == 0),
+                 "problem %d: ROPE epilogue needs cos/sin tables, seq_len >= 1, a head_dim in {64, 128, 256} dividing N and the tile, and "
+                 "32-byte aligned C / cos / sin with ldc %% 16 == 0", i);
     PLAN_REQUIRE((d.epilogue != MC_LINEAR_EPI_BIAS && d.epilogue != MC_LINEAR_EPI_BIAS_GELU) || d.bias, "problem %d: bias is NULL", i);
     PLAN_REQUIRE((d.epilogue != MC_LINEAR_EPI_RESIDUAL && d.epilogue != MC_LINEAR_EPI_SILU_MUL) ||
                      (d.residual && d.ldr >= d.N && d.ldr % 8 == 0), "problem %d: residual / gate operand missing", i);

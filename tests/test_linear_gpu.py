@@ -423,3 +423,14 @@ def test_argument_errors():
         LN.LinearPlan([LN.Problem(a, a, a.clone(), epilogue=LN.EPI_ROWMASK)])
     with pytest.raises(_cabi.McError, match="dtype"):
         LN.LinearPlan([LN.Problem(a.float(), a.float(), a.float())])
+    # ROPE epilogue: 32-byte vectors — an output view that is only 16-byte aligned is refused at plan creation
+    x, W = torch.zeros((16, 64), dtype=torch.bfloat16, device="cuda"), torch.zeros((128, 64), dtype=torch.bfloat16, device="cuda")
+    cos, sin = (t.cuda() for t in XO.rope_cos_sin(64, 32, torch.bfloat16))
+    pos = torch.zeros(1, dtype=torch.int32, device="cuda")
+    wide = torch.zeros((16, 144), dtype=torch.bfloat16, device="cuda")
+    LN.LinearPlan([LN.Problem(x, W, wide[:, :128], epilogue=LN.EPI_ROPE, rope=(cos, sin, pos, 16, 64))])   # aligned view: accepted
+    with pytest.raises(_cabi.McError, match="32-byte"):
+        LN.LinearPlan([LN.Problem(x, W, wide[:, 8:136], epilogue=LN.EPI_ROPE, rope=(cos, sin, pos, 16, 64))])
+    with pytest.raises(_cabi.McError, match="32-byte"):
+        LN.LinearPlan([LN.Problem(x, W, torch.zeros((16, 136), dtype=torch.bfloat16, device="cuda")[:, :128], epilogue=LN.EPI_ROPE,
+                                  rope=(cos, sin, pos, 16, 64))])   # ldc = 136: not a multiple of 16
