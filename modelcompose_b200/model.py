@@ -38,6 +38,10 @@ ADAPTER_ORDER = ("audio", "vision", "video", "point")
 _UP_TUNING_ENV = os.environ.get("MC_LINEAR_UP_TUNING")
 UP_TUNING = int(_UP_TUNING_ENV) if _UP_TUNING_ENV not in (None, "", "auto") else None
 UP_TUNING_PAIR_MIN_ROWS = 8192
+# development switches: tile rasterisation of the base ("up") launches, M tiles per sweep over N (0 = the library's choice), for the
+# CTA-pair kernel (512-row tiles) and the single-CTA kernel (128-row tiles); swept in profiles/r02_raster.txt
+GROUP_M_PAIR = int(os.environ.get("MC_LINEAR_GROUP_M_PAIR", "0"))
+GROUP_M_SINGLE = int(os.environ.get("MC_LINEAR_GROUP_M_SINGLE", "0"))
 # ... except for the launches whose epilogue is heavy or whose K is short: the pair kernel's accumulator is single-buffered (its
 # epilogue is not overlapped with the next tile), and ncu shows its tensor pipe at 63 % on the up_proj launch that carries
 # SiLU(gate)·up and 67 % on o_proj, against 78 - 81 % on gate_proj / down_proj (profiles/r01_linear_pair_ncu_instep.txt).
@@ -314,6 +318,7 @@ class _Workspace:
 
     def _up(self, src, layer: _Layer, names, tbufs, outs, residual=None, epilogue=None, launch=None):
         tuning = 0 if (self.up_mixed and launch in UP_AUTO_SINGLE_CTA) else self.up_tuning
+        tuning |= ((GROUP_M_PAIR if tuning in (3, 4) else GROUP_M_SINGLE) & 0xff) << 8
         if epilogue is None:
             epilogue = LN.EPI_RESIDUAL if residual is not None else LN.EPI_NONE
         probs = []
