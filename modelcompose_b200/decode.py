@@ -27,6 +27,8 @@ from . import _cabi
 from . import linear as LN
 
 SK_NONE, SK_RESIDUAL, SK_COLSCALE, SK_SILU_MUL = 0, 1, 2, 3
+# tuning bits OR-ed into the low-rank "down" launches of the branch form (3 - 9 MB of weights each): 16 = the register kernel
+DOWN_TUNING = int(os.environ.get("MC_DECODE_DOWN_TUNING", "0"))
 MAX_M = 64
 # programmatic dependent launch along the decode chain (mc_set_launch_mode): every kernel of the step may start while its
 # predecessor still runs and the skinny linears prefetch their first ring of weights before they wait for it; 0 = plain launches
@@ -213,7 +215,7 @@ class DecodeWorkspace:
         def down(layer, names, src):
             probs = [dict(A0=src, B0=layer.ad[n].A_all[:R0], C=self.t[i], col_scale=layer.ad[n].col_scale[:R0].contiguous(),
                           epilogue=SK_COLSCALE) for i, n in enumerate(names)]
-            return SkinnyLaunch(probs, tuning, ws)
+            return SkinnyLaunch(probs, tuning | DOWN_TUNING, ws)
 
         def up(layer, names, src, outs, residual=None, tune=tuning):
             probs = []
