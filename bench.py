@@ -1098,7 +1098,7 @@ def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, worl
         "data": "synthetic", "vs_baseline": None,
         "config": {"workload": PREFILL_CONFIGS[cfg_name][0] + " — decode steps after that prefill", "requests_per_gpu": batch,
                    "context_tokens": [int(len0), int(len0 + steps)], "prompt_tokens_after_splice": int(S0),
-                   "linear_form": "materialised W_eff of the default group" if model.materialize else
+                   "linear_form": "materialised W_eff of the default group" if (model.materialize or model.decode_dense) else
                    "base weight + low-rank branch of the default group (rank %d)" % (dws.t[0].shape[1] if dws.t else 0),
                    "l2": "weights %.1f GB + cache %.1f GB per step, far larger than L2" % (w_bytes / 1e9, kv_bytes / 1e9),
                    "step": "one CUDA-graph replay: embedding gather, 32 layers, final norm, lm_head, greedy argmax"},

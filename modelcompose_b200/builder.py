@@ -38,10 +38,12 @@ def _load_base_state_dict(model_base: str) -> Dict[str, torch.Tensor]:
 
 
 def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, load_4bit=False, device_map="auto",
-                          device="cuda", torch_dtype=torch.float16, materialize=None):
+                          device="cuda", torch_dtype=torch.float16, materialize=None, decode_dense=None):
     """Returns ``(tokenizer, model, modal_processors, context_len)`` like the reference (builder.py:231).
     ``materialize`` (extra, default: the MC_MATERIALIZE environment switch): build one dense effective weight per routing
-    group at load (``modelcompose_b200.materialize``) and run every linear as a grouped GEMM instead of base + LoRA branches."""
+    group at load (``modelcompose_b200.materialize``) and run every linear as a grouped GEMM instead of base + LoRA branches.
+    ``decode_dense`` (extra, default: MC_DECODE_DENSE): keep the branch form for the prefill and build the dense weight of the text
+    group only, for the decode steps (model.py: DECODE_DENSE)."""
     if load_8bit or load_4bit:
         raise NotImplementedError("bitsandbytes quantised loading is outside the B200 hot path (SURVEY.md §2.2)")
     if "multimodal" not in model_name.lower():
@@ -66,6 +68,7 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
             adapters.update({k: v.to(torch.float16) for k, v in torch.load(extra, map_location="cpu").items()})
     else:  # merged weights and adapters saved together (builder.py:169-180)
         adapters = base
-    model = MultimodalLlamaForCausalLM(cfg, base, adapters, device=device, dtype=torch_dtype, materialize=materialize)
+    model = MultimodalLlamaForCausalLM(cfg, base, adapters, device=device, dtype=torch_dtype, materialize=materialize,
+                                       decode_dense=decode_dense)
     context_len = getattr(cfg, "max_sequence_length", 2048)
     return tokenizer, model, None, context_len

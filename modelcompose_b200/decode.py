@@ -203,14 +203,14 @@ class DecodeWorkspace:
         self.att_scratch = buf(B * nH * self.n_splits * (D + 2), dtype=torch.float32)
         self.att_counters = buf(B * nH, dtype=torch.int32)
         ws = skinny_workspace(dev)
-        dense = model.materialize
+        dense = model.materialize or getattr(model, "decode_dense", False)
         R0 = 0 if dense else int(model.layers[0].ad["q_proj"].group_cols[1])  # rank columns of the default group
         self.t = [buf(B, max(R0, 8)) for _ in range(3)] if R0 else []
         self.launches: List[List] = []
         self.weight_bytes = 0
 
         def W(layer, n):
-            return layer.Weff[n][0] if dense else layer.W[n]
+            return layer.Weff[n][0] if model.materialize else (layer.Wdec[n] if dense else layer.W[n])
 
         def down(layer, names, src):
             probs = [dict(A0=src, B0=layer.ad[n].A_all[:R0], C=self.t[i], col_scale=layer.ad[n].col_scale[:R0].contiguous(),

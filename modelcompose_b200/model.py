@@ -63,6 +63,11 @@ ATTENTION_NATIVE = os.environ.get("MC_ATTENTION_NATIVE", "1") != "0"
 # traffic.  W_eff is rounded once to the storage dtype, so logits differ from form 0 within the bar stated in
 # tests/test_prefill_gpu.py (reference tooling for the dense form: delta_weights_compare.py:24-31,61).
 MATERIALIZE = os.environ.get("MC_MATERIALIZE", "0") != "0"
+# Branch form for the prefill, dense weights for the DECODE steps only: generated tokens are text, so every decode row takes the
+# default group and its W_eff (W + the default adapters) is all the decode step needs — one extra copy of the decoder weights
+# (13 GB for vicuna-7B) instead of one per group, four launches per layer fewer in the HBM-bound step (+40 % tokens/s at
+# batch 32, profiles/r02_decode.txt).  Decode logits then carry the dense form's single rounding of W_eff, like MC_MATERIALIZE=1.
+DECODE_DENSE = os.environ.get("MC_DECODE_DENSE", "0") != "0"
 
 
 class MultimodalConfig:
@@ -174,6 +179,7 @@ class _Layer:
     W: Dict[str, torch.Tensor] = field(default_factory=dict)
     ad: Dict[str, LN.PackedAdapters] = field(default_factory=dict)
     Weff: Dict[str, List[torch.Tensor]] = field(default_factory=dict)  # materialised form: one dense weight per routing group
+    Wdec: Dict[str, torch.Tensor] = field(default_factory=dict)        # decode_dense: W_eff of the text group, for the decode step only
     ln1: torch.Tensor = None
     ln2: torch.Tensor = None
 
@@ -379,9 +385,10 @@ class MultimodalLlamaForCausalLM:
 
     def __init__(self, config: MultimodalConfig, base_state_dict: Dict[str, torch.Tensor],
                  adapter_state_dict: Optional[Dict[str, torch.Tensor]] = None, device="cuda", dtype=torch.float16,
-                 materialize: Optional[bool] = None):
+                 materialize: Optional[bool] = None, decode_dense: Optional[bool] = None):
         _cabi.lib()  # fail loudly if the CUDA library is missing
         self.materialize = MATERIALIZE if materialize is None else bool(materialize)
+        self.decode_dense = (DECODE_DENSE if decode_dense is None else bool(decode_dense)) and not self.materialize
         if dtype not in (torch.float16, torch.bfloat16):
             raise ValueError("inference dtype must be float16 (reference builder.py:185) or bfloat16")
         self.config, self.device, self.dtype = config, torch.device(device), dtype
@@ -438,6 +445,9 @@ class MultimodalLlamaForCausalLM:
                 else:
                     layer.ad[name] = LN.pack_adapters(A, Bm, self.scaling, self.modal_names, self.default_adapter_names,
                                                       W.shape[1], W.shape[0], dtype, self.device)
+                    if self.decode_dense:  # W_eff of the text group only
+                        layer.Wdec[name] = MZ.effective_weights(W, A, Bm, self.scaling, self.modal_names[:1], self.default_adapter_names,
+                                                                alpha / r)[0]
             self.layers.append(layer)
         self.rank_total = self.layers[0].ad["q_proj"].A_all.shape[0] if self.layers and not self.materialize else LN.K_BLOCK
         for layer in self.layers:

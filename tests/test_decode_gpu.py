@@ -277,6 +277,36 @@ def test_decode_with_linear_rope_scaling(golden):
         logits_close(o.logits[:, 0], full.logits[:, Sp - new + i, :], key, f"decode step {i} vs prefill, linear RoPE scaling")
 
 
+def test_decode_dense_option(golden):
+    """decode_dense: branch form for the prefill, the dense W_eff of the text group for the decode steps only — the same weights the
+    materialised form holds for group 0 (bit for bit), four launches per layer fewer, decode logits within the bar of the prefill."""
+    dtype, key = torch.bfloat16, "bf16"
+    run = golden("merge_c1.pt")["runs"][STRATEGY_C1]
+    cfgd = dict(run["config"])
+    cfgd["num_attention_heads"] = cfgd["num_key_value_heads"] = 2
+    cfg, base = MD.MultimodalConfig.from_dict(cfgd), syn.make_base_llm(seed=1)
+    model = MD.MultimodalLlamaForCausalLM(cfg, base, run["state_dict"], device="cuda", dtype=dtype, decode_dense=True)
+    dense = d128_model(golden, dtype, materialize=True)
+    branch = d128_model(golden, dtype)
+    assert model.decode_dense and not model.materialize and not dense.decode_dense
+    for la, lb in zip(model.layers, dense.layers):
+        for n in la.Wdec:
+            assert torch.equal(la.Wdec[n], lb.Weff[n][0]), n
+    B, new = 3, 4
+    ids, feats = _prompt(B, dtype)
+    out_ids = model.generate(ids, modal_inputs=feats, max_new_tokens=new, do_sample=False)
+    branch.generate(ids, modal_inputs=feats, max_new_tokens=new, do_sample=False)
+    assert model._dws.launches_per_step() == branch._dws.launches_per_step() - 4 * len(model.layers)
+    full = model.forward(out_ids, torch.ones_like(out_ids), modal_inputs=feats)   # branch-form prefill of the extended sequence
+    Sp = full.logits.shape[1]
+    o1 = model.forward(ids, torch.ones_like(ids), modal_inputs=feats, use_cache=True, cache_extra=8)
+    cache = o1.past_key_values
+    for i in range(3):
+        tok = out_ids[:, ids.shape[1] + i:ids.shape[1] + i + 1]
+        o = model.forward(tok, torch.ones((B, cache.length + 1), dtype=torch.int64, device="cuda"), past_key_values=cache, modal_inputs=feats)
+        logits_close(o.logits[:, 0], full.logits[:, Sp - new + i, :], key, f"dense decode step {i} vs branch-form prefill")
+
+
 def test_decode_graph_equals_eager_and_prefill_kernel_path(golden, monkeypatch):
     dtype = torch.bfloat16
     ids, feats = _prompt(4, dtype, seed=5)
