@@ -707,7 +707,7 @@ def bf16_peaks():
     return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def build_prefill(cfg_name: str, device, rank: int, layers=None, materialize=None):
+def build_prefill(cfg_name: str, device, rank: int, layers=None, materialize=None, decode_dense=None):
     """Random-init composed model + one batch of requests (ids on host and device, encoder features on host and device)."""
     from modelcompose_b200 import model as MD
     from modelcompose_b200 import splice as SP
@@ -716,7 +716,7 @@ def build_prefill(cfg_name: str, device, rank: int, layers=None, materialize=Non
     coeff = 0.25 if len(merged) == 4 else 0.333
     cfg, base, adapters = syn.make_composed_on_device(merged, device, torch.bfloat16, coeff=coeff, seed=1, layers=layers)
     model = MD.MultimodalLlamaForCausalLM(MD.MultimodalConfig.from_dict(cfg), base, adapters, device=device, dtype=torch.bfloat16,
-                                          materialize=materialize)
+                                          materialize=materialize, decode_dense=decode_dense)
     # layer 0 as the checkpoint has it (unpacked adapters): the untimed oracle spot-check evaluates the reference schedule on it
     model._bench_layer0 = ({k: v for k, v in base.items() if k.startswith("model.layers.0.")},
                            {k: v for k, v in adapters.items() if k.startswith("model.layers.0.")}, cfg)
@@ -798,8 +798,14 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
     path).  Returns the result dict (rank 0) with tokens/s, roofline of the routed-linear kernel, e2e and verification."""
     from modelcompose_b200 import _cabi
     from modelcompose_b200 import linear as LN
+    # a branch-form model that is also asked for decode steps carries the dense text-group weights as well (model.py: DECODE_DENSE),
+    # so that the decode steps can be timed in both forms after the same branch-form prefill
+    both_decode_forms = with_decode and not materialize and os.environ.get("MC_BENCH_DECODE_DENSE", "1") != "0"
     model, desc, batch, ids_h, mask_h, feats_h, flops = build_prefill(cfg_name, device, rank, layers=args.prefill_layers,
-                                                                      materialize=materialize)
+                                                                      materialize=materialize, decode_dense=True if both_decode_forms else None)
+    dense_requested = model.decode_dense
+    if both_decode_forms:
+        model.decode_dense = False   # the prefill never reads it; the first decode pass below is the branch form
     ids_d, mask_d = ids_h.to(device), mask_h.to(device)
     feats_d = {m: v.to(device) for m, v in feats_h.items()}
     S_out = int(flops["seq_len"])
@@ -929,6 +935,10 @@ def run_prefill(args, device, rank, world, dist, barrier, cfg_name: str, materia
     }
     if with_decode:
         res["decode"] = run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, world, dist, barrier)
+        if both_decode_forms and dense_requested:
+            model.decode_dense = True
+            model._dws = None        # the decode workspace is rebuilt on the dense text-group weights
+            res["decode_dense"] = run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, world, dist, barrier)
     del model
     torch.cuda.empty_cache()
     return res
@@ -1098,7 +1108,8 @@ def run_decode(args, model, cfg_name, ids_d, mask_d, feats_d, device, rank, worl
         "data": "synthetic", "vs_baseline": None,
         "config": {"workload": PREFILL_CONFIGS[cfg_name][0] + " — decode steps after that prefill", "requests_per_gpu": batch,
                    "context_tokens": [int(len0), int(len0 + steps)], "prompt_tokens_after_splice": int(S0),
-                   "linear_form": "materialised W_eff of the default group" if (model.materialize or model.decode_dense) else
+                   "linear_form": "materialised W_eff of the default group" if model.materialize else
+                   "dense W_eff of the default group for the decode steps only, branch-form prefill (decode_dense)" if model.decode_dense else
                    "base weight + low-rank branch of the default group (rank %d)" % (dws.t[0].shape[1] if dws.t else 0),
                    "l2": "weights %.1f GB + cache %.1f GB per step, far larger than L2" % (w_bytes / 1e9, kv_bytes / 1e9),
                    "step": "one CUDA-graph replay: embedding gather, 32 layers, final norm, lm_head, greedy argmax"},
@@ -1250,12 +1261,15 @@ def main():
                 pre["cpu_baseline"] = (cpu_prefill_layer_rate(cfg_name, max_seconds=15.0)
                                        if world == 1 and not args.no_cpu_baseline and i == 0 else None)
                 dec = pre.pop("decode", None)
+                dec_dense = pre.pop("decode_dense", None)
                 suffix = ""
                 if mat != args.materialize:
                     suffix = "_materialized" if mat else "_branch"
                 if args.workload == "decode" and i == 0:
                     line = dec
                     line["prefill"] = pre
+                    if dec_dense is not None:
+                        line["decode_dense"] = dec_dense
                 elif args.workload == "prefill" and i == 0:
                     line = pre
                 elif line is not None:
@@ -1263,6 +1277,8 @@ def main():
                     line[key + suffix] = pre
                     if dec is not None:
                         line["decode" + ("" if i == 0 else "_" + cfg_name) + suffix] = dec
+                    if dec_dense is not None:   # branch-form prefill, dense text-group weights for the decode steps
+                        line["decode_dense" + ("" if i == 0 else "_" + cfg_name)] = dec_dense
     if rank == 0 and line is not None:
         emit(line)
     if world > 1:
