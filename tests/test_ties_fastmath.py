@@ -203,3 +203,21 @@ def test_bf16_trim_as_fp16_bit_patterns():
             finite_or_inf = mags <= 0x7f80
             assert np.array_equal(keep_ref[finite_or_inf], keep_dev[finite_or_inf]), hex(int(t))
             assert keep_dev[~finite_or_inf].all()             # bf16 NaNs stay in the sum (the reference's x * mask keeps them NaN too)
+
+
+def test_census_bit_masks_in_float_accumulators():
+    """ties_chunk_fast keeps the census of 16 elements as bit masks built by FFMAs (mask += indicator * 2^bit): the sums stay below
+    2^16, exact in fp32 whatever the order; counts are popcounts and the class-3 set is some & ~(p | n)."""
+    rng = np.random.default_rng(3)
+    for _ in range(2000):
+        acc_sign = rng.integers(-1, 2, 16)                     # sign of the trimmed sum per element
+        kept = rng.integers(0, 2, 16) | (acc_sign != 0)        # an elected sign implies a kept entry
+        p, n, some = (acc_sign > 0).astype(F32), (acc_sign < 0).astype(F32), kept.astype(F32)
+        m_pos = m_neg = m_some = F32(0)
+        for b in rng.permutation(16):
+            bit = F32(1 << int(b))
+            m_pos, m_neg, m_some = F32(p[b] * bit + m_pos), F32(n[b] * bit + m_neg), F32(some[b] * bit + m_some)
+        bp, bn, bs = int(m_pos), int(m_neg), int(m_some)
+        assert bin(bp).count("1") == int(p.sum()) and bin(bn).count("1") == int(n.sum())
+        amb = bs & ~(bp | bn)
+        assert [b for b in range(16) if amb >> b & 1] == [b for b in range(16) if kept[b] and acc_sign[b] == 0]
