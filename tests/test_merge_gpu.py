@@ -1,7 +1,6 @@
 """GPU parity of the N-source merge kernel (through the C ABI) against oracle/merge_oracle.py.
 
 Bar: bit-exact (integer compare of the raw words; NaN positions compared as NaN-ness)."""
-import itertools
 
 import pytest
 import torch

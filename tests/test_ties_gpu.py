@@ -4,7 +4,6 @@
 Bar: bit-exact (raw words, signed zeros and result dtype included)."""
 import copy
 import hashlib
-import json
 import os
 
 import pytest
