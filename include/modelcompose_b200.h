@@ -148,7 +148,9 @@ typedef struct mc_ties_plan mc_ties_plan_t;
 MC_API int mc_ties_plan_create(mc_ties_plan_t** plan, int n_tensors, int n_src, const void* const* src, void* const* dst,
                         const int64_t* numel, int src_dtype, int dst_dtype);
 /* Enqueues the whole TIES merge.  kth = 1-based rank (ascending magnitude) of the smallest kept element among the
- * plan's total element count d: the reference's `d - int(d * K)` (ties_merging.py:89-96); 1 <= kth <= d. */
+ * plan's total element count d: the reference's `d - int(d * K)` (ties_merging.py:89-96); 1 <= kth <= d.
+ * Six launches, decisions taken on the device, nothing synchronises.  The plan owns the run's device state (thresholds,
+ * census, arrival counters): runs of ONE plan must be ordered (same stream, or events between streams). */
 MC_API int mc_ties_plan_run(const mc_ties_plan_t* plan, int64_t kth, int func, mc_stream_t stream);
 /* Synchronises `stream` and reports the thresholds / census of the last run. */
 MC_API int mc_ties_plan_stats(const mc_ties_plan_t* plan, mc_ties_stats_t* out, mc_stream_t stream);
