@@ -135,7 +135,8 @@ __device__ __forceinline__ uint32_t pack_thr(float thr) {
 // 16-bit sources: the same results bit for bit as ties_one_ref with the arithmetic moved off the
 // half-rate ALU pipe that bounded the first version of this pass (profiles/r01_ties.txt: 57 instructions per element,
 // ALU 65 %, DRAM 39 %) — no predicate, select or min/max per source, everything but the trim compare is FMUL/FADD/FFMA:
-//   * trim by multiplication, m = x * [|x| >= thr] (the reference's own form, ties_merging.py:98-101);
+//   * trim by multiplication, m = x * [|x| >= thr] (the reference's own form, ties_merging.py:98-101) in the scalar form; the vector
+//     path trims the packed words before they are widened (trim_word);
 //   * the sign is elected from the fp32 sum itself: rounding it to the 16-bit dtype first (:121) never changes the sign
 //     and never turns a non-zero sum into zero (the sum is a multiple of the dtype's smallest subnormal, overflow keeps
 //     the sign).  p = [acc > 0] and n = [acc < 0] are mul_sat(+-acc, inf), and half the elected sign is
@@ -146,13 +147,14 @@ __device__ __forceinline__ uint32_t pack_thr(float thr) {
 //     symmetric); fma(sum k, sigma, +0) restores the reference's +0 when nothing is kept;
 //   * MEAN: #kept != 0 is sum of mul_sat(k, inf); the float32 division by that small integer c is
 //     q0 = x r, q1 = fma(fma(-q0, c, x), r, q0) with r ~ 1 / c (MUFU), the correctly rounded quotient for every 16-bit x,
-//     c <= 8 and any r within 2 ulp of 1 / c (checked exhaustively: tests/test_ties_oracle.py); min(q1, x) returns
+//     c <= 8 and any r within 2 ulp of 1 / c (checked exhaustively: tests/test_ties_fastmath.py); min(q1, x) returns
 //     x = inf when the 16-bit rounding of the sum overflowed (q1 = NaN there);
 //   * survivors that cancel exactly (class 3) are acc == 0 with a non-empty candidate, for either default sign:
 //     amb = [sum k > 0] (1 - p - n);
 //   * MAX keeps the running maximum of k instead of the sum; (max k) * sigma is exact and keeps torch's -0.
 // p, n, some (and amb in the scalar form) come back as 0.0 / 1.0, so the census of the vector path is three FFMAs per element
 // (ties_chunk_fast).
+
 // Election half of the element function on already trimmed entries m: the kept sum (or running max) ksum >= +0, the number of
 // kept non-zero entries cnt (MEAN only), the elected sign sg = +-1, the census indicators p = [acc > 0], n = [acc < 0] and
 // some = [a kept entry is non-zero].  DEFPOS: the default sign is known to be + (the speculative pass), so hs = 0.5 - n.
