@@ -2,7 +2,10 @@
 
 torch-CPU restatement of ``modelcompose/model/language_model/multimodal_llama.py`` (line numbers
 into that file unless another is named).  Every op runs in the tensor's own dtype in the same
-order as the reference, so rounding points match the reference's eager path.
+order as the reference, so rounding points match the reference's eager path.  Pinned against fixtures produced by
+running the reference itself (tests/golden/prefill_c1.pt, tests/test_oracle_golden.py); the one part no reference artefact
+pins is ``linear_factor`` of ``rope_cos_sin`` (transformers 4.31's LlamaLinearScalingRotaryEmbedding, a dependency absent
+here): it is anchored on the installed transformers' "linear" rope initialisation instead.
 """
 from __future__ import annotations
 
